@@ -1,0 +1,194 @@
+/* ptgpu.h — C ABI of libptgpu.so: the B200 (sm_100a) implementation of pathtrace-rs's per-pixel
+ * path-tracing loop (`Scene::update` and everything it calls).
+ *
+ * This header is the drop-in boundary.  Every entry point names the reference interface it replaces
+ * (paths relative to the pathtrace-rs source tree).  Plain C types only: pointers, sizes, PODs.
+ * There is no CPU fallback: every compute entry point fails with PT_ERR_NO_DEVICE when no CUDA
+ * device is usable.
+ *
+ * Image convention (src/scene.rs:94-95,108; src/camera.rs:41-44): rgb buffers are `width*height`
+ * packed (r,g,b) f32 triples, row-major, BOTTOM-UP (row 0 is the bottom of the picture), exactly the
+ * `&mut [(f32,f32,f32)]` that `Scene::update` blends into.
+ */
+#ifndef PTGPU_H
+#define PTGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PT_ABI_VERSION 1
+
+/* ---- status codes (the Rust shim `expect`s on non-zero, matching the reference's panic-on-error
+ *      convention: src/offline.rs:10,32,59) ---- */
+enum {
+    PT_OK = 0,
+    PT_ERR_INVALID = 1,      /* null pointer, bad index, zero-sized image ... */
+    PT_ERR_UNSUPPORTED = 2,  /* e.g. use_bvh, or a hitable that is not a sphere */
+    PT_ERR_NO_DEVICE = 3,    /* no CUDA device / wrong architecture (needs sm_100) */
+    PT_ERR_CUDA = 4,         /* a CUDA runtime call failed; see pt_last_error() */
+    PT_ERR_TOO_LARGE = 5
+};
+
+/* ---- Params: src/params.rs:11-18 (`pub struct Params`) ---- */
+typedef struct PtParams {
+    uint32_t width;
+    uint32_t height;
+    uint32_t samples;
+    uint32_t max_depth;
+    uint8_t random_seed; /* bool: per-pixel seeds from host entropy instead of (x,y,frame): src/scene.rs:96-102 */
+    uint8_t use_bvh;     /* bool: must be 0 — the GPU path is the flat list (src/params.rs:36-43 List arm) */
+    uint8_t _pad[6];
+    uint64_t seed_salt;  /* only read when random_seed != 0: the host's `rand::random()` entropy */
+} PtParams;
+
+/* ---- Camera: src/camera.rs:8-19 (10 private fields, built on the host by Camera::new :22-54) ---- */
+typedef struct PtCamera {
+    float origin[3];
+    float lower_left_corner[3];
+    float horizontal[3];
+    float vertical[3];
+    float u[3];
+    float v[3];
+    float w[3]; /* unused by get_ray (src/camera.rs:56-68); carried for completeness */
+    float time0;
+    float time1;
+    float lens_radius;
+} PtCamera;
+
+/* ---- Texture: src/texture.rs:40-55 (arena references become indices into PtSceneDesc.textures) ---- */
+enum { PT_TEX_CONSTANT = 0, PT_TEX_CHECKER = 1, PT_TEX_NOISE = 2 };
+typedef struct PtTexture {
+    int32_t kind;
+    float color[3]; /* Constant */
+    int32_t odd;    /* Checker: texture index */
+    int32_t even;   /* Checker: texture index */
+    float scale;    /* Noise */
+    int32_t _pad;
+} PtTexture;
+
+/* ---- Material: src/material.rs:13-19 ---- */
+enum { PT_MAT_LAMBERTIAN = 0, PT_MAT_METAL = 1, PT_MAT_DIELECTRIC = 2, PT_MAT_DIFFUSE_LIGHT = 3 };
+typedef struct PtMaterial {
+    int32_t kind;
+    int32_t texture; /* Lambertian.albedo / DiffuseLight.emit: texture index; -1 otherwise */
+    float albedo[3]; /* Metal */
+    float fuzz;      /* Metal */
+    float ref_idx;   /* Dielectric */
+    int32_t _pad;
+} PtMaterial;
+
+/* ---- Perlin: src/perlin.rs:7-12 (tables generated on the host by Perlin::new :44-51) ---- */
+typedef struct PtPerlin {
+    float randvec[256][3];
+    uint32_t perm_x[256];
+    uint32_t perm_y[256];
+    uint32_t perm_z[256];
+} PtPerlin;
+
+/* ---- Scene: src/scene.rs:18-22 (`world` flattened) + src/collision/spheres_soa.rs:12-23 (SoA arrays).
+ * The flattener walks Hitable::List and must reject anything that is not Hitable::Sphere
+ * (mirrors the panic at spheres_soa.rs:49-51). `radius` keeps its sign (hollow spheres: presets.rs:265). */
+typedef struct PtSceneDesc {
+    uint32_t struct_size; /* = sizeof(PtSceneDesc) */
+    uint32_t n_spheres;
+    const float* centre_x;
+    const float* centre_y;
+    const float* centre_z;
+    const float* radius;
+    const int32_t* material_index; /* per sphere, into materials[] */
+    uint32_t n_materials;
+    uint32_t n_textures;
+    const PtMaterial* materials;
+    const PtTexture* textures;
+    const PtPerlin* perlin; /* may be NULL when no Noise texture is referenced */
+    uint32_t has_sky;       /* Scene.sky: Option<Vec3>  (src/scene.rs:20,39-47) */
+    float sky[3];
+} PtSceneDesc;
+
+/* ---- partition of one image over several GPUs / calls: interleaved row tiles.
+ * Tile k = rows [k*tile_rows, (k+1)*tile_rows); this part owns tile k iff k % part_count == part_index.
+ * Pixel seeds depend only on (x, y, frame) (src/scene.rs:99-101), so the image is identical for any split. */
+typedef struct PtPartition {
+    uint32_t tile_rows;  /* 0 -> default (4) */
+    uint32_t part_index;
+    uint32_t part_count; /* 0 or 1 -> whole image */
+    uint32_t _pad;
+} PtPartition;
+
+typedef struct PtDeviceInfo {
+    char name[64];
+    int32_t sm_count;
+    int32_t cc_major;
+    int32_t cc_minor;
+    int32_t sm_clock_khz;       /* max SM clock */
+    double fp32_fma_peak_flops; /* sm_count * 128 lanes * 2 flop * max SM clock */
+    uint64_t global_mem_bytes;
+} PtDeviceInfo;
+
+/* per-render statistics of the last pt_render* call on a scene (measurement) */
+typedef struct PtRenderStats {
+    double kernel_ms;   /* CUDA-event time of the megakernel launch(es) (0 for pt_render_device: caller times) */
+    double h2d_ms;      /* host->device copy of the previous frame (0 when frame_num == 0) */
+    double d2h_ms;      /* device->host copy of the result */
+    uint64_t h2d_bytes;
+    uint64_t d2h_bytes;
+    uint64_t ray_count;
+    uint32_t n_spheres;
+    uint32_t kernel_launches;
+    uint32_t grid_ctas;
+    uint32_t cta_threads;
+    uint32_t smem_bytes;
+    uint32_t resident; /* 1: sphere SoA resident in shared memory; 0: streamed through L2 in tiles */
+} PtRenderStats;
+
+typedef struct PtScene PtScene; /* opaque: device copy of one scene on one GPU */
+
+int pt_abi_version(void);
+const char* pt_last_error(void); /* thread-local message of the last failing call */
+int pt_device_count(void);
+int pt_device_info(int device, PtDeviceInfo* out);
+
+/* Replaces `Params::new_scene` (src/params.rs:29-46, List arm) + `SpheresSoA::new`
+ * (src/collision/spheres_soa.rs:26-74): validates and uploads the flat scene to `device`. */
+int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out);
+void pt_scene_destroy(PtScene* scene);
+
+/* Replaces `Scene::update(&self, &Params, &Camera, frame_num, &mut [(f32,f32,f32)]) -> usize`
+ * (src/scene.rs:73-121; call sites src/offline.rs:29, src/glium_window.rs:102).
+ * rgb_inout: HOST buffer, width*height*3 f32; read when frame_num > 0 (running mean, scene.rs:86-87,
+ * 113-116), always written.  *ray_count_out = number of ray_trace calls (scene.rs:57,118-120). */
+int pt_render(PtScene* scene, const PtParams* params, const PtCamera* camera, uint32_t frame_num,
+              float* rgb_inout, uint64_t* ray_count_out);
+
+/* Same, but only the rows of `part` are rendered, read and written (multi-GPU row-tile mode:
+ * one call per GPU into the same host image). part == NULL -> whole image. */
+int pt_render_part(PtScene* scene, const PtParams* params, const PtCamera* camera, uint32_t frame_num,
+                   const PtPartition* part, float* rgb_inout, uint64_t* ray_count_out);
+
+/* Device-resident variant (progressive / windowed use, src/glium_window.rs:98-131: the buffer stays
+ * on the GPU across frames).  d_rgb_inout: DEVICE buffer width*height*3 f32 on the scene's device;
+ * d_ray_count: DEVICE u64, overwritten with this call's ray count.  Asynchronous on `cuda_stream`
+ * (a cudaStream_t; NULL = default stream); no host synchronisation is performed. */
+int pt_render_device(PtScene* scene, const PtParams* params, const PtCamera* camera, uint32_t frame_num,
+                     const PtPartition* part, float* d_rgb_inout, uint64_t* d_ray_count, void* cuda_stream);
+
+/* Output stage of `render_offline` (src/offline.rs:43-51 + src/math.rs:36-48): rows flipped to
+ * top-down, linear -> sRGB (1.055*x^0.41666666-0.055, clamped, *255.99 truncated), packed RGB8.
+ * Host-buffer and device-buffer forms. */
+int pt_srgb8(PtScene* scene, const float* rgb, uint32_t width, uint32_t height, uint8_t* rgb8_out);
+int pt_srgb8_device(PtScene* scene, const float* d_rgb, uint32_t width, uint32_t height, uint8_t* d_rgb8_out,
+                    void* cuda_stream);
+
+int pt_scene_stats(const PtScene* scene, PtRenderStats* out);
+
+/* Measurement helper: sustained FP32 FFMA throughput of `device` (flop/s) from a pure-FMA kernel,
+ * so bench.py can print the measured ceiling beside the nominal sm_count*128*2*clock figure. */
+int pt_probe_fp32_peak(int device, double* flops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTGPU_H */

@@ -1,0 +1,425 @@
+// pt_megakernel.cuh — the persistent render kernel: device side of `Scene::update`
+// (src/scene.rs:73-121) with `ray_trace` (src/scene.rs:49-71) unrolled into a per-lane state machine.
+//
+// Mapping:
+//   * one lane = one pixel's path.  A lane owns a pixel for all of its `samples` (so the pixel's
+//     xoshiro256+ stream is consumed in exactly the reference's order), then pulls the next pixel
+//     from a global atomic queue (warp-aggregated) — the rayon `par_iter_mut` of scene.rs:90-93.
+//   * every trip of the main loop is ONE full sphere sweep for all 32 lanes (convergent, FP32-bound),
+//     followed by a short divergent shading step.  A lane whose path ended starts its next sample
+//     (or next pixel) at the top of the next trip, so the sweep always runs with all live lanes.
+//   * the recursion `emitted + attenuation * ray_trace(..)` becomes `colour += throughput * emitted;
+//     throughput *= attenuation` carried in registers.
+//   * sphere SoA is staged into shared memory once per CTA with TMA bulk copies (cp.async.bulk +
+//     mbarrier); scenes that do not fit are streamed tile by tile (pt_megakernel_streamed below).
+#pragma once
+#include "pt_shade.cuh"
+#include "pt_sweep.cuh"
+
+namespace pt {
+
+struct KernelArgs {
+    const float4* blocks;  // n_blocks * 4 float4 (see pt_sweep.cuh)
+    int n_blocks;
+    int n_spheres;
+    const DevShade* shade;
+    const DevTexture* tex;
+    const PerlinSmem* perlin;  // global copy, staged to shared memory when has_noise
+    int has_noise;
+    DevCamera cam;
+    uint32_t width, height, samples, max_depth, frame_num;
+    float inv_nx, inv_ny, inv_ns, mix_prev, mix_new;
+    int has_sky;
+    V3 sky;
+    uint32_t tile_rows, part_index, part_count, n_owned_pixels;
+    int random_seed;
+    uint64_t seed_salt;
+    float* rgb;
+    unsigned long long* ray_count;
+    unsigned int* next_pixel;
+    // streamed variant only
+    int tile_blocks;  // blocks per shared-memory tile
+    int n_tiles;
+};
+
+constexpr unsigned kFullMask = 0xffffffffu;
+
+// ---- mbarrier / TMA bulk-copy helpers (PTX) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.b32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0u;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// global -> shared bulk copy (TMA, non-tensor form); bytes % 16 == 0, 16-byte aligned both sides
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// issue `bytes` as <= 64 KB bulk copies on one barrier (caller has already done arrive.expect_tx(bytes))
+__device__ __forceinline__ void tma_bulk_g2s_chunked(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    const uint32_t kChunk = 65536u;
+    for (uint32_t off = 0; off < bytes; off += kChunk) {
+        const uint32_t n = bytes - off < kChunk ? bytes - off : kChunk;
+        tma_bulk_g2s(reinterpret_cast<char*>(dst_smem) + off, reinterpret_cast<const char*>(src_gmem) + off, n, bar);
+    }
+}
+
+// ---- per-lane path state ----
+struct Lane {
+    Rng rng;
+    V3 o, d;        // current ray
+    V3 thr;         // product of attenuations so far
+    V3 col;         // sum of radiance over this pixel's samples so far
+    uint32_t px, py;
+    uint32_t sample;  // samples started for this pixel
+    uint32_t depth;
+    bool active;      // a path is in flight
+    bool have_pixel;
+    bool finished;    // queue exhausted
+};
+
+__device__ __forceinline__ void owned_pixel_to_xy(const KernelArgs& a, uint32_t j, uint32_t& x, uint32_t& y) {
+    const uint32_t r = j / a.width;
+    x = j - r * a.width;
+    if (a.part_count <= 1) {
+        y = r;
+    } else {
+        const uint32_t tl = r / a.tile_rows;
+        y = (tl * a.part_count + a.part_index) * a.tile_rows + (r - tl * a.tile_rows);
+    }
+}
+
+// scene.rs:113-116 — blend the finished pixel into the accumulation buffer
+__device__ __forceinline__ void write_pixel(const KernelArgs& a, const Lane& L) {
+    float* out = a.rgb + ((size_t)L.py * a.width + L.px) * 3;
+    const V3 col = L.col * a.inv_ns;
+    float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f;
+    if (a.frame_num != 0) {
+        p0 = out[0];
+        p1 = out[1];
+        p2 = out[2];
+    }
+    out[0] = p0 * a.mix_prev + col.x * a.mix_new;
+    out[1] = p1 * a.mix_prev + col.y * a.mix_new;
+    out[2] = p2 * a.mix_prev + col.z * a.mix_new;
+}
+
+// top-of-trip bookkeeping: finish pixels, pull new ones, start the next sample (scene.rs:94-110)
+__device__ __forceinline__ void lane_refill(const KernelArgs& a, Lane& L, unsigned lane_id) {
+    bool want_pixel = false;
+    if (!L.active && !L.finished) {
+        if (L.have_pixel && L.sample >= a.samples) {
+            write_pixel(a, L);
+            L.have_pixel = false;
+        }
+        want_pixel = !L.have_pixel;
+    }
+    const unsigned need = __ballot_sync(kFullMask, want_pixel);
+    if (need != 0u) {
+        const int leader = __ffs(need) - 1;
+        unsigned base = 0;
+        if ((int)lane_id == leader) base = atomicAdd(a.next_pixel, (unsigned)__popc(need));
+        base = __shfl_sync(kFullMask, base, leader);
+        if (want_pixel) {
+            const unsigned j = base + (unsigned)__popc(need & ((1u << lane_id) - 1u));
+            if (j < a.n_owned_pixels) {
+                owned_pixel_to_xy(a, j, L.px, L.py);
+                uint64_t seed;
+                if (a.random_seed) {
+                    // scene.rs:96-97: an independent host-entropy seed per pixel per frame
+                    uint64_t h = a.seed_salt + ((uint64_t)L.py * a.width + L.px) * 0x9e3779b97f4a7c15ULL +
+                                 (uint64_t)a.frame_num * 0xd1b54a32d192ed03ULL;
+                    seed = splitmix64_next(h);
+                } else {
+                    seed = pixel_seed(L.px, L.py, a.frame_num);
+                }
+                rng_seed(L.rng, seed);
+                L.col = v3(0.0f, 0.0f, 0.0f);
+                L.sample = 0;
+                L.have_pixel = true;
+            } else {
+                L.finished = true;
+            }
+        }
+    }
+    if (!L.active && !L.finished) {
+        // scene.rs:107-110
+        const float u = ((float)L.px + rng_f32(L.rng)) * a.inv_nx;
+        const float v = ((float)L.py + rng_f32(L.rng)) * a.inv_ny;
+        float time;
+        camera_get_ray(a.cam, u, v, L.rng, L.o, L.d, time);
+        (void)time;  // only MovingSphere reads ray.time (out of scope); the draw is kept
+        L.thr = v3(1.0f, 1.0f, 1.0f);
+        L.depth = 0;
+        L.sample += 1;
+        L.active = true;
+    }
+}
+
+// after the sweep: scene.rs:57-70 for the lane's current ray
+__device__ __forceinline__ void lane_shade(const KernelArgs& a, Lane& L, const float4* __restrict__ blk, const PerlinSmem& P,
+                                           float hit_t, int hit_index) {
+    if (hit_index < 0) {
+        L.col = L.col + L.thr * sky_colour(a.has_sky != 0, a.sky, L.d);
+        L.active = false;
+        return;
+    }
+    // spheres_soa.rs:132-139 epilogue
+    const V3 point = L.o + (hit_t * L.d);
+    const float* bf = reinterpret_cast<const float*>(blk) + (hit_index >> 2) * 16 + (hit_index & 3);
+    const V3 centre = v3(bf[0], bf[4], bf[8]);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(a.shade + hit_index));
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(a.shade + hit_index) + 1);
+    DevShade m;
+    m.ar = s0.x; m.ag = s0.y; m.ab = s0.z; m.param = s0.w;
+    m.rinv = s1.x; m.kind = __float_as_int(s1.y); m.tex = __float_as_int(s1.z);
+    const V3 normal = (point - centre) * m.rinv;
+    if (m.kind == MAT_DIFFUSE_LIGHT) {  // material.rs:161-167 (+ :157: lights do not scatter)
+        const V3 em = m.tex < 0 ? v3(m.ar, m.ag, m.ab) : texture_value(a.tex, P, m.tex, point);
+        L.col = L.col + L.thr * em;
+        L.active = false;
+        return;
+    }
+    if (L.depth < a.max_depth) {
+        V3 att, sd;
+        if (material_scatter(m, a.tex, P, L.d, point, normal, L.rng, att, sd)) {
+            L.thr = L.thr * att;
+            L.o = point;
+            L.d = sd;
+            L.depth += 1;
+            return;
+        }
+    }
+    L.active = false;  // absorbed, or depth limit: contributes `emitted` = 0
+}
+
+__device__ __forceinline__ void lane_init(Lane& L) {
+    L.active = false;
+    L.have_pixel = false;
+    L.finished = false;
+    L.sample = 0;
+    L.depth = 0;
+    L.px = L.py = 0;
+    L.o = v3(0.0f, 0.0f, 0.0f);
+    L.d = v3(0.0f, 0.0f, 0.0f);
+    L.thr = v3(0.0f, 0.0f, 0.0f);
+    L.col = v3(0.0f, 0.0f, 0.0f);
+    L.rng.s0 = L.rng.s1 = L.rng.s2 = L.rng.s3 = 0;
+}
+
+__device__ __forceinline__ void flush_ray_count(const KernelArgs& a, unsigned long long rays, unsigned lane_id) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) rays += __shfl_xor_sync(kFullMask, rays, off);
+    if (lane_id == 0 && rays != 0ULL) atomicAdd(a.ray_count, rays);
+}
+
+__device__ __forceinline__ void stage_perlin(const KernelArgs& a, PerlinSmem* P) {
+    if (a.has_noise) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(a.perlin);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(P);
+        for (unsigned i = threadIdx.x; i < sizeof(PerlinSmem) / 4; i += blockDim.x) dst[i] = src[i];
+    }
+}
+
+constexpr int kCtaThreads = 256;
+
+// =====================================================================================================
+// Resident variant: the whole sphere SoA lives in shared memory for the life of the CTA.
+// =====================================================================================================
+template <int UNROLL>
+__global__ void __launch_bounds__(kCtaThreads) pt_megakernel_resident(const __grid_constant__ KernelArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    float4* blk = reinterpret_cast<float4*>(smem_raw);
+    PerlinSmem* P = reinterpret_cast<PerlinSmem*>(smem_raw + (size_t)a.n_blocks * 64);
+
+    const uint32_t bytes = (uint32_t)a.n_blocks * 64u;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && bytes != 0u) {
+        mbar_arrive_expect_tx(&bar, bytes);
+        tma_bulk_g2s_chunked(blk, a.blocks, bytes, &bar);
+    }
+    stage_perlin(a, P);
+    __syncthreads();
+    if (bytes != 0u) mbar_wait(&bar, 0);
+
+    const unsigned lane_id = threadIdx.x & 31u;
+    Lane L;
+    lane_init(L);
+    unsigned long long rays = 0ULL;
+
+    for (;;) {
+        lane_refill(a, L, lane_id);
+        if (__all_sync(kFullMask, L.finished)) break;
+        float ox = L.o.x, oy = L.o.y, oz = L.o.z, dx = L.d.x, dy = L.d.y, dz = L.d.z;
+        if (!L.active) {  // parked lane (queue ran dry): a ray that can never be a candidate
+            ox = 0.0f; oy = 1.0e30f; oz = 0.0f;
+            dx = dy = dz = 0.0f;
+        }
+        float hit_t = kMaxT;
+        int hit_index = -1;
+        sweep_blocks<UNROLL>(blk, a.n_blocks, 0, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
+        if (L.active) {
+            rays += 1ULL;  // scene.rs:57
+            lane_shade(a, L, blk, *P, hit_t, hit_index);
+        }
+    }
+    flush_ray_count(a, rays, lane_id);
+}
+
+// =====================================================================================================
+// Streamed variant: the SoA does not fit in shared memory.  All warps of the CTA sweep the same tile;
+// tiles are double-buffered with TMA bulk copies (full/empty mbarrier pair per buffer), so each trip of
+// the main loop streams the whole SoA once through L2 for every live lane of the CTA.
+// =====================================================================================================
+template <int UNROLL>
+__global__ void __launch_bounds__(kCtaThreads) pt_megakernel_streamed(const __grid_constant__ KernelArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[2];
+    __shared__ __align__(8) uint64_t empty_bar[2];
+    __shared__ int cta_live;  // lanes not finished, recomputed every trip
+    const uint32_t tile_bytes = (uint32_t)a.tile_blocks * 64u;
+    float4* buf[2] = {reinterpret_cast<float4*>(smem_raw), reinterpret_cast<float4*>(smem_raw + tile_bytes)};
+    PerlinSmem* P = reinterpret_cast<PerlinSmem*>(smem_raw + 2 * (size_t)tile_bytes);
+    const int n_warps = kCtaThreads / 32;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&full_bar[0], 1);
+        mbar_init(&full_bar[1], 1);
+        mbar_init(&empty_bar[0], n_warps);
+        mbar_init(&empty_bar[1], n_warps);
+        fence_mbar_init();
+        cta_live = 0;
+    }
+    stage_perlin(a, P);
+    __syncthreads();
+
+    const unsigned lane_id = threadIdx.x & 31u;
+    Lane L;
+    lane_init(L);
+    unsigned long long rays = 0ULL;
+    uint32_t full_phase[2] = {0u, 0u};   // parity to wait for on full_bar[b]
+    uint32_t empty_phase[2] = {0u, 0u};  // producer side: parity to wait for on empty_bar[b]
+    uint32_t produced[2] = {0u, 0u};     // producer: how many times buffer b has been filled
+
+    auto produce = [&](int tile) {  // thread 0 only
+        const int b = tile & 1;
+        if (produced[b] != 0u) {  // wait until every warp has released the previous contents
+            mbar_wait(&empty_bar[b], empty_phase[b]);
+            empty_phase[b] ^= 1u;
+        }
+        produced[b] += 1u;
+        const int first = tile * a.tile_blocks;
+        const int nb = min(a.tile_blocks, a.n_blocks - first);
+        const uint32_t bytes = (uint32_t)nb * 64u;
+        mbar_arrive_expect_tx(&full_bar[b], bytes);
+        tma_bulk_g2s_chunked(buf[b], a.blocks + (size_t)first * 4, bytes, &full_bar[b]);
+    };
+
+    for (;;) {
+        lane_refill(a, L, lane_id);
+        // CTA-wide liveness: every warp must keep consuming tiles while any warp still has work
+        const bool warp_live = !__all_sync(kFullMask, L.finished);
+        __syncthreads();  // previous trip's cta_live reads are done
+        if (threadIdx.x == 0) cta_live = 0;
+        __syncthreads();
+        if (lane_id == 0 && warp_live) atomicAdd(&cta_live, 1);
+        __syncthreads();
+        if (cta_live == 0) break;
+
+        float ox = L.o.x, oy = L.o.y, oz = L.o.z, dx = L.d.x, dy = L.d.y, dz = L.d.z;
+        if (!L.active) {
+            ox = 0.0f; oy = 1.0e30f; oz = 0.0f;
+            dx = dy = dz = 0.0f;
+        }
+        float hit_t = kMaxT;
+        int hit_index = -1;
+        if (threadIdx.x == 0) {
+            produce(0);
+            if (a.n_tiles > 1) produce(1);
+        }
+        for (int tile = 0; tile < a.n_tiles; ++tile) {
+            const int b = tile & 1;
+            mbar_wait(&full_bar[b], full_phase[b]);
+            full_phase[b] ^= 1u;
+            __syncwarp();
+            const int first = tile * a.tile_blocks;
+            const int nb = min(a.tile_blocks, a.n_blocks - first);
+            sweep_blocks<UNROLL>(buf[b], nb, first * 4, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
+            __syncwarp();
+            if (lane_id == 0) mbar_arrive(&empty_bar[b]);
+            if (threadIdx.x == 0 && tile + 2 < a.n_tiles) produce(tile + 2);
+        }
+        if (L.active) {
+            rays += 1ULL;
+            // the hit sphere's centre is no longer in shared memory: read it from the global SoA
+            lane_shade(a, L, a.blocks, *P, hit_t, hit_index);
+        }
+    }
+    flush_ray_count(a, rays, lane_id);
+}
+
+// =====================================================================================================
+// Output stage: src/offline.rs:43-51 + src/math.rs:36-48 (row flip, linear->sRGB, 8-bit pack)
+// =====================================================================================================
+__global__ void pt_srgb8_kernel(const float* __restrict__ rgb, uint32_t width, uint32_t height, uint8_t* __restrict__ out) {
+    const size_t n = (size_t)width * height;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t row = (uint32_t)(i / width);
+        const uint32_t x = (uint32_t)(i - (size_t)row * width);
+        const size_t src = ((size_t)(height - 1 - row) * width + x) * 3;  // `.rev()` over rows
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float lin = fmaxf(rgb[src + c], 0.0f);
+            float s = 1.055f * powf(lin, 0.41666666f) - 0.055f;
+            s = fminf(fmaxf(s, 0.0f), 1.0f);
+            out[i * 3 + c] = (uint8_t)(s * 255.99f);
+        }
+    }
+}
+
+// Measurement helper: dependent-chain FFMA kernel, 8 independent accumulators per lane.
+__global__ void pt_ffma_peak_kernel(float* out, int iters, float a, float b) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = threadIdx.x * 1e-3f + (float)i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = __fmaf_rn(acc[i], a, b);
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += acc[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+}  // namespace pt

@@ -1,0 +1,576 @@
+// ptgpu.cu — host side of libptgpu.so: the C ABI declared in include/ptgpu.h.
+//
+// Scene flattening (the GPU arm of `Params::new_scene`, src/params.rs:29-46, plus `SpheresSoA::new`,
+// src/collision/spheres_soa.rs:26-74), kernel launch (`Scene::update`, src/scene.rs:73-121) and the
+// host<->device traffic around it.  No CPU fallback: every entry point fails without a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ptgpu.h"
+#include "pt_megakernel.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define PT_CUDA(call)                                                                                        \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess) return fail(PT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+constexpr int kSweepUnroll = 2;
+constexpr size_t kMaxDynSmem = 227 * 1024 - 1024;  // leave room for static shared + driver reservation
+
+}  // namespace
+
+struct PtScene {
+    int device = 0;
+    int sm_count = 0;
+    uint32_t n_spheres = 0;
+    int n_blocks = 0;
+    bool has_noise = false;
+    bool has_sky = false;
+    pt::V3 sky{0, 0, 0};
+    float4* d_blocks = nullptr;
+    pt::DevShade* d_shade = nullptr;
+    pt::DevTexture* d_tex = nullptr;
+    pt::PerlinSmem* d_perlin = nullptr;
+    // per-render scratch
+    unsigned long long* d_ray_count = nullptr;  // [0] ray count
+    unsigned int* d_next_pixel = nullptr;
+    float* d_rgb = nullptr;  // device image for the host-buffer entry points
+    size_t d_rgb_floats = 0;
+    uint8_t* d_rgb8 = nullptr;
+    size_t d_rgb8_bytes = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // launch geometry
+    bool resident = true;
+    int tile_blocks = 0, n_tiles = 0;
+    size_t smem_bytes = 0;
+    int ctas_per_sm = 0;
+    PtRenderStats stats{};
+};
+
+namespace {
+
+int check_device(int device, cudaDeviceProp* prop_out) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(PT_ERR_NO_DEVICE, "no CUDA device: %s", e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= n) return fail(PT_ERR_INVALID, "device %d out of range (have %d)", device, n);
+    cudaDeviceProp prop;
+    PT_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(PT_ERR_NO_DEVICE, "device %d is sm_%d%d; libptgpu is built for sm_100a only", device, prop.major, prop.minor);
+    if (prop_out) *prop_out = prop;
+    return PT_OK;
+}
+
+// kernel selection + shared-memory sizing for a scene
+template <typename K>
+int configure_kernel(K kernel, size_t smem, int* ctas_per_sm) {
+    PT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    PT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, pt::kCtaThreads, smem));
+    if (occ < 1) return fail(PT_ERR_TOO_LARGE, "kernel does not fit on an SM with %zu bytes of shared memory", smem);
+    *ctas_per_sm = occ;
+    return PT_OK;
+}
+
+int plan_launch(PtScene* s) {
+    const size_t perlin_bytes = sizeof(pt::PerlinSmem);
+    const size_t all = (size_t)s->n_blocks * 64 + perlin_bytes;
+    if (all <= kMaxDynSmem) {
+        s->resident = true;
+        s->smem_bytes = all;
+        s->tile_blocks = s->n_blocks;
+        s->n_tiles = 1;
+        return configure_kernel(pt::pt_megakernel_resident<kSweepUnroll>, s->smem_bytes, &s->ctas_per_sm);
+    }
+    // streamed: two tile buffers; 2 CTAs per SM keeps the FP32 pipe fed while one CTA waits on a barrier
+    s->resident = false;
+    const size_t per_cta = (kMaxDynSmem + 1024) / 2 - 2048;
+    const size_t tile_bytes = ((per_cta - perlin_bytes) / 2) & ~(size_t)1023;
+    s->tile_blocks = (int)(tile_bytes / 64);
+    s->n_tiles = (s->n_blocks + s->tile_blocks - 1) / s->tile_blocks;
+    s->smem_bytes = 2 * (size_t)s->tile_blocks * 64 + perlin_bytes;
+    return configure_kernel(pt::pt_megakernel_streamed<kSweepUnroll>, s->smem_bytes, &s->ctas_per_sm);
+}
+
+uint32_t owned_rows(uint32_t height, const PtPartition& p) {
+    if (p.part_count <= 1) return height;
+    const uint32_t n_tiles = (height + p.tile_rows - 1) / p.tile_rows;
+    uint32_t rows = 0;
+    for (uint32_t k = p.part_index; k < n_tiles; k += p.part_count) rows += std::min(p.tile_rows, height - k * p.tile_rows);
+    return rows;
+}
+
+int normalise_partition(const PtPartition* in, PtPartition* out) {
+    PtPartition p{4, 0, 1, 0};
+    if (in) {
+        p = *in;
+        if (p.tile_rows == 0) p.tile_rows = 4;
+        if (p.part_count == 0) p.part_count = 1;
+        if (p.part_index >= p.part_count) return fail(PT_ERR_INVALID, "partition index %u >= count %u", p.part_index, p.part_count);
+    }
+    *out = p;
+    return PT_OK;
+}
+
+int validate_params(const PtParams* params, const PtCamera* camera) {
+    if (!params || !camera) return fail(PT_ERR_INVALID, "null params/camera");
+    if (params->width == 0 || params->height == 0) return fail(PT_ERR_INVALID, "zero-sized image %ux%u", params->width, params->height);
+    if ((uint64_t)params->width * params->height > 0xffffffffULL / 4) return fail(PT_ERR_TOO_LARGE, "image too large");
+    if (params->use_bvh) return fail(PT_ERR_UNSUPPORTED, "use_bvh is not supported on the GPU path (flat sphere list only, params.rs:36-43)");
+    return PT_OK;
+}
+
+// enqueue one Scene::update on `stream`; d_rgb is the full-size device image
+int launch_update(PtScene* s, const PtParams* params, const PtCamera* cam, uint32_t frame_num, const PtPartition& part,
+                  float* d_rgb, unsigned long long* d_ray_count, cudaStream_t stream) {
+    pt::KernelArgs a{};
+    a.blocks = s->d_blocks;
+    a.n_blocks = s->n_blocks;
+    a.n_spheres = (int)s->n_spheres;
+    a.shade = s->d_shade;
+    a.tex = s->d_tex;
+    a.perlin = s->d_perlin;
+    a.has_noise = s->has_noise ? 1 : 0;
+    auto V = [](const float* f) { return pt::V3{f[0], f[1], f[2]}; };
+    a.cam.origin = V(cam->origin);
+    a.cam.llc = V(cam->lower_left_corner);
+    a.cam.horizontal = V(cam->horizontal);
+    a.cam.vertical = V(cam->vertical);
+    a.cam.u = V(cam->u);
+    a.cam.v = V(cam->v);
+    a.cam.time0 = cam->time0;
+    a.cam.time1 = cam->time1;
+    a.cam.lens_radius = cam->lens_radius;
+    a.width = params->width;
+    a.height = params->height;
+    a.samples = params->samples;
+    a.max_depth = params->max_depth;
+    a.frame_num = frame_num;
+    // scene.rs:82-87
+    a.inv_nx = 1.0f / (float)params->width;
+    a.inv_ny = 1.0f / (float)params->height;
+    a.inv_ns = 1.0f / (float)params->samples;
+    a.mix_prev = (float)frame_num / (float)(frame_num + 1);
+    a.mix_new = 1.0f - a.mix_prev;
+    a.has_sky = s->has_sky ? 1 : 0;
+    a.sky = s->sky;
+    a.tile_rows = part.tile_rows;
+    a.part_index = part.part_index;
+    a.part_count = part.part_count;
+    a.n_owned_pixels = owned_rows(params->height, part) * params->width;
+    a.random_seed = params->random_seed ? 1 : 0;
+    a.seed_salt = params->seed_salt;
+    a.rgb = d_rgb;
+    a.ray_count = d_ray_count;
+    a.next_pixel = s->d_next_pixel;
+    a.tile_blocks = s->tile_blocks;
+    a.n_tiles = s->n_tiles;
+
+    PT_CUDA(cudaMemsetAsync(s->d_next_pixel, 0, sizeof(unsigned int), stream));
+    PT_CUDA(cudaMemsetAsync(d_ray_count, 0, sizeof(unsigned long long), stream));
+    s->stats.kernel_launches = 0;
+    s->stats.grid_ctas = 0;
+    if (a.n_owned_pixels == 0) return PT_OK;
+
+    // persistent grid: one wave of CTAs, never more lanes than pixels
+    const uint32_t want = (a.n_owned_pixels + pt::kCtaThreads - 1) / pt::kCtaThreads;
+    const uint32_t grid = std::min<uint32_t>((uint32_t)(s->sm_count * s->ctas_per_sm), want);
+    if (s->resident)
+        pt::pt_megakernel_resident<kSweepUnroll><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a);
+    else
+        pt::pt_megakernel_streamed<kSweepUnroll><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a);
+    PT_CUDA(cudaGetLastError());
+    s->stats.kernel_launches = 1;
+    s->stats.grid_ctas = grid;
+    s->stats.cta_threads = pt::kCtaThreads;
+    s->stats.smem_bytes = (uint32_t)s->smem_bytes;
+    s->stats.resident = s->resident ? 1u : 0u;
+    s->stats.n_spheres = s->n_spheres;
+    return PT_OK;
+}
+
+int ensure_image(PtScene* s, size_t floats) {
+    if (s->d_rgb_floats >= floats) return PT_OK;
+    if (s->d_rgb) cudaFree(s->d_rgb);
+    s->d_rgb = nullptr;
+    s->d_rgb_floats = 0;
+    PT_CUDA(cudaMalloc(&s->d_rgb, floats * sizeof(float)));
+    s->d_rgb_floats = floats;
+    return PT_OK;
+}
+
+// copy the rows a partition owns between host and device images (same layout on both sides)
+int copy_owned_rows(PtScene* s, const PtParams* params, const PtPartition& part, float* host, bool to_device, uint64_t* bytes_out) {
+    const size_t row_bytes = (size_t)params->width * 3 * sizeof(float);
+    uint64_t bytes = 0;
+    if (part.part_count <= 1) {
+        bytes = row_bytes * params->height;
+        PT_CUDA(cudaMemcpyAsync(to_device ? (void*)s->d_rgb : (void*)host, to_device ? (const void*)host : (const void*)s->d_rgb, bytes,
+                                to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, s->stream));
+    } else {
+        const uint32_t n_tiles = (params->height + part.tile_rows - 1) / part.tile_rows;
+        for (uint32_t k = part.part_index; k < n_tiles; k += part.part_count) {
+            const uint32_t r0 = k * part.tile_rows;
+            const uint32_t nr = std::min(part.tile_rows, params->height - r0);
+            const size_t off = (size_t)r0 * params->width * 3;
+            const size_t nbytes = row_bytes * nr;
+            PT_CUDA(cudaMemcpyAsync(to_device ? (void*)(s->d_rgb + off) : (void*)(host + off),
+                                    to_device ? (const void*)(host + off) : (const void*)(s->d_rgb + off), nbytes,
+                                    to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, s->stream));
+            bytes += nbytes;
+        }
+    }
+    *bytes_out = bytes;
+    return PT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pt_abi_version(void) { return PT_ABI_VERSION; }
+const char* pt_last_error(void) { return g_last_error.c_str(); }
+
+int pt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int pt_device_info(int device, PtDeviceInfo* out) {
+    if (!out) return fail(PT_ERR_INVALID, "null out");
+    cudaDeviceProp prop;
+    int rc = check_device(device, &prop);
+    if (rc != PT_OK) return rc;
+    std::memset(out, 0, sizeof(*out));
+    std::strncpy(out->name, prop.name, sizeof(out->name) - 1);
+    out->sm_count = prop.multiProcessorCount;
+    out->cc_major = prop.major;
+    out->cc_minor = prop.minor;
+    int khz = 0;
+    PT_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device));
+    out->sm_clock_khz = khz;
+    out->fp32_fma_peak_flops = (double)prop.multiProcessorCount * 128.0 * 2.0 * (double)khz * 1e3;
+    out->global_mem_bytes = prop.totalGlobalMem;
+    return PT_OK;
+}
+
+int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
+    if (!desc || !out) return fail(PT_ERR_INVALID, "null desc/out");
+    *out = nullptr;
+    if (desc->struct_size != sizeof(PtSceneDesc)) return fail(PT_ERR_INVALID, "PtSceneDesc.struct_size %u != %zu (ABI mismatch)", desc->struct_size, sizeof(PtSceneDesc));
+    const uint32_t n = desc->n_spheres;
+    if (n > 0 && (!desc->centre_x || !desc->centre_y || !desc->centre_z || !desc->radius || !desc->material_index))
+        return fail(PT_ERR_INVALID, "null sphere arrays with n_spheres = %u", n);
+    if (n > 0 && (desc->n_materials == 0 || !desc->materials)) return fail(PT_ERR_INVALID, "spheres without materials");
+    if (desc->n_textures > 0 && !desc->textures) return fail(PT_ERR_INVALID, "null textures");
+    if (n > (1u << 28)) return fail(PT_ERR_TOO_LARGE, "too many spheres: %u", n);
+
+    // ---- validate + flatten materials/textures ----
+    bool uses_noise = false;
+    for (uint32_t t = 0; t < desc->n_textures; ++t) {
+        const PtTexture& tx = desc->textures[t];
+        if (tx.kind == PT_TEX_CHECKER) {
+            if (tx.odd < 0 || tx.even < 0 || (uint32_t)tx.odd >= desc->n_textures || (uint32_t)tx.even >= desc->n_textures)
+                return fail(PT_ERR_INVALID, "texture %u: checker child index out of range", t);
+        } else if (tx.kind == PT_TEX_NOISE) {
+            uses_noise = true;
+        } else if (tx.kind != PT_TEX_CONSTANT) {
+            return fail(PT_ERR_UNSUPPORTED, "texture %u: kind %d is not supported (Image textures: texture.rs:27-36, SURVEY §8f)", t, tx.kind);
+        }
+    }
+    if (uses_noise && !desc->perlin) return fail(PT_ERR_INVALID, "a Noise texture is present but desc.perlin is NULL");
+    for (uint32_t m = 0; m < desc->n_materials; ++m) {
+        const PtMaterial& mt = desc->materials[m];
+        if (mt.kind < PT_MAT_LAMBERTIAN || mt.kind > PT_MAT_DIFFUSE_LIGHT)
+            return fail(PT_ERR_UNSUPPORTED, "material %u: kind %d is not supported (Isotropic needs ConstantMedium, out of scope)", m, mt.kind);
+        if ((mt.kind == PT_MAT_LAMBERTIAN || mt.kind == PT_MAT_DIFFUSE_LIGHT) && (mt.texture < 0 || (uint32_t)mt.texture >= desc->n_textures))
+            return fail(PT_ERR_INVALID, "material %u: texture index %d out of range", m, mt.texture);
+    }
+
+    cudaDeviceProp prop;
+    int rc = check_device(device, &prop);
+    if (rc != PT_OK) return rc;
+    PT_CUDA(cudaSetDevice(device));
+
+    PtScene* s = new PtScene();
+    s->device = device;
+    s->sm_count = prop.multiProcessorCount;
+    s->n_spheres = n;
+    s->n_blocks = (int)((n + 3) / 4);
+    s->has_noise = uses_noise;
+    s->has_sky = desc->has_sky != 0;
+    s->sky = pt::V3{desc->sky[0], desc->sky[1], desc->sky[2]};
+
+    // ---- sphere blocks: X,Y,Z,R^2 for 4 spheres; padding = (FLT_MAX centre, r^2 = 0) spheres_soa.rs:53-61 ----
+    std::vector<float4> blocks((size_t)std::max(s->n_blocks, 1) * 4);
+    std::vector<pt::DevShade> shade(std::max<uint32_t>(n, 1));
+    for (int j = 0; j < s->n_blocks; ++j) {
+        float* f = reinterpret_cast<float*>(&blocks[(size_t)j * 4]);
+        for (int e = 0; e < 4; ++e) {
+            const uint32_t i = (uint32_t)j * 4 + e;
+            const bool valid = i < n;
+            f[0 + e] = valid ? desc->centre_x[i] : FLT_MAX;
+            f[4 + e] = valid ? desc->centre_y[i] : FLT_MAX;
+            f[8 + e] = valid ? desc->centre_z[i] : FLT_MAX;
+            f[12 + e] = valid ? desc->radius[i] * desc->radius[i] : 0.0f;  // spheres_soa.rs:46
+        }
+    }
+    for (uint32_t i = 0; i < n; ++i) {
+        const int32_t mi = desc->material_index[i];
+        if (mi < 0 || (uint32_t)mi >= desc->n_materials) {
+            delete s;
+            return fail(PT_ERR_INVALID, "sphere %u: material index %d out of range", i, mi);
+        }
+        const PtMaterial& mt = desc->materials[mi];
+        pt::DevShade d{};
+        d.rinv = 1.0f / desc->radius[i];  // spheres_soa.rs:47
+        d.kind = mt.kind;
+        d.tex = -1;
+        if (mt.kind == PT_MAT_LAMBERTIAN || mt.kind == PT_MAT_DIFFUSE_LIGHT) {
+            const PtTexture& tx = desc->textures[mt.texture];
+            if (tx.kind == PT_TEX_CONSTANT) {  // fold the constant colour into the per-sphere record
+                d.ar = tx.color[0];
+                d.ag = tx.color[1];
+                d.ab = tx.color[2];
+            } else {
+                d.tex = mt.texture;
+            }
+        } else if (mt.kind == PT_MAT_METAL) {
+            d.ar = mt.albedo[0];
+            d.ag = mt.albedo[1];
+            d.ab = mt.albedo[2];
+            d.param = mt.fuzz;
+        } else {
+            d.param = mt.ref_idx;
+        }
+        shade[i] = d;
+    }
+    std::vector<pt::DevTexture> tex(std::max<uint32_t>(desc->n_textures, 1));
+    for (uint32_t t = 0; t < desc->n_textures; ++t) {
+        const PtTexture& tx = desc->textures[t];
+        pt::DevTexture d{};
+        d.r = tx.color[0];
+        d.g = tx.color[1];
+        d.b = tx.color[2];
+        d.scale = tx.scale;
+        d.kind = tx.kind;
+        d.odd = tx.odd;
+        d.even = tx.even;
+        tex[t] = d;
+    }
+
+    auto cleanup_fail = [&](int code) {
+        pt_scene_destroy(s);
+        return code;
+    };
+#define PT_CUDA_S(call)                                                                                     \
+    do {                                                                                                    \
+        cudaError_t e_ = (call);                                                                            \
+        if (e_ != cudaSuccess) return cleanup_fail(fail(PT_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_))); \
+    } while (0)
+    PT_CUDA_S(cudaMalloc(&s->d_blocks, blocks.size() * sizeof(float4)));
+    PT_CUDA_S(cudaMemcpy(s->d_blocks, blocks.data(), blocks.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    PT_CUDA_S(cudaMalloc(&s->d_shade, shade.size() * sizeof(pt::DevShade)));
+    PT_CUDA_S(cudaMemcpy(s->d_shade, shade.data(), shade.size() * sizeof(pt::DevShade), cudaMemcpyHostToDevice));
+    PT_CUDA_S(cudaMalloc(&s->d_tex, tex.size() * sizeof(pt::DevTexture)));
+    PT_CUDA_S(cudaMemcpy(s->d_tex, tex.data(), tex.size() * sizeof(pt::DevTexture), cudaMemcpyHostToDevice));
+    PT_CUDA_S(cudaMalloc(&s->d_perlin, sizeof(pt::PerlinSmem)));
+    {
+        std::vector<unsigned char> raw(sizeof(pt::PerlinSmem), 0);
+        pt::PerlinSmem* ps = reinterpret_cast<pt::PerlinSmem*>(raw.data());
+        if (desc->perlin) {
+            for (int i = 0; i < 256; ++i) {
+                ps->randvec[i] = make_float4(desc->perlin->randvec[i][0], desc->perlin->randvec[i][1], desc->perlin->randvec[i][2], 0.0f);
+                if (desc->perlin->perm_x[i] > 255 || desc->perlin->perm_y[i] > 255 || desc->perlin->perm_z[i] > 255)
+                    return cleanup_fail(fail(PT_ERR_INVALID, "perlin permutation entry %d out of range", i));
+                ps->perm_x[i] = (uint8_t)desc->perlin->perm_x[i];
+                ps->perm_y[i] = (uint8_t)desc->perlin->perm_y[i];
+                ps->perm_z[i] = (uint8_t)desc->perlin->perm_z[i];
+            }
+        }
+        PT_CUDA_S(cudaMemcpy(s->d_perlin, raw.data(), raw.size(), cudaMemcpyHostToDevice));
+    }
+    PT_CUDA_S(cudaMalloc(&s->d_ray_count, sizeof(unsigned long long)));
+    PT_CUDA_S(cudaMalloc(&s->d_next_pixel, sizeof(unsigned int)));
+    PT_CUDA_S(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    for (auto& e : s->ev) PT_CUDA_S(cudaEventCreate(&e));
+#undef PT_CUDA_S
+    rc = plan_launch(s);
+    if (rc != PT_OK) return cleanup_fail(rc);
+    *out = s;
+    return PT_OK;
+}
+
+void pt_scene_destroy(PtScene* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    cudaFree(s->d_blocks);
+    cudaFree(s->d_shade);
+    cudaFree(s->d_tex);
+    cudaFree(s->d_perlin);
+    cudaFree(s->d_ray_count);
+    cudaFree(s->d_next_pixel);
+    cudaFree(s->d_rgb);
+    cudaFree(s->d_rgb8);
+    for (auto& e : s->ev)
+        if (e) cudaEventDestroy(e);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+int pt_render_part(PtScene* s, const PtParams* params, const PtCamera* camera, uint32_t frame_num, const PtPartition* part_in,
+                   float* rgb_inout, uint64_t* ray_count_out) {
+    if (!s || !rgb_inout) return fail(PT_ERR_INVALID, "null scene/buffer");
+    int rc = validate_params(params, camera);
+    if (rc != PT_OK) return rc;
+    PtPartition part;
+    rc = normalise_partition(part_in, &part);
+    if (rc != PT_OK) return rc;
+    PT_CUDA(cudaSetDevice(s->device));
+    const size_t floats = (size_t)params->width * params->height * 3;
+    rc = ensure_image(s, floats);
+    if (rc != PT_OK) return rc;
+
+    s->stats = PtRenderStats{};
+    uint64_t h2d = 0, d2h = 0;
+    PT_CUDA(cudaEventRecord(s->ev[0], s->stream));
+    if (frame_num != 0) {  // the blend reads the previous frame (scene.rs:114-116); frame 0 has mix_prev = 0
+        rc = copy_owned_rows(s, params, part, rgb_inout, true, &h2d);
+        if (rc != PT_OK) return rc;
+    }
+    PT_CUDA(cudaEventRecord(s->ev[1], s->stream));
+    rc = launch_update(s, params, camera, frame_num, part, s->d_rgb, s->d_ray_count, s->stream);
+    if (rc != PT_OK) return rc;
+    PT_CUDA(cudaEventRecord(s->ev[2], s->stream));
+    rc = copy_owned_rows(s, params, part, rgb_inout, false, &d2h);
+    if (rc != PT_OK) return rc;
+    unsigned long long rays = 0;
+    PT_CUDA(cudaMemcpyAsync(&rays, s->d_ray_count, sizeof(rays), cudaMemcpyDeviceToHost, s->stream));
+    PT_CUDA(cudaEventRecord(s->ev[3], s->stream));
+    PT_CUDA(cudaStreamSynchronize(s->stream));
+    float ms = 0;
+    PT_CUDA(cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]));
+    s->stats.h2d_ms = ms;
+    PT_CUDA(cudaEventElapsedTime(&ms, s->ev[1], s->ev[2]));
+    s->stats.kernel_ms = ms;
+    PT_CUDA(cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]));
+    s->stats.d2h_ms = ms;
+    s->stats.h2d_bytes = h2d;
+    s->stats.d2h_bytes = d2h + sizeof(rays);
+    s->stats.ray_count = rays;
+    if (ray_count_out) *ray_count_out = rays;
+    return PT_OK;
+}
+
+int pt_render(PtScene* s, const PtParams* params, const PtCamera* camera, uint32_t frame_num, float* rgb_inout, uint64_t* ray_count_out) {
+    return pt_render_part(s, params, camera, frame_num, nullptr, rgb_inout, ray_count_out);
+}
+
+int pt_render_device(PtScene* s, const PtParams* params, const PtCamera* camera, uint32_t frame_num, const PtPartition* part_in,
+                     float* d_rgb_inout, uint64_t* d_ray_count, void* cuda_stream) {
+    if (!s || !d_rgb_inout || !d_ray_count) return fail(PT_ERR_INVALID, "null scene/buffer");
+    int rc = validate_params(params, camera);
+    if (rc != PT_OK) return rc;
+    PtPartition part;
+    rc = normalise_partition(part_in, &part);
+    if (rc != PT_OK) return rc;
+    PT_CUDA(cudaSetDevice(s->device));
+    s->stats = PtRenderStats{};
+    return launch_update(s, params, camera, frame_num, part, d_rgb_inout, reinterpret_cast<unsigned long long*>(d_ray_count),
+                         reinterpret_cast<cudaStream_t>(cuda_stream));
+}
+
+int pt_srgb8_device(PtScene* s, const float* d_rgb, uint32_t width, uint32_t height, uint8_t* d_rgb8_out, void* cuda_stream) {
+    if (!s || !d_rgb || !d_rgb8_out || width == 0 || height == 0) return fail(PT_ERR_INVALID, "null/empty argument");
+    PT_CUDA(cudaSetDevice(s->device));
+    const size_t n = (size_t)width * height;
+    const int threads = 256;
+    const int blocks = (int)std::min<size_t>((n + threads - 1) / threads, (size_t)s->sm_count * 8);
+    pt::pt_srgb8_kernel<<<blocks, threads, 0, reinterpret_cast<cudaStream_t>(cuda_stream)>>>(d_rgb, width, height, d_rgb8_out);
+    PT_CUDA(cudaGetLastError());
+    return PT_OK;
+}
+
+int pt_srgb8(PtScene* s, const float* rgb, uint32_t width, uint32_t height, uint8_t* rgb8_out) {
+    if (!s || !rgb || !rgb8_out || width == 0 || height == 0) return fail(PT_ERR_INVALID, "null/empty argument");
+    PT_CUDA(cudaSetDevice(s->device));
+    const size_t n = (size_t)width * height;
+    int rc = ensure_image(s, n * 3);
+    if (rc != PT_OK) return rc;
+    if (s->d_rgb8_bytes < n * 3) {
+        if (s->d_rgb8) cudaFree(s->d_rgb8);
+        s->d_rgb8 = nullptr;
+        s->d_rgb8_bytes = 0;
+        PT_CUDA(cudaMalloc(&s->d_rgb8, n * 3));
+        s->d_rgb8_bytes = n * 3;
+    }
+    PT_CUDA(cudaMemcpyAsync(s->d_rgb, rgb, n * 3 * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    rc = pt_srgb8_device(s, s->d_rgb, width, height, s->d_rgb8, s->stream);
+    if (rc != PT_OK) return rc;
+    PT_CUDA(cudaMemcpyAsync(rgb8_out, s->d_rgb8, n * 3, cudaMemcpyDeviceToHost, s->stream));
+    PT_CUDA(cudaStreamSynchronize(s->stream));
+    return PT_OK;
+}
+
+int pt_scene_stats(const PtScene* s, PtRenderStats* out) {
+    if (!s || !out) return fail(PT_ERR_INVALID, "null argument");
+    *out = s->stats;
+    return PT_OK;
+}
+
+int pt_probe_fp32_peak(int device, double* flops_out) {
+    if (!flops_out) return fail(PT_ERR_INVALID, "null out");
+    cudaDeviceProp prop;
+    int rc = check_device(device, &prop);
+    if (rc != PT_OK) return rc;
+    PT_CUDA(cudaSetDevice(device));
+    const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 20000;
+    float* d_out = nullptr;
+    PT_CUDA(cudaMalloc(&d_out, sizeof(float) * threads * blocks));
+    cudaEvent_t e0, e1;
+    PT_CUDA(cudaEventCreate(&e0));
+    PT_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        PT_CUDA(cudaEventRecord(e0));
+        pt::pt_ffma_peak_kernel<<<blocks, threads>>>(d_out, iters, 1.0001f, 0.5f);
+        PT_CUDA(cudaEventRecord(e1));
+        PT_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        PT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d_out);
+    *flops_out = 2.0 * 8.0 * iters * (double)threads * blocks / (best * 1e-3);
+    return PT_OK;
+}
+
+}  // extern "C"
