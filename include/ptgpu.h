@@ -147,6 +147,10 @@ typedef struct PtRenderStats {
 typedef struct PtScene PtScene; /* opaque: device copy of one scene on one GPU */
 
 int pt_abi_version(void);
+/* sizeof() of the ABI structs as this library was compiled, so a binding can assert its own layout:
+ * which = 0 PtParams, 1 PtCamera, 2 PtTexture, 3 PtMaterial, 4 PtPerlin, 5 PtSceneDesc, 6 PtPartition,
+ * 7 PtDeviceInfo, 8 PtRenderStats; anything else -> 0. */
+uint32_t pt_abi_struct_size(int which);
 const char* pt_last_error(void); /* thread-local message of the last failing call */
 int pt_device_count(void);
 int pt_device_info(int device, PtDeviceInfo* out);
@@ -183,6 +187,11 @@ int pt_srgb8_device(PtScene* scene, const float* d_rgb, uint32_t width, uint32_t
                     void* cuda_stream);
 
 int pt_scene_stats(const PtScene* scene, PtRenderStats* out);
+
+/* Rows of an image of `height` rows that `part` owns, ascending (the order the device buffer is walked).
+ * Writes at most `cap` row indices to rows_out (may be NULL) and returns the total count: what a
+ * multi-GPU caller needs to gather per-GPU results. */
+uint32_t pt_partition_rows(const PtPartition* part, uint32_t height, uint32_t* rows_out, uint32_t cap);
 
 /* Measurement helper: sustained FP32 FFMA throughput of `device` (flop/s) from a pure-FMA kernel,
  * so bench.py can print the measured ceiling beside the nominal sm_count*128*2*clock figure. */

@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -99,6 +100,16 @@ int configure_kernel(K kernel, size_t smem, int* ctas_per_sm) {
 int plan_launch(PtScene* s) {
     const size_t perlin_bytes = sizeof(pt::PerlinSmem);
     const size_t all = (size_t)s->n_blocks * 64 + perlin_bytes;
+    // test hook: PTGPU_FORCE_STREAM_TILE_BLOCKS=<n> runs any scene through the streamed kernel with n-block tiles
+    int forced_tile = 0;
+    if (const char* env = std::getenv("PTGPU_FORCE_STREAM_TILE_BLOCKS")) forced_tile = std::atoi(env);
+    if (forced_tile > 0 && s->n_blocks > 0) {
+        s->resident = false;
+        s->tile_blocks = std::min(forced_tile, s->n_blocks);
+        s->n_tiles = (s->n_blocks + s->tile_blocks - 1) / s->tile_blocks;
+        s->smem_bytes = 2 * (size_t)s->tile_blocks * 64 + perlin_bytes;
+        return configure_kernel(pt::pt_megakernel_streamed<kSweepUnroll>, s->smem_bytes, &s->ctas_per_sm);
+    }
     if (all <= kMaxDynSmem) {
         s->resident = true;
         s->smem_bytes = all;
@@ -254,6 +265,37 @@ extern "C" {
 
 int pt_abi_version(void) { return PT_ABI_VERSION; }
 const char* pt_last_error(void) { return g_last_error.c_str(); }
+
+uint32_t pt_abi_struct_size(int which) {
+    switch (which) {
+        case 0: return sizeof(PtParams);
+        case 1: return sizeof(PtCamera);
+        case 2: return sizeof(PtTexture);
+        case 3: return sizeof(PtMaterial);
+        case 4: return sizeof(PtPerlin);
+        case 5: return sizeof(PtSceneDesc);
+        case 6: return sizeof(PtPartition);
+        case 7: return sizeof(PtDeviceInfo);
+        case 8: return sizeof(PtRenderStats);
+        default: return 0;
+    }
+}
+
+uint32_t pt_partition_rows(const PtPartition* part_in, uint32_t height, uint32_t* rows_out, uint32_t cap) {
+    PtPartition p;
+    if (normalise_partition(part_in, &p) != PT_OK) return 0;
+    uint32_t count = 0;
+    const uint32_t n_tiles = (height + p.tile_rows - 1) / p.tile_rows;
+    for (uint32_t k = p.part_index; k < n_tiles; k += p.part_count) {
+        const uint32_t r0 = k * p.tile_rows;
+        const uint32_t nr = std::min(p.tile_rows, height - r0);
+        for (uint32_t r = 0; r < nr; ++r) {
+            if (rows_out && count < cap) rows_out[count] = r0 + r;
+            ++count;
+        }
+    }
+    return count;
+}
 
 int pt_device_count(void) {
     int n = 0;

@@ -100,8 +100,13 @@ def libptgpu():
     if _ptgpu is None:
         L = _load("libptgpu.so")
         vp = C.c_void_p
+        vp = C.c_void_p
         L.pt_abi_version.restype = C.c_int
         L.pt_last_error.restype = C.c_char_p
+        L.pt_abi_struct_size.restype = C.c_uint32
+        L.pt_abi_struct_size.argtypes = [C.c_int]
+        L.pt_partition_rows.restype = C.c_uint32
+        L.pt_partition_rows.argtypes = [C.POINTER(PtPartition), C.c_uint32, vp, C.c_uint32]
         L.pt_device_count.restype = C.c_int
         L.pt_device_info.argtypes = [C.c_int, C.POINTER(PtDeviceInfo)]
         L.pt_scene_create.argtypes = [C.POINTER(PtSceneDesc), C.c_int, C.POINTER(vp)]

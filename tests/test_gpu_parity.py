@@ -1,0 +1,269 @@
+"""Parity of the CUDA path with the CPU oracle, through the C ABI (host mirror -> pt_render / pt_render_part /
+pt_render_device).  Run on a B200: pytest -m gpu.
+
+Tolerances.  north_star's bar is statistical (per-channel mean within 0.5 %, RMSE vs a converged render no worse
+than 1.05x the reference's own).  Because the kernel keeps the reference's per-pixel RNG stream and rounds its
+shading like the unfused CPU code, it actually tracks the oracle far tighter than that; the tests assert both:
+the north-star tolerances against the oracle's LIST mode (the reference's live path) and near bit-exactness
+against the oracle's SoA mode (the arithmetic the kernel implements, spheres_soa.rs:105-155).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import orc
+import pathtrace_rs_b200 as pt
+from pathtrace_rs_b200 import ffi, parallel
+
+pytestmark = pytest.mark.gpu
+
+SOA_ITER = orc.HIT_SOA_SCALAR | 0x100  # SoA arithmetic, radiance accumulated front to back like the kernel
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def gpu_render(preset, w, h, spp, depth, frame=0, buffer=None, part=None, **kw):
+    params = pt.Params(w, h, spp, depth, **kw)
+    pr = pt.Preset(preset, params).create_scene(0)
+    img, rays = pr.update(params, frame_num=frame, buffer=buffer, part=part)
+    return img, rays, pr
+
+
+def rel_mean_diff(a, b):
+    ma, mb = a.reshape(-1, 3).mean(0), b.reshape(-1, 3).mean(0)
+    return np.abs(ma - mb) / np.maximum(np.abs(mb), 1e-12)
+
+
+# ---- scenes whose every branch is decided by bit-identical arithmetic: exact agreement -------------------------
+@pytest.mark.parametrize("preset,w,h,spp,depth", [("small", 100, 50, 16, 10), ("smallpt", 64, 64, 16, 10),
+                                                  ("final", 64, 32, 4, 10), ("small", 37, 23, 5, 0)])
+def test_bit_exact_presets(preset, w, h, spp, depth):
+    img, rays, _ = gpu_render(preset, w, h, spp, depth)
+    ref, ref_rays = orc.Scene(preset, w, h).update(spp, depth, mode=SOA_ITER)
+    assert rays == ref_rays
+    assert np.mean(np.all(img == ref, axis=2)) >= 0.999
+    np.testing.assert_allclose(img, ref, rtol=0, atol=2e-2)
+
+
+def test_cfg1_random_spheres_vs_oracle():
+    """BASELINE config 1: random_spheres 200x100, 100 spp, depth 50."""
+    w, h, spp, depth = 200, 100, 100, 50
+    img, rays, pr = gpu_render("random_spheres", w, h, spp, depth)
+    sc = orc.Scene("random_spheres", w, h)
+    soa, soa_rays = sc.update(spp, depth, mode=SOA_ITER)
+    lst, lst_rays = sc.update(spp, depth, mode=orc.HIT_LIST)
+    # (a) same arithmetic: almost every pixel identical to 1e-5
+    assert np.mean(np.all(np.abs(img - soa) < 1e-5, axis=2)) > 0.99
+    assert abs(rays - soa_rays) <= 1e-3 * soa_rays
+    # (b) north-star tolerance against the reference's live (list) path
+    assert rel_mean_diff(img, lst).max() < 5e-3
+    assert abs(rays / (w * h * spp) - lst_rays / (w * h * spp)) < 0.01 * lst_rays / (w * h * spp)
+    assert w * h * spp <= rays <= w * h * spp * (depth + 1)
+    assert np.isfinite(img).all() and img.min() >= 0.0 and img.max() <= 1.0 + 1e-5
+    st = pr.stats()
+    assert st.kernel_launches == 1 and st.resident == 1 and st.n_spheres == 488 and st.ray_count == rays
+
+
+def test_rmse_against_converged_reference():
+    """RMSE(GPU, converged) <= 1.05 x RMSE(oracle at equal spp, converged).  The converged image is the oracle's
+    equal-weight mean of 64 further frames x 256 spp (frame seeds differ: scene.rs:100), 16 384 spp in total."""
+    w, h, spp, depth = 100, 50, 64, 50
+    sc = orc.Scene("random_spheres", w, h)
+    conv = np.zeros((h, w, 3), np.float32)
+    for k in range(64):
+        sc.update(256, depth, frame_num=k, buffer=conv, mode=orc.HIT_SOA_AVX2 if orc.lib().orc_has_avx2() else orc.HIT_SOA_SCALAR)
+    # frames 1000.. are independent of the 64 frames above
+    gpu = np.zeros((h, w, 3), np.float32)
+    params = pt.Params(w, h, spp, depth)
+    pr = pt.Preset("random_spheres", params).create_scene(0)
+    pr.update(params, frame_num=0, buffer=gpu)  # frame 0 seeds; conv used frames 0..63 too, so use a disjoint set:
+    gpu_imgs, cpu_imgs = [], []
+    for f in (1000, 1001, 1002, 1003):
+        g = np.zeros((h, w, 3), np.float32)
+        # frame f into a zero buffer = col/(f+1): undo the blend weight to get the plain estimate
+        pr.update(params, frame_num=f, buffer=g)
+        gpu_imgs.append(g * (f + 1))
+        c = np.zeros((h, w, 3), np.float32)
+        sc.update(spp, depth, frame_num=f, buffer=c, mode=orc.HIT_LIST)
+        cpu_imgs.append(c * (f + 1))
+    rmse = lambda imgs: float(np.mean([np.sqrt(np.mean((i - conv) ** 2)) for i in imgs]))
+    r_gpu, r_cpu = rmse(gpu_imgs), rmse(cpu_imgs)
+    assert r_cpu > 0 and r_gpu <= 1.05 * r_cpu, (r_gpu, r_cpu)
+
+
+def test_cfg3_two_perlin_spheres_vs_oracle():
+    w, h, spp, depth = 192, 108, 16, 50
+    img, rays, _ = gpu_render("two_perlin_spheres", w, h, spp, depth)
+    sc = orc.Scene("two_perlin_spheres", w, h)
+    soa, soa_rays = sc.update(spp, depth, mode=SOA_ITER)
+    lst, _ = sc.update(spp, depth, mode=orc.HIT_LIST)
+    assert abs(rays - soa_rays) <= 1e-3 * soa_rays
+    assert np.mean(np.all(np.abs(img - soa) < 1e-4, axis=2)) > 0.99  # device sinf vs libm sinf in the noise texture
+    assert rel_mean_diff(img, lst).max() < 5e-3
+
+
+@pytest.mark.parametrize("name", ["random_spheres_40x20_s8_d50", "two_perlin_spheres_40x20_s4_d50", "small_40x20_s8_d10",
+                                  "smallpt_32x32_s16_d10"])
+def test_golden_fixtures(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    w, h, s, d = (int(g[k]) for k in ("width", "height", "samples", "max_depth"))
+    img, rays, _ = gpu_render(str(g["preset"]), w, h, s, d)
+    # fixtures are list-mode (AoS) renders: grazing-incidence decisions can differ from the SoA form on a few pixels
+    assert abs(rays - int(g["rays"])) <= 0.01 * int(g["rays"])
+    # (the oracle's own list and SoA modes differ on the same few percent of pixels: the r=1000 ground sphere's t
+    # carries ~1e-5 relative rounding noise that depends on the operation order, see test_oracle_pins.py)
+    assert np.mean(np.all(np.abs(img - g["image"]) < 1e-4, axis=2)) > 0.90
+    assert rel_mean_diff(img, g["image"]).max() < 2e-2
+
+
+# ---- Scene::update semantics -------------------------------------------------------------------------------------
+def test_frame_blending_matches_reference_formula():
+    w, h, spp, depth = 64, 32, 4, 10
+    params = pt.Params(w, h, spp, depth)
+    pr = pt.Preset("small", params).create_scene(0)
+    sc = orc.Scene("small", w, h)
+    buf = np.zeros((h, w, 3), np.float32)
+    ref = np.zeros((h, w, 3), np.float32)
+    for f in range(3):
+        pr.update(params, frame_num=f, buffer=buf)  # frame > 0 uploads the host buffer, blends, downloads
+        sc.update(spp, depth, frame_num=f, buffer=ref, mode=SOA_ITER)
+        assert pr.stats().h2d_bytes == (0 if f == 0 else w * h * 12)
+    assert np.mean(np.all(buf == ref, axis=2)) >= 0.999
+    # frame 0 ignores whatever is in the buffer (mix_prev = 0)
+    junk = np.full((h, w, 3), 7.0, np.float32)
+    pr.update(params, frame_num=0, buffer=junk)
+    first = np.zeros((h, w, 3), np.float32)
+    pr.update(params, frame_num=0, buffer=first)
+    assert np.array_equal(junk, first)
+
+
+@pytest.mark.parametrize("count,tile", [(2, 4), (3, 4), (8, 4), (3, 5)])
+def test_row_tile_partition_reassembles_bit_exact(count, tile):
+    w, h, spp, depth = 80, 45, 4, 10
+    params = pt.Params(w, h, spp, depth)
+    pr = pt.Preset("random_spheres", params).create_scene(0)
+    whole, rays_whole = pr.update(params)
+    parts = np.full((h, w, 3), -1.0, np.float32)
+    total = 0
+    for idx in range(count):
+        part = ffi.PtPartition(tile, idx, count, 0)
+        before = parts.copy()
+        _, r = pr.update(params, buffer=parts, part=part)
+        total += r
+        rows = parallel.owned_rows(part, h)
+        other = np.setdiff1d(np.arange(h), rows)
+        assert np.array_equal(parts[other], before[other])  # a part only touches its own rows
+    assert total == rays_whole and np.array_equal(parts, whole)
+
+
+def test_device_resident_path_equals_host_path():
+    torch = pytest.importorskip("torch")
+    w, h, spp, depth = 96, 54, 4, 10
+    params = pt.Params(w, h, spp, depth)
+    pr = pt.Preset("random_spheres", params).create_scene(0)
+    host, rays = pr.update(params)
+    d_rgb = torch.zeros((h, w, 3), dtype=torch.float32, device="cuda:0")
+    d_rays = torch.zeros(1, dtype=torch.int64, device="cuda:0")
+    stream = torch.cuda.current_stream().cuda_stream
+    for f in range(2):
+        pr.update_device(params, f, d_rgb.data_ptr(), d_rays.data_ptr(), stream)
+    torch.cuda.synchronize()
+    ref = host.copy()
+    pr.update(params, frame_num=1, buffer=ref)
+    assert np.array_equal(d_rgb.cpu().numpy(), ref)
+    assert int(d_rays.item()) > 0
+
+
+def test_random_seed_mode_uses_the_salt():
+    w, h, spp, depth = 64, 32, 8, 10
+    a, _, _ = gpu_render("random_spheres", w, h, spp, depth, random_seed=True, seed_salt=1)
+    b, _, _ = gpu_render("random_spheres", w, h, spp, depth, random_seed=True, seed_salt=2)
+    c, _, _ = gpu_render("random_spheres", w, h, spp, depth, random_seed=True, seed_salt=1)
+    d, _, _ = gpu_render("random_spheres", w, h, spp, depth)
+    assert np.array_equal(a, c) and not np.array_equal(a, b) and not np.array_equal(a, d)
+    assert rel_mean_diff(a, d).max() < 0.05
+
+
+# ---- scenes larger than shared memory: streamed kernel -------------------------------------------------------------
+def test_streamed_kernel_equals_resident_kernel():
+    w, h, spp, depth = 64, 36, 4, 10
+    res, rays_res, pr = gpu_render("random_spheres", w, h, spp, depth)
+    assert pr.stats().resident == 1
+    os.environ["PTGPU_FORCE_STREAM_TILE_BLOCKS"] = "16"  # 488 spheres = 122 blocks -> 8 tiles, last one ragged
+    try:
+        st, rays_st, pr2 = gpu_render("random_spheres", w, h, spp, depth)
+        assert pr2.stats().resident == 0
+    finally:
+        del os.environ["PTGPU_FORCE_STREAM_TILE_BLOCKS"]
+    assert rays_st == rays_res and np.array_equal(st, res)
+
+
+def test_cfg5_stress100k_small_vs_oracle():
+    w, h, spp, depth = 64, 36, 2, 50
+    img, rays, pr = gpu_render("stress100k", w, h, spp, depth)
+    assert pr.stats().resident == 0 and pr.stats().n_spheres == 99860
+    ref, ref_rays = orc.Scene("stress100k", w, h).update(spp, depth, mode=SOA_ITER)
+    assert abs(rays - ref_rays) <= 0.01 * ref_rays
+    assert np.mean(np.all(np.abs(img - ref) < 1e-5, axis=2)) > 0.99
+
+
+# ---- output stage ----------------------------------------------------------------------------------------------------
+def test_srgb8_output_stage():
+    w, h = 96, 48
+    img, _, pr = gpu_render("random_spheres", w, h, 8, 10)
+    out = pr.srgb8(img)
+    ref = orc.srgb(img[::-1].reshape(-1, 3)).reshape(h, w, 3)  # offline.rs:44 flips the rows
+    diff = np.abs(out.astype(np.int32) - ref.astype(np.int32))
+    assert diff.max() <= 1 and np.mean(diff == 0) > 0.999
+
+
+def test_render_offline_mirror(tmp_path, capfd):
+    png = str(tmp_path / "o.png")
+    secs, rays = pt.render_offline("random_spheres", pt.Params(64, 32, 4, 10), png)
+    out = capfd.readouterr().out
+    assert "generating 'random_spheres' preset at 64x32 with 4 samples per pixel" in out
+    assert "rays" in out and "Mrays/s" in out and secs > 0 and rays >= 64 * 32 * 4
+    assert open(png, "rb").read(8) == b"\x89PNG\r\n\x1a\n"
+
+
+# ---- error behaviour -----------------------------------------------------------------------------------------------------
+def test_errors():
+    L = pt.libptgpu()
+    pr = pt.Preset("small", pt.Params(16, 8, 1, 1)).create_scene(0)
+    buf = np.zeros((8, 16, 3), np.float32)
+    with pytest.raises(RuntimeError, match="use_bvh"):
+        pr.update(pt.Params(16, 8, 1, 1, use_bvh=True), buffer=buf)
+    with pytest.raises(RuntimeError, match="partition index"):
+        pr.update(pt.Params(16, 8, 1, 1), buffer=buf, part=ffi.PtPartition(4, 5, 2, 0))
+    bad = ffi.PtSceneDesc()
+    bad.struct_size = 12
+    h = C.c_void_p()
+    assert L.pt_scene_create(C.byref(bad), 0, C.byref(h)) == ffi.PT_ERR_INVALID
+    assert b"struct_size" in L.pt_last_error()
+    assert pt.libpthost().pth_flatten_rejects_non_sphere() == 1
+    assert b"Expected Hitable::Sphere, got Rect" in pt.libpthost().pth_last_error()
+    with pytest.raises(RuntimeError, match="out of range"):
+        pt.Preset("small", pt.Params(16, 8, 1, 1)).create_scene(99)
+
+
+# ---- BASELINE sizes: size-independent properties ------------------------------------------------------------------------
+def test_cfg2_full_size_properties():
+    """random_spheres 1200x800, 1024 spp, depth 50 (BASELINE config 2) — the whole job, checked through properties
+    that do not need a CPU render of the same size."""
+    w, h, spp, depth = 1200, 800, 1024, 50
+    img, rays, pr = gpu_render("random_spheres", w, h, spp, depth)
+    n = w * h * spp
+    assert n <= rays <= n * (depth + 1)
+    assert 2.5 < rays / n < 2.9  # the oracle measures 2.69 rays/sample on this view
+    assert np.isfinite(img).all() and img.min() >= 0 and img.max() <= 1 + 1e-5
+    # converged image statistics agree with a cheap oracle render of the same view (64x fewer samples)
+    ref, _ = orc.Scene("random_spheres", w, h).update(16, depth, mode=orc.HIT_SOA_AVX2 if orc.lib().orc_has_avx2() else orc.HIT_SOA_SCALAR)
+    assert rel_mean_diff(img, ref).max() < 5e-3
+    # block means (50x50 pixel blocks): the two renders are the same picture
+    bm = lambda a: a.reshape(h // 50, 50, w // 50, 50, 3).mean(axis=(1, 3))
+    assert np.abs(bm(img) - bm(ref)).max() < 0.02
+    # the top rows are sky only: exactly one ray per sample there, and the analytic gradient
+    assert np.all(img[-1, :, 2] > img[-1, :, 0])
+    st = pr.stats()
+    assert st.kernel_launches == 1 and st.d2h_bytes == w * h * 12 + 8

@@ -1,0 +1,152 @@
+"""CPU-side checks of the product: the C ABI library loads and exports what include/ptgpu.h declares, the ctypes
+struct layouts match the compiled ones, the host mirror builds the same scenes as the oracle bit for bit, and the
+error behaviour without a GPU is loud (no fallback)."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import orc
+import pathtrace_rs_b200 as pt
+from pathtrace_rs_b200 import ffi, parallel
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PRESETS = ["random_spheres", "small", "two_perlin_spheres", "smallpt", "final", "stress100k"]
+
+
+def _no_gpu():
+    return pt.libptgpu().pt_device_count() == 0
+
+
+def test_abi_symbols_exported():
+    L = pt.libptgpu()
+    names = pt.abi_symbols()
+    assert len(names) >= 15 and "pt_render" in names and "pt_scene_create" in names
+    for n in names:
+        assert hasattr(L, n), n
+    assert L.pt_abi_version() == 1
+    out = subprocess.check_output(["nm", "-D", "--defined-only", os.path.join(ffi.LIB_DIR, "libptgpu.so")], text=True)
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert set(names) <= exported
+
+
+def test_ctypes_layouts_match_compiled_structs():
+    L = pt.libptgpu()
+    structs = [ffi.PtParams, ffi.PtCamera, ffi.PtTexture, ffi.PtMaterial, ffi.PtPerlin, ffi.PtSceneDesc, ffi.PtPartition,
+               ffi.PtDeviceInfo, ffi.PtRenderStats]
+    for i, s in enumerate(structs):
+        assert L.pt_abi_struct_size(i) == C.sizeof(s), s.__name__
+    assert L.pt_abi_struct_size(99) == 0
+    assert C.sizeof(ffi.PtCamera) == 24 * 4
+
+
+def test_library_is_sm100a_cuda_with_packed_fp32_and_tma():
+    """The shipped kernel is real sm_100a SASS: packed FP32 (FFMA2/FADD2/FMUL2) in the sweep, bulk TMA copy + mbarrier."""
+    so = os.path.join(ffi.LIB_DIR, "libptgpu.so")
+    try:
+        sass = subprocess.check_output(["cuobjdump", "-sass", so], text=True, stderr=subprocess.STDOUT)
+    except (OSError, subprocess.CalledProcessError):
+        pytest.skip("cuobjdump not available")
+    assert "sm_100a" in sass
+    for mnemonic in ("FFMA2", "FADD2", "FMUL2", "UBLKCP", "SYNCS"):
+        assert mnemonic in sass, mnemonic
+
+
+@pytest.mark.parametrize("preset", PRESETS)
+def test_host_mirror_builds_the_oracles_scene(preset):
+    w, h = 120, 80
+    host = pt.Preset(preset, pt.Params(w, h, 1, 10)).flat()
+    o = orc.Scene(preset, w, h).flat()
+    assert np.array_equal(host["centre_radius"], o["centre_radius"])
+    assert np.array_equal(host["camera"], o["camera"])
+    assert np.array_equal(host["randvec"], o["randvec"]) and np.array_equal(host["perm"], o["perm"])
+    assert host["has_sky"] == o["has_sky"] and np.array_equal(host["sky"], o["sky"])
+    okind = o["mat_kind_tex"][o["sphere_material"], 0] if len(o["sphere_material"]) else np.zeros(0, np.int32)
+    assert np.array_equal(host["kind"], okind)
+    # colour: constant-texture colour for Lambertian/DiffuseLight, albedo for Metal; fuzz; ref_idx
+    for i in range(0, len(okind), max(1, len(okind) // 500)):
+        m = o["sphere_material"][i]
+        k, t = o["mat_kind_tex"][m]
+        exp = o["mat_albedo_fuzz_ref"][m].copy()
+        if k in (orc.MAT_LAMBERTIAN, orc.MAT_DIFFUSE_LIGHT) and o["tex_kind_odd_even"][t, 0] == orc.TEX_CONSTANT:
+            exp[:3] = o["tex_color_scale"][t, :3]
+        if k in (orc.MAT_LAMBERTIAN, orc.MAT_DIFFUSE_LIGHT) and o["tex_kind_odd_even"][t, 0] != orc.TEX_CONSTANT:
+            continue
+        assert np.array_equal(host["params5"][i], exp), (i, k)
+
+
+def test_host_rng_continues_like_the_reference():
+    p = pt.Preset("random_spheres", pt.Params(200, 100, 10, 10))
+    assert abs(p.flat()["next_f32"] - 0.17442238) < 1e-8
+
+
+def test_unrecognised_preset():
+    with pytest.raises(ValueError, match="unrecognised preset"):
+        pt.Preset("cornell_smoke", pt.Params(8, 8, 1, 1))
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    if not _no_gpu():
+        pytest.skip("a GPU is present")
+    p = pt.Preset("small", pt.Params(8, 8, 1, 1))
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        p.create_scene(0)
+    with pytest.raises(RuntimeError, match="scene not created"):
+        p.update()
+    info = ffi.PtDeviceInfo()
+    assert pt.libptgpu().pt_device_info(0, C.byref(info)) == ffi.PT_ERR_NO_DEVICE
+
+
+def test_product_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "pathtrace_rs_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if os.path.basename(dirpath) == "lib":
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")) or f == "Makefile":
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "liboracle" not in text and "pt_oracle" not in text and "import orc" not in text, os.path.join(dirpath, f)
+    out = subprocess.check_output(["ldd", os.path.join(ffi.LIB_DIR, "libpthost.so")], text=True)
+    assert "oracle" not in out
+
+
+@pytest.mark.parametrize("height,tile,count", [(30, 4, 3), (100, 4, 8), (2160, 4, 8), (7, 4, 4), (5, 8, 2), (1, 1, 3)])
+def test_partition_rows_cover_the_image_once(height, tile, count):
+    seen = np.zeros(height, np.int32)
+    sizes = []
+    for idx in range(count):
+        rows = parallel.owned_rows(ffi.PtPartition(tile, idx, count, 0), height)
+        assert np.all(np.diff(rows.astype(np.int64)) > 0)
+        assert np.all((rows // tile) % count == idx)
+        seen[rows] += 1
+        sizes.append(len(rows))
+    assert np.all(seen == 1)
+    assert max(sizes) - min(sizes) <= tile
+    whole = parallel.owned_rows(ffi.PtPartition(0, 0, 0, 0), height)  # defaults: tile 4, one part
+    assert np.array_equal(whole, np.arange(height))
+
+
+def test_png_writer_roundtrip(tmp_path):
+    import zlib
+    rgb = (np.arange(5 * 7 * 3) % 251).astype(np.uint8).reshape(5, 7, 3)
+    path = str(tmp_path / "t.png")
+    assert pt.libpthost().pth_write_png(path.encode(), rgb.ctypes.data_as(C.c_void_p), 7, 5) == 0
+    data = open(path, "rb").read()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat, ihdr = 8, b"", None
+    while pos < len(data):
+        n = int.from_bytes(data[pos:pos + 4], "big")
+        typ = data[pos + 4:pos + 8]
+        body = data[pos + 8:pos + 8 + n]
+        assert zlib.crc32(typ + body) == int.from_bytes(data[pos + 8 + n:pos + 12 + n], "big")
+        if typ == b"IHDR":
+            ihdr = body
+        if typ == b"IDAT":
+            idat += body
+        pos += 12 + n
+    assert int.from_bytes(ihdr[:4], "big") == 7 and int.from_bytes(ihdr[4:8], "big") == 5 and ihdr[8:10] == b"\x08\x02"
+    raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(5, 1 + 7 * 3)
+    assert np.all(raw[:, 0] == 0) and np.array_equal(raw[:, 1:].reshape(5, 7, 3), rgb)
