@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the path-tracing hot path (Scene::update) on B200, BASELINE.json's metric.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg2] [--partition samples|rows]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one `Scene::update` of the workload (one frame of `samples` spp over the whole image).
+  value   : Mrays/s, whole job, image resident in HBM (pt_render_device on torch's current stream, CUDA events).
+  e2e     : same metric through the reference-facing call with HOST buffers (N=1: the C++ Scene::update mirror ->
+            pt_render, pinned host accumulation buffer uploaded and downloaded every step, frame_num >= 1).
+  roofline: the megakernel against the FP32 FMA peak (this path is FP32-FMA bound, not HBM or tensor bound:
+            16 flop per (ray, sphere) test x rays x spheres — SURVEY §8d / DESIGN.md).
+  cpu_baseline: the CPU oracle (restated reference, list mode = the reference's live path) on the host cores,
+            bounded sample, rank 0 at N=1 only.
+N > 1 (one process per GPU): default `--partition samples` is weak scaling — every rank renders the same image with
+its own frame seed (the reference's progressive-frame semantics, scene.rs:86-87,99-101) and one NCCL reduce
+forms the equal-weight mean; `--partition rows` is strong scaling of one frame by interleaved row tiles with no
+collective in the data path.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (preset, width, height, spp, depth)   — BASELINE.json configs
+    "cfg1": ("random_spheres", 200, 100, 100, 50),
+    "cfg2": ("random_spheres", 1200, 800, 1024, 50),
+    "cfg3": ("two_perlin_spheres", 1920, 1080, 1024, 50),
+    "cfg4": ("random_spheres", 3840, 2160, 4096, 50),
+    "cfg5": ("stress100k", 1920, 1080, 512, 50),
+}
+FLOP_PER_TEST = 16  # one (ray, sphere) test in the SoA form
+
+
+def workload_name(key, spp):
+    preset, w, h, s, d = WORKLOADS[key]
+    return "%s %dx%d %dspp depth%d (%s)" % (preset, w, h, spp, d, key)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (restated: oracle, list mode) on the host cores, bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
+    preset, w, h, spp_full, depth = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    spp = args.ref_spp
+    scene = orc.Scene(preset, w, h)
+    times, rays_total = [], 0
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        _, rays = scene.update(spp, depth, frame_num=0, mode=orc.HIT_LIST, nthreads=cores)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+            rays_total += rays
+    total = sum(times)
+    mrays = rays_total / 1e6 / total
+    sample = "%s at %d spp of %d (full resolution, list mode = live reference path, %d threads)" % (workload_name(args.workload, spp_full), spp, spp_full, cores)
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload, spp_full), "sample": sample},
+        "samples_per_s": w * h * spp * args.steps / total,
+        "cpu_baseline": {"value": mrays, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference is Rust and cannot be built in this image (no rustc/cargo): this is the C++ restatement in oracle/",
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def cpu_baseline(workload, budget_s=12.0):
+    """Oracle timed on the host cores for a bounded sample of the same workload (reported, not a target)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
+    preset, w, h, spp_full, depth = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    scene = orc.Scene(preset, w, h)
+    out = {}
+    for key, mode in (("list", orc.HIT_LIST), ("soa_avx2", orc.HIT_SOA_AVX2 if orc.lib().orc_has_avx2() else orc.HIT_SOA_SCALAR)):
+        t0 = time.perf_counter()
+        _, rays = scene.update(1, depth, mode=mode, nthreads=cores)  # calibration pass: 1 spp
+        dt = time.perf_counter() - t0
+        spp = int(max(1, min(spp_full, (budget_s / 2) / max(dt, 1e-3))))
+        t0 = time.perf_counter()
+        _, rays = scene.update(spp, depth, mode=mode, nthreads=cores)
+        dt = time.perf_counter() - t0
+        out[key] = (rays / 1e6 / dt, spp, dt)
+    v, spp, dt = out["list"]
+    return {"value": v, "unit": "Mrays/s", "cores": cores, "kind": "port",
+            "sample": "%s at %d spp of %d, full resolution, %.1f s, list mode (the reference's live HitableList path)" % (workload_name(workload, spp_full), spp, spp_full, dt),
+            "soa_avx2_mrays_s": out["soa_avx2"][0],
+            "soa_avx2_sample": "%d spp, %.1f s (spheres_soa.rs hit_avx2: bench-only in the reference)" % (out["soa_avx2"][1], out["soa_avx2"][2])}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--partition", default="samples", choices=["samples", "rows"])
+    ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (a reduced run is labelled as such)")
+    ap.add_argument("--ref-spp", type=int, default=2, help="--impl reference: spp of the bounded CPU sample per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = max(args.warmup, 0)  # the driver passes W; the contract asks for >= 3 and the default is 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import pathtrace_rs_b200 as pt
+    from pathtrace_rs_b200 import parallel
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    preset_name, w, h, spp, depth = WORKLOADS[args.workload]
+    reduced = args.spp > 0 and args.spp != spp
+    if args.spp > 0:
+        spp = args.spp
+    params = pt.Params(w, h, spp, depth)
+    preset = pt.Preset(preset_name, params).create_scene(local_rank)
+    n_spheres = len(preset)
+    info = pt.device_info(local_rank)
+
+    d_rgb = torch.zeros((h, w, 3), dtype=torch.float32, device=dev)
+    d_rays = torch.zeros(1, dtype=torch.int64, device=dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+    stream = torch.cuda.current_stream()
+    rows_mode = world > 1 and args.partition == "rows"
+    part = parallel.partition_for(rank, world) if rows_mode else None
+
+    def step_device(frame):
+        """one Scene::update, image resident in HBM; returns nothing (async on torch's stream)"""
+        preset.update_device(params, frame, d_rgb.data_ptr(), d_rays.data_ptr(), stream.cuda_stream, part)
+        if world > 1 and not rows_mode:
+            dist.reduce(d_rgb, dst=0)          # sample slices: equal-weight mean of the ranks' frames
+            if rank == 0:
+                d_rgb.mul_(1.0 / world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_run(step_fn, n_warm, n_steps):
+        for i in range(n_warm):
+            step_fn(i)
+            flush.fill_(float(i))
+        barrier()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
+        rays = 0
+        t_wall = time.perf_counter()
+        for i in range(n_steps):
+            evs[i][0].record(stream)
+            r = step_fn(i)
+            evs[i][1].record(stream)
+            if r is None:
+                evs[i][1].synchronize()
+                r = int(d_rays.item())
+            rays += r
+            flush.fill_(float(i))  # L2 flush between timed iterations (outside the event pair)
+        barrier()
+        wall = time.perf_counter() - t_wall
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        return ms, rays, wall
+
+    # ---- device-resident throughput (value) -------------------------------------------------------------------
+    frame_of = (lambda i: rank) if (world > 1 and not rows_mode) else (lambda i: 0)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, rays, wall = timed_run(lambda i: step_device(frame_of(i)), args.warmup, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # kernel-only time for the roofline: the same launch without the collective, CUDA events on the launching stream
+    k_ms, k_rays, _ = timed_run(lambda i: preset.update_device(params, frame_of(i), d_rgb.data_ptr(), d_rays.data_ptr(), stream.cuda_stream, part),
+                                1, max(1, min(args.steps, 3)))
+    k_steps = max(1, min(args.steps, 3))
+
+    # ---- end to end through the reference-facing call, host buffers ----------------------------------------------
+    pinned = torch.zeros((h, w, 3), dtype=torch.float32).pin_memory()
+    host_buf = pinned.numpy()
+    if world == 1:
+        def step_e2e(i):
+            _, r = preset.update(params, frame_num=1 + i, buffer=host_buf)  # Scene::update mirror -> pt_render: H2D + kernel + D2H
+            return r
+        h2d_b = d2h_b = w * h * 12
+        d2h_b += 8
+    else:
+        def step_e2e(i):
+            d_rgb.copy_(pinned, non_blocking=True)  # H2D of this rank's accumulation buffer
+            preset.update_device(params, 1 + frame_of(i), d_rgb.data_ptr(), d_rays.data_ptr(), stream.cuda_stream, part)
+            if not rows_mode:
+                dist.reduce(d_rgb, dst=0)
+                if rank == 0:
+                    d_rgb.mul_(1.0 / world)
+                    pinned.copy_(d_rgb, non_blocking=True)
+            else:
+                pinned.copy_(d_rgb, non_blocking=True)  # each rank downloads (only its rows are meaningful)
+            return int(d_rays.item())
+        h2d_b = w * h * 12
+        d2h_b = w * h * 12 + 8
+    e_ms, e_rays, e_wall = timed_run(step_e2e, 1, args.steps)
+
+    # ---- reduce over ranks: time = max, work = sum ------------------------------------------------------------------
+    def allmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    ms_max, rays_sum = allmax(ms), allsum(rays)
+    e_wall_max, e_rays_sum = allmax(e_wall), allsum(e_rays)
+    k_ms_max, k_rays_sum = allmax(k_ms), allsum(k_rays)
+    samples_per_step = w * h * spp * (world if (world > 1 and not rows_mode) else 1)
+
+    if rank == 0:
+        value = rays_sum / 1e6 / (ms_max * 1e-3)
+        peak_nominal = info.fp32_fma_peak_flops * world
+        achieved = k_rays_sum * FLOP_PER_TEST * n_spheres / (k_ms_max * 1e-3)
+        try:
+            peak_probe = pt.probe_fp32_peak(local_rank)
+        except Exception:
+            peak_probe = None
+        line = {
+            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": "strong" if rows_mode else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload, spp) + (" [REDUCED spp]" if reduced else ""),
+                       "n_spheres": n_spheres, "partition": ("rows: interleaved 4-row tiles, no collective" if rows_mode else
+                                                             ("samples: one frame seed per GPU + one NCCL reduce" if world > 1 else "single GPU")),
+                       "l2": "flushed between timed iterations (256 MB fill); inputs are an 8 KB scene resident in shared memory",
+                       "timing": "CUDA events per step on the launching stream, max over ranks"},
+            "samples_per_s": samples_per_step * args.steps / (ms_max * 1e-3),
+            "rays_per_sample": rays_sum / (samples_per_step * args.steps),
+            "e2e": {"value": e_rays_sum / 1e6 / e_wall_max, "unit": "Mrays/s", "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
+                    "ms_per_step": 1e3 * e_wall_max / args.steps,
+                    "path": "Scene::update mirror -> pt_render (pinned host buffer, frame_num>=1)" if world == 1 else
+                            "pinned H2D -> pt_render_device -> NCCL reduce -> D2H on rank 0"},
+            "gpu_launches": args.steps * world,
+            "roofline": {"bound": "fp32_fma", "achieved": achieved / 1e12, "peak": peak_nominal / 1e12, "unit": "TFLOP/s",
+                         "frac": achieved / peak_nominal, "traffic": None,
+                         "peak_source": "sm_count*128*2*max SM clock (%d SMs, %d MHz); MEASURED_PEAKS.json has no FP32 figure — "
+                                        "a pure-FFMA probe kernel measured %s TFLOP/s on this GPU in this run"
+                                        % (info.sm_count, info.sm_clock_khz // 1000, ("%.1f" % (peak_probe / 1e12)) if peak_probe else "n/a"),
+                         "algorithmic": "16 flop x %d spheres x %d rays per launch (brute force, every ray tests every sphere)" % (n_spheres, int(k_rays_sum / k_steps)),
+                         "kernel_ms": k_ms_max / k_steps,
+                         "note": "HBM traffic is 24 B/pixel/launch (accumulation buffer) — irrelevant; see profiles/ for dram bytes"},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline(args.workload)
+            except Exception as e:  # the baseline is a reported extra; never lose the GPU line over it
+                line["cpu_baseline"] = {"error": repr(e)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
