@@ -371,6 +371,13 @@ struct RayHit {
 // ------------------------------------------------------------------------------------------------
 enum HitMode : int32_t { HIT_LIST = 0, HIT_SOA_SCALAR = 1, HIT_SOA_AVX2 = 2 };
 
+// debug recorder (tools/ray_stats.py): every ray handed to ray_hit, in trace order
+struct RayRecorder {
+    float* out = nullptr;  // 6 floats per ray
+    int64_t cap = 0, n = 0;
+};
+static thread_local RayRecorder* g_recorder = nullptr;
+
 struct Scene {
     std::vector<Sphere> spheres;
     std::vector<Material> materials;
@@ -541,6 +548,11 @@ struct Scene {
     }
 #endif
     bool ray_hit(int mode, const Ray& ray, float t_min, float t_max, RayHit& hit, int32_t& index) const {
+        if (g_recorder && g_recorder->n < g_recorder->cap) {
+            float* o = g_recorder->out + 6 * g_recorder->n++;
+            o[0] = ray.origin.x; o[1] = ray.origin.y; o[2] = ray.origin.z;
+            o[3] = ray.direction.x; o[4] = ray.direction.y; o[5] = ray.direction.z;
+        }
         switch (mode) {
             case HIT_SOA_SCALAR: return hit_soa_scalar(ray, t_min, t_max, hit, index);
 #if defined(__AVX2__)
@@ -1036,6 +1048,20 @@ float orc_next_f32_after_random_spheres() {
     s.perlin.init(rng);
     orc::preset_random_spheres(s, pp, rng, 11);
     return rng.gen_f32();
+}
+// debug: trace one pixel and record its rays in order; returns the number of rays recorded
+int64_t orc_trace_pixel_rays(void* h, const OrcParams* p, uint32_t x, uint32_t y, float* rays6, int64_t cap) {
+    auto* s = (orc::Scene*)h;
+    orc::Params pp{p->width, p->height, p->samples, p->max_depth, false, false};
+    orc::RayRecorder rec;
+    rec.out = rays6;
+    rec.cap = cap;
+    orc::g_recorder = &rec;
+    float px[3] = {0, 0, 0};
+    uint64_t rays = 0;
+    orc::update_pixel(*s, s->camera, pp, orc::HIT_SOA_SCALAR | 0x100, 0, (size_t)y * p->width + x, px, rays);
+    orc::g_recorder = nullptr;
+    return rec.n;
 }
 int32_t orc_hw_threads() { return (int32_t)std::thread::hardware_concurrency(); }
 

@@ -25,6 +25,7 @@ struct KernelArgs {
     const DevShade* shade;
     const DevTexture* tex;
     const PerlinSmem* perlin;  // global copy, staged to shared memory when has_noise
+    const float* kvals;        // pre-filter k per sphere (constant-bank sweep), 4 * n_blocks floats
     int has_noise;
     DevCamera cam;
     uint32_t width, height, samples, max_depth, frame_num;
@@ -248,6 +249,88 @@ __device__ __forceinline__ void stage_perlin(const KernelArgs& a, PerlinSmem* P)
 
 constexpr int kCtaThreads = 256;
 
+// Optional phase profile (compile with -DPT_PROFILE; tools/phase_profile.py): per-warp clock64 deltas of the
+// three phases of a trip and trip/lane counters, summed into a global array.  Not compiled into the product.
+#ifdef PT_PROFILE
+__device__ unsigned long long g_prof[8];  // 0 refill clk, 1 sweep clk, 2 shade clk, 3 warp trips, 4 active lane-trips, 5 total clk
+#define PT_PROF_DECL unsigned long long pf_t0 = 0, pf_refill = 0, pf_sweep = 0, pf_shade = 0, pf_trips = 0, pf_lanes = 0, pf_start = clock64();
+#define PT_PROF_TICK() (pf_t0 = clock64())
+#define PT_PROF_TOCK(acc) do { unsigned long long t_ = clock64(); acc += t_ - pf_t0; pf_t0 = t_; } while (0)
+#define PT_PROF_FLUSH(lane_id) do { if ((lane_id) == 0) { atomicAdd(&g_prof[0], pf_refill); atomicAdd(&g_prof[1], pf_sweep); atomicAdd(&g_prof[2], pf_shade); \
+    atomicAdd(&g_prof[3], pf_trips); atomicAdd(&g_prof[5], clock64() - pf_start); } atomicAdd(&g_prof[4], pf_lanes); } while (0)
+#else
+#define PT_PROF_DECL
+#define PT_PROF_TICK()
+#define PT_PROF_TOCK(acc)
+#define PT_PROF_FLUSH(lane_id)
+#endif
+
+
+// =====================================================================================================
+// Tail compaction (active-path compaction).  A pixel cannot be split (its RNG stream is
+// sequential), so once the pixel queue runs dry each lane finishes its last pixel at a different time and a warp
+// keeps sweeping with ever fewer live lanes.  From the first trip in which any lane of the CTA fails to get a pixel
+// the CTA's warps run their trips in lockstep (one named barrier per trip); whenever the live paths would fit in
+// fewer warps than currently hold them, all live lane states are packed into the lowest warps through shared memory
+// and the emptied warps stop sweeping.  Results are unchanged: a path carries its whole state (RNG included).
+// =====================================================================================================
+constexpr int kLaneStateWords = 25;
+struct TailShared {
+    int flag;  // slot counter of a compaction round
+};
+
+__device__ __forceinline__ void lane_store(const Lane& L, uint32_t* pool, int slot) {
+    uint32_t w[kLaneStateWords];
+    w[0] = (uint32_t)L.rng.s0; w[1] = (uint32_t)(L.rng.s0 >> 32); w[2] = (uint32_t)L.rng.s1; w[3] = (uint32_t)(L.rng.s1 >> 32);
+    w[4] = (uint32_t)L.rng.s2; w[5] = (uint32_t)(L.rng.s2 >> 32); w[6] = (uint32_t)L.rng.s3; w[7] = (uint32_t)(L.rng.s3 >> 32);
+    w[8] = __float_as_uint(L.o.x); w[9] = __float_as_uint(L.o.y); w[10] = __float_as_uint(L.o.z);
+    w[11] = __float_as_uint(L.d.x); w[12] = __float_as_uint(L.d.y); w[13] = __float_as_uint(L.d.z);
+    w[14] = __float_as_uint(L.thr.x); w[15] = __float_as_uint(L.thr.y); w[16] = __float_as_uint(L.thr.z);
+    w[17] = __float_as_uint(L.col.x); w[18] = __float_as_uint(L.col.y); w[19] = __float_as_uint(L.col.z);
+    w[20] = L.px; w[21] = L.py; w[22] = L.sample; w[23] = L.depth;
+    w[24] = (L.active ? 1u : 0u) | (L.have_pixel ? 2u : 0u);
+#pragma unroll
+    for (int i = 0; i < kLaneStateWords; ++i) pool[i * kCtaThreads + slot] = w[i];
+}
+__device__ __forceinline__ void lane_load(Lane& L, const uint32_t* pool, int slot) {
+    uint32_t w[kLaneStateWords];
+#pragma unroll
+    for (int i = 0; i < kLaneStateWords; ++i) w[i] = pool[i * kCtaThreads + slot];
+    L.rng.s0 = (uint64_t)w[0] | ((uint64_t)w[1] << 32); L.rng.s1 = (uint64_t)w[2] | ((uint64_t)w[3] << 32);
+    L.rng.s2 = (uint64_t)w[4] | ((uint64_t)w[5] << 32); L.rng.s3 = (uint64_t)w[6] | ((uint64_t)w[7] << 32);
+    L.o = v3(__uint_as_float(w[8]), __uint_as_float(w[9]), __uint_as_float(w[10]));
+    L.d = v3(__uint_as_float(w[11]), __uint_as_float(w[12]), __uint_as_float(w[13]));
+    L.thr = v3(__uint_as_float(w[14]), __uint_as_float(w[15]), __uint_as_float(w[16]));
+    L.col = v3(__uint_as_float(w[17]), __uint_as_float(w[18]), __uint_as_float(w[19]));
+    L.px = w[20]; L.py = w[21]; L.sample = w[22]; L.depth = w[23];
+    L.active = (w[24] & 1u) != 0u; L.have_pixel = (w[24] & 2u) != 0u;
+    L.finished = false;
+}
+
+// One tail-phase step for the whole CTA (every warp calls it once per trip): returns false when no live path is left.
+// __syncthreads_count gives the CTA-wide totals; slots in the staging pool are handed out by a shared atomic.
+__device__ __forceinline__ bool tail_step(TailShared& T, uint32_t* pool, Lane& L, unsigned lane_id) {
+    const unsigned live_mask = __ballot_sync(kFullMask, !L.finished);
+    const int total = __syncthreads_count(!L.finished);
+    const int holders = __syncthreads_count(lane_id == 0 && live_mask != 0u);
+    if (total == 0) return false;
+    if ((total + 31) / 32 < holders) {  // the live paths fit in fewer warps than hold them now: pack them
+        if (threadIdx.x == 0) T.flag = 0;
+        __syncthreads();
+        if (!L.finished) lane_store(L, pool, atomicAdd(&T.flag, 1));
+        __syncthreads();
+        if ((int)threadIdx.x < total) {
+            lane_load(L, pool, threadIdx.x);
+        } else {
+            L.finished = true;
+            L.active = false;
+            L.have_pixel = false;
+        }
+        __syncthreads();
+    }
+    return true;
+}
+
 // =====================================================================================================
 // Resident variant: the whole sphere SoA lives in shared memory for the life of the CTA.
 // =====================================================================================================
@@ -276,8 +359,10 @@ __global__ void __launch_bounds__(kCtaThreads) pt_megakernel_resident(const __gr
     Lane L;
     lane_init(L);
     unsigned long long rays = 0ULL;
+    PT_PROF_DECL
 
     for (;;) {
+        PT_PROF_TICK();
         lane_refill(a, L, lane_id);
         if (__all_sync(kFullMask, L.finished)) break;
         float ox = L.o.x, oy = L.o.y, oz = L.o.z, dx = L.d.x, dy = L.d.y, dz = L.d.z;
@@ -287,12 +372,97 @@ __global__ void __launch_bounds__(kCtaThreads) pt_megakernel_resident(const __gr
         }
         float hit_t = kMaxT;
         int hit_index = -1;
+        __syncwarp();
+        PT_PROF_TOCK(pf_refill);
         sweep_blocks<UNROLL>(blk, a.n_blocks, 0, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
+        __syncwarp();
+        PT_PROF_TOCK(pf_sweep);
         if (L.active) {
             rays += 1ULL;  // scene.rs:57
             lane_shade(a, L, blk, *P, hit_t, hit_index);
         }
+        __syncwarp();
+        PT_PROF_TOCK(pf_shade);
+#ifdef PT_PROFILE
+        pf_trips += 1;
+        pf_lanes += 1;  // counted per lane below (only active lanes reach the add through `rays`)
+#endif
     }
+#ifdef PT_PROFILE
+    pf_lanes = rays;
+#endif
+    PT_PROF_FLUSH(lane_id);
+    flush_ray_count(a, rays, lane_id);
+}
+
+// =====================================================================================================
+// Constant-bank variant (<= kMaxConstSpheres spheres): the pre-filter reads sphere pairs through the uniform
+// datapath (pt_sweep.cuh, sweep_const); the TMA-staged shared-memory copy serves the exact re-test and shading.
+// =====================================================================================================
+template <int WORDS>
+__global__ void __launch_bounds__(kCtaThreads) pt_megakernel_const(const __grid_constant__ KernelArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    float4* blk = reinterpret_cast<float4*>(smem_raw);
+    PerlinSmem* P = reinterpret_cast<PerlinSmem*>(smem_raw + (size_t)a.n_blocks * 64);
+    float* ksm = reinterpret_cast<float*>(smem_raw + (size_t)a.n_blocks * 64 + sizeof(PerlinSmem));  // [4 * n_blocks] pre-filter k per sphere
+    uint32_t* queue = reinterpret_cast<uint32_t*>(ksm + 4 * a.n_blocks) + threadIdx.x;           // [kQueueCap][kCtaThreads] candidate queues
+
+    const uint32_t bytes = (uint32_t)a.n_blocks * 64u;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && bytes != 0u) {
+        mbar_arrive_expect_tx(&bar, bytes);
+        tma_bulk_g2s_chunked(blk, a.blocks, bytes, &bar);
+    }
+    stage_perlin(a, P);
+    for (int i = threadIdx.x; i < 4 * a.n_blocks; i += blockDim.x) ksm[i] = a.kvals[i];
+    __syncthreads();
+    if (bytes != 0u) mbar_wait(&bar, 0);
+
+    const unsigned lane_id = threadIdx.x & 31u;
+    const int n_groups = a.n_blocks / kConstGroupBlocks;  // n_blocks is padded to whole groups by the host
+    Lane L;
+    lane_init(L);
+    unsigned long long rays = 0ULL;
+    PT_PROF_DECL
+
+    // NOTE: the shape of this loop is deliberate.  ptxas keeps the sweep's loop counter and sphere operands in uniform
+    // registers (LDCU + FFMA2 R, R.F32, UR.F32x2, R) only for some control-flow shapes; tests/test_host_and_abi.py checks
+    // the SASS so that a refactor which silently loses them (x2 slower sweep) fails the build.
+    for (;;) {
+        PT_PROF_TICK();
+        lane_refill(a, L, lane_id);
+        if (__all_sync(kFullMask, L.finished)) break;
+        float ox = L.o.x, oy = L.o.y, oz = L.o.z, dx = L.d.x, dy = L.d.y, dz = L.d.z;
+        if (!L.active) {  // parked lane: |o|^2 = 1e36 dwarfs every L, d = 0 -> never a candidate
+            ox = 0.0f; oy = 1.0e18f; oz = 0.0f;
+            dx = dy = dz = 0.0f;
+        }
+        float hit_t = kMaxT;
+        int hit_index = -1;
+        __syncwarp();
+        PT_PROF_TOCK(pf_refill);
+        sweep_const<WORDS>(n_groups, blk, reinterpret_cast<const float2*>(ksm), queue, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
+        __syncwarp();
+        PT_PROF_TOCK(pf_sweep);
+        if (L.active) {
+            rays += 1ULL;  // scene.rs:57
+            lane_shade(a, L, blk, *P, hit_t, hit_index);
+        }
+        __syncwarp();
+        PT_PROF_TOCK(pf_shade);
+#ifdef PT_PROFILE
+        pf_trips += 1;
+#endif
+    }
+#ifdef PT_PROFILE
+    pf_lanes = rays;
+#endif
+    PT_PROF_FLUSH(lane_id);
     flush_ray_count(a, rays, lane_id);
 }
 

@@ -38,7 +38,10 @@ int fail(int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(PT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-constexpr int kSweepUnroll = 2;
+#ifndef PT_SWEEP_GROUP
+#define PT_SWEEP_GROUP 2
+#endif
+constexpr int kSweepUnroll = PT_SWEEP_GROUP;  // blocks (of 4 spheres) tested per branch in the sweep
 constexpr size_t kMaxDynSmem = 227 * 1024 - 1024;  // leave room for static shared + driver reservation
 
 }  // namespace
@@ -55,6 +58,7 @@ struct PtScene {
     pt::DevShade* d_shade = nullptr;
     pt::DevTexture* d_tex = nullptr;
     pt::PerlinSmem* d_perlin = nullptr;
+    float* d_kvals = nullptr;  // pre-filter k per sphere (constant-bank sweep)
     // per-render scratch
     unsigned long long* d_ray_count = nullptr;  // [0] ray count
     unsigned int* d_next_pixel = nullptr;
@@ -66,6 +70,9 @@ struct PtScene {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // launch geometry
     bool resident = true;
+    bool use_const = false;                 // pre-filter through the constant bank (<= kMaxConstSpheres)
+    int const_words = 2;                    // flag words per lane (kernel instantiation)
+    std::vector<float4> h_prefilter;        // host copy of the constant-bank image of this scene
     int tile_blocks = 0, n_tiles = 0;
     size_t smem_bytes = 0;
     int ctas_per_sm = 0;
@@ -109,6 +116,17 @@ int plan_launch(PtScene* s) {
         s->n_tiles = (s->n_blocks + s->tile_blocks - 1) / s->tile_blocks;
         s->smem_bytes = 2 * (size_t)s->tile_blocks * 64 + perlin_bytes;
         return configure_kernel(pt::pt_megakernel_streamed<kSweepUnroll>, s->smem_bytes, &s->ctas_per_sm);
+    }
+    const bool no_const = std::getenv("PTGPU_DISABLE_CONST_SWEEP") != nullptr;  // test hook: exercise the LDS sweep
+    if (!no_const && s->n_blocks <= pt::kMaxConstBlocks) {
+        s->resident = true;
+        s->use_const = true;
+        s->smem_bytes = all + (size_t)s->n_blocks * 4 * sizeof(float) + (size_t)pt::kQueueCap * pt::kCtaThreads * sizeof(uint32_t);
+        s->tile_blocks = s->n_blocks;
+        s->n_tiles = 1;
+        s->const_words = s->n_blocks / pt::kConstGroupBlocks <= 64 ? 2 : 16;  // 32 groups (256 spheres) per flag word
+        return s->const_words == 2 ? configure_kernel(pt::pt_megakernel_const<2>, s->smem_bytes, &s->ctas_per_sm)
+                                   : configure_kernel(pt::pt_megakernel_const<16>, s->smem_bytes, &s->ctas_per_sm);
     }
     if (all <= kMaxDynSmem) {
         s->resident = true;
@@ -165,6 +183,7 @@ int launch_update(PtScene* s, const PtParams* params, const PtCamera* cam, uint3
     a.shade = s->d_shade;
     a.tex = s->d_tex;
     a.perlin = s->d_perlin;
+    a.kvals = s->d_kvals;
     a.has_noise = s->has_noise ? 1 : 0;
     auto V = [](const float* f) { return pt::V3{f[0], f[1], f[2]}; };
     a.cam.origin = V(cam->origin);
@@ -210,7 +229,15 @@ int launch_update(PtScene* s, const PtParams* params, const PtCamera* cam, uint3
     // persistent grid: one wave of CTAs, never more lanes than pixels
     const uint32_t want = (a.n_owned_pixels + pt::kCtaThreads - 1) / pt::kCtaThreads;
     const uint32_t grid = std::min<uint32_t>((uint32_t)(s->sm_count * s->ctas_per_sm), want);
-    if (s->resident)
+    if (s->use_const) {
+        // the constant bank is per device, not per scene: (re)load this scene's image in stream order
+        PT_CUDA(cudaMemcpyToSymbolAsync(pt::c_prefilter, s->h_prefilter.data(), s->h_prefilter.size() * sizeof(float4), 0,
+                                        cudaMemcpyHostToDevice, stream));
+        if (s->const_words == 2)
+            pt::pt_megakernel_const<2><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a);
+        else
+            pt::pt_megakernel_const<16><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a);
+    } else if (s->resident)
         pt::pt_megakernel_resident<kSweepUnroll><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a);
     else
         pt::pt_megakernel_streamed<kSweepUnroll><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a);
@@ -364,6 +391,7 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
     s->sm_count = prop.multiProcessorCount;
     s->n_spheres = n;
     s->n_blocks = (int)((n + 3) / 4);
+    s->n_blocks = (s->n_blocks + pt::kConstGroupBlocks - 1) / pt::kConstGroupBlocks * pt::kConstGroupBlocks;  // whole groups; padding spheres can never be hit
     s->has_noise = uses_noise;
     s->has_sky = desc->has_sky != 0;
     s->sky = pt::V3{desc->sky[0], desc->sky[1], desc->sky[2]};
@@ -380,6 +408,30 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
             f[4 + e] = valid ? desc->centre_y[i] : FLT_MAX;
             f[8 + e] = valid ? desc->centre_z[i] : FLT_MAX;
             f[12 + e] = valid ? desc->radius[i] * desc->radius[i] : 0.0f;  // spheres_soa.rs:46
+        }
+    }
+    // constant-bank image for the pre-filter (pt_sweep.cuh): X, Y, Z, K = r^2 - |c|^2 + 2^-19 (|c|^2 + r^2), padded to the group
+    if (s->n_blocks <= pt::kMaxConstBlocks) {
+        s->h_prefilter.assign((size_t)std::max(s->n_blocks, 1) * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+        for (int j = 0; j < s->n_blocks; ++j) {
+            float* f = reinterpret_cast<float*>(&s->h_prefilter[(size_t)j * 4]);
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t i = (uint32_t)j * 4 + e;
+                f[0 + e] = f[4 + e] = f[8 + e] = 0.0f;
+                f[12 + e] = -3.0e38f;  // padding: never a candidate
+                if (i >= n) continue;
+                const double cx = desc->centre_x[i], cy = desc->centre_y[i], cz = desc->centre_z[i], r = desc->radius[i];
+                const double c2 = cx * cx + cy * cy + cz * cz, r2 = r * r;
+                if (!(c2 + r2 < 1.0e24)) {  // too large (or NaN) for the expanded form: always a candidate, the exact test decides
+                    f[12 + e] = INFINITY;
+                    continue;
+                }
+                f[0 + e] = (float)cx;
+                f[4 + e] = (float)cy;
+                f[8 + e] = (float)cz;
+                const double k = r2 - c2 + 1.9073486328125e-06 * (c2 + r2);
+                f[12 + e] = std::nextafter((float)k, INFINITY);  // round towards "candidate"
+            }
         }
     }
     for (uint32_t i = 0; i < n; ++i) {
@@ -441,6 +493,13 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
     PT_CUDA_S(cudaMemcpy(s->d_shade, shade.data(), shade.size() * sizeof(pt::DevShade), cudaMemcpyHostToDevice));
     PT_CUDA_S(cudaMalloc(&s->d_tex, tex.size() * sizeof(pt::DevTexture)));
     PT_CUDA_S(cudaMemcpy(s->d_tex, tex.data(), tex.size() * sizeof(pt::DevTexture), cudaMemcpyHostToDevice));
+    if (!s->h_prefilter.empty()) {
+        std::vector<float> kv((size_t)std::max(s->n_blocks, 1) * 4, -3.0e38f);
+        for (int j = 0; j < s->n_blocks; ++j)
+            for (int e = 0; e < 4; ++e) kv[(size_t)j * 4 + e] = reinterpret_cast<const float*>(&s->h_prefilter[(size_t)j * 4 + 3])[e];
+        PT_CUDA_S(cudaMalloc(&s->d_kvals, kv.size() * sizeof(float)));
+        PT_CUDA_S(cudaMemcpy(s->d_kvals, kv.data(), kv.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
     PT_CUDA_S(cudaMalloc(&s->d_perlin, sizeof(pt::PerlinSmem)));
     {
         std::vector<unsigned char> raw(sizeof(pt::PerlinSmem), 0);
@@ -476,6 +535,7 @@ void pt_scene_destroy(PtScene* s) {
     cudaFree(s->d_shade);
     cudaFree(s->d_tex);
     cudaFree(s->d_perlin);
+    cudaFree(s->d_kvals);
     cudaFree(s->d_ray_count);
     cudaFree(s->d_next_pixel);
     cudaFree(s->d_rgb);
@@ -585,6 +645,16 @@ int pt_scene_stats(const PtScene* s, PtRenderStats* out) {
     *out = s->stats;
     return PT_OK;
 }
+
+#ifdef PT_PROFILE
+// profile build only (tools/phase_profile.py): read and clear the phase counters
+int pt_profile_read(unsigned long long* out8) {
+    PT_CUDA(cudaMemcpyFromSymbol(out8, pt::g_prof, sizeof(unsigned long long) * 8));
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    PT_CUDA(cudaMemcpyToSymbol(pt::g_prof, z, sizeof(z)));
+    return PT_OK;
+}
+#endif
 
 int pt_probe_fp32_peak(int device, double* flops_out) {
     if (!flops_out) return fail(PT_ERR_INVALID, "null out");

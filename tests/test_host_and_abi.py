@@ -53,6 +53,16 @@ def test_library_is_sm100a_cuda_with_packed_fp32_and_tma():
     assert "sm_100a" in sass
     for mnemonic in ("FFMA2", "FADD2", "FMUL2", "UBLKCP", "SYNCS"):
         assert mnemonic in sass, mnemonic
+    # The constant-bank sweep must read sphere pairs through the uniform datapath (LDCU -> UR operand of FFMA2).
+    # ptxas only does that for some control-flow shapes (DESIGN.md "uniform operands"); losing it halves the sweep's speed.
+    import re
+    kernels = re.split(r"Function : ", sass)
+    const = [k for k in kernels if k.startswith("_ZN2pt19pt_megakernel_constILi2E")]
+    assert const, "pt_megakernel_const<2> not found"
+    body = const[0]
+    assert len(re.findall(r"LDCU\.64 UR\d+, c\[0x3\]", body)) >= 12, "sphere operands are no longer uniform loads"
+    assert len(re.findall(r"FFMA2 R\d+, R\d+(?:\.reuse)?\.F32, UR\d+\.F32x2", body)) >= 20, "FFMA2 no longer takes the uniform sphere pair"
+    assert not re.search(r"LDC\.64 R\d+, c\[0x3\]", body), "per-thread constant loads in the sweep"
 
 
 @pytest.mark.parametrize("preset", PRESETS)

@@ -144,6 +144,59 @@ __global__ void __launch_bounds__(256) k_sweep_packed(const float4* __restrict__
     }
 }
 
+// V3: 1 ray per lane, sphere PAIRS as uniform operands from the constant bank, expanded algebra (7 FFMA2 per pair):
+//   A = c.d - o.d ; B = 2 c.o + k (k = r^2 - |c|^2 + slack) ; candidate <=> A*A + B > |o|^2 (1 - 2^-19)
+__constant__ float4 c_blk[4000];
+template <int GROUP, bool SLOW>
+__global__ void __launch_bounds__(256) k_sweep_const(const float4* __restrict__ sp_aos, int n4, const RayIn* __restrict__ rays, int rays_per_thread, float* out_t, int* out_i) {
+    int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (int r = 0; r < rays_per_thread; ++r) {
+        RayIn ry = rays[(size_t)r * stride + tid];
+        const float nod = -(ry.ox * ry.dx + ry.oy * ry.dy + ry.oz * ry.dz);
+        const float o2x = 2.f * ry.ox, o2y = 2.f * ry.oy, o2z = 2.f * ry.oz;
+        const float oo = (ry.ox * ry.ox + ry.oy * ry.oy + ry.oz * ry.oz) * (1.0f - 1.9073486e-6f);
+        float ht = 3.402823466e38f; int hi = SLOW ? -1 : 0;
+        for (int j = 0; j < n4; j += GROUP) {
+            float2 L[2 * GROUP];
+#pragma unroll
+            for (int g = 0; g < GROUP; ++g) {
+                const float4 X = c_blk[4 * (j + g)], Y = c_blk[4 * (j + g) + 1], Z = c_blk[4 * (j + g) + 2], K = c_blk[4 * (j + g) + 3];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float2 cx = h ? make_float2(X.z, X.w) : make_float2(X.x, X.y), cy = h ? make_float2(Y.z, Y.w) : make_float2(Y.x, Y.y);
+                    const float2 cz = h ? make_float2(Z.z, Z.w) : make_float2(Z.x, Z.y), k = h ? make_float2(K.z, K.w) : make_float2(K.x, K.y);
+                    const float2 A = fma2(cz, make_float2(ry.dz, ry.dz), fma2(cy, make_float2(ry.dy, ry.dy), fma2(cx, make_float2(ry.dx, ry.dx), make_float2(nod, nod))));
+                    const float2 B = fma2(cz, make_float2(o2z, o2z), fma2(cy, make_float2(o2y, o2y), fma2(cx, make_float2(o2x, o2x), k)));
+                    L[2 * g + h] = fma2(A, A, B);
+                }
+            }
+            bool any = false;
+#pragma unroll
+            for (int q = 0; q < 2 * GROUP; ++q) any = any | (L[q].x > oo) | (L[q].y > oo);
+            if (!SLOW) { hi += any; }
+            else if (any) {
+#pragma unroll
+                for (int q = 0; q < 2 * GROUP; ++q) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        if ((e ? L[q].y : L[q].x) > oo) {
+                            const int idx = 4 * j + 2 * q + e;
+                            const float4 S = sp_aos[idx];
+                            float cx = S.x - ry.ox, cy = S.y - ry.oy, cz = S.z - ry.oz;
+                            float nb = fmaf(cz, ry.dz, fmaf(cy, ry.dy, cx * ry.dx));
+                            float cc = fmaf(cz, cz, fmaf(cy, cy, fmaf(cx, cx, -S.w)));
+                            float disc = fmaf(nb, nb, -cc);
+                            if (disc > 0.f) { float sq = sqrtf(disc); float t = nb - sq; if (t < 0.001f) t = nb + sq; if (t > 0.001f && t < ht) { ht = t; hi = idx; } }
+                        }
+                    }
+                }
+            }
+        }
+        out_t[(size_t)r * stride + tid] = ht; out_i[(size_t)r * stride + tid] = hi;
+    }
+}
+
 static float frand(uint64_t& s) { s = s * 6364136223846793005ULL + 1442695040888963407ULL; return (float)((s >> 40) & 0xFFFFFF) / 16777216.0f; }
 
 int main(int argc, char** argv) {
@@ -179,6 +232,13 @@ int main(int argc, char** argv) {
     std::vector<float4> aos(n4 * 4), blk(n4 * 4);
     for (int i = 0; i < n4 * 4; ++i) { bool v = i < n; aos[i] = make_float4(v ? cx[i] : 3.0e38f, v ? cy[i] : 3.0e38f, v ? cz[i] : 3.0e38f, v ? rr[i] * rr[i] : 0.f); }
     for (int j = 0; j < n4; ++j) { float* X = (float*)&blk[4 * j]; for (int e = 0; e < 4; ++e) { int i = 4 * j + e; bool v = i < n; X[e] = v ? cx[i] : 1.0e18f; X[4 + e] = v ? cy[i] : 1.0e18f; X[8 + e] = v ? cz[i] : 1.0e18f; X[12 + e] = v ? rr[i] * rr[i] : 0.f; } }
+    {
+        std::vector<float4> cb(((n4 + 3) / 4 * 4 + 4) * 4);
+        for (size_t j = 0; j < cb.size() / 4; ++j) { float* X = (float*)&cb[4 * j]; for (int e = 0; e < 4; ++e) { size_t i = 4 * j + e; bool v = i < (size_t)n;
+            double c2 = v ? (double)cx[i] * cx[i] + (double)cy[i] * cy[i] + (double)cz[i] * cz[i] : 0.0; double r2 = v ? (double)rr[i] * rr[i] : 0.0;
+            X[e] = v ? cx[i] : 0.f; X[4 + e] = v ? cy[i] : 0.f; X[8 + e] = v ? cz[i] : 0.f; X[12 + e] = v ? (float)(r2 - c2 + 32 * 5.96e-8 * (c2 + r2)) : -3.0e38f; } }
+        CK(cudaMemcpyToSymbol(c_blk, cb.data(), sizeof(float4) * cb.size()));
+    }
     float4 *d_aos, *d_blk; CK(cudaMalloc(&d_aos, sizeof(float4) * n4 * 4)); CK(cudaMalloc(&d_blk, sizeof(float4) * n4 * 4));
     CK(cudaMemcpy(d_aos, aos.data(), sizeof(float4) * n4 * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(d_blk, blk.data(), sizeof(float4) * n4 * 4, cudaMemcpyHostToDevice));
     // rays: half primary-like from (13,2,3) towards origin region, half secondary from the ground plane into the upper hemisphere
@@ -212,6 +272,14 @@ int main(int argc, char** argv) {
         printf("mix %d sweep_packed<1,noslow> warps/SM %2d : %.3f ms  %.1f Gtests/s  %.2f TFLOP/s (%.1f%% of peak)\n", mix, wps, ms, tests / ms / 1e6, 16 * tests / ms / 1e9, 100 * 16 * tests / (ms * 1e-3) / peak);
         ms = timeit([&] { k_sweep_packed<2, false><<<blocks, threads, smem>>>(d_blk, n4, d_rays, RPT, d_t, d_i); }, 3);
         printf("mix %d sweep_packed<2,noslow> warps/SM %2d : %.3f ms  %.1f Gtests/s  %.2f TFLOP/s (%.1f%% of peak)\n", mix, wps, ms, tests / ms / 1e6, 16 * tests / ms / 1e9, 100 * 16 * tests / (ms * 1e-3) / peak);
+        ms = timeit([&] { k_sweep_const<2, true><<<blocks, threads>>>(d_aos, (n4 + 1) / 2 * 2, d_rays, RPT, d_t, d_i); }, 3);
+        CK(cudaMemcpy(i1.data(), d_i, 4 * nr, cudaMemcpyDeviceToHost)); diff = 0; for (size_t i = 0; i < nr; ++i) diff += i0[i] != i1[i];
+        printf("mix %d sweep_const<2>      warps/SM %2d : %.3f ms  %.1f Gtests/s  %.2f TFLOP/s (%.1f%% of peak)  mismatches %zu\n", mix, wps, ms, tests / ms / 1e6, 16 * tests / ms / 1e9, 100 * 16 * tests / (ms * 1e-3) / peak, diff);
+        ms = timeit([&] { k_sweep_const<4, true><<<blocks, threads>>>(d_aos, (n4 + 3) / 4 * 4, d_rays, RPT, d_t, d_i); }, 3);
+        CK(cudaMemcpy(i1.data(), d_i, 4 * nr, cudaMemcpyDeviceToHost)); diff = 0; for (size_t i = 0; i < nr; ++i) diff += i0[i] != i1[i];
+        printf("mix %d sweep_const<4>      warps/SM %2d : %.3f ms  %.1f Gtests/s  %.2f TFLOP/s (%.1f%% of peak)  mismatches %zu\n", mix, wps, ms, tests / ms / 1e6, 16 * tests / ms / 1e9, 100 * 16 * tests / (ms * 1e-3) / peak, diff);
+        ms = timeit([&] { k_sweep_const<2, false><<<blocks, threads>>>(d_aos, (n4 + 1) / 2 * 2, d_rays, RPT, d_t, d_i); }, 3);
+        printf("mix %d sweep_const<2,noslow> warps/SM %2d : %.3f ms  %.1f Gtests/s  %.2f TFLOP/s (%.1f%% of peak)\n", mix, wps, ms, tests / ms / 1e6, 16 * tests / ms / 1e9, 100 * 16 * tests / (ms * 1e-3) / peak);
         CK(cudaFree(d_rays)); CK(cudaFree(d_t)); CK(cudaFree(d_i));
     }
     }
