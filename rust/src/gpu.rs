@@ -1,0 +1,133 @@
+//! gpu.rs — `mod gpu;` in src/main.rs (feature "gpu").  Thin FFI over include/ptgpu.h: flattens a `Scene` whose world is
+//! a `Hitable::List` of spheres and forwards `Scene::update` to the CUDA library.  NOT compiled in this repository's CI
+//! (no Rust toolchain in the build image); the identical C ABI is exercised by the C++ mirror and the ctypes tests.
+//!
+//! Needs four small `pub(crate)` accessors in the reference:
+//!   Camera::to_ffi(&self) -> PtCamera                      (src/camera.rs, fields are private)
+//!   Scene::world(&self) -> &Hitable, Scene::sky(&self) -> Option<Vec3>      (src/scene.rs:18-22)
+//!   HitableList::hitables(&self) -> &[Hitable]             (src/collision/hitable_list.rs:9-11)
+//!   Perlin::tables(&self) -> (&[Vec3], &[u32], &[u32], &[u32])               (src/perlin.rs:7-12)
+#![cfg(feature = "gpu")]
+use crate::{camera::Camera, collision::Hitable, material::Material, params::Params, perlin::Perlin, scene::Scene, texture::Texture};
+use std::{collections::HashMap, ffi::CStr, os::raw::{c_char, c_int, c_void}, ptr};
+
+#[repr(C)] #[derive(Copy, Clone, Default)]
+pub struct PtParams { pub width: u32, pub height: u32, pub samples: u32, pub max_depth: u32, pub random_seed: u8, pub use_bvh: u8, pub _pad: [u8; 6], pub seed_salt: u64 }
+#[repr(C)] #[derive(Copy, Clone, Default)]
+pub struct PtCamera { pub origin: [f32; 3], pub lower_left_corner: [f32; 3], pub horizontal: [f32; 3], pub vertical: [f32; 3], pub u: [f32; 3], pub v: [f32; 3], pub w: [f32; 3], pub time0: f32, pub time1: f32, pub lens_radius: f32 }
+#[repr(C)] #[derive(Copy, Clone, Default)]
+pub struct PtTexture { pub kind: i32, pub color: [f32; 3], pub odd: i32, pub even: i32, pub scale: f32, pub _pad: i32 }
+#[repr(C)] #[derive(Copy, Clone, Default)]
+pub struct PtMaterial { pub kind: i32, pub texture: i32, pub albedo: [f32; 3], pub fuzz: f32, pub ref_idx: f32, pub _pad: i32 }
+#[repr(C)]
+pub struct PtPerlin { pub randvec: [[f32; 3]; 256], pub perm_x: [u32; 256], pub perm_y: [u32; 256], pub perm_z: [u32; 256] }
+#[repr(C)]
+pub struct PtSceneDesc {
+    pub struct_size: u32, pub n_spheres: u32,
+    pub centre_x: *const f32, pub centre_y: *const f32, pub centre_z: *const f32, pub radius: *const f32, pub material_index: *const i32,
+    pub n_materials: u32, pub n_textures: u32, pub materials: *const PtMaterial, pub textures: *const PtTexture, pub perlin: *const PtPerlin,
+    pub has_sky: u32, pub sky: [f32; 3],
+}
+#[repr(C)] pub struct PtScene { _private: [u8; 0] }
+
+extern "C" {
+    fn pt_abi_version() -> c_int;
+    fn pt_abi_struct_size(which: c_int) -> u32;
+    fn pt_last_error() -> *const c_char;
+    fn pt_scene_create(desc: *const PtSceneDesc, device: c_int, out: *mut *mut PtScene) -> c_int;
+    fn pt_scene_destroy(scene: *mut PtScene);
+    fn pt_render(scene: *mut PtScene, params: *const PtParams, camera: *const PtCamera, frame_num: u32, rgb_inout: *mut f32, ray_count_out: *mut u64) -> c_int;
+}
+
+fn last_error() -> String { unsafe { CStr::from_ptr(pt_last_error()).to_string_lossy().into_owned() } }
+
+/// Device copy of a flattened `Scene`.  Dropping it frees the device memory (ties `pt_scene_destroy` to a Rust `Drop`).
+pub struct GpuScene { handle: *mut PtScene }
+unsafe impl Send for GpuScene {} // `update` is called from one thread at a time (main thread offline, worker thread windowed)
+
+impl GpuScene {
+    /// The GPU arm of `Params::new_scene` (src/params.rs:29-46): walk `Hitable::List`, reject anything that is not a sphere
+    /// (same message as the panic in src/collision/spheres_soa.rs:49-51), dedupe arena pointers into indices, upload.
+    pub fn new(scene: &Scene, perlin: &Perlin, device: i32) -> GpuScene {
+        assert_eq!(unsafe { pt_abi_version() }, 1);
+        assert_eq!(unsafe { pt_abi_struct_size(5) } as usize, std::mem::size_of::<PtSceneDesc>());
+        let hitables = match scene.world() { Hitable::List(list) => list.hitables(), other => panic!("Expected Hitable::List, got {:?}", other) };
+        let (mut cx, mut cy, mut cz, mut radius, mut mat_index) = (vec![], vec![], vec![], vec![], vec![]);
+        let (mut materials, mut textures): (Vec<PtMaterial>, Vec<PtTexture>) = (vec![], vec![]);
+        let mut mat_ids: HashMap<*const Material, i32> = HashMap::new();
+        let mut tex_ids: HashMap<*const Texture, i32> = HashMap::new();
+        let mut uses_noise = false;
+        fn texture_id(t: &Texture, textures: &mut Vec<PtTexture>, ids: &mut HashMap<*const Texture, i32>, uses_noise: &mut bool) -> i32 {
+            if let Some(id) = ids.get(&(t as *const Texture)) { return *id; }
+            let mut f = PtTexture { odd: -1, even: -1, ..Default::default() };
+            match t {
+                Texture::Constant { color } => { f.kind = 0; f.color = [color.x, color.y, color.z]; }
+                Texture::Checker { odd, even } => { f.kind = 1; f.odd = texture_id(odd, textures, ids, uses_noise); f.even = texture_id(even, textures, ids, uses_noise); }
+                Texture::Noise { scale, .. } => { f.kind = 2; f.scale = *scale; *uses_noise = true; }
+                Texture::Image { .. } => panic!("Texture::Image is not supported on the GPU path"),
+            }
+            textures.push(f);
+            let id = textures.len() as i32 - 1;
+            ids.insert(t as *const Texture, id);
+            id
+        }
+        for hitable in hitables {
+            if let Hitable::Sphere(sphere, material) = hitable {
+                cx.push(sphere.centre().x); cy.push(sphere.centre().y); cz.push(sphere.centre().z); radius.push(sphere.radius());
+                let key = *material as *const Material;
+                let id = *mat_ids.entry(key).or_insert_with(|| {
+                    let mut f = PtMaterial { texture: -1, ..Default::default() };
+                    match material {
+                        Material::Lambertian { albedo } => { f.kind = 0; f.texture = texture_id(albedo, &mut textures, &mut tex_ids, &mut uses_noise); }
+                        Material::Metal { albedo, fuzz } => { f.kind = 1; f.albedo = [albedo.x, albedo.y, albedo.z]; f.fuzz = *fuzz; }
+                        Material::Dielectric { ref_idx } => { f.kind = 2; f.ref_idx = *ref_idx; }
+                        Material::DiffuseLight { emit } => { f.kind = 3; f.texture = texture_id(emit, &mut textures, &mut tex_ids, &mut uses_noise); }
+                        Material::Isotropic { .. } => panic!("Material::Isotropic is not supported on the GPU path"),
+                    }
+                    materials.push(f);
+                    materials.len() as i32 - 1
+                });
+                mat_index.push(id);
+            } else {
+                panic!("Expected Hitable::Sphere, got {:?}", hitable);
+            }
+        }
+        let tables = if uses_noise {
+            let (rv, px, py, pz) = perlin.tables();
+            let mut t = Box::new(PtPerlin { randvec: [[0.0; 3]; 256], perm_x: [0; 256], perm_y: [0; 256], perm_z: [0; 256] });
+            for i in 0..256 { t.randvec[i] = [rv[i].x, rv[i].y, rv[i].z]; t.perm_x[i] = px[i]; t.perm_y[i] = py[i]; t.perm_z[i] = pz[i]; }
+            Some(t)
+        } else { None };
+        let sky = scene.sky();
+        let desc = PtSceneDesc {
+            struct_size: std::mem::size_of::<PtSceneDesc>() as u32, n_spheres: cx.len() as u32,
+            centre_x: cx.as_ptr(), centre_y: cy.as_ptr(), centre_z: cz.as_ptr(), radius: radius.as_ptr(), material_index: mat_index.as_ptr(),
+            n_materials: materials.len() as u32, n_textures: textures.len() as u32, materials: materials.as_ptr(), textures: textures.as_ptr(),
+            perlin: tables.as_ref().map_or(ptr::null(), |t| &**t as *const PtPerlin),
+            has_sky: sky.is_some() as u32, sky: sky.map_or([0.0; 3], |s| [s.x, s.y, s.z]),
+        };
+        let mut handle: *mut PtScene = ptr::null_mut();
+        let rc = unsafe { pt_scene_create(&desc, device, &mut handle) };
+        if rc != 0 { panic!("pt_scene_create failed: {}", last_error()); }
+        GpuScene { handle }
+    }
+
+    /// Same signature and return as `Scene::update` (src/scene.rs:73-79).
+    pub fn update(&self, params: &Params, camera: &Camera, frame_num: u32, buffer: &mut [(f32, f32, f32)]) -> usize {
+        assert_eq!(std::mem::size_of::<(f32, f32, f32)>(), 12); // tuple layout is not guaranteed: checked, then reinterpreted
+        assert_eq!(buffer.len(), (params.width * params.height) as usize);
+        let p = PtParams { width: params.width, height: params.height, samples: params.samples, max_depth: params.max_depth,
+                           random_seed: params.random_seed as u8, use_bvh: params.use_bvh as u8, _pad: [0; 6],
+                           seed_salt: if params.random_seed { rand::random() } else { 0 } };
+        let cam = camera.to_ffi();
+        let mut rays = 0u64;
+        let rc = unsafe { pt_render(self.handle, &p, &cam, frame_num, buffer.as_mut_ptr() as *mut f32, &mut rays) };
+        if rc != 0 { panic!("pt_render failed: {}", last_error()); }
+        rays as usize
+    }
+}
+
+impl Drop for GpuScene {
+    fn drop(&mut self) { unsafe { pt_scene_destroy(self.handle) } }
+}
+#[allow(dead_code)] fn _unused(_: *mut c_void) {}
