@@ -399,8 +399,14 @@ __global__ void __launch_bounds__(kCtaThreads) pt_megakernel_resident(const __gr
 // Constant-bank variant (<= kMaxConstSpheres spheres): the pre-filter reads sphere pairs through the uniform
 // datapath (pt_sweep.cuh, sweep_const); the TMA-staged shared-memory copy serves the exact re-test and shading.
 // =====================================================================================================
+// (launch bounds are part of the shape ptxas keys its uniform-register decision on: see the note in the main loop)
+#ifdef PT_CONST_MIN_CTAS
+#define PT_CONST_LAUNCH_BOUNDS __launch_bounds__(kCtaThreads, PT_CONST_MIN_CTAS)
+#else
+#define PT_CONST_LAUNCH_BOUNDS __launch_bounds__(kCtaThreads)
+#endif
 template <int WORDS>
-__global__ void __launch_bounds__(kCtaThreads) pt_megakernel_const(const __grid_constant__ KernelArgs a) {
+__global__ void PT_CONST_LAUNCH_BOUNDS pt_megakernel_const(const __grid_constant__ KernelArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     float4* blk = reinterpret_cast<float4*>(smem_raw);

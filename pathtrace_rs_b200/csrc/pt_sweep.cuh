@@ -167,7 +167,11 @@ __device__ __forceinline__ void sweep_blocks(const float4* __restrict__ blk, int
 // branch per (lane, sphere) event, and the hot loop is straight-line code the compiler keeps in uniform registers.
 // =====================================================================================================
 constexpr int kSweepThreads = 256;  // == kCtaThreads (queue stride)
-constexpr int kConstGroupBlocks = 2;                       // blocks per flag bit
+#ifndef PT_CONST_GROUP
+#define PT_CONST_GROUP 2
+#endif
+constexpr int kConstGroupBlocks = PT_CONST_GROUP;          // blocks (of 4 spheres) per pre-filter branch / queue entry
+constexpr int kEntryMaskBits = 4 * kConstGroupBlocks;       // one flag bit per sphere of the group
 constexpr int kMaxConstBlocks = 1000;                      // 4000 spheres * 16 B = 64 000 B of the 64 KB constant bank
 constexpr int kMaxConstSpheres = 4 * kMaxConstBlocks;
 __constant__ float4 c_prefilter[4 * kMaxConstBlocks];      // per block: X(cx0..3) Y Z K(k0..3)
@@ -186,14 +190,14 @@ __device__ __forceinline__ void sweep_resolve_group(const float4* __restrict__ b
 }
 
 // n_groups = n_blocks / 2; both the constant image and the shared-memory copy are padded to whole groups.
-// Candidate queue: one 32-bit entry per flagged group = (first block << 8) | 8 flag bits, kQueueCap entries per lane in
+// Candidate queue: one 32-bit entry per flagged group = (first block << kEntryMaskBits) | one flag bit per sphere, kQueueCap entries per lane in
 // shared memory ([entry][thread] layout, conflict-free).  A full queue (rare) tests the group on the spot.
 constexpr int kQueueCap = 12;
 
 __device__ __forceinline__ void sweep_resolve_entry(const float4* __restrict__ blk, uint32_t entry, float ox, float oy, float oz, float dx,
                                                     float dy, float dz, float& hit_t, int& hit_index) {
-    const int base = (int)(entry >> 8) * 4;
-    uint32_t mask = entry & 0xffu;
+    const int base = (int)(entry >> kEntryMaskBits) * 4;
+    uint32_t mask = entry & ((1u << kEntryMaskBits) - 1u);
 #pragma unroll 1
     while (mask != 0u) {
         const int index = base + __ffs(mask) - 1;
@@ -235,7 +239,7 @@ __device__ __forceinline__ void sweep_const(int n_groups, const float4* __restri
             uint32_t mask = 0u;
 #pragma unroll
             for (int p = 0; p < 2 * kConstGroupBlocks; ++p) mask |= (L[p].x > oo ? 1u << (2 * p) : 0u) | (L[p].y > oo ? 2u << (2 * p) : 0u);
-            const uint32_t entry = ((uint32_t)j << 8) | mask;
+            const uint32_t entry = ((uint32_t)j << kEntryMaskBits) | mask;
             if (cnt < kQueueCap) {
                 q[cnt * kSweepThreads] = entry;
                 cnt += 1;
