@@ -37,7 +37,13 @@ struct KernelArgs {
     uint64_t seed_salt;
     float* rgb;
     unsigned long long* ray_count;
-    unsigned int* next_pixel;
+    unsigned int* next_pixel;  // ticket counter of the chunk queue (see lane_refill)
+    // chunk queue: ticket t = chunk (t / n_owned_pixels) of owned pixel (t % n_owned_pixels); chunk c covers samples
+    // [c * chunk_samples, min((c+1) * chunk_samples, samples)).  chunk_samples is a power of two and chunk_mask =
+    // chunk_samples - 1, or chunk_samples >= samples and chunk_mask = 0xffffffff (one chunk per pixel, no state table).
+    // pixstate: kPixStateWords words per owned pixel.
+    uint32_t chunk_samples, chunk_mask, n_tickets;
+    uint32_t* pixstate;
     // streamed variant only
     int tile_blocks;  // blocks per shared-memory tile
     int n_tiles;
@@ -104,6 +110,28 @@ struct Lane {
     bool finished;    // queue exhausted
 };
 
+// Pixel-state table (global memory, 48 B per owned pixel): what a pixel carries from one chunk of samples to the
+// next.  The RNG stream of a pixel is sequential (scene.rs:96-110: one generator per pixel, consumed sample after
+// sample), so chunks of one pixel run one after another, but on whichever lane pulls the ticket: words 0-7 xoshiro256+
+// state, 8-10 colour sum so far, 11 = number of samples completed (published with st.release, read with ld.acquire).
+constexpr int kPixStateWords = 12;
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+#ifdef EXP_NOASM
+    return __ldcg(p);
+#else
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+#endif
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
+#ifdef EXP_NOASM
+    __threadfence(); __stcg(p, v);
+#else
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#endif
+}
+
 __device__ __forceinline__ void owned_pixel_to_xy(const KernelArgs& a, uint32_t j, uint32_t& x, uint32_t& y) {
     const uint32_t r = j / a.width;
     x = j - r * a.width;
@@ -113,6 +141,13 @@ __device__ __forceinline__ void owned_pixel_to_xy(const KernelArgs& a, uint32_t 
         const uint32_t tl = r / a.tile_rows;
         y = (tl * a.part_count + a.part_index) * a.tile_rows + (r - tl * a.tile_rows);
     }
+}
+
+__device__ __forceinline__ uint32_t xy_to_owned_pixel(const KernelArgs& a, uint32_t x, uint32_t y) {
+    if (a.part_count <= 1) return y * a.width + x;
+    const uint32_t tile = y / a.tile_rows;
+    const uint32_t tl = tile / a.part_count;
+    return (tl * a.tile_rows + (y - tile * a.tile_rows)) * a.width + x;
 }
 
 // scene.rs:113-116 — blend the finished pixel into the accumulation buffer
@@ -130,15 +165,54 @@ __device__ __forceinline__ void write_pixel(const KernelArgs& a, const Lane& L) 
     out[2] = p2 * a.mix_prev + col.z * a.mix_new;
 }
 
-// top-of-trip bookkeeping: finish pixels, pull new ones, start the next sample (scene.rs:94-110)
-__device__ __forceinline__ void lane_refill(const KernelArgs& a, Lane& L, unsigned lane_id) {
+// hand the pixel to whoever pulls its next chunk: state first, then the sample count with release semantics
+__device__ __forceinline__ void publish_pixel_state(const KernelArgs& a, const Lane& L) {
+    uint32_t* st = a.pixstate + (size_t)xy_to_owned_pixel(a, L.px, L.py) * kPixStateWords;
+    uint4* v = reinterpret_cast<uint4*>(st);
+    __stcg(v, make_uint4((uint32_t)L.rng.s0, (uint32_t)(L.rng.s0 >> 32), (uint32_t)L.rng.s1, (uint32_t)(L.rng.s1 >> 32)));
+    __stcg(v + 1, make_uint4((uint32_t)L.rng.s2, (uint32_t)(L.rng.s2 >> 32), (uint32_t)L.rng.s3, (uint32_t)(L.rng.s3 >> 32)));
+    __stcg(reinterpret_cast<uint2*>(st + 8), make_uint2(__float_as_uint(L.col.x), __float_as_uint(L.col.y)));
+    __stcg(st + 10, __float_as_uint(L.col.z));
+    st_release_u32(st + 11, L.sample);
+}
+// true when the predecessor chunk has been published; loads the state (L2 loads: another SM wrote it)
+__device__ __forceinline__ bool acquire_pixel_state(const KernelArgs& a, Lane& L) {
+    const uint32_t* st = a.pixstate + (size_t)xy_to_owned_pixel(a, L.px, L.py) * kPixStateWords;
+    if (ld_acquire_u32(st + 11) != L.sample) return false;
+    const uint4* v = reinterpret_cast<const uint4*>(st);
+    const uint4 r0 = __ldcg(v), r1 = __ldcg(v + 1), c = __ldcg(v + 2);
+    L.rng.s0 = (uint64_t)r0.x | ((uint64_t)r0.y << 32);
+    L.rng.s1 = (uint64_t)r0.z | ((uint64_t)r0.w << 32);
+    L.rng.s2 = (uint64_t)r1.x | ((uint64_t)r1.y << 32);
+    L.rng.s3 = (uint64_t)r1.z | ((uint64_t)r1.w << 32);
+    L.col = v3(__uint_as_float(c.x), __uint_as_float(c.y), __uint_as_float(c.z));
+    return true;
+}
+
+// top-of-trip bookkeeping: finish chunks/pixels, pull new tickets, start the next sample (scene.rs:94-110).
+//
+// Work queue.  The reference hands whole pixels to its rayon workers (scene.rs:90-93).  With ~10^5 lanes a pixel
+// (samples x ~2.7 sweeps, strictly sequential because of its RNG stream) is too coarse a unit: once the queue runs dry
+// every warp idles lane by lane for up to one pixel's duration.  So the queue holds CHUNKS of `chunk_samples` samples in
+// sample-major order (all pixels' chunk 0, then all pixels' chunk 1, ...): every pixel advances at the same pace and the
+// tail of a launch is one chunk, not one pixel.  A pixel's generator and colour sum travel through the pixel-state
+// table, so each pixel still consumes exactly the reference's stream and sums its samples in the reference's order.
+// A lane whose ticket's predecessor chunk is not published yet (rare: the predecessor was handed out n_owned_pixels
+// tickets earlier) parks for a trip and asks again — it never spins, the predecessor may be a lane of the same warp.
+// `pend` is that lane's "holding an unready ticket" flag; it lives in shared memory, and the end-of-chunk test uses the
+// uniform chunk_mask rather than a per-lane bound, because extra per-lane registers carried across the sweep make ptxas
+// drop the sweep's uniform operands (tests/test_host_and_abi.py guards the SASS).
+__device__ __forceinline__ void lane_refill(const KernelArgs& a, Lane& L, unsigned lane_id, volatile uint32_t* pend) {
     bool want_pixel = false;
     if (!L.active && !L.finished) {
-        if (L.have_pixel && L.sample >= a.samples) {
-            write_pixel(a, L);
+        if (L.have_pixel && ((L.sample & a.chunk_mask) == 0u || L.sample >= a.samples)) {
+            if (L.sample >= a.samples)
+                write_pixel(a, L);
+            else
+                publish_pixel_state(a, L);
             L.have_pixel = false;
         }
-        want_pixel = !L.have_pixel;
+        want_pixel = !L.have_pixel && *pend == 0u;
     }
     const unsigned need = __ballot_sync(kFullMask, want_pixel);
     if (need != 0u) {
@@ -147,8 +221,10 @@ __device__ __forceinline__ void lane_refill(const KernelArgs& a, Lane& L, unsign
         if ((int)lane_id == leader) base = atomicAdd(a.next_pixel, (unsigned)__popc(need));
         base = __shfl_sync(kFullMask, base, leader);
         if (want_pixel) {
-            const unsigned j = base + (unsigned)__popc(need & ((1u << lane_id) - 1u));
-            if (j < a.n_owned_pixels) {
+            const unsigned t = base + (unsigned)__popc(need & ((1u << lane_id) - 1u));
+            if (t < a.n_tickets) {
+                const uint32_t chunk = t / a.n_owned_pixels;
+                const uint32_t j = t - chunk * a.n_owned_pixels;
                 owned_pixel_to_xy(a, j, L.px, L.py);
                 uint64_t seed;
                 if (a.random_seed) {
@@ -159,16 +235,23 @@ __device__ __forceinline__ void lane_refill(const KernelArgs& a, Lane& L, unsign
                 } else {
                     seed = pixel_seed(L.px, L.py, a.frame_num);
                 }
-                rng_seed(L.rng, seed);
+                rng_seed(L.rng, seed);  // kept by chunk 0 only: later chunks load the published state
                 L.col = v3(0.0f, 0.0f, 0.0f);
-                L.sample = 0;
-                L.have_pixel = true;
+                L.sample = chunk * a.chunk_samples;
+                L.have_pixel = chunk == 0u;
+                *pend = chunk != 0u ? 1u : 0u;
             } else {
                 L.finished = true;
             }
         }
     }
-    if (!L.active && !L.finished) {
+    if (!L.active && !L.finished && !L.have_pixel) {
+        if (*pend != 0u && acquire_pixel_state(a, L)) {  // not yet published: the lane sits this trip out and asks again
+            *pend = 0u;
+            L.have_pixel = true;
+        }
+    }
+    if (!L.active && L.have_pixel) {
         // scene.rs:107-110
         const float u = ((float)L.px + rng_f32(L.rng)) * a.inv_nx;
         const float v = ((float)L.py + rng_f32(L.rng)) * a.inv_ny;
@@ -249,6 +332,7 @@ __device__ __forceinline__ void stage_perlin(const KernelArgs& a, PerlinSmem* P)
 
 constexpr int kCtaThreads = 256;
 
+
 // Optional phase profile (compile with -DPT_PROFILE; tools/phase_profile.py): per-warp clock64 deltas of the
 // three phases of a trip and trip/lane counters, summed into a global array.  Not compiled into the product.
 #ifdef PT_PROFILE
@@ -267,71 +351,6 @@ __device__ unsigned long long g_prof[8];  // 0 refill clk, 1 sweep clk, 2 shade 
 
 
 // =====================================================================================================
-// Tail compaction (active-path compaction).  A pixel cannot be split (its RNG stream is
-// sequential), so once the pixel queue runs dry each lane finishes its last pixel at a different time and a warp
-// keeps sweeping with ever fewer live lanes.  From the first trip in which any lane of the CTA fails to get a pixel
-// the CTA's warps run their trips in lockstep (one named barrier per trip); whenever the live paths would fit in
-// fewer warps than currently hold them, all live lane states are packed into the lowest warps through shared memory
-// and the emptied warps stop sweeping.  Results are unchanged: a path carries its whole state (RNG included).
-// =====================================================================================================
-constexpr int kLaneStateWords = 25;
-struct TailShared {
-    int flag;  // slot counter of a compaction round
-};
-
-__device__ __forceinline__ void lane_store(const Lane& L, uint32_t* pool, int slot) {
-    uint32_t w[kLaneStateWords];
-    w[0] = (uint32_t)L.rng.s0; w[1] = (uint32_t)(L.rng.s0 >> 32); w[2] = (uint32_t)L.rng.s1; w[3] = (uint32_t)(L.rng.s1 >> 32);
-    w[4] = (uint32_t)L.rng.s2; w[5] = (uint32_t)(L.rng.s2 >> 32); w[6] = (uint32_t)L.rng.s3; w[7] = (uint32_t)(L.rng.s3 >> 32);
-    w[8] = __float_as_uint(L.o.x); w[9] = __float_as_uint(L.o.y); w[10] = __float_as_uint(L.o.z);
-    w[11] = __float_as_uint(L.d.x); w[12] = __float_as_uint(L.d.y); w[13] = __float_as_uint(L.d.z);
-    w[14] = __float_as_uint(L.thr.x); w[15] = __float_as_uint(L.thr.y); w[16] = __float_as_uint(L.thr.z);
-    w[17] = __float_as_uint(L.col.x); w[18] = __float_as_uint(L.col.y); w[19] = __float_as_uint(L.col.z);
-    w[20] = L.px; w[21] = L.py; w[22] = L.sample; w[23] = L.depth;
-    w[24] = (L.active ? 1u : 0u) | (L.have_pixel ? 2u : 0u);
-#pragma unroll
-    for (int i = 0; i < kLaneStateWords; ++i) pool[i * kCtaThreads + slot] = w[i];
-}
-__device__ __forceinline__ void lane_load(Lane& L, const uint32_t* pool, int slot) {
-    uint32_t w[kLaneStateWords];
-#pragma unroll
-    for (int i = 0; i < kLaneStateWords; ++i) w[i] = pool[i * kCtaThreads + slot];
-    L.rng.s0 = (uint64_t)w[0] | ((uint64_t)w[1] << 32); L.rng.s1 = (uint64_t)w[2] | ((uint64_t)w[3] << 32);
-    L.rng.s2 = (uint64_t)w[4] | ((uint64_t)w[5] << 32); L.rng.s3 = (uint64_t)w[6] | ((uint64_t)w[7] << 32);
-    L.o = v3(__uint_as_float(w[8]), __uint_as_float(w[9]), __uint_as_float(w[10]));
-    L.d = v3(__uint_as_float(w[11]), __uint_as_float(w[12]), __uint_as_float(w[13]));
-    L.thr = v3(__uint_as_float(w[14]), __uint_as_float(w[15]), __uint_as_float(w[16]));
-    L.col = v3(__uint_as_float(w[17]), __uint_as_float(w[18]), __uint_as_float(w[19]));
-    L.px = w[20]; L.py = w[21]; L.sample = w[22]; L.depth = w[23];
-    L.active = (w[24] & 1u) != 0u; L.have_pixel = (w[24] & 2u) != 0u;
-    L.finished = false;
-}
-
-// One tail-phase step for the whole CTA (every warp calls it once per trip): returns false when no live path is left.
-// __syncthreads_count gives the CTA-wide totals; slots in the staging pool are handed out by a shared atomic.
-__device__ __forceinline__ bool tail_step(TailShared& T, uint32_t* pool, Lane& L, unsigned lane_id) {
-    const unsigned live_mask = __ballot_sync(kFullMask, !L.finished);
-    const int total = __syncthreads_count(!L.finished);
-    const int holders = __syncthreads_count(lane_id == 0 && live_mask != 0u);
-    if (total == 0) return false;
-    if ((total + 31) / 32 < holders) {  // the live paths fit in fewer warps than hold them now: pack them
-        if (threadIdx.x == 0) T.flag = 0;
-        __syncthreads();
-        if (!L.finished) lane_store(L, pool, atomicAdd(&T.flag, 1));
-        __syncthreads();
-        if ((int)threadIdx.x < total) {
-            lane_load(L, pool, threadIdx.x);
-        } else {
-            L.finished = true;
-            L.active = false;
-            L.have_pixel = false;
-        }
-        __syncthreads();
-    }
-    return true;
-}
-
-// =====================================================================================================
 // Resident variant: the whole sphere SoA lives in shared memory for the life of the CTA.
 // =====================================================================================================
 template <int UNROLL>
@@ -340,6 +359,8 @@ __global__ void __launch_bounds__(kCtaThreads) pt_megakernel_resident(const __gr
     __shared__ __align__(8) uint64_t bar;
     float4* blk = reinterpret_cast<float4*>(smem_raw);
     PerlinSmem* P = reinterpret_cast<PerlinSmem*>(smem_raw + (size_t)a.n_blocks * 64);
+    volatile uint32_t* pend = reinterpret_cast<uint32_t*>(P + 1) + threadIdx.x;
+    *pend = 0u;
 
     const uint32_t bytes = (uint32_t)a.n_blocks * 64u;
     if (threadIdx.x == 0) {
@@ -363,7 +384,7 @@ __global__ void __launch_bounds__(kCtaThreads) pt_megakernel_resident(const __gr
 
     for (;;) {
         PT_PROF_TICK();
-        lane_refill(a, L, lane_id);
+        lane_refill(a, L, lane_id, pend);
         if (__all_sync(kFullMask, L.finished)) break;
         float ox = L.o.x, oy = L.o.y, oz = L.o.z, dx = L.d.x, dy = L.d.y, dz = L.d.z;
         if (!L.active) {  // parked lane (queue ran dry): a ray that can never be a candidate
@@ -413,6 +434,8 @@ __global__ void PT_CONST_LAUNCH_BOUNDS pt_megakernel_const(const __grid_constant
     PerlinSmem* P = reinterpret_cast<PerlinSmem*>(smem_raw + (size_t)a.n_blocks * 64);
     float* ksm = reinterpret_cast<float*>(smem_raw + (size_t)a.n_blocks * 64 + sizeof(PerlinSmem));  // [4 * n_blocks] pre-filter k per sphere
     uint32_t* queue = reinterpret_cast<uint32_t*>(ksm + 4 * a.n_blocks) + threadIdx.x;           // [kQueueCap][kCtaThreads] candidate queues
+    volatile uint32_t* pend = queue + kQueueCap * kCtaThreads;
+    *pend = 0u;
 
     const uint32_t bytes = (uint32_t)a.n_blocks * 64u;
     if (threadIdx.x == 0) {
@@ -441,7 +464,7 @@ __global__ void PT_CONST_LAUNCH_BOUNDS pt_megakernel_const(const __grid_constant
     // the SASS so that a refactor which silently loses them (x2 slower sweep) fails the build.
     for (;;) {
         PT_PROF_TICK();
-        lane_refill(a, L, lane_id);
+        lane_refill(a, L, lane_id, pend);
         if (__all_sync(kFullMask, L.finished)) break;
         float ox = L.o.x, oy = L.o.y, oz = L.o.z, dx = L.d.x, dy = L.d.y, dz = L.d.z;
         if (!L.active) {  // parked lane: |o|^2 = 1e36 dwarfs every L, d = 0 -> never a candidate
@@ -486,6 +509,8 @@ __global__ void __launch_bounds__(kCtaThreads) pt_megakernel_streamed(const __gr
     const uint32_t tile_bytes = (uint32_t)a.tile_blocks * 64u;
     float4* buf[2] = {reinterpret_cast<float4*>(smem_raw), reinterpret_cast<float4*>(smem_raw + tile_bytes)};
     PerlinSmem* P = reinterpret_cast<PerlinSmem*>(smem_raw + 2 * (size_t)tile_bytes);
+    volatile uint32_t* pend = reinterpret_cast<uint32_t*>(P + 1) + threadIdx.x;
+    *pend = 0u;
     const int n_warps = kCtaThreads / 32;
 
     if (threadIdx.x == 0) {
@@ -522,7 +547,7 @@ __global__ void __launch_bounds__(kCtaThreads) pt_megakernel_streamed(const __gr
     };
 
     for (;;) {
-        lane_refill(a, L, lane_id);
+        lane_refill(a, L, lane_id, pend);
         // CTA-wide liveness: every warp must keep consuming tiles while any warp still has work
         const bool warp_live = !__all_sync(kFullMask, L.finished);
         __syncthreads();  // previous trip's cta_live reads are done

@@ -62,6 +62,8 @@ struct PtScene {
     // per-render scratch
     unsigned long long* d_ray_count = nullptr;  // [0] ray count
     unsigned int* d_next_pixel = nullptr;
+    uint32_t* d_pixstate = nullptr;  // chunk queue: 12 words per owned pixel (pt_megakernel.cuh, PixState)
+    size_t d_pixstate_pixels = 0;
     float* d_rgb = nullptr;  // device image for the host-buffer entry points
     size_t d_rgb_floats = 0;
     uint8_t* d_rgb8 = nullptr;
@@ -105,7 +107,7 @@ int configure_kernel(K kernel, size_t smem, int* ctas_per_sm) {
 }
 
 int plan_launch(PtScene* s) {
-    const size_t perlin_bytes = sizeof(pt::PerlinSmem);
+    const size_t perlin_bytes = sizeof(pt::PerlinSmem) + pt::kCtaThreads * sizeof(uint32_t);  // Perlin tables + the lanes' `pend` words
     const size_t all = (size_t)s->n_blocks * 64 + perlin_bytes;
     // test hook: PTGPU_FORCE_STREAM_TILE_BLOCKS=<n> runs any scene through the streamed kernel with n-block tiles
     int forced_tile = 0;
@@ -229,6 +231,51 @@ int launch_update(PtScene* s, const PtParams* params, const PtCamera* cam, uint3
     // persistent grid: one wave of CTAs, never more lanes than pixels
     const uint32_t want = (a.n_owned_pixels + pt::kCtaThreads - 1) / pt::kCtaThreads;
     const uint32_t grid = std::min<uint32_t>((uint32_t)(s->sm_count * s->ctas_per_sm), want);
+
+    // chunk queue (pt_megakernel.cuh, lane_refill): samples are handed out in chunks, sample-major, so that all pixels
+    // finish together.  With fewer than two pixels per lane every pixel starts at once and the launch lasts as long as
+    // its slowest pixel whatever the unit: one chunk per pixel then, which skips the state table altogether.
+    uint32_t chunk = 0;  // 0 = one chunk per pixel
+    const uint64_t lanes = (uint64_t)grid * pt::kCtaThreads;
+    if (params->samples > 8 && (uint64_t)a.n_owned_pixels >= 2 * lanes) {
+        const uint32_t max_chunks = std::max<uint32_t>(1u, std::min<uint32_t>(64u, 0xF0000000u / a.n_owned_pixels));
+        const uint32_t at_least = std::max<uint32_t>((params->samples + max_chunks - 1) / max_chunks, 8u);
+        chunk = 8;
+        while (chunk < at_least) chunk *= 2;
+    }
+    if (const char* env = std::getenv("PTGPU_CHUNK_SAMPLES")) {  // test/tuning hook: a power of two, 0 = whole pixels
+        const long v = std::atol(env);
+        chunk = 0;
+        if (v > 0) {
+            chunk = 1;
+            while ((long)chunk < v && chunk < (1u << 30)) chunk *= 2;
+        }
+    }
+    uint32_t n_chunks = 1;
+    if (chunk != 0 && chunk < params->samples) {
+        n_chunks = (params->samples + chunk - 1) / chunk;
+        if ((uint64_t)n_chunks * a.n_owned_pixels > 0xF0000000ull)
+            return fail(PT_ERR_TOO_LARGE, "%u chunks x %u pixels overflow the ticket counter", n_chunks, a.n_owned_pixels);
+        a.chunk_samples = chunk;
+        a.chunk_mask = chunk - 1;
+    } else {
+        a.chunk_samples = std::max<uint32_t>(params->samples, 1u);
+        a.chunk_mask = 0xffffffffu;
+    }
+    a.n_tickets = n_chunks * a.n_owned_pixels;
+    a.pixstate = nullptr;
+    if (n_chunks > 1) {
+        if (s->d_pixstate_pixels < a.n_owned_pixels) {
+            if (s->d_pixstate) cudaFree(s->d_pixstate);
+            s->d_pixstate = nullptr;
+            s->d_pixstate_pixels = 0;
+            PT_CUDA(cudaMalloc(&s->d_pixstate, (size_t)a.n_owned_pixels * pt::kPixStateWords * sizeof(uint32_t)));
+            s->d_pixstate_pixels = a.n_owned_pixels;
+        }
+        // word 11 of every record (= samples completed) must read 0 before the first chunk is published
+        PT_CUDA(cudaMemsetAsync(s->d_pixstate, 0, (size_t)a.n_owned_pixels * pt::kPixStateWords * sizeof(uint32_t), stream));
+        a.pixstate = s->d_pixstate;
+    }
     if (s->use_const) {
         // the constant bank is per device, not per scene: (re)load this scene's image in stream order
         PT_CUDA(cudaMemcpyToSymbolAsync(pt::c_prefilter, s->h_prefilter.data(), s->h_prefilter.size() * sizeof(float4), 0,
@@ -538,6 +585,7 @@ void pt_scene_destroy(PtScene* s) {
     cudaFree(s->d_kvals);
     cudaFree(s->d_ray_count);
     cudaFree(s->d_next_pixel);
+    cudaFree(s->d_pixstate);
     cudaFree(s->d_rgb);
     cudaFree(s->d_rgb8);
     for (auto& e : s->ev)

@@ -185,6 +185,68 @@ def test_random_seed_mode_uses_the_salt():
     assert rel_mean_diff(a, d).max() < 0.05
 
 
+# ---- chunk queue: samples handed out in chunks through the pixel-state table (pt_megakernel.cuh, lane_refill) ------------
+def _with_env(name, value, fn):
+    old = os.environ.get(name)
+    os.environ[name] = value
+    try:
+        return fn()
+    finally:
+        if old is None:
+            del os.environ[name]
+        else:
+            os.environ[name] = old
+
+
+@pytest.mark.parametrize("chunk", ["1", "2", "8", "64"])
+def test_chunk_queue_is_bit_exact_for_any_chunk_size(chunk):
+    """A pixel's RNG state and colour sum travel through global memory between chunks; the image and the ray count must
+    not change by a bit, whatever the chunk size (0 = whole pixels, the reference's unit of work, scene.rs:90-93).
+    spp = 21 is not a multiple of any chunk size; 96x54 pixels on >100k lanes makes every later chunk wait for its
+    predecessor, which exercises the parked-lane path hard."""
+    w, h, spp, depth = 96, 54, 21, 50
+    whole, rays_whole, _ = _with_env("PTGPU_CHUNK_SAMPLES", "0", lambda: gpu_render("random_spheres", w, h, spp, depth))
+    img, rays, _ = _with_env("PTGPU_CHUNK_SAMPLES", chunk, lambda: gpu_render("random_spheres", w, h, spp, depth))
+    assert rays == rays_whole and np.array_equal(img, whole)
+    ref, ref_rays = orc.Scene("random_spheres", w, h).update(spp, depth, mode=SOA_ITER)
+    assert rays == ref_rays and np.mean(np.all(img == ref, axis=2)) >= 0.999
+
+
+def test_chunk_queue_default_engages_on_large_images_and_blends_frames():
+    """Default policy: >= 2 pixels per lane -> chunks of >= 8 samples.  640x400 = 256k pixels on <= 113 664 lanes."""
+    w, h, spp, depth = 640, 400, 24, 50
+    whole, rays_whole, _ = _with_env("PTGPU_CHUNK_SAMPLES", "0", lambda: gpu_render("random_spheres", w, h, spp, depth))
+    params = pt.Params(w, h, spp, depth)
+    pr = pt.Preset("random_spheres", params).create_scene(0)
+    img, rays = pr.update(params)
+    assert rays == rays_whole and np.array_equal(img, whole)
+    # a second frame over the same scene object (state table re-zeroed), blended, vs whole-pixel scheduling
+    buf_a, buf_b = img.copy(), whole.copy()
+    pr.update(params, frame_num=1, buffer=buf_a)
+    _with_env("PTGPU_CHUNK_SAMPLES", "0", lambda: pr.update(params, frame_num=1, buffer=buf_b))
+    assert np.array_equal(buf_a, buf_b)
+
+
+def test_chunk_queue_with_partition_and_streamed_kernel():
+    w, h, spp, depth = 80, 45, 12, 10
+    whole, rays_whole, pr = _with_env("PTGPU_CHUNK_SAMPLES", "0", lambda: gpu_render("random_spheres", w, h, spp, depth))
+
+    def parts():
+        out = np.full((h, w, 3), -1.0, np.float32)
+        total = 0
+        for idx in range(3):
+            _, r = pr.update(pt.Params(w, h, spp, depth), buffer=out, part=ffi.PtPartition(5, idx, 3, 0))
+            total += r
+        return out, total
+    img, rays = _with_env("PTGPU_CHUNK_SAMPLES", "4", parts)
+    assert rays == rays_whole and np.array_equal(img, whole)
+
+    def streamed():
+        return _with_env("PTGPU_FORCE_STREAM_TILE_BLOCKS", "16", lambda: gpu_render("random_spheres", w, h, spp, depth))
+    st, rays_st, pr2 = _with_env("PTGPU_CHUNK_SAMPLES", "4", streamed)
+    assert pr2.stats().resident == 0 and rays_st == rays_whole and np.array_equal(st, whole)
+
+
 # ---- scenes larger than shared memory: streamed kernel -------------------------------------------------------------
 def test_streamed_kernel_equals_resident_kernel():
     w, h, spp, depth = 64, 36, 4, 10
