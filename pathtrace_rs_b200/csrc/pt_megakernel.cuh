@@ -26,6 +26,7 @@ struct KernelArgs {
     const DevTexture* tex;
     const PerlinSmem* perlin;  // global copy, staged to shared memory when has_noise
     const float* kvals;        // pre-filter k per sphere (constant-bank sweep), 4 * n_blocks floats
+    const float4* prefilter;   // pre-filter image X,Y,Z,K per block (global copy; staged/streamed by the LDS kernels)
     int has_noise;
     DevCamera cam;
     uint32_t width, height, samples, max_depth, frame_num;
@@ -357,9 +358,10 @@ template <int UNROLL>
 __global__ void __launch_bounds__(kCtaThreads) pt_megakernel_resident(const __grid_constant__ KernelArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
-    float4* blk = reinterpret_cast<float4*>(smem_raw);
+    float4* pf = reinterpret_cast<float4*>(smem_raw);  // pre-filter image of the whole scene; exact blocks stay in global/L2
     PerlinSmem* P = reinterpret_cast<PerlinSmem*>(smem_raw + (size_t)a.n_blocks * 64);
-    volatile uint32_t* pend = reinterpret_cast<uint32_t*>(P + 1) + threadIdx.x;
+    uint32_t* queue = reinterpret_cast<uint32_t*>(P + 1) + threadIdx.x;  // [kQueueCap][kCtaThreads] candidate queues
+    volatile uint32_t* pend = queue + kQueueCap * kCtaThreads;
     *pend = 0u;
 
     const uint32_t bytes = (uint32_t)a.n_blocks * 64u;
@@ -370,7 +372,7 @@ __global__ void __launch_bounds__(kCtaThreads) pt_megakernel_resident(const __gr
     __syncthreads();
     if (threadIdx.x == 0 && bytes != 0u) {
         mbar_arrive_expect_tx(&bar, bytes);
-        tma_bulk_g2s_chunked(blk, a.blocks, bytes, &bar);
+        tma_bulk_g2s_chunked(pf, a.prefilter, bytes, &bar);
     }
     stage_perlin(a, P);
     __syncthreads();
@@ -387,26 +389,31 @@ __global__ void __launch_bounds__(kCtaThreads) pt_megakernel_resident(const __gr
         lane_refill(a, L, lane_id, pend);
         if (__all_sync(kFullMask, L.finished)) break;
         float ox = L.o.x, oy = L.o.y, oz = L.o.z, dx = L.d.x, dy = L.d.y, dz = L.d.z;
-        if (!L.active) {  // parked lane (queue ran dry): a ray that can never be a candidate
-            ox = 0.0f; oy = 1.0e30f; oz = 0.0f;
+        if (!L.active) {  // parked lane: |o|^2 = 1e36 dwarfs every L, d = 0 -> never a candidate
+            ox = 0.0f; oy = 1.0e18f; oz = 0.0f;
             dx = dy = dz = 0.0f;
         }
         float hit_t = kMaxT;
         int hit_index = -1;
         __syncwarp();
         PT_PROF_TOCK(pf_refill);
-        sweep_blocks<UNROLL>(blk, a.n_blocks, 0, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
+        {
+            const float nod = -((ox * dx + oy * dy) + oz * dz);
+            const float oo = ((ox * ox + oy * oy) + oz * oz) * (1.0f - 1.9073486328125e-06f);
+            int cnt = 0;
+            sweep_expanded(pf, a.n_blocks, 0, a.blocks, queue, cnt, ox, oy, oz, dx, dy, dz, nod, ox + ox, oy + oy, oz + oz, oo, hit_t, hit_index);
+            sweep_drain(a.blocks, queue, cnt, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
+        }
         __syncwarp();
         PT_PROF_TOCK(pf_sweep);
         if (L.active) {
             rays += 1ULL;  // scene.rs:57
-            lane_shade(a, L, blk, *P, hit_t, hit_index);
+            lane_shade(a, L, a.blocks, *P, hit_t, hit_index);
         }
         __syncwarp();
         PT_PROF_TOCK(pf_shade);
 #ifdef PT_PROFILE
         pf_trips += 1;
-        pf_lanes += 1;  // counted per lane below (only active lanes reach the add through `rays`)
 #endif
     }
 #ifdef PT_PROFILE
@@ -507,9 +514,12 @@ __global__ void __launch_bounds__(kCtaThreads) pt_megakernel_streamed(const __gr
     __shared__ __align__(8) uint64_t empty_bar[2];
     __shared__ int cta_live;  // lanes not finished, recomputed every trip
     const uint32_t tile_bytes = (uint32_t)a.tile_blocks * 64u;
-    float4* buf[2] = {reinterpret_cast<float4*>(smem_raw), reinterpret_cast<float4*>(smem_raw + tile_bytes)};
+    // tile buffer b lives at smem_raw + b * tile_bytes (computed, not looked up: an array of pointers would be demoted to
+    // local memory and the sweep's loads would lose their shared-memory address space)
+    auto tile_buf = [&](int b) { return reinterpret_cast<float4*>(smem_raw + (size_t)b * tile_bytes); };
     PerlinSmem* P = reinterpret_cast<PerlinSmem*>(smem_raw + 2 * (size_t)tile_bytes);
-    volatile uint32_t* pend = reinterpret_cast<uint32_t*>(P + 1) + threadIdx.x;
+    uint32_t* queue = reinterpret_cast<uint32_t*>(P + 1) + threadIdx.x;  // [kQueueCap][kCtaThreads] candidate queues
+    volatile uint32_t* pend = queue + kQueueCap * kCtaThreads;
     *pend = 0u;
     const int n_warps = kCtaThreads / 32;
 
@@ -543,7 +553,7 @@ __global__ void __launch_bounds__(kCtaThreads) pt_megakernel_streamed(const __gr
         const int nb = min(a.tile_blocks, a.n_blocks - first);
         const uint32_t bytes = (uint32_t)nb * 64u;
         mbar_arrive_expect_tx(&full_bar[b], bytes);
-        tma_bulk_g2s_chunked(buf[b], a.blocks + (size_t)first * 4, bytes, &full_bar[b]);
+        tma_bulk_g2s_chunked(tile_buf(b), a.prefilter + (size_t)first * 4, bytes, &full_bar[b]);
     };
 
     for (;;) {
@@ -558,12 +568,15 @@ __global__ void __launch_bounds__(kCtaThreads) pt_megakernel_streamed(const __gr
         if (cta_live == 0) break;
 
         float ox = L.o.x, oy = L.o.y, oz = L.o.z, dx = L.d.x, dy = L.d.y, dz = L.d.z;
-        if (!L.active) {
-            ox = 0.0f; oy = 1.0e30f; oz = 0.0f;
+        if (!L.active) {  // parked lane: |o|^2 = 1e36 dwarfs every L, d = 0 -> never a candidate
+            ox = 0.0f; oy = 1.0e18f; oz = 0.0f;
             dx = dy = dz = 0.0f;
         }
         float hit_t = kMaxT;
         int hit_index = -1;
+        const float nod = -((ox * dx + oy * dy) + oz * dz);
+        const float oo = ((ox * ox + oy * oy) + oz * oz) * (1.0f - 1.9073486328125e-06f);
+        int cnt = 0;
         if (threadIdx.x == 0) {
             produce(0);
             if (a.n_tiles > 1) produce(1);
@@ -575,10 +588,12 @@ __global__ void __launch_bounds__(kCtaThreads) pt_megakernel_streamed(const __gr
             __syncwarp();
             const int first = tile * a.tile_blocks;
             const int nb = min(a.tile_blocks, a.n_blocks - first);
-            sweep_blocks<UNROLL>(buf[b], nb, first * 4, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
+            sweep_expanded(tile_buf(b), nb, first, a.blocks, queue, cnt, ox, oy, oz, dx, dy, dz, nod, ox + ox, oy + oy, oz + oz, oo, hit_t, hit_index);
             __syncwarp();
             if (lane_id == 0) mbar_arrive(&empty_bar[b]);
             if (threadIdx.x == 0 && tile + 2 < a.n_tiles) produce(tile + 2);
+            // this tile's candidates: exact re-test against the global SoA (L2), off the tile buffer's critical path
+            sweep_drain(a.blocks, queue, cnt, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
         }
         if (L.active) {
             rays += 1ULL;

@@ -253,4 +253,71 @@ __device__ __forceinline__ void sweep_const(int n_groups, const float4* __restri
     for (int i = 0; i < cnt; ++i) sweep_resolve_entry(blk, q[i * kSweepThreads], ox, oy, oz, dx, dy, dz, hit_t, hit_index);
 }
 
+// =====================================================================================================
+// Expanded pre-filter with shared-memory operands (scenes beyond the constant bank: resident and streamed kernels).
+//
+// Same algebra as sweep_const (A = c.d - o.d, B = 2 c.o + k, L = A*A + B, candidate <=> L > |o|^2 (1 - 2^-19)) but the
+// sphere pairs come from the pre-filter image staged in shared memory (LDS.128 broadcast): 7 packed instructions per
+// 2 tests of the shape FFMA2 Rpair, Rpair(spheres), Rscalar(ray), Rpair — against 11 for the sphere-relative form of
+// sweep_blocks, whose packed instructions mostly read two or three register pairs (profiles/probe_forms_r1.txt).
+// `pf` holds blocks [first_block, first_block + n_blocks) of the image (n_blocks a multiple of the group size);
+// flagged groups go to the lane's queue as (absolute block << kEntryMaskBits | flags) and are re-tested by the
+// caller with the reference's exact expression against `exact` (global memory for the streamed kernel).
+// =====================================================================================================
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sweep_expanded(const float4* __restrict__ pf, int n_blocks, int first_block, const float4* __restrict__ exact,
+                                               uint32_t* __restrict__ q, int& cnt, float ox, float oy, float oz, float dx, float dy, float dz,
+                                               float nod, float o2x, float o2y, float o2z, float oo, float& hit_t, int& hit_index) {
+    // pin the per-ray operands in registers: without this ptxas rematerialises them (9 scalar FP instructions) in every trip
+    asm volatile("" : "+f"(nod), "+f"(o2x), "+f"(o2y), "+f"(o2z), "+f"(oo));
+    // explicit shared-window address, advanced by one group per trip (keeps the loop's address arithmetic to one add)
+    uint32_t addr = (uint32_t)__cvta_generic_to_shared(pf);
+    asm volatile("" : "+r"(addr));
+#pragma unroll 1
+    for (int j = 0; j < n_blocks; j += kConstGroupBlocks, addr += 64u * kConstGroupBlocks) {
+        float2 L[2 * kConstGroupBlocks];
+#pragma unroll
+        for (int g = 0; g < kConstGroupBlocks; ++g) {
+            const float4 X = lds128(addr + 64u * g), Y = lds128(addr + 64u * g + 16u), Z = lds128(addr + 64u * g + 32u), K = lds128(addr + 64u * g + 48u);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float2 cx = h ? make_float2(X.z, X.w) : make_float2(X.x, X.y);
+                const float2 cy = h ? make_float2(Y.z, Y.w) : make_float2(Y.x, Y.y);
+                const float2 cz = h ? make_float2(Z.z, Z.w) : make_float2(Z.x, Z.y);
+                const float2 k = h ? make_float2(K.z, K.w) : make_float2(K.x, K.y);
+                const float2 A = f2_fma(cz, make_float2(dz, dz), f2_fma(cy, make_float2(dy, dy), f2_fma(cx, make_float2(dx, dx), make_float2(nod, nod))));
+                const float2 B = f2_fma(cz, make_float2(o2z, o2z), f2_fma(cy, make_float2(o2y, o2y), f2_fma(cx, make_float2(o2x, o2x), k)));
+                L[2 * g + h] = f2_fma(A, A, B);
+            }
+        }
+        bool any = false;
+#pragma unroll
+        for (int p = 0; p < 2 * kConstGroupBlocks; ++p) any = any | (L[p].x > oo) | (L[p].y > oo);
+        if (any) {
+            uint32_t mask = 0u;
+#pragma unroll
+            for (int p = 0; p < 2 * kConstGroupBlocks; ++p) mask |= (L[p].x > oo ? 1u << (2 * p) : 0u) | (L[p].y > oo ? 2u << (2 * p) : 0u);
+            const uint32_t entry = ((uint32_t)(first_block + j) << kEntryMaskBits) | mask;
+            if (cnt < kQueueCap) {
+                q[cnt * kSweepThreads] = entry;
+                cnt += 1;
+            } else {  // queue full (rare): test this group now; sweep_exact's tie rule makes the visiting order irrelevant
+                sweep_resolve_entry(exact, entry, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
+            }
+        }
+    }
+}
+
+// drain the lane's queue: exact re-test of every flagged sphere (all lanes in parallel)
+__device__ __forceinline__ void sweep_drain(const float4* __restrict__ exact, const uint32_t* __restrict__ q, int& cnt, float ox, float oy, float oz,
+                                            float dx, float dy, float dz, float& hit_t, int& hit_index) {
+#pragma unroll 1
+    for (int i = 0; i < cnt; ++i) sweep_resolve_entry(exact, q[i * kSweepThreads], ox, oy, oz, dx, dy, dz, hit_t, hit_index);
+    cnt = 0;
+}
+
 }  // namespace pt

@@ -59,6 +59,7 @@ struct PtScene {
     pt::DevTexture* d_tex = nullptr;
     pt::PerlinSmem* d_perlin = nullptr;
     float* d_kvals = nullptr;  // pre-filter k per sphere (constant-bank sweep)
+    float4* d_prefilter = nullptr;  // pre-filter image X,Y,Z,K per block (LDS kernels stage/stream it)
     // per-render scratch
     unsigned long long* d_ray_count = nullptr;  // [0] ray count
     unsigned int* d_next_pixel = nullptr;
@@ -107,13 +108,15 @@ int configure_kernel(K kernel, size_t smem, int* ctas_per_sm) {
 }
 
 int plan_launch(PtScene* s) {
-    const size_t perlin_bytes = sizeof(pt::PerlinSmem) + pt::kCtaThreads * sizeof(uint32_t);  // Perlin tables + the lanes' `pend` words
+    const size_t queue_bytes = (size_t)pt::kQueueCap * pt::kCtaThreads * sizeof(uint32_t);  // per-lane candidate queues
+    const size_t perlin_bytes = sizeof(pt::PerlinSmem) + pt::kCtaThreads * sizeof(uint32_t) + queue_bytes;  // Perlin tables + `pend` words + queues
     const size_t all = (size_t)s->n_blocks * 64 + perlin_bytes;
     // test hook: PTGPU_FORCE_STREAM_TILE_BLOCKS=<n> runs any scene through the streamed kernel with n-block tiles
     int forced_tile = 0;
     if (const char* env = std::getenv("PTGPU_FORCE_STREAM_TILE_BLOCKS")) forced_tile = std::atoi(env);
     if (forced_tile > 0 && s->n_blocks > 0) {
         s->resident = false;
+        forced_tile = (forced_tile + pt::kConstGroupBlocks - 1) / pt::kConstGroupBlocks * pt::kConstGroupBlocks;  // whole groups
         s->tile_blocks = std::min(forced_tile, s->n_blocks);
         s->n_tiles = (s->n_blocks + s->tile_blocks - 1) / s->tile_blocks;
         s->smem_bytes = 2 * (size_t)s->tile_blocks * 64 + perlin_bytes;
@@ -123,7 +126,7 @@ int plan_launch(PtScene* s) {
     if (!no_const && s->n_blocks <= pt::kMaxConstBlocks) {
         s->resident = true;
         s->use_const = true;
-        s->smem_bytes = all + (size_t)s->n_blocks * 4 * sizeof(float) + (size_t)pt::kQueueCap * pt::kCtaThreads * sizeof(uint32_t);
+        s->smem_bytes = all + (size_t)s->n_blocks * 4 * sizeof(float);
         s->tile_blocks = s->n_blocks;
         s->n_tiles = 1;
         s->const_words = s->n_blocks / pt::kConstGroupBlocks <= 64 ? 2 : 16;  // 32 groups (256 spheres) per flag word
@@ -186,6 +189,7 @@ int launch_update(PtScene* s, const PtParams* params, const PtCamera* cam, uint3
     a.tex = s->d_tex;
     a.perlin = s->d_perlin;
     a.kvals = s->d_kvals;
+    a.prefilter = s->d_prefilter;
     a.has_noise = s->has_noise ? 1 : 0;
     auto V = [](const float* f) { return pt::V3{f[0], f[1], f[2]}; };
     a.cam.origin = V(cam->origin);
@@ -458,7 +462,7 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
         }
     }
     // constant-bank image for the pre-filter (pt_sweep.cuh): X, Y, Z, K = r^2 - |c|^2 + 2^-19 (|c|^2 + r^2), padded to the group
-    if (s->n_blocks <= pt::kMaxConstBlocks) {
+    {
         s->h_prefilter.assign((size_t)std::max(s->n_blocks, 1) * 4, make_float4(0.f, 0.f, 0.f, 0.f));
         for (int j = 0; j < s->n_blocks; ++j) {
             float* f = reinterpret_cast<float*>(&s->h_prefilter[(size_t)j * 4]);
@@ -540,7 +544,9 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
     PT_CUDA_S(cudaMemcpy(s->d_shade, shade.data(), shade.size() * sizeof(pt::DevShade), cudaMemcpyHostToDevice));
     PT_CUDA_S(cudaMalloc(&s->d_tex, tex.size() * sizeof(pt::DevTexture)));
     PT_CUDA_S(cudaMemcpy(s->d_tex, tex.data(), tex.size() * sizeof(pt::DevTexture), cudaMemcpyHostToDevice));
-    if (!s->h_prefilter.empty()) {
+    PT_CUDA_S(cudaMalloc(&s->d_prefilter, s->h_prefilter.size() * sizeof(float4)));
+    PT_CUDA_S(cudaMemcpy(s->d_prefilter, s->h_prefilter.data(), s->h_prefilter.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    if (s->n_blocks <= pt::kMaxConstBlocks) {
         std::vector<float> kv((size_t)std::max(s->n_blocks, 1) * 4, -3.0e38f);
         for (int j = 0; j < s->n_blocks; ++j)
             for (int e = 0; e < 4; ++e) kv[(size_t)j * 4 + e] = reinterpret_cast<const float*>(&s->h_prefilter[(size_t)j * 4 + 3])[e];
@@ -583,6 +589,7 @@ void pt_scene_destroy(PtScene* s) {
     cudaFree(s->d_tex);
     cudaFree(s->d_perlin);
     cudaFree(s->d_kvals);
+    cudaFree(s->d_prefilter);
     cudaFree(s->d_ray_count);
     cudaFree(s->d_next_pixel);
     cudaFree(s->d_pixstate);
