@@ -354,8 +354,13 @@ __device__ unsigned long long g_prof[8];  // 0 refill clk, 1 sweep clk, 2 shade 
 // =====================================================================================================
 // Resident variant: the whole sphere SoA lives in shared memory for the life of the CTA.
 // =====================================================================================================
+#ifdef PT_LDS_MIN_CTAS
+#define PT_LDS_LAUNCH_BOUNDS __launch_bounds__(kCtaThreads, PT_LDS_MIN_CTAS)
+#else
+#define PT_LDS_LAUNCH_BOUNDS __launch_bounds__(kCtaThreads)
+#endif
 template <int UNROLL>
-__global__ void __launch_bounds__(kCtaThreads) pt_megakernel_resident(const __grid_constant__ KernelArgs a) {
+__global__ void PT_LDS_LAUNCH_BOUNDS pt_megakernel_resident(const __grid_constant__ KernelArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     float4* pf = reinterpret_cast<float4*>(smem_raw);  // pre-filter image of the whole scene; exact blocks stay in global/L2
@@ -401,7 +406,7 @@ __global__ void __launch_bounds__(kCtaThreads) pt_megakernel_resident(const __gr
             const float nod = -((ox * dx + oy * dy) + oz * dz);
             const float oo = ((ox * ox + oy * oy) + oz * oz) * (1.0f - 1.9073486328125e-06f);
             int cnt = 0;
-            sweep_expanded(pf, a.n_blocks, 0, a.blocks, queue, cnt, ox, oy, oz, dx, dy, dz, nod, ox + ox, oy + oy, oz + oz, oo, hit_t, hit_index);
+            sweep_expanded<false>(pf, a.n_blocks, 0, a.blocks, queue, cnt, ox, oy, oz, dx, dy, dz, nod, ox + ox, oy + oy, oz + oz, oo, hit_t, hit_index);
             sweep_drain(a.blocks, queue, cnt, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
         }
         __syncwarp();
@@ -508,7 +513,7 @@ __global__ void PT_CONST_LAUNCH_BOUNDS pt_megakernel_const(const __grid_constant
 // the main loop streams the whole SoA once through L2 for every live lane of the CTA.
 // =====================================================================================================
 template <int UNROLL>
-__global__ void __launch_bounds__(kCtaThreads) pt_megakernel_streamed(const __grid_constant__ KernelArgs a) {
+__global__ void PT_LDS_LAUNCH_BOUNDS pt_megakernel_streamed(const __grid_constant__ KernelArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[2];
     __shared__ __align__(8) uint64_t empty_bar[2];
@@ -588,7 +593,7 @@ __global__ void __launch_bounds__(kCtaThreads) pt_megakernel_streamed(const __gr
             __syncwarp();
             const int first = tile * a.tile_blocks;
             const int nb = min(a.tile_blocks, a.n_blocks - first);
-            sweep_expanded(tile_buf(b), nb, first, a.blocks, queue, cnt, ox, oy, oz, dx, dy, dz, nod, ox + ox, oy + oy, oz + oz, oo, hit_t, hit_index);
+            sweep_expanded<true>(tile_buf(b), nb, first, a.blocks, queue, cnt, ox, oy, oz, dx, dy, dz, nod, ox + ox, oy + oy, oz + oz, oo, hit_t, hit_index);
             __syncwarp();
             if (lane_id == 0) mbar_arrive(&empty_bar[b]);
             if (threadIdx.x == 0 && tile + 2 < a.n_tiles) produce(tile + 2);

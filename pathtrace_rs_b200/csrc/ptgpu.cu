@@ -116,7 +116,7 @@ int plan_launch(PtScene* s) {
     if (const char* env = std::getenv("PTGPU_FORCE_STREAM_TILE_BLOCKS")) forced_tile = std::atoi(env);
     if (forced_tile > 0 && s->n_blocks > 0) {
         s->resident = false;
-        forced_tile = (forced_tile + pt::kConstGroupBlocks - 1) / pt::kConstGroupBlocks * pt::kConstGroupBlocks;  // whole groups
+        forced_tile = (forced_tile + pt::kLdsGroupBlocks - 1) / pt::kLdsGroupBlocks * pt::kLdsGroupBlocks;  // whole groups
         s->tile_blocks = std::min(forced_tile, s->n_blocks);
         s->n_tiles = (s->n_blocks + s->tile_blocks - 1) / s->tile_blocks;
         s->smem_bytes = 2 * (size_t)s->tile_blocks * 64 + perlin_bytes;

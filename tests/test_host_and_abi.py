@@ -44,14 +44,14 @@ def test_ctypes_layouts_match_compiled_structs():
 
 
 def test_library_is_sm100a_cuda_with_packed_fp32_and_tma():
-    """The shipped kernel is real sm_100a SASS: packed FP32 (FFMA2/FADD2/FMUL2) in the sweep, bulk TMA copy + mbarrier."""
+    """The shipped kernel is real sm_100a SASS: packed FP32 (FFMA2) in the sweep, bulk TMA copy + mbarrier."""
     so = os.path.join(ffi.LIB_DIR, "libptgpu.so")
     try:
         sass = subprocess.check_output(["cuobjdump", "-sass", so], text=True, stderr=subprocess.STDOUT)
     except (OSError, subprocess.CalledProcessError):
         pytest.skip("cuobjdump not available")
     assert "sm_100a" in sass
-    for mnemonic in ("FFMA2", "FADD2", "FMUL2", "UBLKCP", "SYNCS"):
+    for mnemonic in ("FFMA2", "UBLKCP", "SYNCS"):
         assert mnemonic in sass, mnemonic
     # The constant-bank sweep must read sphere pairs through the uniform datapath (LDCU -> UR operand of FFMA2).
     # ptxas only does that for some control-flow shapes (DESIGN.md "uniform operands"); losing it halves the sweep's speed.
@@ -63,6 +63,12 @@ def test_library_is_sm100a_cuda_with_packed_fp32_and_tma():
     assert len(re.findall(r"LDCU\.64 UR\d+, c\[0x3\]", body)) >= 12, "sphere operands are no longer uniform loads"
     assert len(re.findall(r"FFMA2 R\d+, R\d+(?:\.reuse)?\.F32, UR\d+\.F32x2", body)) >= 20, "FFMA2 no longer takes the uniform sphere pair"
     assert not re.search(r"LDC\.64 R\d+, c\[0x3\]", body), "per-thread constant loads in the sweep"
+    # The LDS kernels' sweep: broadcast LDS.128 of the pre-filter image (not generic loads, not local memory) feeding FFMA2.
+    for name in ("_ZN2pt22pt_megakernel_resident", "_ZN2pt22pt_megakernel_streamed"):
+        body = [k for k in kernels if k.startswith(name)]
+        assert body, name
+        assert len(re.findall(r"LDS\.128", body[0])) >= 8, name + ": sweep loads are not LDS.128"
+        assert len(re.findall(r"FFMA2 R\d+, R\d+(?:\.reuse)?\.F32x2\.HI_LO, R\d+(?:\.reuse)?\.F32, ", body[0])) >= 20, name + ": packed sweep lost"
 
 
 @pytest.mark.parametrize("preset", PRESETS)
