@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define PT_ABI_VERSION 1
+#define PT_ABI_VERSION 2
 
 /* ---- status codes (the Rust shim `expect`s on non-zero, matching the reference's panic-on-error
  *      convention: src/offline.rs:10,32,59) ---- */
@@ -88,8 +88,19 @@ typedef struct PtPerlin {
     uint32_t perm_z[256];
 } PtPerlin;
 
+/* ---- MovingSphere: src/collision/moving_sphere.rs:7-31 (`MovingSphere::new(centre0, centre1, time0, time1, radius)`).
+ * One record per sphere when PtSceneDesc.motion != NULL; centre0 and radius are the sphere's centre_x/y/z and radius.
+ * centre(t) = centre0 + ((t - time0) / (time1 - time0)) * (centre1 - centre0), evaluated at the ray's time
+ * (src/camera.rs:59).  The camera's shutter interval must lie inside [time0, time1] of every moving sphere. ---- */
+typedef struct PtMotion {
+    float centre1[3];
+    float time0;
+    float time1;
+    uint32_t moving; /* 0: Hitable::Sphere (the other fields are ignored); 1: Hitable::MovingSphere */
+} PtMotion;
+
 /* ---- Scene: src/scene.rs:18-22 (`world` flattened) + src/collision/spheres_soa.rs:12-23 (SoA arrays).
- * The flattener walks Hitable::List and must reject anything that is not Hitable::Sphere
+ * The flattener walks Hitable::List and must reject anything that is not Hitable::Sphere or Hitable::MovingSphere
  * (mirrors the panic at spheres_soa.rs:49-51). `radius` keeps its sign (hollow spheres: presets.rs:265). */
 typedef struct PtSceneDesc {
     uint32_t struct_size; /* = sizeof(PtSceneDesc) */
@@ -106,6 +117,7 @@ typedef struct PtSceneDesc {
     const PtPerlin* perlin; /* may be NULL when no Noise texture is referenced */
     uint32_t has_sky;       /* Scene.sky: Option<Vec3>  (src/scene.rs:20,39-47) */
     float sky[3];
+    const PtMotion* motion; /* per sphere, or NULL when the scene has no Hitable::MovingSphere (src/collision/hitable.rs:17) */
 } PtSceneDesc;
 
 /* ---- partition of one image over several GPUs / calls: interleaved row tiles.

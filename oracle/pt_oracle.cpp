@@ -308,9 +308,15 @@ struct Material {
     float ref_idx; // Dielectric
 };
 struct Sphere {
-    V3 centre;
+    V3 centre;  // Sphere.centre / MovingSphere.centre_start
     float radius;
     int32_t material;
+    // collision/moving_sphere.rs:7-26 — MovingSphere::new(centre0, centre1, time0, time1, radius)
+    bool moving = false;
+    V3 centre_delta = {0, 0, 0};
+    float time_start = 0.0f, inv_time_delta = 0.0f;
+    // moving_sphere.rs:28-31
+    V3 centre_at(float time) const { return centre + ((time - time_start) * inv_time_delta) * centre_delta; }
 };
 
 // camera.rs:8-19
@@ -389,6 +395,7 @@ struct Scene {
     // SoA mirror (spheres_soa.rs:12-23, :26-74), padded to 8 with centre=f32::MAX, r^2=0
     std::vector<float> cx, cy, cz, rsq, rinv;
     size_t soa_len = 0;
+    std::vector<int32_t> moving_index;  // Hitable::MovingSphere entries (hybrid SoA modes, see ray_hit)
 
     void build_soa() {
         size_t n = spheres.size();
@@ -398,7 +405,12 @@ struct Scene {
         cz.assign(soa_len, std::numeric_limits<float>::max());
         rsq.assign(soa_len, 0.0f);
         rinv.assign(soa_len, 0.0f);
+        moving_index.clear();
         for (size_t i = 0; i < n; ++i) {
+            if (spheres[i].moving) {  // not representable in SpheresSoA (spheres_soa.rs:49-51 panics): tested by the live form
+                moving_index.push_back((int32_t)i);
+                continue;
+            }
             cx[i] = spheres[i].centre.x;
             cy[i] = spheres[i].centre.y;
             cz[i] = spheres[i].centre.z;
@@ -452,13 +464,48 @@ struct Scene {
         }
         return false;
     }
+    // collision/moving_sphere.rs:38-73 (same roots test as Sphere::ray_hit, centre evaluated at ray.time)
+    static bool moving_sphere_hit(const Sphere& s, const Ray& ray, float t_min, float t_max, RayHit& out) {
+        V3 centre = s.centre_at(ray.time);
+        V3 oc = ray.origin - centre;
+        float a = dot(ray.direction, ray.direction);
+        float b = dot(oc, ray.direction);
+        float c = dot(oc, oc) - s.radius * s.radius;
+        float discriminant = b * b - a * c;
+        if (discriminant > 0.0f) {
+            float dsq = std::sqrt(discriminant);
+            float t = (-b - dsq) / a;
+            if (t < t_max && t > t_min) {
+                out.point = point_at(ray, t);
+                out.normal = (out.point - centre) / s.radius;
+                out.t = t;
+                out.u = 0.0f;
+                out.v = 0.0f;
+                return true;
+            }
+            t = (-b + dsq) / a;
+            if (t < t_max && t > t_min) {
+                out.point = point_at(ray, t);
+                out.normal = (out.point - centre) / s.radius;
+                out.t = t;
+                out.u = 0.0f;
+                out.v = 0.0f;
+                return true;
+            }
+        }
+        return false;
+    }
+    // collision/hitable.rs:39-65 — the enum dispatch for the two arms in scope
+    static bool hitable_hit(const Sphere& s, const Ray& ray, float t_min, float t_max, RayHit& out) {
+        return s.moving ? moving_sphere_hit(s, ray, t_min, t_max, out) : sphere_hit(s, ray, t_min, t_max, out);
+    }
     // collision/hitable_list.rs:40-56
     bool hit_list(const Ray& ray, float t_min, float t_max, RayHit& hit, int32_t& index) const {
         bool any = false;
         float closest = t_max;
         RayHit h;
         for (size_t i = 0; i < spheres.size(); ++i) {
-            if (sphere_hit(spheres[i], ray, t_min, closest, h)) {
+            if (hitable_hit(spheres[i], ray, t_min, closest, h)) {
                 any = true;
                 closest = h.t;
                 hit = h;
@@ -553,13 +600,27 @@ struct Scene {
             o[0] = ray.origin.x; o[1] = ray.origin.y; o[2] = ray.origin.z;
             o[3] = ray.direction.x; o[4] = ray.direction.y; o[5] = ray.direction.z;
         }
+        bool found;
         switch (mode) {
-            case HIT_SOA_SCALAR: return hit_soa_scalar(ray, t_min, t_max, hit, index);
+            case HIT_SOA_SCALAR: found = hit_soa_scalar(ray, t_min, t_max, hit, index); break;
 #if defined(__AVX2__)
-            case HIT_SOA_AVX2: return hit_soa_avx2(ray, t_min, t_max, hit, index);
+            case HIT_SOA_AVX2: found = hit_soa_avx2(ray, t_min, t_max, hit, index); break;
 #endif
             default: return hit_list(ray, t_min, t_max, hit, index);
         }
+        // Hybrid (NOT a reference configuration: SpheresSoA::new panics on a MovingSphere, spheres_soa.rs:49-51).  The GPU
+        // path tests static spheres in the SoA form and moving spheres in the live form of moving_sphere.rs:38-73; this
+        // restates exactly that so the two can be compared bit for bit.  Nearest hit, lowest index among equal t — what
+        // the strict `<` of the in-order list walk (hitable_list.rs:49-54) yields.
+        for (int32_t mi : moving_index) {
+            RayHit h;
+            if (moving_sphere_hit(spheres[mi], ray, t_min, t_max, h) && (!found || h.t < hit.t || (h.t == hit.t && mi < index))) {
+                found = true;
+                hit = h;
+                index = mi;
+            }
+        }
+        return found;
     }
 
     // material.rs:52-67
@@ -779,15 +840,30 @@ static int32_t add_mat(Scene& s, int32_t kind, int32_t tex, V3 albedo, float fuz
     s.materials.push_back(m);
     return (int32_t)s.materials.size() - 1;
 }
-static void add_sphere(Scene& s, V3 c, float r, int32_t mat) { s.spheres.push_back(Sphere{c, r, mat}); }
+static void add_sphere(Scene& s, V3 c, float r, int32_t mat) {
+    Sphere sp;
+    sp.centre = c; sp.radius = r; sp.material = mat;
+    s.spheres.push_back(sp);
+}
+// presets.rs:122-127 + moving_sphere.rs:16-26
+static void add_moving_sphere(Scene& s, V3 c0, V3 c1, float t0, float t1, float r, int32_t mat) {
+    Sphere sp;
+    sp.centre = c0; sp.radius = r; sp.material = mat;
+    sp.moving = true;
+    sp.centre_delta = c1 - c0;
+    sp.time_start = t0;
+    sp.inv_time_delta = 1.0f / (t1 - t0);
+    s.spheres.push_back(sp);
+}
 
 static Camera rtiow_camera(const Params& p, float aperture, float t1) {  // presets.rs:95-109, :275-289
     return camera_new(v3(13, 2, 3), v3(0, 0, 0), v3(0, 1, 0), 20.0f, (float)p.width / (float)p.height, aperture, 10.0f,
                       0.0f, t1);
 }
 
-// presets.rs:89-215 with only_spheres=true; `half` = 11 for the reference preset, 158 for stress100k
-static void preset_random_spheres(Scene& s, const Params& p, Rng& rng, int half) {
+// presets.rs:89-215; only_spheres=true is `random_spheres`, false is `random` (Lambertian spheres move, :150-172);
+// `half` = 11 for the reference presets, 158 for stress100k
+static void preset_random_spheres(Scene& s, const Params& p, Rng& rng, int half, bool only_spheres = true) {
     s.camera = rtiow_camera(p, 0.1f, 1.0f);
     int32_t odd = add_tex_constant(s, v3(0.2f, 0.3f, 0.1f));
     int32_t even = add_tex_constant(s, v3(0.9f, 0.9f, 0.9f));
@@ -800,12 +876,14 @@ static void preset_random_spheres(Scene& s, const Params& p, Rng& rng, int half)
             float czv = (float)b + 0.9f * rng.gen_f32();
             V3 centre = v3(cxv, 0.2f, czv);
             if (choose_material < 0.8f) {
-                (void)rng.gen_f32();  // centre1 draw, consumed even when only_spheres (presets.rs:150)
+                V3 centre1 = centre + v3(0.0f, 0.5f * rng.gen_f32(), 0.0f);  // drawn even when only_spheres (presets.rs:150)
                 float r0 = rng.gen_f32(); float r1 = rng.gen_f32();
                 float g0 = rng.gen_f32(); float g1 = rng.gen_f32();
                 float b0 = rng.gen_f32(); float b1 = rng.gen_f32();
                 int32_t t = add_tex_constant(s, v3(r0 * r1, g0 * g1, b0 * b1));
-                add_sphere(s, centre, 0.2f, add_mat(s, MAT_LAMBERTIAN, t, v3(0, 0, 0), 0, 0));
+                int32_t m = add_mat(s, MAT_LAMBERTIAN, t, v3(0, 0, 0), 0, 0);
+                if (only_spheres) add_sphere(s, centre, 0.2f, m);
+                else add_moving_sphere(s, centre, centre1, 0.0f, 1.0f, 0.2f, m);
             } else if (choose_material < 0.95f) {
                 float r = 0.5f * (1.0f + rng.gen_f32());
                 float g = 0.5f * (1.0f + rng.gen_f32());
@@ -865,6 +943,7 @@ static Scene* build_preset(const char* name, const Params& p) {
     s->perlin.init(rng);
     std::string n(name);
     if (n == "random_spheres") preset_random_spheres(*s, p, rng, 11);
+    else if (n == "random") preset_random_spheres(*s, p, rng, 11, false);
     else if (n == "stress100k") preset_random_spheres(*s, p, rng, 158);
     else if (n == "small") preset_small(*s, p);
     else if (n == "two_perlin_spheres") preset_two_perlin_spheres(*s, p);
@@ -908,6 +987,18 @@ void orc_scene_spheres(void* h, float* centre_radius /*n*4*/, int32_t* material 
         centre_radius[4 * i + 2] = s->spheres[i].centre.z;
         centre_radius[4 * i + 3] = s->spheres[i].radius;
         material[i] = s->spheres[i].material;
+    }
+}
+// per sphere: centre1 (3), time0, time1, moving flag (as float) — moving_sphere.rs:16-26 inverted to its constructor arguments
+void orc_scene_motion(void* h, float* out /*n*6*/) {
+    auto* s = (orc::Scene*)h;
+    for (size_t i = 0; i < s->spheres.size(); ++i) {
+        const orc::Sphere& sp = s->spheres[i];
+        orc::V3 c1 = sp.moving ? sp.centre + sp.centre_delta : sp.centre;
+        out[6 * i + 0] = c1.x; out[6 * i + 1] = c1.y; out[6 * i + 2] = c1.z;
+        out[6 * i + 3] = sp.time_start;
+        out[6 * i + 4] = sp.moving ? sp.time_start + 1.0f / sp.inv_time_delta : 0.0f;
+        out[6 * i + 5] = sp.moving ? 1.0f : 0.0f;
     }
 }
 void orc_scene_materials(void* h, int32_t* kind_tex /*n*2*/, float* albedo_fuzz_ref /*n*5*/) {

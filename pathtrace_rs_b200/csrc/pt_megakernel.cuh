@@ -25,7 +25,7 @@ struct KernelArgs {
     const DevShade* shade;
     const DevTexture* tex;
     const PerlinSmem* perlin;  // global copy, staged to shared memory when has_noise
-    const float* kvals;        // pre-filter k per sphere (constant-bank sweep), 4 * n_blocks floats
+    const DevMotion* motion;   // per-sphere MovingSphere records, nullptr when the scene has none (moving_sphere.rs)
     const float4* prefilter;   // pre-filter image X,Y,Z,K per block (global copy; staged/streamed by the LDS kernels)
     int has_noise;
     DevCamera cam;
@@ -203,7 +203,8 @@ __device__ __forceinline__ bool acquire_pixel_state(const KernelArgs& a, Lane& L
 // `pend` is that lane's "holding an unready ticket" flag; it lives in shared memory, and the end-of-chunk test uses the
 // uniform chunk_mask rather than a per-lane bound, because extra per-lane registers carried across the sweep make ptxas
 // drop the sweep's uniform operands (tests/test_host_and_abi.py guards the SASS).
-__device__ __forceinline__ void lane_refill(const KernelArgs& a, Lane& L, unsigned lane_id, volatile uint32_t* pend) {
+template <bool MOTION>
+__device__ __forceinline__ void lane_refill(const KernelArgs& a, Lane& L, unsigned lane_id, volatile uint32_t* pend, volatile float* tslot) {
     bool want_pixel = false;
     if (!L.active && !L.finished) {
         if (L.have_pixel && ((L.sample & a.chunk_mask) == 0u || L.sample >= a.samples)) {
@@ -258,7 +259,9 @@ __device__ __forceinline__ void lane_refill(const KernelArgs& a, Lane& L, unsign
         const float v = ((float)L.py + rng_f32(L.rng)) * a.inv_ny;
         float time;
         camera_get_ray(a.cam, u, v, L.rng, L.o, L.d, time);
-        (void)time;  // only MovingSphere reads ray.time (out of scope); the draw is kept
+        // ray.time is read only by MovingSphere (moving_sphere.rs:39) and is constant along a path (material.rs:62,83,117):
+        // it lives in the lane's shared-memory slot, not in a register carried across the sweep
+        if (MOTION) *tslot = time;
         L.thr = v3(1.0f, 1.0f, 1.0f);
         L.depth = 0;
         L.sample += 1;
@@ -267,8 +270,9 @@ __device__ __forceinline__ void lane_refill(const KernelArgs& a, Lane& L, unsign
 }
 
 // after the sweep: scene.rs:57-70 for the lane's current ray
+template <bool MOTION>
 __device__ __forceinline__ void lane_shade(const KernelArgs& a, Lane& L, const float4* __restrict__ blk, const PerlinSmem& P,
-                                           float hit_t, int hit_index) {
+                                           const MotionCtx& mc, float hit_t, int hit_index) {
     if (hit_index < 0) {
         L.col = L.col + L.thr * sky_colour(a.has_sky != 0, a.sky, L.d);
         L.active = false;
@@ -283,7 +287,15 @@ __device__ __forceinline__ void lane_shade(const KernelArgs& a, Lane& L, const f
     DevShade m;
     m.ar = s0.x; m.ag = s0.y; m.ab = s0.z; m.param = s0.w;
     m.rinv = s1.x; m.kind = __float_as_int(s1.y); m.tex = __float_as_int(s1.z);
-    const V3 normal = (point - centre) * m.rinv;
+    V3 normal;
+    if (MOTION && __float_as_int(s1.w) != 0) {  // MovingSphere: centre at ray.time, normal = (p - centre) / radius (moving_sphere.rs:28-31,49)
+        const DevMotion mo = mc.table[hit_index];
+        const float s = (*mc.time - mo.time_start) * mo.inv_time_delta;
+        const V3 c = v3(centre.x + s * mo.dx, centre.y + s * mo.dy, centre.z + s * mo.dz);
+        normal = v3((point.x - c.x) / mo.radius, (point.y - c.y) / mo.radius, (point.z - c.z) / mo.radius);
+    } else {
+        normal = (point - centre) * m.rinv;
+    }
     if (m.kind == MAT_DIFFUSE_LIGHT) {  // material.rs:161-167 (+ :157: lights do not scatter)
         const V3 em = m.tex < 0 ? v3(m.ar, m.ag, m.ab) : texture_value(a.tex, P, m.tex, point);
         L.col = L.col + L.thr * em;
@@ -359,7 +371,8 @@ __device__ unsigned long long g_prof[8];  // 0 refill clk, 1 sweep clk, 2 shade 
 #else
 #define PT_LDS_LAUNCH_BOUNDS __launch_bounds__(kCtaThreads)
 #endif
-template <int UNROLL>
+// MOTION: the scene has Hitable::MovingSphere entries (compiled out of the static instantiation)
+template <bool MOTION>
 __global__ void PT_LDS_LAUNCH_BOUNDS pt_megakernel_resident(const __grid_constant__ KernelArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
@@ -367,7 +380,10 @@ __global__ void PT_LDS_LAUNCH_BOUNDS pt_megakernel_resident(const __grid_constan
     PerlinSmem* P = reinterpret_cast<PerlinSmem*>(smem_raw + (size_t)a.n_blocks * 64);
     uint32_t* queue = reinterpret_cast<uint32_t*>(P + 1) + threadIdx.x;  // [kQueueCap][kCtaThreads] candidate queues
     volatile uint32_t* pend = queue + kQueueCap * kCtaThreads;
+    volatile float* tslot = reinterpret_cast<volatile float*>(pend + kCtaThreads);  // [kCtaThreads] ray.time per lane
     *pend = 0u;
+    *tslot = 0.0f;
+    const MotionCtx mc{a.motion, tslot};
 
     const uint32_t bytes = (uint32_t)a.n_blocks * 64u;
     if (threadIdx.x == 0) {
@@ -391,7 +407,7 @@ __global__ void PT_LDS_LAUNCH_BOUNDS pt_megakernel_resident(const __grid_constan
 
     for (;;) {
         PT_PROF_TICK();
-        lane_refill(a, L, lane_id, pend);
+        lane_refill<MOTION>(a, L, lane_id, pend, tslot);
         if (__all_sync(kFullMask, L.finished)) break;
         float ox = L.o.x, oy = L.o.y, oz = L.o.z, dx = L.d.x, dy = L.d.y, dz = L.d.z;
         if (!L.active) {  // parked lane: |o|^2 = 1e36 dwarfs every L, d = 0 -> never a candidate
@@ -406,93 +422,14 @@ __global__ void PT_LDS_LAUNCH_BOUNDS pt_megakernel_resident(const __grid_constan
             const float nod = -((ox * dx + oy * dy) + oz * dz);
             const float oo = ((ox * ox + oy * oy) + oz * oz) * (1.0f - 1.9073486328125e-06f);
             int cnt = 0;
-            sweep_expanded<false>(pf, a.n_blocks, 0, a.blocks, queue, cnt, ox, oy, oz, dx, dy, dz, nod, ox + ox, oy + oy, oz + oz, oo, hit_t, hit_index);
-            sweep_drain(a.blocks, queue, cnt, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
+            sweep_expanded<false, MOTION>(pf, a.n_blocks, 0, a.blocks, mc, queue, cnt, ox, oy, oz, dx, dy, dz, nod, ox + ox, oy + oy, oz + oz, oo, hit_t, hit_index);
+            sweep_drain<MOTION>(a.blocks, mc, queue, cnt, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
         }
         __syncwarp();
         PT_PROF_TOCK(pf_sweep);
         if (L.active) {
             rays += 1ULL;  // scene.rs:57
-            lane_shade(a, L, a.blocks, *P, hit_t, hit_index);
-        }
-        __syncwarp();
-        PT_PROF_TOCK(pf_shade);
-#ifdef PT_PROFILE
-        pf_trips += 1;
-#endif
-    }
-#ifdef PT_PROFILE
-    pf_lanes = rays;
-#endif
-    PT_PROF_FLUSH(lane_id);
-    flush_ray_count(a, rays, lane_id);
-}
-
-// =====================================================================================================
-// Constant-bank variant (<= kMaxConstSpheres spheres): the pre-filter reads sphere pairs through the uniform
-// datapath (pt_sweep.cuh, sweep_const); the TMA-staged shared-memory copy serves the exact re-test and shading.
-// =====================================================================================================
-// (launch bounds are part of the shape ptxas keys its uniform-register decision on: see the note in the main loop)
-#ifdef PT_CONST_MIN_CTAS
-#define PT_CONST_LAUNCH_BOUNDS __launch_bounds__(kCtaThreads, PT_CONST_MIN_CTAS)
-#else
-#define PT_CONST_LAUNCH_BOUNDS __launch_bounds__(kCtaThreads)
-#endif
-template <int WORDS>
-__global__ void PT_CONST_LAUNCH_BOUNDS pt_megakernel_const(const __grid_constant__ KernelArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bar;
-    float4* blk = reinterpret_cast<float4*>(smem_raw);
-    PerlinSmem* P = reinterpret_cast<PerlinSmem*>(smem_raw + (size_t)a.n_blocks * 64);
-    float* ksm = reinterpret_cast<float*>(smem_raw + (size_t)a.n_blocks * 64 + sizeof(PerlinSmem));  // [4 * n_blocks] pre-filter k per sphere
-    uint32_t* queue = reinterpret_cast<uint32_t*>(ksm + 4 * a.n_blocks) + threadIdx.x;           // [kQueueCap][kCtaThreads] candidate queues
-    volatile uint32_t* pend = queue + kQueueCap * kCtaThreads;
-    *pend = 0u;
-
-    const uint32_t bytes = (uint32_t)a.n_blocks * 64u;
-    if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && bytes != 0u) {
-        mbar_arrive_expect_tx(&bar, bytes);
-        tma_bulk_g2s_chunked(blk, a.blocks, bytes, &bar);
-    }
-    stage_perlin(a, P);
-    for (int i = threadIdx.x; i < 4 * a.n_blocks; i += blockDim.x) ksm[i] = a.kvals[i];
-    __syncthreads();
-    if (bytes != 0u) mbar_wait(&bar, 0);
-
-    const unsigned lane_id = threadIdx.x & 31u;
-    const int n_groups = a.n_blocks / kConstGroupBlocks;  // n_blocks is padded to whole groups by the host
-    Lane L;
-    lane_init(L);
-    unsigned long long rays = 0ULL;
-    PT_PROF_DECL
-
-    // NOTE: the shape of this loop is deliberate.  ptxas keeps the sweep's loop counter and sphere operands in uniform
-    // registers (LDCU + FFMA2 R, R.F32, UR.F32x2, R) only for some control-flow shapes; tests/test_host_and_abi.py checks
-    // the SASS so that a refactor which silently loses them (x2 slower sweep) fails the build.
-    for (;;) {
-        PT_PROF_TICK();
-        lane_refill(a, L, lane_id, pend);
-        if (__all_sync(kFullMask, L.finished)) break;
-        float ox = L.o.x, oy = L.o.y, oz = L.o.z, dx = L.d.x, dy = L.d.y, dz = L.d.z;
-        if (!L.active) {  // parked lane: |o|^2 = 1e36 dwarfs every L, d = 0 -> never a candidate
-            ox = 0.0f; oy = 1.0e18f; oz = 0.0f;
-            dx = dy = dz = 0.0f;
-        }
-        float hit_t = kMaxT;
-        int hit_index = -1;
-        __syncwarp();
-        PT_PROF_TOCK(pf_refill);
-        sweep_const<WORDS>(n_groups, blk, reinterpret_cast<const float2*>(ksm), queue, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
-        __syncwarp();
-        PT_PROF_TOCK(pf_sweep);
-        if (L.active) {
-            rays += 1ULL;  // scene.rs:57
-            lane_shade(a, L, blk, *P, hit_t, hit_index);
+            lane_shade<MOTION>(a, L, a.blocks, *P, mc, hit_t, hit_index);
         }
         __syncwarp();
         PT_PROF_TOCK(pf_shade);
@@ -512,7 +449,7 @@ __global__ void PT_CONST_LAUNCH_BOUNDS pt_megakernel_const(const __grid_constant
 // tiles are double-buffered with TMA bulk copies (full/empty mbarrier pair per buffer), so each trip of
 // the main loop streams the whole SoA once through L2 for every live lane of the CTA.
 // =====================================================================================================
-template <int UNROLL>
+template <bool MOTION>
 __global__ void PT_LDS_LAUNCH_BOUNDS pt_megakernel_streamed(const __grid_constant__ KernelArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[2];
@@ -525,7 +462,10 @@ __global__ void PT_LDS_LAUNCH_BOUNDS pt_megakernel_streamed(const __grid_constan
     PerlinSmem* P = reinterpret_cast<PerlinSmem*>(smem_raw + 2 * (size_t)tile_bytes);
     uint32_t* queue = reinterpret_cast<uint32_t*>(P + 1) + threadIdx.x;  // [kQueueCap][kCtaThreads] candidate queues
     volatile uint32_t* pend = queue + kQueueCap * kCtaThreads;
+    volatile float* tslot = reinterpret_cast<volatile float*>(pend + kCtaThreads);  // [kCtaThreads] ray.time per lane
     *pend = 0u;
+    *tslot = 0.0f;
+    const MotionCtx mc{a.motion, tslot};
     const int n_warps = kCtaThreads / 32;
 
     if (threadIdx.x == 0) {
@@ -562,7 +502,7 @@ __global__ void PT_LDS_LAUNCH_BOUNDS pt_megakernel_streamed(const __grid_constan
     };
 
     for (;;) {
-        lane_refill(a, L, lane_id, pend);
+        lane_refill<MOTION>(a, L, lane_id, pend, tslot);
         // CTA-wide liveness: every warp must keep consuming tiles while any warp still has work
         const bool warp_live = !__all_sync(kFullMask, L.finished);
         __syncthreads();  // previous trip's cta_live reads are done
@@ -593,17 +533,17 @@ __global__ void PT_LDS_LAUNCH_BOUNDS pt_megakernel_streamed(const __grid_constan
             __syncwarp();
             const int first = tile * a.tile_blocks;
             const int nb = min(a.tile_blocks, a.n_blocks - first);
-            sweep_expanded<true>(tile_buf(b), nb, first, a.blocks, queue, cnt, ox, oy, oz, dx, dy, dz, nod, ox + ox, oy + oy, oz + oz, oo, hit_t, hit_index);
+            sweep_expanded<true, MOTION>(tile_buf(b), nb, first, a.blocks, mc, queue, cnt, ox, oy, oz, dx, dy, dz, nod, ox + ox, oy + oy, oz + oz, oo, hit_t, hit_index);
             __syncwarp();
             if (lane_id == 0) mbar_arrive(&empty_bar[b]);
             if (threadIdx.x == 0 && tile + 2 < a.n_tiles) produce(tile + 2);
             // this tile's candidates: exact re-test against the global SoA (L2), off the tile buffer's critical path
-            sweep_drain(a.blocks, queue, cnt, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
+            sweep_drain<MOTION>(a.blocks, mc, queue, cnt, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
         }
         if (L.active) {
             rays += 1ULL;
             // the hit sphere's centre is no longer in shared memory: read it from the global SoA
-            lane_shade(a, L, a.blocks, *P, hit_t, hit_index);
+            lane_shade<MOTION>(a, L, a.blocks, *P, mc, hit_t, hit_index);
         }
     }
     flush_ray_count(a, rays, lane_id);

@@ -47,7 +47,7 @@ struct __align__(16) DevShade {  // 32 B
     float rinv;        // 1 / radius (signed) — spheres_soa.rs:47
     int32_t kind;      // MAT_*
     int32_t tex;       // texture index when the texture is not Constant, else -1
-    int32_t _pad;
+    int32_t moving;    // 1: Hitable::MovingSphere (centre and normal follow ray.time, DevMotion in pt_sweep.cuh)
 };
 
 struct DevCamera {  // src/camera.rs:8-19 minus `w`

@@ -53,107 +53,76 @@ __device__ __forceinline__ void sweep_exact(float cox, float coy, float coz, flo
     }
 }
 
-// =====================================================================================================
-// Constant-bank sweep (scenes of up to kMaxConstSpheres spheres — every preset of the reference).
-//
-// Measured on B200 (tools/probe_forms.cu, profiles/probe_forms_r1.txt): a packed FP32 instruction costs
-// ~2.1 clk/warp when it reads one register pair, ~2.5 with two, >3 with two pairs + a scalar — the register
-// file, not the FMA pipe, bounds the LDS form above at ~52 % of peak.  Sphere data is warp-uniform, so here it
-// is read through the uniform datapath (LDCU from the constant bank -> uniform registers) and every packed
-// instruction has the shape  FFMA2 Rpair, Rscalar(ray), URpair(2 spheres), Rpair|Rscalar : one pair read.
-// To make every operation of that shape the discriminant is expanded around the ray instead of the sphere:
-//
-//   disc = (c.d - o.d)^2 + 2 c.o + (r^2 - |c|^2) - |o|^2
-//   A = c.d - o.d            3 FFMA2   (ray: dx,dy,dz, -o.d)
-//   B = 2 c.o + k            3 FFMA2   (ray: 2ox,2oy,2oz; sphere: k = r^2 - |c|^2 + slack)
-//   L = A*A + B              1 FFMA2   candidate  <=>  L > |o|^2 (1 - 2^-19)
-//
-// = 7 packed instructions per 2 tests (14 flop executed per test; the algorithmic count stays 16).
-// The expansion cancels badly (|c|^2 against r^2), so it is used ONLY as a conservative pre-filter: `slack` =
-// 2^-19 (|c|^2 + r^2) on the sphere side and the 2^-19 relative margin on the ray side dominate the rounding
-// error of both this form and the reference's (32 ulp of the largest terms), so every hit the exact test would
-// accept is flagged.
-//
-// The sweep itself is BRANCH-FREE: a group of 8 spheres (2 blocks) reduces its 8 tests with FMNMX3 to one compare
-// that sets one bit of a per-lane flag word (32 groups = 256 spheres per word, words live in registers).  After
-// the whole sweep the lanes walk their set bits in parallel: the flagged group is re-filtered from the shared-
-// memory copy (sweep_pair, LDS form) and the surviving spheres are re-tested with the reference's exact unfused
-// expression (sweep_exact).  Divergence costs a few trips of one SIMD loop per sweep instead of a serialized
-// branch per (lane, sphere) event, and the hot loop is straight-line code the compiler keeps in uniform registers.
-// =====================================================================================================
-constexpr int kSweepThreads = 256;  // == kCtaThreads (queue stride)
-#ifndef PT_CONST_GROUP
-#define PT_CONST_GROUP 4
-#endif
-constexpr int kConstGroupBlocks = PT_CONST_GROUP;          // blocks (of 4 spheres) per pre-filter branch / queue entry
-constexpr int kEntryMaskBits = 4 * kConstGroupBlocks;       // one flag bit per sphere of the group
-constexpr int kMaxConstBlocks = 1000;                      // 4000 spheres * 16 B = 64 000 B of the 64 KB constant bank
-constexpr int kMaxConstSpheres = 4 * kMaxConstBlocks;
-__constant__ float4 c_prefilter[4 * kMaxConstBlocks];      // per block: X(cx0..3) Y Z K(k0..3)
+// ---- Hitable::MovingSphere (src/collision/moving_sphere.rs) ----
+// A moving sphere enters the pre-filter as the static sphere that bounds its whole sweep (centre0 + delta/2, radius
+// r + |delta|/2), so stage 1 never looks at the ray's time.  Its exact block carries centre0 and a NEGATIVE r^2 as the
+// "moving" tag; stage 2 then evaluates the reference's own expression with the centre at ray.time.
+struct __align__(16) DevMotion {  // 32 B, one record per sphere (zeros for static spheres), read only on the rare path
+    float dx, dy, dz;        // centre_delta = centre1 - centre0   (moving_sphere.rs:21)
+    float time_start;        // moving_sphere.rs:23
+    float inv_time_delta;    // 1 / (time1 - time0)               (moving_sphere.rs:24)
+    float radius;            // signed, as given
+    float _pad[2];
+};
 
-// n_groups = n_blocks / 2; both the constant image and the shared-memory copy are padded to whole groups.
-// Candidate queue: one 32-bit entry per flagged group = (first block << kEntryMaskBits) | one flag bit per sphere, kQueueCap entries per lane in
-// shared memory ([entry][thread] layout, conflict-free).  A full queue (rare) tests the group on the spot.
+// moving_sphere.rs:38-73 for one sphere: returns the accepted root (near if inside (t_min, t_max), else far), or -1.
+// Out of line on purpose: it is rare, and inlining it into the resolve loop costs the hot kernels registers.
+__device__ __forceinline__ float moving_sphere_hit_t(const DevMotion* __restrict__ mo, float time, float c0x, float c0y, float c0z, float ox,
+                                                  float oy, float oz, float dx, float dy, float dz) {
+    const DevMotion m = *mo;
+    const float s = (time - m.time_start) * m.inv_time_delta;  // moving_sphere.rs:29
+    const float cx = c0x + s * m.dx, cy = c0y + s * m.dy, cz = c0z + s * m.dz;
+    const float ocx = ox - cx, ocy = oy - cy, ocz = oz - cz;
+    const float a = (dx * dx + dy * dy) + dz * dz;
+    const float b = (ocx * dx + ocy * dy) + ocz * dz;
+    const float c = ((ocx * ocx + ocy * ocy) + ocz * ocz) - m.radius * m.radius;
+    const float discriminant = b * b - a * c;
+    if (discriminant > 0.0f) {
+        const float discriminant_sqrt = sqrtf(discriminant);
+        float t = (-b - discriminant_sqrt) / a;
+        if (t < kMaxT && t > kMinT) return t;
+        t = (-b + discriminant_sqrt) / a;
+        if (t < kMaxT && t > kMinT) return t;
+    }
+    return -1.0f;
+}
+
+// what the rare paths need to know about motion: the table and where this lane keeps its ray's time
+struct MotionCtx {
+    const DevMotion* table;        // nullptr when the scene has no moving sphere
+    const volatile float* time;    // this lane's ray.time (shared memory slot)
+};
+
+constexpr int kSweepThreads = 256;  // == kCtaThreads (queue stride)
+
+// Candidate queue: one 32-bit entry per flagged group = (group index << MASK_BITS) | one flag bit per sphere of the group,
+// kQueueCap entries per lane in shared memory ([entry][thread] layout, conflict-free).  A full queue (rare) tests the
+// group on the spot.  Stage 2: every lane walks its own queue after the sweep, all lanes in parallel — divergence costs
+// a few trips of one SIMD loop per sweep instead of a serialized branch body per (lane, sphere) event.
 constexpr int kQueueCap = 12;
 
-template <int MASK_BITS>
-__device__ __forceinline__ void sweep_resolve_entry(const float4* __restrict__ blk, uint32_t entry, float ox, float oy, float oz, float dx,
-                                                    float dy, float dz, float& hit_t, int& hit_index) {
-    const int base = (int)(entry >> MASK_BITS) * 4;
+template <int MASK_BITS, bool MOTION>
+__device__ __forceinline__ void sweep_resolve_entry(const float4* __restrict__ blk, const MotionCtx& mc, uint32_t entry, float ox, float oy, float oz,
+                                                    float dx, float dy, float dz, float& hit_t, int& hit_index) {
+    const int base = (int)(entry >> MASK_BITS) * MASK_BITS;  // MASK_BITS spheres per group
     uint32_t mask = entry & ((1u << MASK_BITS) - 1u);
 #pragma unroll 1
     while (mask != 0u) {
         const int index = base + __ffs(mask) - 1;
         mask &= mask - 1u;
         const float* bf = reinterpret_cast<const float*>(blk) + (index >> 2) * 16 + (index & 3);
-        sweep_exact(bf[0] - ox, bf[4] - oy, bf[8] - oz, bf[12], dx, dy, dz, index, hit_t, hit_index);
-    }
-}
-
-template <int WORDS>
-__device__ __forceinline__ void sweep_const(int n_groups, const float4* __restrict__ blk, const float2* __restrict__ ksm, uint32_t* __restrict__ q,
-                                            float ox, float oy, float oz, float dx, float dy, float dz, float& hit_t, int& hit_index) {
-    const int n_blocks_padded = n_groups * kConstGroupBlocks;
-    const float nod = -((ox * dx + oy * dy) + oz * dz);
-    const float o2x = ox + ox, o2y = oy + oy, o2z = oz + oz;
-    const float oo = ((ox * ox + oy * oy) + oz * oz) * (1.0f - 1.9073486328125e-06f);
-    int cnt = 0;
-#pragma unroll 1
-    for (int j = 0; j < n_blocks_padded; j += kConstGroupBlocks) {
-        float2 L[2 * kConstGroupBlocks];
-#pragma unroll
-        for (int g = 0; g < kConstGroupBlocks; ++g) {
-            const float4 X = c_prefilter[4 * (j + g) + 0], Y = c_prefilter[4 * (j + g) + 1], Z = c_prefilter[4 * (j + g) + 2];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const float2 cx = h ? make_float2(X.z, X.w) : make_float2(X.x, X.y);
-                const float2 cy = h ? make_float2(Y.z, Y.w) : make_float2(Y.x, Y.y);
-                const float2 cz = h ? make_float2(Z.z, Z.w) : make_float2(Z.x, Z.y);
-                const float2 k = ksm[2 * (j + g) + h];  // LDS.64 broadcast: k in a vector pair keeps every FFMA2 at one uniform operand
-                const float2 A = f2_fma(cz, make_float2(dz, dz), f2_fma(cy, make_float2(dy, dy), f2_fma(cx, make_float2(dx, dx), make_float2(nod, nod))));
-                const float2 B = f2_fma(cz, make_float2(o2z, o2z), f2_fma(cy, make_float2(o2y, o2y), f2_fma(cx, make_float2(o2x, o2x), k)));
-                L[2 * g + h] = f2_fma(A, A, B);
+        const float r2 = bf[12];
+        if (MOTION && r2 < 0.0f) {  // MovingSphere tag (MOTION is a kernel template parameter: static scenes compile none of this)
+            const float t = moving_sphere_hit_t(mc.table + index, *mc.time, bf[0], bf[4], bf[8], ox, oy, oz, dx, dy, dz);
+            // nearest hit, lowest index among equal t (the strict `<` of the in-order walk, hitable_list.rs:49-54)
+            if (t > 0.0f && (t < hit_t || (t == hit_t && index < hit_index))) {
+                hit_t = t;
+                hit_index = index;
             }
-        }
-        bool any = false;
-#pragma unroll
-        for (int p = 0; p < 2 * kConstGroupBlocks; ++p) any = any | (L[p].x > oo) | (L[p].y > oo);
-        if (any) {
-            uint32_t mask = 0u;
-#pragma unroll
-            for (int p = 0; p < 2 * kConstGroupBlocks; ++p) mask |= (L[p].x > oo ? 1u << (2 * p) : 0u) | (L[p].y > oo ? 2u << (2 * p) : 0u);
-            const uint32_t entry = ((uint32_t)j << kEntryMaskBits) | mask;
-            if (cnt < kQueueCap) {
-                q[cnt * kSweepThreads] = entry;
-                cnt += 1;
-            } else {  // queue full (rare): test this group now; sweep_exact's tie rule makes the visiting order irrelevant
-                sweep_resolve_entry<kEntryMaskBits>(blk, entry, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
-            }
+        } else {
+            sweep_exact(bf[0] - ox, bf[4] - oy, bf[8] - oz, r2, dx, dy, dz, index, hit_t, hit_index);
         }
     }
-    // resolve: every lane walks its own queue, all lanes in parallel
-#pragma unroll 1
-    for (int i = 0; i < cnt; ++i) sweep_resolve_entry<kEntryMaskBits>(blk, q[i * kSweepThreads], ox, oy, oz, dx, dy, dz, hit_t, hit_index);
 }
 
 // =====================================================================================================
@@ -167,16 +136,20 @@ __device__ __forceinline__ void sweep_const(int n_groups, const float4* __restri
 // flagged groups go to the lane's queue as (absolute block << kLdsMaskBits | flags) and are re-tested by the
 // caller with the reference's exact expression against `exact` (global memory for the streamed kernel).
 // =====================================================================================================
-constexpr int kLdsGroupBlocks = 2;                 // blocks per pre-filter branch / queue entry of the LDS sweep
-constexpr int kLdsMaskBits = 4 * kLdsGroupBlocks;  // entry = absolute block << 8 | flags: up to 2^24 blocks
+#ifndef PT_LDS_GROUP
+#define PT_LDS_GROUP 4
+#endif
+constexpr int kLdsGroupBlocks = PT_LDS_GROUP;      // blocks (of 4 spheres) per pre-filter branch / queue entry
+constexpr int kLdsMaskBits = 4 * kLdsGroupBlocks;  // entry = absolute group << kLdsMaskBits | flags
+constexpr long long kMaxSweepBlocks = (1ll << (32 - kLdsMaskBits)) * kLdsGroupBlocks;  // what the entry's group field can address
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
     float4 v;
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
-template <bool PIPE>
+template <bool PIPE, bool MOTION>
 __device__ __forceinline__ void sweep_expanded(const float4* __restrict__ pf, int n_blocks, int first_block, const float4* __restrict__ exact,
-                                               uint32_t* __restrict__ q, int& cnt, float ox, float oy, float oz, float dx, float dy, float dz,
+                                               const MotionCtx& mc, uint32_t* __restrict__ q, int& cnt, float ox, float oy, float oz, float dx, float dy, float dz,
                                                float nod, float o2x, float o2y, float o2z, float oo, float& hit_t, int& hit_index) {
     // pin the per-ray operands (and the trip count) in registers: without this ptxas rematerialises them — 9 scalar FP
     // instructions and a constant-bank reload of n_blocks — in every trip
@@ -228,22 +201,23 @@ __device__ __forceinline__ void sweep_expanded(const float4* __restrict__ pf, in
             uint32_t mask = 0u;
 #pragma unroll
             for (int p = 0; p < 2 * kLdsGroupBlocks; ++p) mask |= (L[p].x > oo ? 1u << (2 * p) : 0u) | (L[p].y > oo ? 2u << (2 * p) : 0u);
-            const uint32_t entry = (((uint32_t)first_block + ((addr - base) >> 6)) << kLdsMaskBits) | mask;
+            const uint32_t entry = ((((uint32_t)first_block + ((addr - base) >> 6)) / kLdsGroupBlocks) << kLdsMaskBits) | mask;
             if (cnt < kQueueCap) {
                 q[cnt * kSweepThreads] = entry;
                 cnt += 1;
             } else {  // queue full (rare): test this group now; sweep_exact's tie rule makes the visiting order irrelevant
-                sweep_resolve_entry<kLdsMaskBits>(exact, entry, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
+                sweep_resolve_entry<kLdsMaskBits, MOTION>(exact, mc, entry, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
             }
         }
     }
 }
 
 // drain the lane's queue: exact re-test of every flagged sphere (all lanes in parallel)
-__device__ __forceinline__ void sweep_drain(const float4* __restrict__ exact, const uint32_t* __restrict__ q, int& cnt, float ox, float oy, float oz,
+template <bool MOTION>
+__device__ __forceinline__ void sweep_drain(const float4* __restrict__ exact, const MotionCtx& mc, const uint32_t* __restrict__ q, int& cnt, float ox, float oy, float oz,
                                             float dx, float dy, float dz, float& hit_t, int& hit_index) {
 #pragma unroll 1
-    for (int i = 0; i < cnt; ++i) sweep_resolve_entry<kLdsMaskBits>(exact, q[i * kSweepThreads], ox, oy, oz, dx, dy, dz, hit_t, hit_index);
+    for (int i = 0; i < cnt; ++i) sweep_resolve_entry<kLdsMaskBits, MOTION>(exact, mc, q[i * kSweepThreads], ox, oy, oz, dx, dy, dz, hit_t, hit_index);
     cnt = 0;
 }
 

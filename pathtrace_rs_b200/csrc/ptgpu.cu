@@ -38,10 +38,6 @@ int fail(int code, const char* fmt, ...) {
         if (e_ != cudaSuccess) return fail(PT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
-#ifndef PT_SWEEP_GROUP
-#define PT_SWEEP_GROUP 2
-#endif
-constexpr int kSweepUnroll = PT_SWEEP_GROUP;  // blocks (of 4 spheres) tested per branch in the sweep
 constexpr size_t kMaxDynSmem = 227 * 1024 - 1024;  // leave room for static shared + driver reservation
 
 }  // namespace
@@ -58,7 +54,8 @@ struct PtScene {
     pt::DevShade* d_shade = nullptr;
     pt::DevTexture* d_tex = nullptr;
     pt::PerlinSmem* d_perlin = nullptr;
-    float* d_kvals = nullptr;  // pre-filter k per sphere (constant-bank sweep)
+    pt::DevMotion* d_motion = nullptr;  // MovingSphere records (nullptr: none)
+    float motion_t_lo = 0.0f, motion_t_hi = 0.0f;  // intersection of the moving spheres' [time0, time1]
     float4* d_prefilter = nullptr;  // pre-filter image X,Y,Z,K per block (LDS kernels stage/stream it)
     // per-render scratch
     unsigned long long* d_ray_count = nullptr;  // [0] ray count
@@ -73,9 +70,6 @@ struct PtScene {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // launch geometry
     bool resident = true;
-    bool use_const = false;                 // pre-filter through the constant bank (<= kMaxConstSpheres)
-    int const_words = 2;                    // flag words per lane (kernel instantiation)
-    std::vector<float4> h_prefilter;        // host copy of the constant-bank image of this scene
     int tile_blocks = 0, n_tiles = 0;
     size_t smem_bytes = 0;
     int ctas_per_sm = 0;
@@ -107,9 +101,14 @@ int configure_kernel(K kernel, size_t smem, int* ctas_per_sm) {
     return PT_OK;
 }
 
+int configure_streamed(PtScene* s) {
+    return s->d_motion ? configure_kernel(pt::pt_megakernel_streamed<true>, s->smem_bytes, &s->ctas_per_sm)
+                       : configure_kernel(pt::pt_megakernel_streamed<false>, s->smem_bytes, &s->ctas_per_sm);
+}
+
 int plan_launch(PtScene* s) {
     const size_t queue_bytes = (size_t)pt::kQueueCap * pt::kCtaThreads * sizeof(uint32_t);  // per-lane candidate queues
-    const size_t perlin_bytes = sizeof(pt::PerlinSmem) + pt::kCtaThreads * sizeof(uint32_t) + queue_bytes;  // Perlin tables + `pend` words + queues
+    const size_t perlin_bytes = sizeof(pt::PerlinSmem) + 2 * pt::kCtaThreads * sizeof(uint32_t) + queue_bytes;  // Perlin tables + `pend` words + ray.time slots + queues
     const size_t all = (size_t)s->n_blocks * 64 + perlin_bytes;
     // test hook: PTGPU_FORCE_STREAM_TILE_BLOCKS=<n> runs any scene through the streamed kernel with n-block tiles
     int forced_tile = 0;
@@ -120,25 +119,15 @@ int plan_launch(PtScene* s) {
         s->tile_blocks = std::min(forced_tile, s->n_blocks);
         s->n_tiles = (s->n_blocks + s->tile_blocks - 1) / s->tile_blocks;
         s->smem_bytes = 2 * (size_t)s->tile_blocks * 64 + perlin_bytes;
-        return configure_kernel(pt::pt_megakernel_streamed<kSweepUnroll>, s->smem_bytes, &s->ctas_per_sm);
-    }
-    const bool no_const = std::getenv("PTGPU_DISABLE_CONST_SWEEP") != nullptr;  // test hook: exercise the LDS sweep
-    if (!no_const && s->n_blocks <= pt::kMaxConstBlocks) {
-        s->resident = true;
-        s->use_const = true;
-        s->smem_bytes = all + (size_t)s->n_blocks * 4 * sizeof(float);
-        s->tile_blocks = s->n_blocks;
-        s->n_tiles = 1;
-        s->const_words = s->n_blocks / pt::kConstGroupBlocks <= 64 ? 2 : 16;  // 32 groups (256 spheres) per flag word
-        return s->const_words == 2 ? configure_kernel(pt::pt_megakernel_const<2>, s->smem_bytes, &s->ctas_per_sm)
-                                   : configure_kernel(pt::pt_megakernel_const<16>, s->smem_bytes, &s->ctas_per_sm);
+        return configure_streamed(s);
     }
     if (all <= kMaxDynSmem) {
         s->resident = true;
         s->smem_bytes = all;
         s->tile_blocks = s->n_blocks;
         s->n_tiles = 1;
-        return configure_kernel(pt::pt_megakernel_resident<kSweepUnroll>, s->smem_bytes, &s->ctas_per_sm);
+        return s->d_motion ? configure_kernel(pt::pt_megakernel_resident<true>, s->smem_bytes, &s->ctas_per_sm)
+                           : configure_kernel(pt::pt_megakernel_resident<false>, s->smem_bytes, &s->ctas_per_sm);
     }
     // streamed: two tile buffers; 2 CTAs per SM keeps the FP32 pipe fed while one CTA waits on a barrier
     s->resident = false;
@@ -147,7 +136,7 @@ int plan_launch(PtScene* s) {
     s->tile_blocks = (int)(tile_bytes / 64);
     s->n_tiles = (s->n_blocks + s->tile_blocks - 1) / s->tile_blocks;
     s->smem_bytes = 2 * (size_t)s->tile_blocks * 64 + perlin_bytes;
-    return configure_kernel(pt::pt_megakernel_streamed<kSweepUnroll>, s->smem_bytes, &s->ctas_per_sm);
+    return configure_streamed(s);
 }
 
 uint32_t owned_rows(uint32_t height, const PtPartition& p) {
@@ -188,8 +177,8 @@ int launch_update(PtScene* s, const PtParams* params, const PtCamera* cam, uint3
     a.shade = s->d_shade;
     a.tex = s->d_tex;
     a.perlin = s->d_perlin;
-    a.kvals = s->d_kvals;
     a.prefilter = s->d_prefilter;
+    a.motion = s->d_motion;
     a.has_noise = s->has_noise ? 1 : 0;
     auto V = [](const float* f) { return pt::V3{f[0], f[1], f[2]}; };
     a.cam.origin = V(cam->origin);
@@ -226,6 +215,9 @@ int launch_update(PtScene* s, const PtParams* params, const PtCamera* cam, uint3
     a.tile_blocks = s->tile_blocks;
     a.n_tiles = s->n_tiles;
 
+    if (s->d_motion && !(cam->time0 >= s->motion_t_lo && cam->time1 <= s->motion_t_hi && cam->time0 <= cam->time1))
+        return fail(PT_ERR_UNSUPPORTED, "camera shutter [%g, %g] is not inside the moving spheres' interval [%g, %g] (the pre-filter bounds their sweep over that interval)",
+                    cam->time0, cam->time1, s->motion_t_lo, s->motion_t_hi);
     PT_CUDA(cudaMemsetAsync(s->d_next_pixel, 0, sizeof(unsigned int), stream));
     PT_CUDA(cudaMemsetAsync(d_ray_count, 0, sizeof(unsigned long long), stream));
     s->stats.kernel_launches = 0;
@@ -280,18 +272,13 @@ int launch_update(PtScene* s, const PtParams* params, const PtCamera* cam, uint3
         PT_CUDA(cudaMemsetAsync(s->d_pixstate, 0, (size_t)a.n_owned_pixels * pt::kPixStateWords * sizeof(uint32_t), stream));
         a.pixstate = s->d_pixstate;
     }
-    if (s->use_const) {
-        // the constant bank is per device, not per scene: (re)load this scene's image in stream order
-        PT_CUDA(cudaMemcpyToSymbolAsync(pt::c_prefilter, s->h_prefilter.data(), s->h_prefilter.size() * sizeof(float4), 0,
-                                        cudaMemcpyHostToDevice, stream));
-        if (s->const_words == 2)
-            pt::pt_megakernel_const<2><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a);
-        else
-            pt::pt_megakernel_const<16><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a);
-    } else if (s->resident)
-        pt::pt_megakernel_resident<kSweepUnroll><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a);
-    else
-        pt::pt_megakernel_streamed<kSweepUnroll><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a);
+    if (s->resident) {
+        if (s->d_motion) pt::pt_megakernel_resident<true><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a);
+        else pt::pt_megakernel_resident<false><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a);
+    } else {
+        if (s->d_motion) pt::pt_megakernel_streamed<true><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a);
+        else pt::pt_megakernel_streamed<false><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a);
+    }
     PT_CUDA(cudaGetLastError());
     s->stats.kernel_launches = 1;
     s->stats.grid_ctas = grid;
@@ -432,6 +419,20 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
             return fail(PT_ERR_INVALID, "material %u: texture index %d out of range", m, mt.texture);
     }
 
+    bool any_moving = false;
+    float t_lo = -FLT_MAX, t_hi = FLT_MAX;
+    if (desc->motion) {
+        for (uint32_t i = 0; i < n; ++i) {
+            const PtMotion& mo = desc->motion[i];
+            if (!mo.moving) continue;
+            if (!(mo.time1 > mo.time0)) return fail(PT_ERR_INVALID, "sphere %u: MovingSphere needs time1 > time0 (got %g, %g)", i, mo.time0, mo.time1);
+            any_moving = true;
+            t_lo = std::max(t_lo, mo.time0);
+            t_hi = std::min(t_hi, mo.time1);
+        }
+    }
+    auto is_moving = [&](uint32_t i) { return any_moving && desc->motion[i].moving != 0; };
+
     cudaDeviceProp prop;
     int rc = check_device(device, &prop);
     if (rc != PT_OK) return rc;
@@ -442,7 +443,8 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
     s->sm_count = prop.multiProcessorCount;
     s->n_spheres = n;
     s->n_blocks = (int)((n + 3) / 4);
-    s->n_blocks = (s->n_blocks + pt::kConstGroupBlocks - 1) / pt::kConstGroupBlocks * pt::kConstGroupBlocks;  // whole groups; padding spheres can never be hit
+    s->n_blocks = (s->n_blocks + pt::kLdsGroupBlocks - 1) / pt::kLdsGroupBlocks * pt::kLdsGroupBlocks;  // whole groups; padding spheres can never be hit
+    if (s->n_blocks > pt::kMaxSweepBlocks) { delete s; return fail(PT_ERR_TOO_LARGE, "too many spheres for the candidate-queue encoding: %u", n); }
     s->has_noise = uses_noise;
     s->has_sky = desc->has_sky != 0;
     s->sky = pt::V3{desc->sky[0], desc->sky[1], desc->sky[2]};
@@ -459,19 +461,26 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
             f[4 + e] = valid ? desc->centre_y[i] : FLT_MAX;
             f[8 + e] = valid ? desc->centre_z[i] : FLT_MAX;
             f[12 + e] = valid ? desc->radius[i] * desc->radius[i] : 0.0f;  // spheres_soa.rs:46
+            if (valid && is_moving(i)) f[12 + e] = -std::max(f[12 + e], FLT_MIN);  // negative r^2 tags a MovingSphere (pt_sweep.cuh)
         }
     }
-    // constant-bank image for the pre-filter (pt_sweep.cuh): X, Y, Z, K = r^2 - |c|^2 + 2^-19 (|c|^2 + r^2), padded to the group
+    // pre-filter image (pt_sweep.cuh): X, Y, Z, K = r^2 - |c|^2 + 2^-19 (|c|^2 + r^2), padded to the group
+    std::vector<float4> h_prefilter;
     {
-        s->h_prefilter.assign((size_t)std::max(s->n_blocks, 1) * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+        h_prefilter.assign((size_t)std::max(s->n_blocks, 1) * 4, make_float4(0.f, 0.f, 0.f, 0.f));
         for (int j = 0; j < s->n_blocks; ++j) {
-            float* f = reinterpret_cast<float*>(&s->h_prefilter[(size_t)j * 4]);
+            float* f = reinterpret_cast<float*>(&h_prefilter[(size_t)j * 4]);
             for (int e = 0; e < 4; ++e) {
                 const uint32_t i = (uint32_t)j * 4 + e;
                 f[0 + e] = f[4 + e] = f[8 + e] = 0.0f;
                 f[12 + e] = -3.0e38f;  // padding: never a candidate
                 if (i >= n) continue;
-                const double cx = desc->centre_x[i], cy = desc->centre_y[i], cz = desc->centre_z[i], r = desc->radius[i];
+                double cx = desc->centre_x[i], cy = desc->centre_y[i], cz = desc->centre_z[i], r = std::fabs((double)desc->radius[i]);
+                if (is_moving(i)) {  // static bound of the whole sweep: centre0 + delta/2, radius r + |delta|/2 (+ f32 rounding of the lerp)
+                    const double ex = desc->motion[i].centre1[0] - cx, ey = desc->motion[i].centre1[1] - cy, ez = desc->motion[i].centre1[2] - cz;
+                    cx += 0.5 * ex; cy += 0.5 * ey; cz += 0.5 * ez;
+                    r += 0.5 * std::sqrt(ex * ex + ey * ey + ez * ez) * (1.0 + 1e-5) + 1e-6 * (std::fabs(cx) + std::fabs(cy) + std::fabs(cz) + r);
+                }
                 const double c2 = cx * cx + cy * cy + cz * cz, r2 = r * r;
                 if (!(c2 + r2 < 1.0e24)) {  // too large (or NaN) for the expanded form: always a candidate, the exact test decides
                     f[12 + e] = INFINITY;
@@ -496,6 +505,7 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
         d.rinv = 1.0f / desc->radius[i];  // spheres_soa.rs:47
         d.kind = mt.kind;
         d.tex = -1;
+        d.moving = is_moving(i) ? 1 : 0;
         if (mt.kind == PT_MAT_LAMBERTIAN || mt.kind == PT_MAT_DIFFUSE_LIGHT) {
             const PtTexture& tx = desc->textures[mt.texture];
             if (tx.kind == PT_TEX_CONSTANT) {  // fold the constant colour into the per-sphere record
@@ -544,15 +554,28 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
     PT_CUDA_S(cudaMemcpy(s->d_shade, shade.data(), shade.size() * sizeof(pt::DevShade), cudaMemcpyHostToDevice));
     PT_CUDA_S(cudaMalloc(&s->d_tex, tex.size() * sizeof(pt::DevTexture)));
     PT_CUDA_S(cudaMemcpy(s->d_tex, tex.data(), tex.size() * sizeof(pt::DevTexture), cudaMemcpyHostToDevice));
-    PT_CUDA_S(cudaMalloc(&s->d_prefilter, s->h_prefilter.size() * sizeof(float4)));
-    PT_CUDA_S(cudaMemcpy(s->d_prefilter, s->h_prefilter.data(), s->h_prefilter.size() * sizeof(float4), cudaMemcpyHostToDevice));
-    if (s->n_blocks <= pt::kMaxConstBlocks) {
-        std::vector<float> kv((size_t)std::max(s->n_blocks, 1) * 4, -3.0e38f);
-        for (int j = 0; j < s->n_blocks; ++j)
-            for (int e = 0; e < 4; ++e) kv[(size_t)j * 4 + e] = reinterpret_cast<const float*>(&s->h_prefilter[(size_t)j * 4 + 3])[e];
-        PT_CUDA_S(cudaMalloc(&s->d_kvals, kv.size() * sizeof(float)));
-        PT_CUDA_S(cudaMemcpy(s->d_kvals, kv.data(), kv.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if (any_moving) {
+        std::vector<pt::DevMotion> motion(n);
+        for (uint32_t i = 0; i < n; ++i) {
+            pt::DevMotion m{};
+            if (is_moving(i)) {  // MovingSphere::new, moving_sphere.rs:16-26
+                const PtMotion& mo = desc->motion[i];
+                m.dx = mo.centre1[0] - desc->centre_x[i];
+                m.dy = mo.centre1[1] - desc->centre_y[i];
+                m.dz = mo.centre1[2] - desc->centre_z[i];
+                m.time_start = mo.time0;
+                m.inv_time_delta = 1.0f / (mo.time1 - mo.time0);
+                m.radius = desc->radius[i];
+            }
+            motion[i] = m;
+        }
+        PT_CUDA_S(cudaMalloc(&s->d_motion, motion.size() * sizeof(pt::DevMotion)));
+        PT_CUDA_S(cudaMemcpy(s->d_motion, motion.data(), motion.size() * sizeof(pt::DevMotion), cudaMemcpyHostToDevice));
+        s->motion_t_lo = t_lo;
+        s->motion_t_hi = t_hi;
     }
+    PT_CUDA_S(cudaMalloc(&s->d_prefilter, h_prefilter.size() * sizeof(float4)));
+    PT_CUDA_S(cudaMemcpy(s->d_prefilter, h_prefilter.data(), h_prefilter.size() * sizeof(float4), cudaMemcpyHostToDevice));
     PT_CUDA_S(cudaMalloc(&s->d_perlin, sizeof(pt::PerlinSmem)));
     {
         std::vector<unsigned char> raw(sizeof(pt::PerlinSmem), 0);
@@ -588,8 +611,8 @@ void pt_scene_destroy(PtScene* s) {
     cudaFree(s->d_shade);
     cudaFree(s->d_tex);
     cudaFree(s->d_perlin);
-    cudaFree(s->d_kvals);
     cudaFree(s->d_prefilter);
+    cudaFree(s->d_motion);
     cudaFree(s->d_ray_count);
     cudaFree(s->d_next_pixel);
     cudaFree(s->d_pixstate);

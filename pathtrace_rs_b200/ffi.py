@@ -46,13 +46,17 @@ class PtPerlin(C.Structure):
                 ("perm_z", C.c_uint32 * 256)]
 
 
+class PtMotion(C.Structure):  # src/collision/moving_sphere.rs:7-26
+    _fields_ = [("centre1", C.c_float * 3), ("time0", C.c_float), ("time1", C.c_float), ("moving", C.c_uint32)]
+
+
 class PtSceneDesc(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("n_spheres", C.c_uint32),
                 ("centre_x", C.POINTER(C.c_float)), ("centre_y", C.POINTER(C.c_float)), ("centre_z", C.POINTER(C.c_float)),
                 ("radius", C.POINTER(C.c_float)), ("material_index", C.POINTER(C.c_int32)),
                 ("n_materials", C.c_uint32), ("n_textures", C.c_uint32),
                 ("materials", C.POINTER(PtMaterial)), ("textures", C.POINTER(PtTexture)), ("perlin", C.POINTER(PtPerlin)),
-                ("has_sky", C.c_uint32), ("sky", C.c_float * 3)]
+                ("has_sky", C.c_uint32), ("sky", C.c_float * 3), ("motion", C.POINTER(PtMotion))]
 
 
 class PtPartition(C.Structure):
@@ -141,6 +145,7 @@ def libpthost():
         L.pth_preset_next_f32.argtypes = [vp]
         L.pth_preset_next_f32.restype = C.c_float
         L.pth_preset_spheres.argtypes = [vp, vp, vp, vp]
+        L.pth_preset_motion.argtypes = [vp, vp]
         L.pth_preset_perlin.argtypes = [vp, C.POINTER(PtPerlin)]
         L.pth_preset_sky.argtypes = [vp, vp]
         L.pth_scene_create.argtypes = [vp, C.c_int32]

@@ -112,6 +112,8 @@ Material diffuse_light(const Texture* emit) { Material m; m.kind = Material::Dif
 namespace {
 struct Flattener {
     std::vector<float> cx, cy, cz, radius;
+    std::vector<PtMotion> motion;  // one per sphere; handed to the library only when some hitable moves
+    bool any_moving = false;
     std::vector<int32_t> material_index;
     std::vector<PtMaterial> materials;
     std::vector<PtTexture> textures;
@@ -163,12 +165,27 @@ struct Flattener {
 Scene::Scene(const std::vector<Hitable>& world, std::optional<Vec3> sky, int device) {
     Flattener fl;
     for (const Hitable& h : world) {
-        if (h.kind != Hitable::SphereKind || !h.sphere)  // spheres_soa.rs:49-51
+        PtMotion mo{};
+        if (h.kind == Hitable::MovingSphereKind && h.moving_sphere) {  // hitable.rs:17,52-58
+            const MovingSphere& ms = *h.moving_sphere;
+            fl.cx.push_back(ms.centre0().x);
+            fl.cy.push_back(ms.centre0().y);
+            fl.cz.push_back(ms.centre0().z);
+            fl.radius.push_back(ms.radius());
+            mo.centre1[0] = ms.centre1().x; mo.centre1[1] = ms.centre1().y; mo.centre1[2] = ms.centre1().z;
+            mo.time0 = ms.time0();
+            mo.time1 = ms.time1();
+            mo.moving = 1;
+            fl.any_moving = true;
+        } else if (h.kind == Hitable::SphereKind && h.sphere) {
+            fl.cx.push_back(h.sphere->centre().x);
+            fl.cy.push_back(h.sphere->centre().y);
+            fl.cz.push_back(h.sphere->centre().z);
+            fl.radius.push_back(h.sphere->radius());
+        } else {  // spheres_soa.rs:49-51
             throw std::runtime_error("Expected Hitable::Sphere, got " + (h.what.empty() ? std::string("<unknown>") : h.what));
-        fl.cx.push_back(h.sphere->centre().x);
-        fl.cy.push_back(h.sphere->centre().y);
-        fl.cz.push_back(h.sphere->centre().z);
-        fl.radius.push_back(h.sphere->radius());
+        }
+        fl.motion.push_back(mo);
         fl.material_index.push_back(fl.material_id(h.material));
     }
     PtSceneDesc d{};
@@ -184,6 +201,7 @@ Scene::Scene(const std::vector<Hitable>& world, std::optional<Vec3> sky, int dev
     d.n_textures = (uint32_t)fl.textures.size();
     d.textures = fl.textures.data();
     d.perlin = fl.perlin ? &fl.perlin->tables() : nullptr;
+    d.motion = fl.any_moving ? fl.motion.data() : nullptr;
     d.has_sky = sky.has_value() ? 1u : 0u;
     if (sky) { d.sky[0] = sky->x; d.sky[1] = sky->y; d.sky[2] = sky->z; }
     n_spheres_ = d.n_spheres;
@@ -232,8 +250,13 @@ Hitable sphere(Storage& st, Vec3 centre, float radius, Material m) {
 }
 const Texture* constant(Storage& st, Vec3 c) { return st.alloc_texture(texture::constant(c)); }
 
-// presets.rs:89-215 with only_spheres = true.  grid_half = 11 is the reference preset; 158 is stress100k.
-Preset random_impl(const Params& params, Xoshiro256Plus& rng, Storage& st, int grid_half) {
+Hitable moving_sphere(Storage& st, Vec3 centre0, Vec3 centre1, float radius, Material m) {  // presets.rs:122-127
+    return Hitable::make_moving_sphere(st.alloc_moving_sphere(MovingSphere(centre0, centre1, 0.0f, 1.0f, radius)), st.alloc_material(m));
+}
+
+// presets.rs:89-215.  only_spheres = true is `random_spheres`, false is `random` (the Lambertian spheres move).
+// grid_half = 11 is the reference preset; 158 is stress100k.
+Preset random_impl(const Params& params, Xoshiro256Plus& rng, Storage& st, int grid_half, bool only_spheres = true) {
     Camera camera = rtiow_camera(params, 0.1f, 1.0f);
     std::vector<Hitable> hitables;
     hitables.reserve((size_t)4 * grid_half * grid_half + 4);
@@ -247,14 +270,15 @@ Preset random_impl(const Params& params, Xoshiro256Plus& rng, Storage& st, int g
             const float z = (float)b + 0.9f * rng.gen_f32();
             const Vec3 centre(x, 0.2f, z);
             if (choose_material < 0.8f) {
-                rng.gen_f32();  // `centre1` (motion-blur end point) is drawn even for the static variant
+                const Vec3 centre1 = centre + Vec3(0.0f, 0.5f * rng.gen_f32(), 0.0f);  // drawn even for the static variant (presets.rs:150)
                 float ch[3];
                 for (float& c : ch) {
                     const float p = rng.gen_f32();
                     const float q = rng.gen_f32();
                     c = p * q;
                 }
-                hitables.push_back(sphere(st, centre, 0.2f, material::lambertian(constant(st, Vec3(ch[0], ch[1], ch[2])))));
+                const Material m = material::lambertian(constant(st, Vec3(ch[0], ch[1], ch[2])));
+                hitables.push_back(only_spheres ? sphere(st, centre, 0.2f, m) : moving_sphere(st, centre, centre1, 0.2f, m));
             } else if (choose_material < 0.95f) {
                 float ch[3];
                 for (float& c : ch) c = 0.5f * (1.0f + rng.gen_f32());
@@ -310,6 +334,7 @@ Preset smallpt(const Params& params, Storage& st) {  // presets.rs:853-930
 std::optional<Preset> from_name(const std::string& name, const Params& params, Xoshiro256Plus& rng, Storage& storage, bool quiet) {
     if (!quiet)  // presets.rs:19-22
         std::printf("generating '%s' preset at %ux%u with %u samples per pixel\n", name.c_str(), params.width, params.height, params.samples);
+    if (name == "random") return random_impl(params, rng, storage, 11, false);
     if (name == "random_spheres") return random_impl(params, rng, storage, 11);
     if (name == "stress100k") return random_impl(params, rng, storage, 158);
     if (name == "small") return small(params, storage);
@@ -472,14 +497,29 @@ void pth_preset_spheres(void* hv, float* centre_radius, int32_t* kind, float* pa
     auto* h = (PresetHandle*)hv;
     for (size_t i = 0; i < h->hitables.size(); ++i) {
         const auto& hit = h->hitables[i];
-        centre_radius[4 * i] = hit.sphere->centre().x; centre_radius[4 * i + 1] = hit.sphere->centre().y;
-        centre_radius[4 * i + 2] = hit.sphere->centre().z; centre_radius[4 * i + 3] = hit.sphere->radius();
+        const bool mv = hit.kind == pathtrace::Hitable::MovingSphereKind;
+        const pathtrace::Vec3 c0 = mv ? hit.moving_sphere->centre0() : hit.sphere->centre();
+        centre_radius[4 * i] = c0.x; centre_radius[4 * i + 1] = c0.y;
+        centre_radius[4 * i + 2] = c0.z; centre_radius[4 * i + 3] = mv ? hit.moving_sphere->radius() : hit.sphere->radius();
         const pathtrace::Material& m = *hit.material;
         kind[i] = m.kind;
         pathtrace::Vec3 c = m.albedo;
         if ((m.kind == pathtrace::Material::Lambertian || m.kind == pathtrace::Material::DiffuseLight) && m.albedo_tex->kind == pathtrace::Texture::Constant)
             c = m.albedo_tex->color;
         params5[5 * i] = c.x; params5[5 * i + 1] = c.y; params5[5 * i + 2] = c.z; params5[5 * i + 3] = m.fuzz; params5[5 * i + 4] = m.ref_idx;
+    }
+}
+// per sphere: centre1 (3), time0, time1, moving flag — same layout as the oracle's orc_scene_motion
+void pth_preset_motion(void* hv, float* out6) {
+    auto* h = (PresetHandle*)hv;
+    for (size_t i = 0; i < h->hitables.size(); ++i) {
+        const auto& hit = h->hitables[i];
+        const bool mv = hit.kind == pathtrace::Hitable::MovingSphereKind;
+        const pathtrace::Vec3 c1 = mv ? hit.moving_sphere->centre1() : hit.sphere->centre();
+        out6[6 * i] = c1.x; out6[6 * i + 1] = c1.y; out6[6 * i + 2] = c1.z;
+        out6[6 * i + 3] = mv ? hit.moving_sphere->time0() : 0.0f;
+        out6[6 * i + 4] = mv ? hit.moving_sphere->time1() : 0.0f;
+        out6[6 * i + 5] = mv ? 1.0f : 0.0f;
     }
 }
 void pth_preset_perlin(void* hv, PtPerlin* out) { *out = ((PresetHandle*)hv)->storage->perlin_noise.tables(); }

@@ -122,15 +122,33 @@ private:
     float radius_;
 };
 
+// src/collision/moving_sphere.rs:7-36
+class MovingSphere {
+public:
+    MovingSphere(Vec3 centre0, Vec3 centre1, float time0, float time1, float radius)  // MovingSphere::new
+        : centre0_(centre0), centre1_(centre1), time0_(time0), time1_(time1), radius_(radius) {}
+    Vec3 centre0() const { return centre0_; }
+    Vec3 centre1() const { return centre1_; }
+    float time0() const { return time0_; }
+    float time1() const { return time1_; }
+    float radius() const { return radius_; }
+
+private:
+    Vec3 centre0_, centre1_;
+    float time0_, time1_, radius_;
+};
+
 // src/collision/hitable.rs:12-21 — only the arms the GPU path accepts are constructible; anything else
 // is represented as `Unsupported` so the flattener can reject it the way spheres_soa.rs:49-51 panics.
 struct Hitable {
-    enum Kind { SphereKind, Unsupported } kind = SphereKind;
+    enum Kind { SphereKind, MovingSphereKind, Unsupported } kind = SphereKind;
     const Sphere* sphere = nullptr;
     const Material* material = nullptr;
     std::string what;  // name of the unsupported variant
-    static Hitable make_sphere(const Sphere* s, const Material* m) { return Hitable{SphereKind, s, m, {}}; }
-    static Hitable unsupported(std::string name) { return Hitable{Unsupported, nullptr, nullptr, std::move(name)}; }
+    const MovingSphere* moving_sphere = nullptr;
+    static Hitable make_sphere(const Sphere* s, const Material* m) { return Hitable{SphereKind, s, m, {}, nullptr}; }
+    static Hitable make_moving_sphere(const MovingSphere* s, const Material* m) { return Hitable{MovingSphereKind, nullptr, m, {}, s}; }
+    static Hitable unsupported(std::string name) { return Hitable{Unsupported, nullptr, nullptr, std::move(name), nullptr}; }
 };
 
 // src/storage.rs:12-96 — arenas (pointer-stable deques) + the one Perlin table
@@ -140,12 +158,14 @@ public:
     const Texture* alloc_texture(Texture t) { textures_.push_back(t); return &textures_.back(); }
     const Material* alloc_material(Material m) { materials_.push_back(m); return &materials_.back(); }
     const Sphere* alloc_sphere(Sphere s) { spheres_.push_back(s); return &spheres_.back(); }
+    const MovingSphere* alloc_moving_sphere(MovingSphere s) { moving_spheres_.push_back(s); return &moving_spheres_.back(); }
     Perlin perlin_noise;
 
 private:
     std::deque<Texture> textures_;
     std::deque<Material> materials_;
     std::deque<Sphere> spheres_;
+    std::deque<MovingSphere> moving_spheres_;
 };
 
 struct Params;
@@ -183,7 +203,7 @@ struct Params {
 
 namespace presets {
 using Preset = std::tuple<std::vector<Hitable>, Camera, std::optional<Vec3>>;
-// presets::from_name — sphere-only presets: random_spheres, small, two_perlin_spheres, smallpt, final,
+// presets::from_name — sphere-only presets: random (moving spheres), random_spheres, small, two_perlin_spheres, smallpt, final,
 // plus the synthetic stress100k.  Other names -> nullopt ("unrecognised preset").
 std::optional<Preset> from_name(const std::string& name, const Params& params, Xoshiro256Plus& rng, Storage& storage, bool quiet = false);
 }  // namespace presets

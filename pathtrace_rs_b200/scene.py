@@ -75,13 +75,15 @@ class Preset:
         kind = np.zeros(n, np.int32)
         p5 = np.zeros((n, 5), np.float32)
         self._L.pth_preset_spheres(self._h, _vp(cr), _vp(kind), _vp(p5))
+        motion = np.zeros((n, 6), np.float32)  # centre1 (3), time0, time1, moving flag (moving_sphere.rs:16-26)
+        self._L.pth_preset_motion(self._h, _vp(motion))
         per = ffi.PtPerlin()
         self._L.pth_preset_perlin(self._h, C.byref(per))
         sky = np.zeros(3, np.float32)
         has_sky = self._L.pth_preset_sky(self._h, _vp(sky))
         cam = self.camera
         cam24 = np.frombuffer(bytes(cam), dtype=np.float32).copy()
-        return dict(centre_radius=cr, kind=kind, params5=p5,
+        return dict(centre_radius=cr, kind=kind, params5=p5, motion=motion,
                     randvec=np.ctypeslib.as_array(per.randvec).reshape(256, 3).copy(),
                     perm=np.stack([np.ctypeslib.as_array(per.perm_x), np.ctypeslib.as_array(per.perm_y),
                                    np.ctypeslib.as_array(per.perm_z)]).copy(),

@@ -46,8 +46,8 @@ def lib():
         L.orc_update.argtypes = [C.c_void_p, C.POINTER(OrcParams), C.c_uint32, C.c_void_p, C.c_int32, C.c_int32,
                                  C.c_uint32, C.c_uint32]
         for name in ("orc_scene_counts", "orc_scene_spheres", "orc_scene_materials", "orc_scene_textures",
-                     "orc_scene_perlin", "orc_scene_camera", "orc_scene_sky"):
-            getattr(L, name).argtypes = [C.c_void_p] + [C.c_void_p] * {"orc_scene_counts": 3, "orc_scene_camera": 1}.get(name, 2)
+                     "orc_scene_perlin", "orc_scene_camera", "orc_scene_sky", "orc_scene_motion"):
+            getattr(L, name).argtypes = [C.c_void_p] + [C.c_void_p] * {"orc_scene_counts": 3, "orc_scene_camera": 1, "orc_scene_motion": 1}.get(name, 2)
         L.orc_rng_seed.argtypes = [C.c_uint64, C.c_void_p]
         L.orc_rng_u64.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         L.orc_rng_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
@@ -121,7 +121,9 @@ class Scene:
         hs = C.c_int32()
         sky = np.zeros(3, np.float32)
         lib().orc_scene_sky(self.h, C.byref(hs), _p(sky))
-        return dict(centre_radius=cr, sphere_material=mat, mat_kind_tex=mk, mat_albedo_fuzz_ref=mf,
+        motion = np.zeros((ns, 6), np.float32)  # centre1 (3), time0, time1, moving flag
+        lib().orc_scene_motion(self.h, _p(motion))
+        return dict(centre_radius=cr, sphere_material=mat, motion=motion, mat_kind_tex=mk, mat_albedo_fuzz_ref=mf,
                     tex_kind_odd_even=tk, tex_color_scale=tf, randvec=rv, perm=perm, camera=cam,
                     has_sky=int(hs.value), sky=sky)
 

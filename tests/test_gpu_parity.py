@@ -65,6 +65,42 @@ def test_cfg1_random_spheres_vs_oracle():
     assert st.kernel_launches == 1 and st.resident == 1 and st.n_spheres == 488 and st.ray_count == rays
 
 
+def test_random_preset_moving_spheres_vs_oracle():
+    """Preset `random` (presets.rs:150-172): the Lambertian spheres are Hitable::MovingSphere (moving_sphere.rs).
+    Bit-level against the oracle's hybrid mode (static spheres in the SoA form, moving ones in the live form of
+    moving_sphere.rs:38-73 — what the kernel computes), north-star tolerance against the list mode (the reference's path)."""
+    w, h, spp, depth = 160, 80, 32, 50
+    img, rays, pr = gpu_render("random", w, h, spp, depth)
+    sc = orc.Scene("random", w, h)
+    assert int(sc.flat()["motion"][:, 5].sum()) == 393
+    hyb, hyb_rays = sc.update(spp, depth, mode=SOA_ITER)
+    lst, lst_rays = sc.update(spp, depth, mode=orc.HIT_LIST)
+    assert np.mean(np.all(np.abs(img - hyb) < 1e-5, axis=2)) > 0.99
+    assert abs(rays - hyb_rays) <= 1e-3 * hyb_rays
+    assert rel_mean_diff(img, lst).max() < 5e-3
+    assert abs(rays - lst_rays) < 0.01 * lst_rays
+    # motion blur is really there: the same pixels of the static preset differ
+    still, _, _ = gpu_render("random_spheres", w, h, spp, depth)
+    assert np.mean(np.abs(img - still)) > 1e-3
+    # the LDS-streamed kernel takes the same path
+    st, st_rays, _ = _with_env("PTGPU_FORCE_STREAM_TILE_BLOCKS", "16", lambda: gpu_render("random", w, h, spp, depth))
+    assert st_rays == rays and np.array_equal(st, img)
+
+
+def test_moving_sphere_shutter_must_lie_inside_the_motion_interval():
+    """The pre-filter bounds a MovingSphere over its own [time0, time1]; a camera that samples times outside it is refused."""
+    params = pt.Params(32, 16, 1, 5)
+    pr = pt.Preset("random", params).create_scene(0)
+    L = ffi.libptgpu()
+    cam = pr.camera
+    cam.time1 = 2.0
+    buf = np.zeros((16, 32, 3), np.float32)
+    rays = C.c_uint64(0)
+    p = params.to_ffi()
+    rc = L.pt_render(pr.scene_handle, C.byref(p), C.byref(cam), 0, buf.ctypes.data_as(C.c_void_p), C.byref(rays))
+    assert rc == ffi.PT_ERR_UNSUPPORTED and b"shutter" in L.pt_last_error()
+
+
 def test_rmse_against_converged_reference():
     """RMSE(GPU, converged) <= 1.05 x RMSE(oracle at equal spp, converged).  The converged image is the oracle's
     equal-weight mean of 64 further frames x 256 spp (frame seeds differ: scene.rs:100), 16 384 spp in total."""
@@ -104,7 +140,7 @@ def test_cfg3_two_perlin_spheres_vs_oracle():
 
 
 @pytest.mark.parametrize("name", ["random_spheres_40x20_s8_d50", "two_perlin_spheres_40x20_s4_d50", "small_40x20_s8_d10",
-                                  "smallpt_32x32_s16_d10"])
+                                  "smallpt_32x32_s16_d10", "random_40x20_s8_d50"])
 def test_golden_fixtures(name):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     w, h, s, d = (int(g[k]) for k in ("width", "height", "samples", "max_depth"))

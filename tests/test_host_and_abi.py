@@ -14,7 +14,7 @@ import pathtrace_rs_b200 as pt
 from pathtrace_rs_b200 import ffi, parallel
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-PRESETS = ["random_spheres", "small", "two_perlin_spheres", "smallpt", "final", "stress100k"]
+PRESETS = ["random", "random_spheres", "small", "two_perlin_spheres", "smallpt", "final", "stress100k"]
 
 
 def _no_gpu():
@@ -27,7 +27,7 @@ def test_abi_symbols_exported():
     assert len(names) >= 15 and "pt_render" in names and "pt_scene_create" in names
     for n in names:
         assert hasattr(L, n), n
-    assert L.pt_abi_version() == 1
+    assert L.pt_abi_version() == 2
     out = subprocess.check_output(["nm", "-D", "--defined-only", os.path.join(ffi.LIB_DIR, "libptgpu.so")], text=True)
     exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
     assert set(names) <= exported
@@ -53,18 +53,10 @@ def test_library_is_sm100a_cuda_with_packed_fp32_and_tma():
     assert "sm_100a" in sass
     for mnemonic in ("FFMA2", "UBLKCP", "SYNCS"):
         assert mnemonic in sass, mnemonic
-    # The constant-bank sweep must read sphere pairs through the uniform datapath (LDCU -> UR operand of FFMA2).
-    # ptxas only does that for some control-flow shapes (DESIGN.md "uniform operands"); losing it halves the sweep's speed.
     import re
     kernels = re.split(r"Function : ", sass)
-    const = [k for k in kernels if k.startswith("_ZN2pt19pt_megakernel_constILi2E")]
-    assert const, "pt_megakernel_const<2> not found"
-    body = const[0]
-    assert len(re.findall(r"LDCU\.64 UR\d+, c\[0x3\]", body)) >= 12, "sphere operands are no longer uniform loads"
-    assert len(re.findall(r"FFMA2 R\d+, R\d+(?:\.reuse)?\.F32, UR\d+\.F32x2", body)) >= 20, "FFMA2 no longer takes the uniform sphere pair"
-    assert not re.search(r"LDC\.64 R\d+, c\[0x3\]", body), "per-thread constant loads in the sweep"
     # The LDS kernels' sweep: broadcast LDS.128 of the pre-filter image (not generic loads, not local memory) feeding FFMA2.
-    for name in ("_ZN2pt22pt_megakernel_resident", "_ZN2pt22pt_megakernel_streamed"):
+    for name in ("_ZN2pt22pt_megakernel_resident", "_ZN2pt22pt_megakernel_streamed"):  # mangled prefixes
         body = [k for k in kernels if k.startswith(name)]
         assert body, name
         assert len(re.findall(r"LDS\.128", body[0])) >= 8, name + ": sweep loads are not LDS.128"
@@ -77,6 +69,8 @@ def test_host_mirror_builds_the_oracles_scene(preset):
     host = pt.Preset(preset, pt.Params(w, h, 1, 10)).flat()
     o = orc.Scene(preset, w, h).flat()
     assert np.array_equal(host["centre_radius"], o["centre_radius"])
+    assert np.array_equal(host["motion"], o["motion"])  # MovingSphere end points / times / flags (moving_sphere.rs:16-26)
+    assert (host["motion"][:, 5].sum() > 0) == (preset == "random")
     assert np.array_equal(host["camera"], o["camera"])
     assert np.array_equal(host["randvec"], o["randvec"]) and np.array_equal(host["perm"], o["perm"])
     assert host["has_sky"] == o["has_sky"] and np.array_equal(host["sky"], o["sky"])

@@ -77,6 +77,40 @@ def test_random_spheres_census_and_draw_order():
     assert abs(orc.lib().orc_next_f32_after_random_spheres() - 0.17442238) < 1e-8
 
 
+def test_random_preset_moves_exactly_the_lambertian_spheres():
+    """presets.rs:150-172: `random` = `random_spheres` with the 393 small Lambertian spheres turned into MovingSphere
+    (same draws, same order); centre1 = centre + (0, 0.5*f32, 0), times 0..1 (presets.rs:122-127)."""
+    mv = orc.Scene("random", 200, 100).flat()
+    st = orc.Scene("random_spheres", 200, 100).flat()
+    assert np.array_equal(mv["centre_radius"], st["centre_radius"])
+    assert np.array_equal(mv["mat_albedo_fuzz_ref"], st["mat_albedo_fuzz_ref"]) and np.array_equal(mv["tex_color_scale"], st["tex_color_scale"])
+    moving = mv["motion"][:, 5] == 1
+    kinds = mv["mat_kind_tex"][mv["sphere_material"], 0]
+    small = np.abs(mv["centre_radius"][:, 3] - 0.2) < 1e-6
+    assert np.array_equal(moving, small & (kinds == orc.MAT_LAMBERTIAN)) and moving.sum() == 393
+    assert st["motion"][:, 5].sum() == 0
+    d = mv["motion"][moving, :3] - mv["centre_radius"][moving, :3]
+    assert np.all(d[:, 0] == 0) and np.all(d[:, 2] == 0) and np.all((d[:, 1] >= 0) & (d[:, 1] < 0.5 + 1e-6)) and d[:, 1].std() > 0.1
+    assert np.all(mv["motion"][moving, 3] == 0) and np.all(mv["motion"][moving, 4] == 1)
+
+
+def test_moving_spheres_list_vs_hybrid_modes():
+    """The hybrid SoA modes (static spheres: spheres_soa.rs form; moving: moving_sphere.rs:38-73) must see the same
+    scene as the in-order list walk: equal ray counts within grazing-ray noise, equal image within the statistical bar,
+    and motion blur must actually change the picture."""
+    w, h, spp, depth = 96, 48, 16, 50
+    sc = orc.Scene("random", w, h)
+    lst, lr = sc.update(spp, depth, mode=orc.HIT_LIST)
+    hyb, hr = sc.update(spp, depth, mode=orc.HIT_SOA_SCALAR)
+    assert abs(lr - hr) <= 0.01 * lr
+    assert np.mean(np.all(np.abs(lst - hyb) < 1e-4, axis=2)) > 0.9
+    if orc.lib().orc_has_avx2():
+        avx, ar = sc.update(spp, depth, mode=orc.HIT_SOA_AVX2)
+        assert ar == hr and np.array_equal(avx, hyb)
+    still, _ = orc.Scene("random_spheres", w, h).update(spp, depth, mode=orc.HIT_LIST)
+    assert np.mean(np.abs(lst - still)) > 1e-3
+
+
 def test_perlin_tables_seed0():
     f = orc.Scene("two_perlin_spheres", 64, 32).flat()
     np.testing.assert_allclose(f["randvec"][0], [0.53038144, -0.4601204, 0.71202856], rtol=1e-6)
@@ -248,7 +282,7 @@ def test_row_range_rendering_matches_full_image():
 
 # ---- (4) regression fixtures --------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["random_spheres_40x20_s8_d50", "two_perlin_spheres_40x20_s4_d50", "small_40x20_s8_d10",
-                                  "smallpt_32x32_s16_d10"])
+                                  "smallpt_32x32_s16_d10", "random_40x20_s8_d50"])
 def test_golden_regression(name):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     preset = str(g["preset"])
