@@ -198,9 +198,16 @@ __device__ __forceinline__ void sweep_expanded(const float4* __restrict__ pf, in
             for (int p = 0; p < 2 * kLdsGroupBlocks; ++p) any = any | (L[p].x > oo) | (L[p].y > oo);
         }
         if (any) {
+            // flag bits from sign bits: oo - L is negative exactly when L > oo (a float difference is zero only for equal
+            // operands), so one packed subtract per pair and one funnel shift per sphere build the mask — half the
+            // instructions of a compare + select + add per sphere.  Highest sphere first, so bit e = sphere e of the group.
             uint32_t mask = 0u;
 #pragma unroll
-            for (int p = 0; p < 2 * kLdsGroupBlocks; ++p) mask |= (L[p].x > oo ? 1u << (2 * p) : 0u) | (L[p].y > oo ? 2u << (2 * p) : 0u);
+            for (int p = 2 * kLdsGroupBlocks - 1; p >= 0; --p) {
+                const float2 d = f2_fma(L[p], make_float2(-1.0f, -1.0f), make_float2(oo, oo));
+                mask = __funnelshift_l(__float_as_uint(d.y), mask, 1);
+                mask = __funnelshift_l(__float_as_uint(d.x), mask, 1);
+            }
             const uint32_t entry = ((((uint32_t)first_block + ((addr - base) >> 6)) / kLdsGroupBlocks) << kLdsMaskBits) | mask;
             if (cnt < kQueueCap) {
                 q[cnt * kSweepThreads] = entry;
