@@ -1,5 +1,5 @@
 //! gpu.rs — `mod gpu;` in src/main.rs (feature "gpu").  Thin FFI over include/ptgpu.h: flattens a `Scene` whose world is
-//! a `Hitable::List` of spheres and forwards `Scene::update` to the CUDA library.  NOT compiled in this repository's CI
+//! a `Hitable::List` of spheres / moving spheres and forwards `Scene::update` to the CUDA library.  NOT compiled in this repository's CI
 //! (no Rust toolchain in the build image); the identical C ABI is exercised by the C++ mirror and the ctypes tests.
 //!
 //! Needs four small `pub(crate)` accessors in the reference:
@@ -27,7 +27,11 @@ pub struct PtSceneDesc {
     pub centre_x: *const f32, pub centre_y: *const f32, pub centre_z: *const f32, pub radius: *const f32, pub material_index: *const i32,
     pub n_materials: u32, pub n_textures: u32, pub materials: *const PtMaterial, pub textures: *const PtTexture, pub perlin: *const PtPerlin,
     pub has_sky: u32, pub sky: [f32; 3],
+    pub motion: *const PtMotion, // per sphere, or null when nothing moves
 }
+/// src/collision/moving_sphere.rs:16-26 inverted to its constructor arguments (centre0/radius travel in the sphere arrays)
+#[repr(C)] #[derive(Copy, Clone, Default)]
+pub struct PtMotion { pub centre1: [f32; 3], pub time0: f32, pub time1: f32, pub moving: u32 }
 #[repr(C)] pub struct PtScene { _private: [u8; 0] }
 
 extern "C" {
@@ -49,11 +53,13 @@ impl GpuScene {
     /// The GPU arm of `Params::new_scene` (src/params.rs:29-46): walk `Hitable::List`, reject anything that is not a sphere
     /// (same message as the panic in src/collision/spheres_soa.rs:49-51), dedupe arena pointers into indices, upload.
     pub fn new(scene: &Scene, perlin: &Perlin, device: i32) -> GpuScene {
-        assert_eq!(unsafe { pt_abi_version() }, 1);
+        assert_eq!(unsafe { pt_abi_version() }, 2);
         assert_eq!(unsafe { pt_abi_struct_size(5) } as usize, std::mem::size_of::<PtSceneDesc>());
         let hitables = match scene.world() { Hitable::List(list) => list.hitables(), other => panic!("Expected Hitable::List, got {:?}", other) };
         let (mut cx, mut cy, mut cz, mut radius, mut mat_index) = (vec![], vec![], vec![], vec![], vec![]);
         let (mut materials, mut textures): (Vec<PtMaterial>, Vec<PtTexture>) = (vec![], vec![]);
+        let mut motion: Vec<PtMotion> = vec![];
+        let mut any_moving = false;
         let mut mat_ids: HashMap<*const Material, i32> = HashMap::new();
         let mut tex_ids: HashMap<*const Texture, i32> = HashMap::new();
         let mut uses_noise = false;
@@ -72,8 +78,24 @@ impl GpuScene {
             id
         }
         for hitable in hitables {
-            if let Hitable::Sphere(sphere, material) = hitable {
-                cx.push(sphere.centre().x); cy.push(sphere.centre().y); cz.push(sphere.centre().z); radius.push(sphere.radius());
+            // Hitable::Sphere and Hitable::MovingSphere (src/collision/hitable.rs:16-17) are the two arms the GPU path takes.
+            // MovingSphere needs `pub(crate)` accessors centre0()/centre1()/time0()/time1() next to radius() (moving_sphere.rs:33-36).
+            let material = match hitable {
+                Hitable::Sphere(sphere, material) => {
+                    cx.push(sphere.centre().x); cy.push(sphere.centre().y); cz.push(sphere.centre().z); radius.push(sphere.radius());
+                    motion.push(PtMotion::default());
+                    Some(material)
+                }
+                Hitable::MovingSphere(ms, material) => {
+                    let (c0, c1) = (ms.centre0(), ms.centre1());
+                    cx.push(c0.x); cy.push(c0.y); cz.push(c0.z); radius.push(ms.radius());
+                    motion.push(PtMotion { centre1: [c1.x, c1.y, c1.z], time0: ms.time0(), time1: ms.time1(), moving: 1 });
+                    any_moving = true;
+                    Some(material)
+                }
+                _ => None,
+            };
+            if let Some(material) = material {
                 let key = *material as *const Material;
                 let id = *mat_ids.entry(key).or_insert_with(|| {
                     let mut f = PtMaterial { texture: -1, ..Default::default() };
@@ -105,6 +127,7 @@ impl GpuScene {
             n_materials: materials.len() as u32, n_textures: textures.len() as u32, materials: materials.as_ptr(), textures: textures.as_ptr(),
             perlin: tables.as_ref().map_or(ptr::null(), |t| &**t as *const PtPerlin),
             has_sky: sky.is_some() as u32, sky: sky.map_or([0.0; 3], |s| [s.x, s.y, s.z]),
+            motion: if any_moving { motion.as_ptr() } else { ptr::null() },
         };
         let mut handle: *mut PtScene = ptr::null_mut();
         let rc = unsafe { pt_scene_create(&desc, device, &mut handle) };
