@@ -303,6 +303,14 @@ def main():
             peak_probe = pt.probe_fp32_peak(local_rank)
         except Exception:
             peak_probe = None
+        traffic, traffic_note = None, "no ncu capture of this workload at this size is committed (profiles/ncu_traffic.json)"
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload)
+            if t and not reduced:
+                traffic = (t["dram_read_bytes"] + t["dram_write_bytes"]) * (1 if rows_mode or world == 1 else world)
+                traffic_note = "dram bytes read+written per launch, ncu --set full: %s; %s" % (t["source"], t["note"])
+        except (OSError, ValueError, KeyError):
+            pass
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -310,7 +318,7 @@ def main():
             "config": {"workload": workload_name(args.workload, spp) + (" [REDUCED spp]" if reduced else ""),
                        "n_spheres": n_spheres, "partition": ("rows: interleaved 4-row tiles, no collective" if rows_mode else
                                                              ("samples: one frame seed per GPU + one NCCL reduce" if world > 1 else "single GPU")),
-                       "l2": "flushed between timed iterations (256 MB fill); inputs are an 8 KB scene resident in shared memory",
+                       "l2": "flushed between timed iterations (256 MB fill); the scene is a %d KB pre-filter image %s" % (max(1, n_spheres * 16 // 1024), "resident in shared memory" if n_spheres * 16 < 200 * 1024 else "streamed from L2 in TMA tiles"),
                        "timing": "CUDA events per step on the launching stream, max over ranks"},
             "samples_per_s": samples_per_step * args.steps / (ms_max * 1e-3),
             "rays_per_sample": rays_sum / (samples_per_step * args.steps),
@@ -320,13 +328,13 @@ def main():
                             "pinned H2D -> pt_render_device -> NCCL reduce -> D2H on rank 0"},
             "gpu_launches": args.steps * world,
             "roofline": {"bound": "fp32_fma", "achieved": achieved / 1e12, "peak": peak_nominal / 1e12, "unit": "TFLOP/s",
-                         "frac": achieved / peak_nominal, "traffic": None,
+                         "frac": achieved / peak_nominal, "traffic": traffic, "traffic_unit": "bytes", "traffic_note": traffic_note,
                          "peak_source": "sm_count*128*2*max SM clock (%d SMs, %d MHz); MEASURED_PEAKS.json has no FP32 figure — "
                                         "a pure-FFMA probe kernel measured %s TFLOP/s on this GPU in this run"
                                         % (info.sm_count, info.sm_clock_khz // 1000, ("%.1f" % (peak_probe / 1e12)) if peak_probe else "n/a"),
                          "algorithmic": "16 flop x %d spheres x %d rays per launch (brute force, every ray tests every sphere)" % (n_spheres, int(k_rays_sum / k_steps)),
                          "kernel_ms": k_ms_max / k_steps,
-                         "note": "HBM traffic is 24 B/pixel/launch (accumulation buffer) — irrelevant; see profiles/ for dram bytes"},
+                         "note": "bound by the FP32 FMA pipe, not by HBM: algorithmic HBM bytes are 12-24 B/pixel/launch (accumulation buffer)"},
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -449,8 +449,18 @@ __global__ void PT_LDS_LAUNCH_BOUNDS pt_megakernel_resident(const __grid_constan
 // tiles are double-buffered with TMA bulk copies (full/empty mbarrier pair per buffer), so each trip of
 // the main loop streams the whole SoA once through L2 for every live lane of the CTA.
 // =====================================================================================================
+#ifdef PT_STREAM_NOPIPE
+constexpr bool kStreamPipe = false;
+#else
+constexpr bool kStreamPipe = true;  // LDS one block ahead (see sweep_expanded)
+#endif
+#ifdef PT_STREAM_MIN_CTAS
+#define PT_STREAM_LAUNCH_BOUNDS __launch_bounds__(kCtaThreads, PT_STREAM_MIN_CTAS)
+#else
+#define PT_STREAM_LAUNCH_BOUNDS __launch_bounds__(kCtaThreads)
+#endif
 template <bool MOTION>
-__global__ void PT_LDS_LAUNCH_BOUNDS pt_megakernel_streamed(const __grid_constant__ KernelArgs a) {
+__global__ void PT_STREAM_LAUNCH_BOUNDS pt_megakernel_streamed(const __grid_constant__ KernelArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[2];
     __shared__ __align__(8) uint64_t empty_bar[2];
@@ -533,7 +543,7 @@ __global__ void PT_LDS_LAUNCH_BOUNDS pt_megakernel_streamed(const __grid_constan
             __syncwarp();
             const int first = tile * a.tile_blocks;
             const int nb = min(a.tile_blocks, a.n_blocks - first);
-            sweep_expanded<true, MOTION>(tile_buf(b), nb, first, a.blocks, mc, queue, cnt, ox, oy, oz, dx, dy, dz, nod, ox + ox, oy + oy, oz + oz, oo, hit_t, hit_index);
+            sweep_expanded<kStreamPipe, MOTION>(tile_buf(b), nb, first, a.blocks, mc, queue, cnt, ox, oy, oz, dx, dy, dz, nod, ox + ox, oy + oy, oz + oz, oo, hit_t, hit_index);
             __syncwarp();
             if (lane_id == 0) mbar_arrive(&empty_bar[b]);
             if (threadIdx.x == 0 && tile + 2 < a.n_tiles) produce(tile + 2);

@@ -131,7 +131,9 @@ int plan_launch(PtScene* s) {
     }
     // streamed: two tile buffers; 2 CTAs per SM keeps the FP32 pipe fed while one CTA waits on a barrier
     s->resident = false;
-    const size_t per_cta = (kMaxDynSmem + 1024) / 2 - 2048;
+    int stream_ctas = 2;
+    if (const char* env = std::getenv("PTGPU_STREAM_CTAS")) stream_ctas = std::max(1, std::min(4, std::atoi(env)));  // tuning hook
+    const size_t per_cta = (kMaxDynSmem + 1024) / stream_ctas - 2048;
     const size_t tile_bytes = ((per_cta - perlin_bytes) / 2) & ~(size_t)1023;
     s->tile_blocks = (int)(tile_bytes / 64);
     s->n_tiles = (s->n_blocks + s->tile_blocks - 1) / s->tile_blocks;
