@@ -191,6 +191,16 @@ int pt_render_part(PtScene* scene, const PtParams* params, const PtCamera* camer
 int pt_render_device(PtScene* scene, const PtParams* params, const PtCamera* camera, uint32_t frame_num,
                      const PtPartition* part, float* d_rgb_inout, uint64_t* d_ray_count, void* cuda_stream);
 
+/* Progressive accumulation with the image RESIDENT on the device between calls — the worker loop of the windowed mode,
+ * src/glium_window.rs:96-131 (`ray_count += scene.update(&params, &camera, frame_num, &mut rgb_buffer); frame_num += 1`),
+ * without the per-frame upload/download of pt_render.  frame_num == 0 (re)starts the accumulation (scene.rs:86-87:
+ * mix_prev = 0); frame_num > 0 blends into the image the previous call left on the device and must follow it
+ * (same width/height, frame_num == previous + 1), otherwise PT_ERR_INVALID.  Either output may be NULL:
+ *   rgb_out   width*height*3 f32, bottom-up  — the accumulation buffer itself (what Scene::update leaves in `buffer`)
+ *   rgb8_out  width*height*3 u8, top-down sRGB — what the window uploads / offline.rs:43-51 writes                    */
+int pt_render_progressive(PtScene* scene, const PtParams* params, const PtCamera* camera, uint32_t frame_num, float* rgb_out,
+                          uint8_t* rgb8_out, uint64_t* ray_count_out);
+
 /* Output stage of `render_offline` (src/offline.rs:43-51 + src/math.rs:36-48): rows flipped to
  * top-down, linear -> sRGB (1.055*x^0.41666666-0.055, clamped, *255.99 truncated), packed RGB8.
  * Host-buffer and device-buffer forms. */

@@ -66,6 +66,9 @@ struct PtScene {
     size_t d_rgb_floats = 0;
     uint8_t* d_rgb8 = nullptr;
     size_t d_rgb8_bytes = 0;
+    // pt_render_progressive: what the resident image currently holds
+    bool prog_valid = false;
+    uint32_t prog_w = 0, prog_h = 0, prog_next_frame = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // launch geometry
@@ -640,6 +643,7 @@ int pt_render_part(PtScene* s, const PtParams* params, const PtCamera* camera, u
     if (rc != PT_OK) return rc;
 
     s->stats = PtRenderStats{};
+    s->prog_valid = false;  // this call reuses the scene's device image
     uint64_t h2d = 0, d2h = 0;
     PT_CUDA(cudaEventRecord(s->ev[0], s->stream));
     if (frame_num != 0) {  // the blend reads the previous frame (scene.rs:114-116); frame 0 has mix_prev = 0
@@ -672,6 +676,62 @@ int pt_render_part(PtScene* s, const PtParams* params, const PtCamera* camera, u
 
 int pt_render(PtScene* s, const PtParams* params, const PtCamera* camera, uint32_t frame_num, float* rgb_inout, uint64_t* ray_count_out) {
     return pt_render_part(s, params, camera, frame_num, nullptr, rgb_inout, ray_count_out);
+}
+
+int pt_render_progressive(PtScene* s, const PtParams* params, const PtCamera* camera, uint32_t frame_num, float* rgb_out, uint8_t* rgb8_out,
+                          uint64_t* ray_count_out) {
+    if (!s) return fail(PT_ERR_INVALID, "null scene");
+    int rc = validate_params(params, camera);
+    if (rc != PT_OK) return rc;
+    if (frame_num != 0 && !(s->prog_valid && s->prog_w == params->width && s->prog_h == params->height && s->prog_next_frame == frame_num))
+        return fail(PT_ERR_INVALID, "frame %u does not continue the resident accumulation (have %ux%u, next frame %u)", frame_num, s->prog_w,
+                    s->prog_h, s->prog_valid ? s->prog_next_frame : 0u);
+    PT_CUDA(cudaSetDevice(s->device));
+    const size_t n = (size_t)params->width * params->height;
+    s->prog_valid = false;  // any failure below leaves the resident image undefined
+    rc = ensure_image(s, n * 3);
+    if (rc != PT_OK) return rc;
+    const PtPartition whole{4, 0, 1, 0};
+    s->stats = PtRenderStats{};
+    PT_CUDA(cudaEventRecord(s->ev[1], s->stream));
+    rc = launch_update(s, params, camera, frame_num, whole, s->d_rgb, s->d_ray_count, s->stream);
+    if (rc != PT_OK) return rc;
+    PT_CUDA(cudaEventRecord(s->ev[2], s->stream));
+    uint64_t d2h = 0;
+    if (rgb_out) {
+        PT_CUDA(cudaMemcpyAsync(rgb_out, s->d_rgb, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+        d2h += n * 3 * sizeof(float);
+    }
+    if (rgb8_out) {
+        if (s->d_rgb8_bytes < n * 3) {
+            if (s->d_rgb8) cudaFree(s->d_rgb8);
+            s->d_rgb8 = nullptr;
+            s->d_rgb8_bytes = 0;
+            PT_CUDA(cudaMalloc(&s->d_rgb8, n * 3));
+            s->d_rgb8_bytes = n * 3;
+        }
+        rc = pt_srgb8_device(s, s->d_rgb, params->width, params->height, s->d_rgb8, s->stream);
+        if (rc != PT_OK) return rc;
+        PT_CUDA(cudaMemcpyAsync(rgb8_out, s->d_rgb8, n * 3, cudaMemcpyDeviceToHost, s->stream));
+        d2h += n * 3;
+    }
+    unsigned long long rays = 0;
+    PT_CUDA(cudaMemcpyAsync(&rays, s->d_ray_count, sizeof(rays), cudaMemcpyDeviceToHost, s->stream));
+    PT_CUDA(cudaEventRecord(s->ev[3], s->stream));
+    PT_CUDA(cudaStreamSynchronize(s->stream));
+    float ms = 0;
+    PT_CUDA(cudaEventElapsedTime(&ms, s->ev[1], s->ev[2]));
+    s->stats.kernel_ms = ms;
+    PT_CUDA(cudaEventElapsedTime(&ms, s->ev[2], s->ev[3]));
+    s->stats.d2h_ms = ms;
+    s->stats.d2h_bytes = d2h + sizeof(rays);
+    s->stats.ray_count = rays;
+    if (ray_count_out) *ray_count_out = rays;
+    s->prog_valid = true;
+    s->prog_w = params->width;
+    s->prog_h = params->height;
+    s->prog_next_frame = frame_num + 1;
+    return PT_OK;
 }
 
 int pt_render_device(PtScene* s, const PtParams* params, const PtCamera* camera, uint32_t frame_num, const PtPartition* part_in,
@@ -712,6 +772,7 @@ int pt_srgb8(PtScene* s, const float* rgb, uint32_t width, uint32_t height, uint
         PT_CUDA(cudaMalloc(&s->d_rgb8, n * 3));
         s->d_rgb8_bytes = n * 3;
     }
+    s->prog_valid = false;  // this call reuses the scene's device image
     PT_CUDA(cudaMemcpyAsync(s->d_rgb, rgb, n * 3 * sizeof(float), cudaMemcpyHostToDevice, s->stream));
     rc = pt_srgb8_device(s, s->d_rgb, width, height, s->d_rgb8, s->stream);
     if (rc != PT_OK) return rc;

@@ -119,6 +119,7 @@ def libptgpu():
         L.pt_render.argtypes = [vp, C.POINTER(PtParams), C.POINTER(PtCamera), C.c_uint32, vp, C.POINTER(C.c_uint64)]
         L.pt_render_part.argtypes = [vp, C.POINTER(PtParams), C.POINTER(PtCamera), C.c_uint32, C.POINTER(PtPartition), vp,
                                      C.POINTER(C.c_uint64)]
+        L.pt_render_progressive.argtypes = [vp, C.POINTER(PtParams), C.POINTER(PtCamera), C.c_uint32, vp, vp, C.POINTER(C.c_uint64)]
         L.pt_render_device.argtypes = [vp, C.POINTER(PtParams), C.POINTER(PtCamera), C.c_uint32, C.POINTER(PtPartition), vp, vp, vp]
         L.pt_srgb8.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp]
         L.pt_srgb8_device.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, vp]

@@ -117,6 +117,19 @@ class Preset:
             raise RuntimeError(self._L.pth_last_error().decode())
         return buffer, int(rays.value)
 
+    def update_progressive(self, params, frame_num, want_rgb=False, want_rgb8=False):
+        """pt_render_progressive: the windowed worker loop (glium_window.rs:96-131) with the accumulation buffer resident on
+        the device.  Returns (rgb or None, rgb8 or None, ray_count)."""
+        L = ffi.libptgpu()
+        p = params.to_ffi()
+        cam = self.camera
+        rgb = np.zeros((params.height, params.width, 3), np.float32) if want_rgb else None
+        rgb8 = np.zeros((params.height, params.width, 3), np.uint8) if want_rgb8 else None
+        rays = C.c_uint64(0)
+        ffi.check(L.pt_render_progressive(self.scene_handle, C.byref(p), C.byref(cam), frame_num, _vp(rgb) if want_rgb else None,
+                                          _vp(rgb8) if want_rgb8 else None, C.byref(rays)))
+        return rgb, rgb8, int(rays.value)
+
     def update_device(self, params, frame_num, d_rgb_ptr, d_rays_ptr, stream_ptr=0, part=None):
         """pt_render_device: device-resident buffers (torch tensors' data_ptr()), asynchronous on `stream_ptr`."""
         L = ffi.libptgpu()

@@ -154,6 +154,35 @@ def test_golden_fixtures(name):
 
 
 # ---- Scene::update semantics -------------------------------------------------------------------------------------
+def test_progressive_resident_accumulation_equals_host_round_trips():
+    """pt_render_progressive (the windowed worker loop, glium_window.rs:96-131) keeps the accumulation buffer on the device;
+    it must leave exactly the image that Scene::update round-tripping a host buffer leaves, frame after frame."""
+    w, h, spp, depth = 96, 48, 4, 20
+    params = pt.Params(w, h, spp, depth)
+    pr = pt.Preset("random_spheres", params).create_scene(0)
+    host = np.zeros((h, w, 3), np.float32)
+    for f in range(4):
+        pr.update(params, frame_num=f, buffer=host)
+    pr2 = pt.Preset("random_spheres", params).create_scene(0)
+    total = 0
+    for f in range(4):
+        rgb, rgb8, rays = pr2.update_progressive(params, f, want_rgb=(f == 3), want_rgb8=(f == 3))
+        total += rays
+        st = pr2.stats()
+        assert st.h2d_bytes == 0 and st.d2h_bytes == (8 if f < 3 else 8 + w * h * 12 + w * h * 3)
+    assert np.array_equal(rgb, host)
+    assert np.array_equal(rgb8, pr.srgb8(host))  # row flip + sRGB, offline.rs:43-51
+    assert w * h * spp * 4 <= total
+    # a frame that does not continue the resident image is refused, and so is one after the image was reused
+    L = ffi.libptgpu()
+    p, cam, rays = params.to_ffi(), pr2.camera, C.c_uint64(0)
+    assert L.pt_render_progressive(pr2.scene_handle, C.byref(p), C.byref(cam), 7, None, None, C.byref(rays)) == ffi.PT_ERR_INVALID
+    pr2.update_progressive(params, 4)
+    pr2.update(params, frame_num=0, buffer=np.zeros((h, w, 3), np.float32))
+    assert L.pt_render_progressive(pr2.scene_handle, C.byref(p), C.byref(cam), 5, None, None, C.byref(rays)) == ffi.PT_ERR_INVALID
+
+
+
 def test_frame_blending_matches_reference_formula():
     w, h, spp, depth = 64, 32, 4, 10
     params = pt.Params(w, h, spp, depth)
