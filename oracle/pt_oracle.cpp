@@ -971,6 +971,38 @@ void* orc_scene_build(const char* preset, const OrcParams* p) {
     return orc::build_preset(preset, pp);
 }
 void orc_scene_free(void* h) { delete (orc::Scene*)h; }
+
+// A scene from flat arrays (randomised-scene parity tests): per sphere centre(3)+radius, material kind, colour(3)+fuzz+
+// ref_idx (Lambertian/DiffuseLight get a Constant texture of that colour), optional motion rows (centre1(3), time0,
+// time1, moving flag) and a Camera::new argument list: lookfrom(3), lookat(3), vup(3), vfov, aspect, aperture,
+// focus_dist, time0, time1 (camera.rs:22-32).  sky3 == nullptr means the default gradient (scene.rs:43-46).
+void* orc_scene_custom(int32_t n, const float* centre_radius, const int32_t* kind, const float* params5, const float* motion6,
+                       const float* cam15, const float* sky3) {
+    using namespace orc;
+    Scene* s = new Scene();
+    Rng rng = Rng::seed_from_u64(0);
+    s->perlin.init(rng);
+    for (int32_t i = 0; i < n; ++i) {
+        const float* p5 = params5 + 5 * i;
+        int32_t tex = -1;
+        if (kind[i] == MAT_LAMBERTIAN || kind[i] == MAT_DIFFUSE_LIGHT) tex = add_tex_constant(*s, v3(p5[0], p5[1], p5[2]));
+        const int32_t m = add_mat(*s, kind[i], tex, v3(p5[0], p5[1], p5[2]), p5[3], p5[4]);
+        const V3 c = v3(centre_radius[4 * i], centre_radius[4 * i + 1], centre_radius[4 * i + 2]);
+        if (motion6 && motion6[6 * i + 5] != 0.0f)
+            add_moving_sphere(*s, c, v3(motion6[6 * i], motion6[6 * i + 1], motion6[6 * i + 2]), motion6[6 * i + 3], motion6[6 * i + 4],
+                              centre_radius[4 * i + 3], m);
+        else
+            add_sphere(*s, c, centre_radius[4 * i + 3], m);
+    }
+    s->camera = camera_new(v3(cam15[0], cam15[1], cam15[2]), v3(cam15[3], cam15[4], cam15[5]), v3(cam15[6], cam15[7], cam15[8]), cam15[9],
+                           cam15[10], cam15[11], cam15[12], cam15[13], cam15[14]);
+    if (sky3) {
+        s->has_sky = true;
+        s->sky = v3(sky3[0], sky3[1], sky3[2]);
+    }
+    s->build_soa();
+    return s;
+}
 int32_t orc_scene_counts(void* h, int32_t* n_spheres, int32_t* n_materials, int32_t* n_textures) {
     auto* s = (orc::Scene*)h;
     *n_spheres = (int32_t)s->spheres.size();

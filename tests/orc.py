@@ -42,6 +42,8 @@ def lib():
         L.orc_scene_build.restype = C.c_void_p
         L.orc_scene_build.argtypes = [C.c_char_p, C.POINTER(OrcParams)]
         L.orc_scene_free.argtypes = [C.c_void_p]
+        L.orc_scene_custom.restype = C.c_void_p
+        L.orc_scene_custom.argtypes = [C.c_int32] + [C.c_void_p] * 6
         L.orc_update.restype = C.c_uint64
         L.orc_update.argtypes = [C.c_void_p, C.POINTER(OrcParams), C.c_uint32, C.c_void_p, C.c_int32, C.c_int32,
                                  C.c_uint32, C.c_uint32]
@@ -78,9 +80,17 @@ def params(width, height, samples, max_depth):
 class Scene:
     """A preset built by the oracle's restatement of presets.rs (scene rng seed 0)."""
 
-    def __init__(self, preset, width, height, samples=1, max_depth=50):
+    def __init__(self, preset, width, height, samples=1, max_depth=50, custom=None):
         self.preset = preset
         self.p = params(width, height, samples, max_depth)
+        if custom is not None:
+            # custom = dict(centre_radius[n,4], kind[n], params5[n,5], motion[n,6] or None, cam15[15], sky[3] or None)
+            self._keep = {k: (None if v is None else np.ascontiguousarray(v, np.int32 if k == "kind" else np.float32)) for k, v in custom.items()}
+            k = self._keep
+            ptr = lambda a: None if a is None else _p(a)
+            self.h = lib().orc_scene_custom(len(k["kind"]), ptr(k["centre_radius"]), ptr(k["kind"]), ptr(k["params5"]), ptr(k.get("motion")),
+                                            ptr(k["cam15"]), ptr(k.get("sky")))
+            return
         self.h = lib().orc_scene_build(preset.encode(), C.byref(self.p))
         if not self.h:
             raise ValueError("unrecognised preset " + preset)

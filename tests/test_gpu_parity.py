@@ -374,6 +374,101 @@ def test_errors():
         pt.Preset("small", pt.Params(16, 8, 1, 1)).create_scene(99)
 
 
+# ---- randomised scenes straight through the C ABI (ragged sphere counts, hollow / huge / moving spheres, every material) ----
+def _random_scene(seed, n, moving=False, sky=False):
+    r = np.random.default_rng(seed)
+    cr = np.zeros((n, 4), np.float32)
+    cr[:, 0] = r.uniform(-4, 4, n)
+    cr[:, 1] = r.uniform(-1, 2, n)
+    cr[:, 2] = r.uniform(-6, 1, n)
+    cr[:, 3] = r.uniform(0.1, 0.7, n)
+    kind = r.integers(0, 4, n).astype(np.int32)
+    kind[kind == 3] = np.where(r.uniform(size=(kind == 3).sum()) < 0.5, 3, 0)  # fewer lights
+    p5 = np.zeros((n, 5), np.float32)
+    p5[:, :3] = r.uniform(0.1, 0.95, (n, 3))
+    p5[:, 3] = r.uniform(0, 0.5, n)
+    p5[:, 4] = 1.5
+    if n > 0:  # a big ground sphere, as every reference preset has (the cancellation-heavy case of the pre-filter)
+        cr[0] = [0, -1000.5, -1, 1000]
+        kind[0] = 0
+    if n > 2:  # a hollow glass shell: negative radius flips the normal (presets.rs:265)
+        cr[1] = [0.3, 0.2, -1.5, 0.5]; kind[1] = 2
+        cr[2] = [0.3, 0.2, -1.5, -0.45]; kind[2] = 2
+    motion = None
+    if moving and n > 3:
+        motion = np.zeros((n, 6), np.float32)
+        motion[:, :3] = cr[:, :3]
+        mv = r.uniform(size=n) < 0.4
+        mv[:3] = False
+        motion[mv, :3] += r.uniform(-0.4, 0.4, (int(mv.sum()), 3)).astype(np.float32)
+        motion[mv, 3], motion[mv, 4], motion[mv, 5] = -0.5, 1.5, 1.0
+    cam15 = np.array([1.5, 1.2, 3.0, 0, 0.2, -1.5, 0, 1, 0, 45.0, 1.5, 0.08, 4.5, 0.0, 1.0], np.float32)
+    return dict(centre_radius=cr, kind=kind, params5=p5, motion=motion, cam15=cam15, sky=np.array([0.7, 0.8, 1.0], np.float32) if sky else None)
+
+
+def _gpu_render_custom(custom, cam24, w, h, spp, depth):
+    L = ffi.libptgpu()
+    n = len(custom["kind"])
+    cr = custom["centre_radius"]
+    cols = [np.ascontiguousarray(cr[:, i]) for i in range(4)] if n else [np.zeros(1, np.float32)] * 4
+    mats = (ffi.PtMaterial * max(n, 1))()
+    texs = (ffi.PtTexture * max(n, 1))()
+    midx = np.arange(max(n, 1), dtype=np.int32)
+    for i in range(n):
+        k, p5 = int(custom["kind"][i]), custom["params5"][i]
+        mats[i].kind, mats[i].texture = k, (i if k in (0, 3) else -1)
+        mats[i].albedo[:] = [float(x) for x in p5[:3]]
+        mats[i].fuzz, mats[i].ref_idx = float(p5[3]), float(p5[4])
+        texs[i].kind, texs[i].odd, texs[i].even = ffi.PT_TEX_CONSTANT if hasattr(ffi, "PT_TEX_CONSTANT") else 0, -1, -1
+        texs[i].color[:] = [float(x) for x in p5[:3]]
+    d = ffi.PtSceneDesc()
+    d.struct_size, d.n_spheres = C.sizeof(ffi.PtSceneDesc), n
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    d.centre_x, d.centre_y, d.centre_z, d.radius = fp(cols[0]), fp(cols[1]), fp(cols[2]), fp(cols[3])
+    d.material_index = midx.ctypes.data_as(C.POINTER(C.c_int32))
+    d.n_materials = d.n_textures = n
+    d.materials, d.textures = mats, texs
+    if custom.get("sky") is not None:
+        d.has_sky = 1
+        d.sky[:] = [float(x) for x in custom["sky"]]
+    mot = None
+    if custom.get("motion") is not None:
+        mot = (ffi.PtMotion * n)()
+        for i in range(n):
+            m = custom["motion"][i]
+            mot[i].centre1[:] = [float(x) for x in m[:3]]
+            mot[i].time0, mot[i].time1, mot[i].moving = float(m[3]), float(m[4]), int(m[5])
+        d.motion = mot
+    scene = C.c_void_p()
+    ffi.check(L.pt_scene_create(C.byref(d), 0, C.byref(scene)))
+    try:
+        cam = ffi.PtCamera.from_buffer_copy(np.ascontiguousarray(cam24, np.float32).tobytes())
+        p = pt.Params(w, h, spp, depth).to_ffi()
+        img = np.zeros((h, w, 3), np.float32)
+        rays = C.c_uint64(0)
+        ffi.check(L.pt_render(scene, C.byref(p), C.byref(cam), 0, img.ctypes.data_as(C.c_void_p), C.byref(rays)))
+        return img, int(rays.value)
+    finally:
+        L.pt_scene_destroy(scene)
+
+
+@pytest.mark.parametrize("n,moving,sky", [(0, False, False), (1, False, True), (3, False, False), (4, False, False), (5, True, False),
+                                          (15, False, True), (16, True, False), (17, True, True), (63, False, False), (64, True, False),
+                                          (65, True, False), (333, True, True)])
+def test_random_scenes_through_the_c_abi(n, moving, sky):
+    """pt_scene_create / pt_render on scenes that are not presets: sphere counts around the block (4) and group (16) sizes,
+    a 1000-radius ground, a hollow glass shell (negative radius), lights, moving spheres with a [-0.5, 1.5] motion interval
+    around the camera's [0, 1] shutter, constant sky or gradient.  Same arithmetic as the oracle's SoA/hybrid mode."""
+    w, h, spp, depth = 61, 37, 6, 12  # ragged image: neither dimension a multiple of the row tile or the warp
+    custom = _random_scene(1000 + n, n, moving, sky)
+    sc = orc.Scene("custom", w, h, custom=custom)
+    ref, ref_rays = sc.update(spp, depth, mode=SOA_ITER)
+    img, rays = _gpu_render_custom(custom, sc.flat()["camera"], w, h, spp, depth)
+    assert abs(rays - ref_rays) <= max(2, 1e-3 * ref_rays)
+    assert np.mean(np.all(np.abs(img - ref) <= 1e-5 * np.maximum(1.0, np.abs(ref)), axis=2)) > 0.99
+    assert np.isfinite(img).all()
+
+
 # ---- BASELINE sizes: size-independent properties ------------------------------------------------------------------------
 def test_cfg2_full_size_properties():
     """random_spheres 1200x800, 1024 spp, depth 50 (BASELINE config 2) — the whole job, checked through properties
