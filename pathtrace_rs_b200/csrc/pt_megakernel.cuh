@@ -343,7 +343,10 @@ __device__ __forceinline__ void stage_perlin(const KernelArgs& a, PerlinSmem* P)
     }
 }
 
-constexpr int kCtaThreads = 256;
+#ifndef PT_CTA_THREADS
+#define PT_CTA_THREADS 256
+#endif
+constexpr int kCtaThreads = PT_CTA_THREADS;
 
 
 // Optional phase profile (compile with -DPT_PROFILE; tools/phase_profile.py): per-warp clock64 deltas of the
@@ -364,6 +367,99 @@ __device__ unsigned long long g_prof[8];  // 0 refill clk, 1 sweep clk, 2 shade 
 
 
 // =====================================================================================================
+// CTA-level regrouping of paths by what they do next.
+//
+// After the sweep the 256 lanes of a CTA are about to run different code: Lambertian / textured Lambertian / metal /
+// dielectric scatter, or end their path (miss, light, depth limit) and start a new sample at the next refill.  Left in
+// place, every warp executes the union of those branches with a quarter of its lanes (ncu, cfg2: 8.5 of 32 lanes active
+// outside the sweep).  Lanes are interchangeable — a lane is only the register home of one path's state — so once per
+// trip the CTA counting-sorts its paths by category through shared memory: ballots give each lane its rank inside its
+// warp, one shared-memory atomicAdd per (warp, category) reserves the warp's range inside the category, and the whole
+// path state (30 words) is written to its new slot and read back by the thread that now owns it.  Every path still
+// consumes exactly its own RNG stream and performs exactly the same arithmetic, so images stay bit-identical; only the
+// assignment of paths to lanes changes.  Finished lanes collect in whole warps, which then skip the sweep.
+// =====================================================================================================
+#ifndef PT_REGROUP
+#define PT_REGROUP 1
+#endif
+constexpr int kRegroupCats = 6;
+constexpr int kRegroupWords = 28;  // 8 rng + 6 ray + 3 thr + 3 col + px, py, sample, depth, flags, hit_t, hit_index, time
+enum { CAT_LAMBERT_CONST = 0, CAT_LAMBERT_TEX = 1, CAT_METAL = 2, CAT_DIELECTRIC = 3, CAT_ENDING = 4, CAT_IDLE = 5 };
+
+__device__ __forceinline__ int lane_category(const KernelArgs& a, const Lane& L, int hit_index) {
+    if (!L.active) return CAT_IDLE;
+    if (hit_index < 0 || L.depth >= a.max_depth) return CAT_ENDING;
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(a.shade + hit_index) + 1);
+    const int kind = __float_as_int(s1.y);
+    if (kind == MAT_LAMBERTIAN) return __float_as_int(s1.z) < 0 ? CAT_LAMBERT_CONST : CAT_LAMBERT_TEX;
+    if (kind == MAT_METAL) return CAT_METAL;
+    if (kind == MAT_DIELECTRIC) return CAT_DIELECTRIC;
+    return CAT_ENDING;  // DiffuseLight
+}
+
+// xchg: [kRegroupWords][kCtaThreads] words; cat_count: this trip's [kRegroupCats] counters (two sets alternate: the set
+// used by trip t is cleared after trip t's second barrier and next touched after trip t+1's first barrier).
+// Two CTA barriers per trip; the second also ORs "some lane still has work" over the CTA and returns it.  Trip t+1's
+// first barrier separates trip t's reads of xchg from trip t+1's writes.
+__device__ __forceinline__ bool cta_regroup(const KernelArgs& a, Lane& L, float& hit_t, int& hit_index, volatile uint32_t* pend,
+                                            volatile float* tslot, uint32_t* __restrict__ xchg, uint32_t* __restrict__ cat_count,
+                                            unsigned lane_id) {
+    const int cat = lane_category(a, L, hit_index);
+    unsigned mine = 0u;     // ballot of this lane's category
+    unsigned warp_off = 0u;  // where this warp's lanes of that category start inside the category
+#pragma unroll
+    for (int c = 0; c < kRegroupCats; ++c) {
+        const unsigned b = __ballot_sync(kFullMask, cat == c);
+        unsigned off = 0u;
+        if (lane_id == 0u && b != 0u) off = atomicAdd(&cat_count[c], (unsigned)__popc(b));
+        off = __shfl_sync(kFullMask, off, 0);
+        if (cat == c) {
+            mine = b;
+            warp_off = off;
+        }
+    }
+    __syncthreads();  // all counts are final
+    unsigned base = 0u;
+#pragma unroll
+    for (int c = 0; c < kRegroupCats - 1; ++c) base += (c < cat) ? cat_count[c] : 0u;
+    const unsigned dest = base + warp_off + (unsigned)__popc(mine & ((1u << lane_id) - 1u));
+    uint32_t* w = xchg + dest;
+    const uint32_t flags = (L.active ? 1u : 0u) | (L.have_pixel ? 2u : 0u) | (L.finished ? 4u : 0u) | (*pend != 0u ? 8u : 0u);
+    w[0 * kCtaThreads] = (uint32_t)L.rng.s0;  w[1 * kCtaThreads] = (uint32_t)(L.rng.s0 >> 32);
+    w[2 * kCtaThreads] = (uint32_t)L.rng.s1;  w[3 * kCtaThreads] = (uint32_t)(L.rng.s1 >> 32);
+    w[4 * kCtaThreads] = (uint32_t)L.rng.s2;  w[5 * kCtaThreads] = (uint32_t)(L.rng.s2 >> 32);
+    w[6 * kCtaThreads] = (uint32_t)L.rng.s3;  w[7 * kCtaThreads] = (uint32_t)(L.rng.s3 >> 32);
+    w[8 * kCtaThreads] = __float_as_uint(L.o.x);  w[9 * kCtaThreads] = __float_as_uint(L.o.y);  w[10 * kCtaThreads] = __float_as_uint(L.o.z);
+    w[11 * kCtaThreads] = __float_as_uint(L.d.x); w[12 * kCtaThreads] = __float_as_uint(L.d.y); w[13 * kCtaThreads] = __float_as_uint(L.d.z);
+    w[14 * kCtaThreads] = __float_as_uint(L.thr.x); w[15 * kCtaThreads] = __float_as_uint(L.thr.y); w[16 * kCtaThreads] = __float_as_uint(L.thr.z);
+    w[17 * kCtaThreads] = __float_as_uint(L.col.x); w[18 * kCtaThreads] = __float_as_uint(L.col.y); w[19 * kCtaThreads] = __float_as_uint(L.col.z);
+    w[20 * kCtaThreads] = L.px;  w[21 * kCtaThreads] = L.py;  w[22 * kCtaThreads] = L.sample;  w[23 * kCtaThreads] = L.depth;
+    w[24 * kCtaThreads] = flags;
+    w[25 * kCtaThreads] = __float_as_uint(hit_t);
+    w[26 * kCtaThreads] = (uint32_t)hit_index;
+    w[27 * kCtaThreads] = __float_as_uint(*tslot);
+    const bool live = __syncthreads_or(L.finished ? 0 : 1) != 0;  // every path is in its new slot
+    if (threadIdx.x < kRegroupCats) cat_count[threadIdx.x] = 0u;
+    const uint32_t* r = xchg + threadIdx.x;
+    L.rng.s0 = (uint64_t)r[0 * kCtaThreads] | ((uint64_t)r[1 * kCtaThreads] << 32);
+    L.rng.s1 = (uint64_t)r[2 * kCtaThreads] | ((uint64_t)r[3 * kCtaThreads] << 32);
+    L.rng.s2 = (uint64_t)r[4 * kCtaThreads] | ((uint64_t)r[5 * kCtaThreads] << 32);
+    L.rng.s3 = (uint64_t)r[6 * kCtaThreads] | ((uint64_t)r[7 * kCtaThreads] << 32);
+    L.o = v3(__uint_as_float(r[8 * kCtaThreads]), __uint_as_float(r[9 * kCtaThreads]), __uint_as_float(r[10 * kCtaThreads]));
+    L.d = v3(__uint_as_float(r[11 * kCtaThreads]), __uint_as_float(r[12 * kCtaThreads]), __uint_as_float(r[13 * kCtaThreads]));
+    L.thr = v3(__uint_as_float(r[14 * kCtaThreads]), __uint_as_float(r[15 * kCtaThreads]), __uint_as_float(r[16 * kCtaThreads]));
+    L.col = v3(__uint_as_float(r[17 * kCtaThreads]), __uint_as_float(r[18 * kCtaThreads]), __uint_as_float(r[19 * kCtaThreads]));
+    L.px = r[20 * kCtaThreads];  L.py = r[21 * kCtaThreads];  L.sample = r[22 * kCtaThreads];  L.depth = r[23 * kCtaThreads];
+    const uint32_t f = r[24 * kCtaThreads];
+    L.active = (f & 1u) != 0u;  L.have_pixel = (f & 2u) != 0u;  L.finished = (f & 4u) != 0u;
+    *pend = (f >> 3) & 1u;
+    hit_t = __uint_as_float(r[25 * kCtaThreads]);
+    hit_index = (int)r[26 * kCtaThreads];
+    *tslot = __uint_as_float(r[27 * kCtaThreads]);
+    return live;
+}
+
+// =====================================================================================================
 // Resident variant: the whole sphere SoA lives in shared memory for the life of the CTA.
 // =====================================================================================================
 #ifdef PT_LDS_MIN_CTAS
@@ -381,8 +477,11 @@ __global__ void PT_LDS_LAUNCH_BOUNDS pt_megakernel_resident(const __grid_constan
     uint32_t* queue = reinterpret_cast<uint32_t*>(P + 1) + threadIdx.x;  // [kQueueCap][kCtaThreads] candidate queues
     volatile uint32_t* pend = queue + kQueueCap * kCtaThreads;
     volatile float* tslot = reinterpret_cast<volatile float*>(pend + kCtaThreads);  // [kCtaThreads] ray.time per lane
+    uint32_t* xchg = const_cast<uint32_t*>(reinterpret_cast<volatile uint32_t*>(tslot)) - threadIdx.x + kCtaThreads;  // [kRegroupWords][kCtaThreads]
+    uint32_t* cat_count = xchg + kRegroupWords * kCtaThreads;                                                          // [kRegroupCats]
     *pend = 0u;
     *tslot = 0.0f;
+    if (threadIdx.x < 16) cat_count[threadIdx.x] = 0u;  // two sets of kRegroupCats counters, 8 words apart
     const MotionCtx mc{a.motion, tslot};
 
     const uint32_t bytes = (uint32_t)a.n_blocks * 64u;
@@ -405,10 +504,15 @@ __global__ void PT_LDS_LAUNCH_BOUNDS pt_megakernel_resident(const __grid_constan
     unsigned long long rays = 0ULL;
     PT_PROF_DECL
 
-    for (;;) {
+#if PT_REGROUP
+    lane_refill<MOTION>(a, L, lane_id, pend, tslot);
+#endif
+    for (uint32_t trip = 0;; ++trip) {
         PT_PROF_TICK();
+#if !PT_REGROUP
         lane_refill<MOTION>(a, L, lane_id, pend, tslot);
         if (__all_sync(kFullMask, L.finished)) break;
+#endif
         float ox = L.o.x, oy = L.o.y, oz = L.o.z, dx = L.d.x, dy = L.d.y, dz = L.d.z;
         if (!L.active) {  // parked lane: |o|^2 = 1e36 dwarfs every L, d = 0 -> never a candidate
             ox = 0.0f; oy = 1.0e18f; oz = 0.0f;
@@ -418,7 +522,7 @@ __global__ void PT_LDS_LAUNCH_BOUNDS pt_megakernel_resident(const __grid_constan
         int hit_index = -1;
         __syncwarp();
         PT_PROF_TOCK(pf_refill);
-        {
+        if (__any_sync(kFullMask, L.active)) {  // regrouping collects idle lanes in whole warps: they skip the sweep
             const float nod = -((ox * dx + oy * dy) + oz * dz);
             const float oo = ((ox * ox + oy * oy) + oz * oz) * (1.0f - 1.9073486328125e-06f);
             int cnt = 0;
@@ -427,10 +531,16 @@ __global__ void PT_LDS_LAUNCH_BOUNDS pt_megakernel_resident(const __grid_constan
         }
         __syncwarp();
         PT_PROF_TOCK(pf_sweep);
+#if PT_REGROUP
+        if (!cta_regroup(a, L, hit_t, hit_index, pend, tslot, xchg, cat_count + (trip & 1u) * 8u, lane_id)) break;
+#endif
         if (L.active) {
             rays += 1ULL;  // scene.rs:57
             lane_shade<MOTION>(a, L, a.blocks, *P, mc, hit_t, hit_index);
         }
+#if PT_REGROUP
+        lane_refill<MOTION>(a, L, lane_id, pend, tslot);  // ended paths sit side by side now: next sample / next ticket together
+#endif
         __syncwarp();
         PT_PROF_TOCK(pf_shade);
 #ifdef PT_PROFILE

@@ -93,7 +93,10 @@ struct MotionCtx {
     const volatile float* time;    // this lane's ray.time (shared memory slot)
 };
 
-constexpr int kSweepThreads = 256;  // == kCtaThreads (queue stride)
+#ifndef PT_CTA_THREADS
+#define PT_CTA_THREADS 256
+#endif
+constexpr int kSweepThreads = PT_CTA_THREADS;  // == kCtaThreads (queue stride)
 
 // Candidate queue: one 32-bit entry per flagged group = (group index << MASK_BITS) | one flag bit per sphere of the group,
 // kQueueCap entries per lane in shared memory ([entry][thread] layout, conflict-free).  A full queue (rare) tests the

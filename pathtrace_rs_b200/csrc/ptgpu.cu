@@ -124,9 +124,10 @@ int plan_launch(PtScene* s) {
         s->smem_bytes = 2 * (size_t)s->tile_blocks * 64 + perlin_bytes;
         return configure_streamed(s);
     }
-    if (all <= kMaxDynSmem) {
+    const size_t regroup_bytes = (size_t)pt::kRegroupWords * pt::kCtaThreads * sizeof(uint32_t) + 64;  // path-state exchange + category counters
+    if (all + regroup_bytes <= kMaxDynSmem) {
         s->resident = true;
-        s->smem_bytes = all;
+        s->smem_bytes = all + regroup_bytes;
         s->tile_blocks = s->n_blocks;
         s->n_tiles = 1;
         return s->d_motion ? configure_kernel(pt::pt_megakernel_resident<true>, s->smem_bytes, &s->ctas_per_sm)
