@@ -206,11 +206,11 @@ def main():
 
     def step_device(frame):
         """one Scene::update, image resident in HBM; returns nothing (async on torch's stream)"""
+        if world > 1 and not rows_mode:
+            d_rgb.zero_()                      # sample slices: every rank renders its frame seed into an empty buffer ...
         preset.update_device(params, frame, d_rgb.data_ptr(), d_rays.data_ptr(), stream.cuda_stream, part)
         if world > 1 and not rows_mode:
-            dist.reduce(d_rgb, dst=0)          # sample slices: equal-weight mean of the ranks' frames
-            if rank == 0:
-                d_rgb.mul_(1.0 / world)
+            parallel.combine_sample_slices(d_rgb, frame, world, dist)  # ... and ONE NCCL reduce forms the equal-weight mean
 
     def barrier():
         if world > 1:
@@ -262,16 +262,24 @@ def main():
         h2d_b = d2h_b = w * h * 12
         d2h_b += 8
     else:
+        d_prev = torch.zeros_like(d_rgb) if (rank == 0 and not rows_mode) else None
+
         def step_e2e(i):
-            d_rgb.copy_(pinned, non_blocking=True)  # H2D of this rank's accumulation buffer
-            preset.update_device(params, 1 + frame_of(i), d_rgb.data_ptr(), d_rays.data_ptr(), stream.cuda_stream, part)
-            if not rows_mode:
-                dist.reduce(d_rgb, dst=0)
-                if rank == 0:
-                    d_rgb.mul_(1.0 / world)
-                    pinned.copy_(d_rgb, non_blocking=True)
+            if rows_mode:
+                # strong scaling of one progressive frame: every rank uploads the previous accumulation (its rows are the ones
+                # read), blends frame 1 + i into it and downloads
+                d_rgb.copy_(pinned, non_blocking=True)
+                preset.update_device(params, 1 + i, d_rgb.data_ptr(), d_rays.data_ptr(), stream.cuda_stream, part)
+                pinned.copy_(d_rgb, non_blocking=True)
             else:
-                pinned.copy_(d_rgb, non_blocking=True)  # each rank downloads (only its rows are meaningful)
+                # sample slices: G new frames per step.  Rank 0 uploads the accumulation so far, all ranks render their
+                # frame seed, one reduce forms the mean of the G frames, rank 0 blends it in (running mean) and downloads.
+                if rank == 0:
+                    d_prev.copy_(pinned, non_blocking=True)
+                step_device(frame_of(i))
+                if rank == 0:
+                    torch.lerp(d_rgb, d_prev, float(i + 1) / float(i + 2), out=d_rgb)
+                    pinned.copy_(d_rgb, non_blocking=True)
             return int(d_rays.item())
         h2d_b = w * h * 12
         d2h_b = w * h * 12 + 8

@@ -63,3 +63,27 @@ def render_distributed(render_rows, height, width, rank, world_size, dist=None, 
         dist.all_reduce(total)
     full = gather_image(local, height, width, rank, world_size, tile_rows, dist) if gather else None
     return full, int(total.item())
+
+
+def combine_sample_slices(local_image, frame_num, world_size, dist=None):
+    """Sample-slice mode: rank r rendered the WHOLE image with frame seed `frame_num` = r into a zeroed
+    buffer, so it holds col_r / (r + 1) (the blend of scene.rs:86-87,113-116 against an empty previous frame).  Undo
+    that weight, sum over ranks with ONE reduce and scale by 1/G: the equal-weight mean of G frames — exactly what the
+    reference's progressive accumulation over frames 0..G-1 converges to (running mean algebra of scene.rs:86-87).
+    In place; the result is valid on rank 0."""
+    local_image.mul_(float(frame_num + 1))
+    if world_size > 1:
+        dist.reduce(local_image, dst=0)
+        local_image.mul_(1.0 / world_size)
+    return local_image
+
+
+def render_sample_slices(render_frame, rank, world_size, dist=None):
+    """render_frame(frame_num) -> (torch tensor [h,w,3] rendered into a zeroed buffer, ray_count).
+    Returns (mean image on rank 0, total ray count on every rank)."""
+    import torch
+    local, rays = render_frame(rank)
+    total = torch.tensor([rays], dtype=torch.int64, device=local.device)
+    if world_size > 1:
+        dist.all_reduce(total)
+    return combine_sample_slices(local, rank, world_size, dist), int(total.item())
