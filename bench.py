@@ -159,10 +159,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--partition", default="samples", choices=["samples", "rows"])
+    ap.add_argument("--partition", default="samples", choices=["samples", "rows", "samples-strong"],
+                    help="N>1: samples = every rank renders the workload's full spp with its own frame seed (weak scaling); rows = one frame "
+                         "split by interleaved row tiles (strong); samples-strong = the workload's spp split into N frame seeds of spp/N (strong)")
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (a reduced run is labelled as such)")
     ap.add_argument("--ref-spp", type=int, default=2, help="--impl reference: spp of the bounded CPU sample per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--fast", action="store_true", help="long workloads: the kernel-only and e2e legs run one step each without their own warm-up")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = max(args.warmup, 0)  # the driver passes W; the contract asks for >= 3 and the default is 3
@@ -192,6 +195,12 @@ def main():
     reduced = args.spp > 0 and args.spp != spp
     if args.spp > 0:
         spp = args.spp
+    full_spp = spp
+    samples_strong = world > 1 and args.partition == "samples-strong"
+    if samples_strong:
+        if spp % world:
+            raise SystemExit("--partition samples-strong needs spp divisible by the number of GPUs")
+        spp //= world  # each rank renders spp/N samples of every pixel with its own frame seed; one reduce forms the mean
     params = pt.Params(w, h, spp, depth)
     preset = pt.Preset(preset_name, params).create_scene(local_rank)
     n_spheres = len(preset)
@@ -249,8 +258,8 @@ def main():
 
     # kernel-only time for the roofline: the same launch without the collective, CUDA events on the launching stream
     k_ms, k_rays, _ = timed_run(lambda i: preset.update_device(params, frame_of(i), d_rgb.data_ptr(), d_rays.data_ptr(), stream.cuda_stream, part),
-                                1, max(1, min(args.steps, 3)))
-    k_steps = max(1, min(args.steps, 3))
+                                0 if args.fast else 1, 1 if args.fast else max(1, min(args.steps, 3)))
+    k_steps = 1 if args.fast else max(1, min(args.steps, 3))
 
     # ---- end to end through the reference-facing call, host buffers ----------------------------------------------
     pinned = torch.zeros((h, w, 3), dtype=torch.float32).pin_memory()
@@ -283,7 +292,8 @@ def main():
             return int(d_rays.item())
         h2d_b = w * h * 12
         d2h_b = w * h * 12 + 8
-    e_ms, e_rays, e_wall = timed_run(step_e2e, 1, args.steps)
+    e_steps = 1 if args.fast else args.steps
+    e_ms, e_rays, e_wall = timed_run(step_e2e, 0 if args.fast else 1, e_steps)
 
     # ---- reduce over ranks: time = max, work = sum ------------------------------------------------------------------
     def allmax(x):
@@ -322,16 +332,17 @@ def main():
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-            "scaling": "strong" if rows_mode else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.workload, spp) + (" [REDUCED spp]" if reduced else ""),
+            "scaling": "strong" if (rows_mode or samples_strong) else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload, full_spp) + (" [REDUCED spp]" if reduced else ""),
                        "n_spheres": n_spheres, "partition": ("rows: interleaved 4-row tiles, no collective" if rows_mode else
-                                                             ("samples: one frame seed per GPU + one NCCL reduce" if world > 1 else "single GPU")),
+                                                             (("samples-strong: %d spp per GPU x %d frame seeds + one NCCL reduce" % (spp, world)) if samples_strong else
+                                                              ("samples: one frame seed per GPU + one NCCL reduce" if world > 1 else "single GPU"))),
                        "l2": "flushed between timed iterations (256 MB fill); the scene is a %d KB pre-filter image %s" % (max(1, n_spheres * 16 // 1024), "resident in shared memory" if n_spheres * 16 < 200 * 1024 else "streamed from L2 in TMA tiles"),
                        "timing": "CUDA events per step on the launching stream, max over ranks"},
             "samples_per_s": samples_per_step * args.steps / (ms_max * 1e-3),
             "rays_per_sample": rays_sum / (samples_per_step * args.steps),
             "e2e": {"value": e_rays_sum / 1e6 / e_wall_max, "unit": "Mrays/s", "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
-                    "ms_per_step": 1e3 * e_wall_max / args.steps,
+                    "ms_per_step": 1e3 * e_wall_max / e_steps,
                     "path": "Scene::update mirror -> pt_render (pinned host buffer, frame_num>=1)" if world == 1 else
                             "pinned H2D -> pt_render_device -> NCCL reduce -> D2H on rank 0"},
             "gpu_launches": args.steps * world,

@@ -38,6 +38,7 @@ struct KernelArgs {
     uint64_t seed_salt;
     float* rgb;
     unsigned long long* ray_count;
+    unsigned long long* sweep_count;  // warp-level sweeps performed (x32 = lane slots offered; rays / that = lane efficiency)
     unsigned int* next_pixel;  // ticket counter of the chunk queue (see lane_refill)
     // chunk queue: ticket t = chunk (t / n_owned_pixels) of owned pixel (t % n_owned_pixels); chunk c covers samples
     // [c * chunk_samples, min((c+1) * chunk_samples, samples)).  chunk_samples is a power of two and chunk_mask =
@@ -329,10 +330,11 @@ __device__ __forceinline__ void lane_init(Lane& L) {
     L.rng.s0 = L.rng.s1 = L.rng.s2 = L.rng.s3 = 0;
 }
 
-__device__ __forceinline__ void flush_ray_count(const KernelArgs& a, unsigned long long rays, unsigned lane_id) {
+__device__ __forceinline__ void flush_ray_count(const KernelArgs& a, unsigned long long rays, unsigned lane_id, unsigned sweeps) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) rays += __shfl_xor_sync(kFullMask, rays, off);
     if (lane_id == 0 && rays != 0ULL) atomicAdd(a.ray_count, rays);
+    if (lane_id == 0 && sweeps != 0u) atomicAdd(a.sweep_count, (unsigned long long)sweeps);
 }
 
 __device__ __forceinline__ void stage_perlin(const KernelArgs& a, PerlinSmem* P) {
@@ -502,6 +504,7 @@ __global__ void PT_LDS_LAUNCH_BOUNDS pt_megakernel_resident(const __grid_constan
     Lane L;
     lane_init(L);
     unsigned long long rays = 0ULL;
+    unsigned sweeps = 0u;
     PT_PROF_DECL
 
 #if PT_REGROUP
@@ -523,6 +526,7 @@ __global__ void PT_LDS_LAUNCH_BOUNDS pt_megakernel_resident(const __grid_constan
         __syncwarp();
         PT_PROF_TOCK(pf_refill);
         if (__any_sync(kFullMask, L.active)) {  // regrouping collects idle lanes in whole warps: they skip the sweep
+            sweeps += 1u;
             const float nod = -((ox * dx + oy * dy) + oz * dz);
             const float oo = ((ox * ox + oy * oy) + oz * oz) * (1.0f - 1.9073486328125e-06f);
             int cnt = 0;
@@ -551,7 +555,7 @@ __global__ void PT_LDS_LAUNCH_BOUNDS pt_megakernel_resident(const __grid_constan
     pf_lanes = rays;
 #endif
     PT_PROF_FLUSH(lane_id);
-    flush_ray_count(a, rays, lane_id);
+    flush_ray_count(a, rays, lane_id, sweeps);
 }
 
 // =====================================================================================================
@@ -603,6 +607,7 @@ __global__ void PT_STREAM_LAUNCH_BOUNDS pt_megakernel_streamed(const __grid_cons
     Lane L;
     lane_init(L);
     unsigned long long rays = 0ULL;
+    unsigned sweeps = 0u;
     uint32_t full_phase[2] = {0u, 0u};   // parity to wait for on full_bar[b]
     uint32_t empty_phase[2] = {0u, 0u};  // producer side: parity to wait for on empty_bar[b]
     uint32_t produced[2] = {0u, 0u};     // producer: how many times buffer b has been filled
@@ -642,6 +647,7 @@ __global__ void PT_STREAM_LAUNCH_BOUNDS pt_megakernel_streamed(const __grid_cons
         const float nod = -((ox * dx + oy * dy) + oz * dz);
         const float oo = ((ox * ox + oy * oy) + oz * oz) * (1.0f - 1.9073486328125e-06f);
         int cnt = 0;
+        sweeps += 1u;  // every warp of the CTA sweeps every tile of every trip
         if (threadIdx.x == 0) {
             produce(0);
             if (a.n_tiles > 1) produce(1);
@@ -666,7 +672,7 @@ __global__ void PT_STREAM_LAUNCH_BOUNDS pt_megakernel_streamed(const __grid_cons
             lane_shade<MOTION>(a, L, a.blocks, *P, mc, hit_t, hit_index);
         }
     }
-    flush_ray_count(a, rays, lane_id);
+    flush_ray_count(a, rays, lane_id, sweeps);
 }
 
 // =====================================================================================================

@@ -59,6 +59,7 @@ struct PtScene {
     float4* d_prefilter = nullptr;  // pre-filter image X,Y,Z,K per block (LDS kernels stage/stream it)
     // per-render scratch
     unsigned long long* d_ray_count = nullptr;  // [0] ray count
+    unsigned long long* d_sweep_count = nullptr;  // warp-level sweeps of the last launch (lane-efficiency diagnostic)
     unsigned int* d_next_pixel = nullptr;
     uint32_t* d_pixstate = nullptr;  // chunk queue: 12 words per owned pixel (pt_megakernel.cuh, PixState)
     size_t d_pixstate_pixels = 0;
@@ -217,6 +218,7 @@ int launch_update(PtScene* s, const PtParams* params, const PtCamera* cam, uint3
     a.seed_salt = params->seed_salt;
     a.rgb = d_rgb;
     a.ray_count = d_ray_count;
+    a.sweep_count = s->d_sweep_count;
     a.next_pixel = s->d_next_pixel;
     a.tile_blocks = s->tile_blocks;
     a.n_tiles = s->n_tiles;
@@ -226,6 +228,7 @@ int launch_update(PtScene* s, const PtParams* params, const PtCamera* cam, uint3
                     cam->time0, cam->time1, s->motion_t_lo, s->motion_t_hi);
     PT_CUDA(cudaMemsetAsync(s->d_next_pixel, 0, sizeof(unsigned int), stream));
     PT_CUDA(cudaMemsetAsync(d_ray_count, 0, sizeof(unsigned long long), stream));
+    PT_CUDA(cudaMemsetAsync(s->d_sweep_count, 0, sizeof(unsigned long long), stream));
     s->stats.kernel_launches = 0;
     s->stats.grid_ctas = 0;
     if (a.n_owned_pixels == 0) return PT_OK;
@@ -599,6 +602,7 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
         PT_CUDA_S(cudaMemcpy(s->d_perlin, raw.data(), raw.size(), cudaMemcpyHostToDevice));
     }
     PT_CUDA_S(cudaMalloc(&s->d_ray_count, sizeof(unsigned long long)));
+    PT_CUDA_S(cudaMalloc(&s->d_sweep_count, sizeof(unsigned long long)));
     PT_CUDA_S(cudaMalloc(&s->d_next_pixel, sizeof(unsigned int)));
     PT_CUDA_S(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     for (auto& e : s->ev) PT_CUDA_S(cudaEventCreate(&e));
@@ -620,6 +624,7 @@ void pt_scene_destroy(PtScene* s) {
     cudaFree(s->d_prefilter);
     cudaFree(s->d_motion);
     cudaFree(s->d_ray_count);
+    cudaFree(s->d_sweep_count);
     cudaFree(s->d_next_pixel);
     cudaFree(s->d_pixstate);
     cudaFree(s->d_rgb);
@@ -672,6 +677,11 @@ int pt_render_part(PtScene* s, const PtParams* params, const PtCamera* camera, u
     s->stats.d2h_bytes = d2h + sizeof(rays);
     s->stats.ray_count = rays;
     if (ray_count_out) *ray_count_out = rays;
+    if (std::getenv("PTGPU_DEBUG_SWEEPS")) {  // diagnostic: lane efficiency of the sweep = rays / (32 x warp sweeps)
+        unsigned long long sweeps = 0;
+        cudaMemcpy(&sweeps, s->d_sweep_count, sizeof(sweeps), cudaMemcpyDeviceToHost);
+        std::fprintf(stderr, "[ptgpu] warp sweeps %llu, rays %llu, lane efficiency %.3f\n", sweeps, rays, sweeps ? (double)rays / (32.0 * (double)sweeps) : 0.0);
+    }
     return PT_OK;
 }
 
