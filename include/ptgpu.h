@@ -19,14 +19,14 @@
 extern "C" {
 #endif
 
-#define PT_ABI_VERSION 2
+#define PT_ABI_VERSION 3
 
 /* ---- status codes (the Rust shim `expect`s on non-zero, matching the reference's panic-on-error
  *      convention: src/offline.rs:10,32,59) ---- */
 enum {
     PT_OK = 0,
     PT_ERR_INVALID = 1,      /* null pointer, bad index, zero-sized image ... */
-    PT_ERR_UNSUPPORTED = 2,  /* e.g. use_bvh, or a hitable that is not a sphere */
+    PT_ERR_UNSUPPORTED = 2,  /* e.g. use_bvh, or a material/texture kind outside the path */
     PT_ERR_NO_DEVICE = 3,    /* no CUDA device / wrong architecture (needs sm_100) */
     PT_ERR_CUDA = 4,         /* a CUDA runtime call failed; see pt_last_error() */
     PT_ERR_TOO_LARGE = 5
@@ -58,16 +58,26 @@ typedef struct PtCamera {
     float lens_radius;
 } PtCamera;
 
-/* ---- Texture: src/texture.rs:40-55 (arena references become indices into PtSceneDesc.textures) ---- */
-enum { PT_TEX_CONSTANT = 0, PT_TEX_CHECKER = 1, PT_TEX_NOISE = 2 };
+/* ---- Texture: src/texture.rs:40-55 (arena references become indices into PtSceneDesc.textures / .images) ---- */
+enum { PT_TEX_CONSTANT = 0, PT_TEX_CHECKER = 1, PT_TEX_NOISE = 2, PT_TEX_IMAGE = 3 };
 typedef struct PtTexture {
     int32_t kind;
     float color[3]; /* Constant */
     int32_t odd;    /* Checker: texture index */
     int32_t even;   /* Checker: texture index */
     float scale;    /* Noise */
-    int32_t _pad;
+    int32_t image;  /* Image: index into PtSceneDesc.images (ignored by the other kinds) */
 } PtTexture;
+
+/* ---- RgbImage: src/texture.rs:6-37 (`image.to_rgb8().into_raw()`: width*height packed 8-bit RGB, row 0 = top).
+ * Looked up by `RgbImage::value(u, v)` (texture.rs:27-36) with the sphere (u, v) of `get_sphere_uv`
+ * (src/material.rs:41-49).  (u, v) are computed only when the Image texture is the material's own albedo / emit
+ * texture (material.rs:169-180); an Image nested inside a Checker is sampled at (0, 0), as in the reference. ---- */
+typedef struct PtImage {
+    uint32_t width;
+    uint32_t height;
+    const uint8_t* data; /* width*height*3 bytes; copied by pt_scene_create */
+} PtImage;
 
 /* ---- Material: src/material.rs:13-19 ---- */
 enum { PT_MAT_LAMBERTIAN = 0, PT_MAT_METAL = 1, PT_MAT_DIELECTRIC = 2, PT_MAT_DIFFUSE_LIGHT = 3 };
@@ -118,6 +128,9 @@ typedef struct PtSceneDesc {
     uint32_t has_sky;       /* Scene.sky: Option<Vec3>  (src/scene.rs:20,39-47) */
     float sky[3];
     const PtMotion* motion; /* per sphere, or NULL when the scene has no Hitable::MovingSphere (src/collision/hitable.rs:17) */
+    uint32_t n_images;      /* Storage.image_arena entries referenced by Image textures (src/storage.rs) */
+    uint32_t _pad;
+    const PtImage* images;  /* may be NULL when n_images == 0 */
 } PtSceneDesc;
 
 /* ---- partition of one image over several GPUs / calls: interleaved row tiles.
@@ -161,7 +174,7 @@ typedef struct PtScene PtScene; /* opaque: device copy of one scene on one GPU *
 int pt_abi_version(void);
 /* sizeof() of the ABI structs as this library was compiled, so a binding can assert its own layout:
  * which = 0 PtParams, 1 PtCamera, 2 PtTexture, 3 PtMaterial, 4 PtPerlin, 5 PtSceneDesc, 6 PtPartition,
- * 7 PtDeviceInfo, 8 PtRenderStats; anything else -> 0. */
+ * 7 PtDeviceInfo, 8 PtRenderStats, 9 PtMotion, 10 PtImage; anything else -> 0. */
 uint32_t pt_abi_struct_size(int which);
 const char* pt_last_error(void); /* thread-local message of the last failing call */
 int pt_device_count(void);

@@ -292,13 +292,44 @@ struct Perlin {
 // ------------------------------------------------------------------------------------------------
 // texture.rs / material.rs data model (arena refs become indices)
 // ------------------------------------------------------------------------------------------------
-enum TexKind : int32_t { TEX_CONSTANT = 0, TEX_CHECKER = 1, TEX_NOISE = 2 };
+enum TexKind : int32_t { TEX_CONSTANT = 0, TEX_CHECKER = 1, TEX_NOISE = 2, TEX_IMAGE = 3 };
 struct Texture {
     int32_t kind;
     V3 color;           // Constant
     int32_t odd, even;  // Checker (indices)
     float scale;        // Noise
+    int32_t image = -1; // Image (index into Scene::images)
 };
+// Rust `f32 as i32`: truncation towards zero, saturating, NaN -> 0
+static inline int32_t rust_f32_as_i32(float x) {
+    if (x != x) return 0;
+    if (x >= 2147483648.0f) return INT32_MAX;
+    if (x <= -2147483648.0f) return INT32_MIN;
+    return (int32_t)x;
+}
+// texture.rs:6-37
+struct RgbImage {
+    uint32_t width = 0, height = 0;
+    std::vector<uint8_t> data;  // image.to_rgb8().into_raw(): row 0 = top
+    V3 value(float u, float v) const {  // texture.rs:27-36
+        int32_t i = rust_f32_as_i32(u * (float)width);
+        int32_t j = rust_f32_as_i32((1.0f - v) * (float)height - 0.001f);
+        size_t ii = (size_t)std::min(std::max(i, 0), (int32_t)width - 1);
+        size_t jj = (size_t)std::min(std::max(j, 0), (int32_t)height - 1);
+        float r = (float)data[3 * ii + 3 * (size_t)width * jj] / 255.0f;
+        float g = (float)data[3 * ii + 3 * (size_t)width * jj + 1] / 255.0f;
+        float b = (float)data[3 * ii + 3 * (size_t)width * jj + 2] / 255.0f;
+        return v3(r, g, b);
+    }
+};
+// material.rs:41-49 (`x.atan2(y)` = atan2(x, y))
+static inline void get_sphere_uv(V3 normal, float& u, float& v) {
+    const float PI = 3.14159265358979323846f, FRAC_1_2PI = 1.0f / (2.0f * PI);
+    float phi = std::atan2(normal.x, normal.y);
+    float theta = std::asin(normal.y);
+    u = 1.0f - (phi + PI) * FRAC_1_2PI;
+    v = (theta + 1.57079632679489661923f) * 0.318309886183790671538f;
+}
 enum MatKind : int32_t { MAT_LAMBERTIAN = 0, MAT_METAL = 1, MAT_DIELECTRIC = 2, MAT_DIFFUSE_LIGHT = 3 };
 struct Material {
     int32_t kind;
@@ -388,6 +419,7 @@ struct Scene {
     std::vector<Sphere> spheres;
     std::vector<Material> materials;
     std::vector<Texture> textures;
+    std::vector<RgbImage> images;
     Perlin perlin;
     bool has_sky = false;
     V3 sky = {0, 0, 0};
@@ -423,6 +455,7 @@ struct Scene {
     V3 tex_value(int32_t ti, float u, float v, V3 p) const {
         const Texture& t = textures[ti];
         switch (t.kind) {
+            case TEX_IMAGE: return images[t.image].value(u, v);
             case TEX_CONSTANT: return t.color;
             case TEX_CHECKER: {
                 V3 s = v3(10.0f, 10.0f, 10.0f) * p;
@@ -514,15 +547,21 @@ struct Scene {
         }
         return any;
     }
-    // spheres_soa.rs:132-154 epilogue (u,v = 0 for every texture in scope: material.rs:169-180)
+    // material.rs:169-180 — (u, v) exist only when the material's own texture is an Image; (0, 0) otherwise
+    void material_sphere_uv(int32_t sphere_index, V3 normal, float& u, float& v) const {
+        u = v = 0.0f;
+        const Material& m = materials[spheres[sphere_index].material];
+        if ((m.kind == MAT_LAMBERTIAN || m.kind == MAT_DIFFUSE_LIGHT) && textures[m.tex].kind == TEX_IMAGE) get_sphere_uv(normal, u, v);
+    }
+    // spheres_soa.rs:132-154 epilogue.  NOTE the live path differs: Sphere::ray_hit returns u = v = 0 for every material
+    // (sphere.rs:44-45,56-57), so `earth` renders one texel there; the SoA form — the GPU path's spec — asks the material.
     bool soa_epilogue(const Ray& ray, float hit_t, size_t hit_index, RayHit& hit, int32_t& index) const {
-        if (hit_index >= soa_len) return false;
+        if (hit_index >= soa_len || hit_index >= spheres.size()) return false;
         hit.point = point_at(ray, hit_t);
         V3 centre = v3(cx[hit_index], cy[hit_index], cz[hit_index]);
         hit.normal = (hit.point - centre) * rinv[hit_index];
         hit.t = hit_t;
-        hit.u = 0.0f;
-        hit.v = 0.0f;
+        material_sphere_uv((int32_t)hit_index, hit.normal, hit.u, hit.v);
         index = (int32_t)hit_index;
         return true;
     }
@@ -936,6 +975,26 @@ static void preset_smallpt(Scene& s, const Params& p) {
     s.sky = v3(0, 0, 0);
 }
 
+static int32_t add_tex_image(Scene& s, int32_t image) {
+    Texture t{};
+    t.kind = TEX_IMAGE;
+    t.odd = t.even = -1;
+    t.image = image;
+    s.textures.push_back(t);
+    return (int32_t)s.textures.size() - 1;
+}
+// presets.rs:555-594.  The asset (media/earthmap.jpg) is not in the reference tree: the caller supplies the decoded
+// pixels (orc_set_earth_image) — what `RgbImage::open` would have produced.
+static RgbImage g_earth_image;
+static bool preset_earth(Scene& s, const Params& p) {
+    if (g_earth_image.data.empty()) return false;
+    s.camera = rtiow_camera(p, 0.0f, 0.0f);
+    s.images.push_back(g_earth_image);
+    int32_t tex = add_tex_image(s, 0);
+    add_sphere(s, v3(0, 0, 0), 2.0f, add_mat(s, MAT_LAMBERTIAN, tex, v3(0, 0, 0), 0, 0));
+    return true;
+}
+
 // offline.rs:16-23 — rng = seed_from_u64(0) (params.rs:21-27); Storage::new (Perlin) first; then the preset.
 static Scene* build_preset(const char* name, const Params& p) {
     Scene* s = new Scene();
@@ -948,6 +1007,7 @@ static Scene* build_preset(const char* name, const Params& p) {
     else if (n == "small") preset_small(*s, p);
     else if (n == "two_perlin_spheres") preset_two_perlin_spheres(*s, p);
     else if (n == "smallpt") preset_smallpt(*s, p);
+    else if (n == "earth") { if (!preset_earth(*s, p)) { delete s; return nullptr; } }
     else if (n == "final") s->camera = rtiow_camera(p, 0.1f, 1.0f);  // presets.rs:40-71: empty stub, same camera
     else { delete s; return nullptr; }
     s->build_soa();
@@ -971,6 +1031,42 @@ void* orc_scene_build(const char* preset, const OrcParams* p) {
     return orc::build_preset(preset, pp);
 }
 void orc_scene_free(void* h) { delete (orc::Scene*)h; }
+// the decoded pixels the next orc_scene_build("earth") uses (RGB8, row 0 = top)
+void orc_set_earth_image(uint32_t width, uint32_t height, const uint8_t* rgb) {
+    orc::g_earth_image.width = width;
+    orc::g_earth_image.height = height;
+    orc::g_earth_image.data.assign(rgb, rgb + (size_t)width * height * 3);
+}
+// Append an image / an Image texture / a Checker texture to a scene and point a sphere's material at a texture
+// (randomised-scene parity tests of the Image path).  Return the new index.
+int32_t orc_scene_add_image(void* h, uint32_t width, uint32_t height, const uint8_t* rgb) {
+    auto* s = (orc::Scene*)h;
+    orc::RgbImage im;
+    im.width = width; im.height = height;
+    im.data.assign(rgb, rgb + (size_t)width * height * 3);
+    s->images.push_back(std::move(im));
+    return (int32_t)s->images.size() - 1;
+}
+int32_t orc_scene_add_image_texture(void* h, int32_t image) { return orc::add_tex_image(*(orc::Scene*)h, image); }
+int32_t orc_scene_add_checker_texture(void* h, int32_t odd, int32_t even) { return orc::add_tex_checker(*(orc::Scene*)h, odd, even); }
+void orc_scene_set_sphere_texture(void* h, int32_t sphere, int32_t tex) {
+    auto* s = (orc::Scene*)h;
+    s->materials[s->spheres[sphere].material].tex = tex;
+}
+int32_t orc_scene_image_count(void* h) { return (int32_t)((orc::Scene*)h)->images.size(); }
+// width/height of image `image`; copies the pixels when rgb_out != nullptr
+void orc_scene_image(void* h, int32_t image, uint32_t* width, uint32_t* height, uint8_t* rgb_out) {
+    const orc::RgbImage& im = ((orc::Scene*)h)->images[image];
+    *width = im.width;
+    *height = im.height;
+    if (rgb_out) std::memcpy(rgb_out, im.data.data(), im.data.size());
+}
+// RgbImage::value and get_sphere_uv on their own (unit pins)
+void orc_image_value(void* h, int32_t image, float u, float v, float* out3) {
+    orc::V3 c = ((orc::Scene*)h)->images[image].value(u, v);
+    out3[0] = c.x; out3[1] = c.y; out3[2] = c.z;
+}
+void orc_sphere_uv(float nx, float ny, float nz, float* uv2) { orc::get_sphere_uv(orc::v3(nx, ny, nz), uv2[0], uv2[1]); }
 
 // A scene from flat arrays (randomised-scene parity tests): per sphere centre(3)+radius, material kind, colour(3)+fuzz+
 // ref_idx (Lambertian/DiffuseLight get a Constant texture of that colour), optional motion rows (centre1(3), time0,
@@ -1051,7 +1147,7 @@ void orc_scene_textures(void* h, int32_t* kind_odd_even /*n*3*/, float* color_sc
     for (size_t i = 0; i < s->textures.size(); ++i) {
         const auto& t = s->textures[i];
         kind_odd_even[3 * i] = t.kind;
-        kind_odd_even[3 * i + 1] = t.odd;
+        kind_odd_even[3 * i + 1] = t.kind == orc::TEX_IMAGE ? t.image : t.odd;  // Image: the image index rides in the `odd` slot
         kind_odd_even[3 * i + 2] = t.even;
         color_scale[4 * i + 0] = t.color.x;
         color_scale[4 * i + 1] = t.color.y;

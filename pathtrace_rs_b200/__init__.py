@@ -15,10 +15,10 @@ from .ffi import (  # noqa: F401
     PtCamera, PtParams, PtPartition, PtRenderStats, PtDeviceInfo, PtError,
     libptgpu, libpthost, abi_symbols,
 )
-from .scene import Params, Preset, device_info, probe_fp32_peak, render_offline  # noqa: F401
+from .scene import Params, Preset, device_info, image_open, probe_fp32_peak, render_offline, write_ppm  # noqa: F401
 
 __all__ = [
-    "Params", "Preset", "device_info", "probe_fp32_peak", "render_offline",
+    "Params", "Preset", "device_info", "image_open", "probe_fp32_peak", "render_offline", "write_ppm",
     "PtCamera", "PtParams", "PtPartition", "PtRenderStats", "PtDeviceInfo", "PtError",
     "libptgpu", "libpthost", "abi_symbols",
 ]

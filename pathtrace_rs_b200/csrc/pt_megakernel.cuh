@@ -24,6 +24,7 @@ struct KernelArgs {
     int n_spheres;
     const DevShade* shade;
     const DevTexture* tex;
+    const uint8_t* images;     // RGB8 pool of the scene's Image textures (texture.rs:6-37), nullptr when there is none
     const PerlinSmem* perlin;  // global copy, staged to shared memory when has_noise
     const DevMotion* motion;   // per-sphere MovingSphere records, nullptr when the scene has none (moving_sphere.rs)
     const float4* prefilter;   // pre-filter image X,Y,Z,K per block (global copy; staged/streamed by the LDS kernels)
@@ -289,7 +290,8 @@ __device__ __forceinline__ void lane_shade(const KernelArgs& a, Lane& L, const f
     m.ar = s0.x; m.ag = s0.y; m.ab = s0.z; m.param = s0.w;
     m.rinv = s1.x; m.kind = __float_as_int(s1.y); m.tex = __float_as_int(s1.z);
     V3 normal;
-    if (MOTION && __float_as_int(s1.w) != 0) {  // MovingSphere: centre at ray.time, normal = (p - centre) / radius (moving_sphere.rs:28-31,49)
+    const bool moving = MOTION && __float_as_int(s1.w) != 0;
+    if (moving) {  // MovingSphere: centre at ray.time, normal = (p - centre) / radius (moving_sphere.rs:28-31,49)
         const DevMotion mo = mc.table[hit_index];
         const float s = (*mc.time - mo.time_start) * mo.inv_time_delta;
         const V3 c = v3(centre.x + s * mo.dx, centre.y + s * mo.dy, centre.z + s * mo.dz);
@@ -298,14 +300,14 @@ __device__ __forceinline__ void lane_shade(const KernelArgs& a, Lane& L, const f
         normal = (point - centre) * m.rinv;
     }
     if (m.kind == MAT_DIFFUSE_LIGHT) {  // material.rs:161-167 (+ :157: lights do not scatter)
-        const V3 em = m.tex < 0 ? v3(m.ar, m.ag, m.ab) : texture_value(a.tex, P, m.tex, point);
+        const V3 em = m.tex < 0 ? v3(m.ar, m.ag, m.ab) : texture_value(TexCtx{a.tex, a.images, !moving}, P, m.tex, point, normal);
         L.col = L.col + L.thr * em;
         L.active = false;
         return;
     }
     if (L.depth < a.max_depth) {
         V3 att, sd;
-        if (material_scatter(m, a.tex, P, L.d, point, normal, L.rng, att, sd)) {
+        if (material_scatter(m, TexCtx{a.tex, a.images, !moving}, P, L.d, point, normal, L.rng, att, sd)) {
             L.thr = L.thr * att;
             L.o = point;
             L.d = sd;

@@ -31,13 +31,15 @@ __device__ __forceinline__ float length(V3 a) { return sqrtf(dot(a, a)); }
 __device__ __forceinline__ V3 normalize(V3 a) { return a * (1.0f / length(a)); }
 
 // ---- device-side scene records (built by the host flattener in ptgpu.cu) ----
-enum : int32_t { TEX_CONSTANT = 0, TEX_CHECKER = 1, TEX_NOISE = 2 };
+enum : int32_t { TEX_CONSTANT = 0, TEX_CHECKER = 1, TEX_NOISE = 2, TEX_IMAGE = 3 };
 enum : int32_t { MAT_LAMBERTIAN = 0, MAT_METAL = 1, MAT_DIELECTRIC = 2, MAT_DIFFUSE_LIGHT = 3 };
 
 struct __align__(16) DevTexture {  // 32 B
     float r, g, b;   // Constant colour
     float scale;     // Noise
-    int32_t kind, odd, even, _pad;
+    int32_t kind;
+    int32_t odd, even;  // Checker: child texture indices; Image: width, height
+    int32_t offset;     // Image: byte offset of the RGB8 pixels in the scene's image pool
 };
 
 // one record per sphere, read only when that sphere is the nearest hit
@@ -198,14 +200,47 @@ __device__ __forceinline__ float perlin_turb(const PerlinSmem& P, V3 p) {  // pe
     return fabsf(accum);
 }
 
+// ---- src/material.rs:41-49: get_sphere_uv.  `x.atan2(y)` is atan2(x, y) — the reference's argument order. ----
+__device__ __forceinline__ void get_sphere_uv(V3 normal, float& u, float& v) {
+    const float phi = atan2f(normal.x, normal.y);
+    const float theta = asinf(normal.y);
+    u = 1.0f - (phi + 3.14159265358979323846f) * (1.0f / (2.0f * 3.14159265358979323846f));
+    v = (theta + 1.57079632679489661923f) * 0.318309886183790671538f;
+}
+// ---- src/texture.rs:27-36: RgbImage::value.  Rust `as i32` saturates and maps NaN to 0, like cvt.rzi.s32.f32. ----
+__device__ __noinline__ V3 image_value(const uint8_t* __restrict__ pixels, int32_t width, int32_t height, float u, float v) {
+    int32_t i = __float2int_rz(u * (float)width);
+    int32_t j = __float2int_rz((1.0f - v) * (float)height - 0.001f);
+    i = min(max(i, 0), width - 1);
+    j = min(max(j, 0), height - 1);
+    const uint8_t* t = pixels + 3 * (size_t)i + 3 * (size_t)width * (size_t)j;
+    return v3((float)__ldg(t) / 255.0f, (float)__ldg(t + 1) / 255.0f, (float)__ldg(t + 2) / 255.0f);
+}
+
+// what texture_value needs beyond the texture table: the scene's image pool, and whether this hit carries sphere (u, v)
+// (Sphere via the SoA epilogue spheres_soa.rs:141 does; MovingSphere::ray_hit returns u = v = 0, moving_sphere.rs:53-54)
+struct TexCtx {
+    const DevTexture* __restrict__ tex;
+    const uint8_t* __restrict__ images;
+    bool sphere_uv;
+};
+
 // ---- src/texture.rs:74-91 ---- (Checker recursion unrolled into a bounded walk: the arena graph
-// is a DAG of at most n_textures nodes; 16 levels is far beyond any preset)
-__device__ __forceinline__ V3 texture_value(const DevTexture* __restrict__ tex, const PerlinSmem& P, int32_t ti, V3 p) {
+// is a DAG of at most n_textures nodes; 16 levels is far beyond any preset).  `normal` feeds get_sphere_uv, which the
+// reference evaluates only when the material's OWN texture is an Image (material.rs:169-180: level 0 here); an Image
+// reached through a Checker sees (u, v) = (0, 0).
+__device__ __forceinline__ V3 texture_value(const TexCtx& tc, const PerlinSmem& P, int32_t ti, V3 p, V3 normal) {
+    const DevTexture* __restrict__ tex = tc.tex;
 #pragma unroll 1
     for (int level = 0; level < 16; ++level) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(tex + ti));
         const int4 b = __ldg(reinterpret_cast<const int4*>(tex + ti) + 1);
         if (b.x == TEX_CONSTANT) return v3(a.x, a.y, a.z);
+        if (b.x == TEX_IMAGE) {
+            float u = 0.0f, v = 0.0f;
+            if (level == 0 && tc.sphere_uv) get_sphere_uv(normal, u, v);
+            return image_value(tc.images + (uint32_t)b.w, b.y, b.z, u, v);
+        }
         if (b.x == TEX_CHECKER) {
             const V3 s = v3(10.0f, 10.0f, 10.0f) * p;
             const float sines = sinf(s.x) * sinf(s.y) * sinf(s.z);
@@ -237,11 +272,11 @@ __device__ __forceinline__ void camera_get_ray(const DevCamera& c, float s, floa
 }
 
 // ---- src/material.rs:138-159: scatter.  Returns false when the path is absorbed. ----
-__device__ __forceinline__ bool material_scatter(const DevShade& m, const DevTexture* __restrict__ tex, const PerlinSmem& P,
+__device__ __forceinline__ bool material_scatter(const DevShade& m, const TexCtx& tex, const PerlinSmem& P,
                                                  V3 rd, V3 point, V3 normal, Rng& rng, V3& attenuation, V3& scattered) {
     if (m.kind == MAT_LAMBERTIAN) {  // material.rs:52-67
         const V3 target = point + normal + random_unit_vector(rng);
-        attenuation = m.tex < 0 ? v3(m.ar, m.ag, m.ab) : texture_value(tex, P, m.tex, point);
+        attenuation = m.tex < 0 ? v3(m.ar, m.ag, m.ab) : texture_value(tex, P, m.tex, point, normal);
         scattered = normalize(target - point);
         return true;
     }

@@ -53,6 +53,7 @@ struct PtScene {
     float4* d_blocks = nullptr;
     pt::DevShade* d_shade = nullptr;
     pt::DevTexture* d_tex = nullptr;
+    uint8_t* d_images = nullptr;  // RGB8 pool of the Image textures (nullptr: none)
     pt::PerlinSmem* d_perlin = nullptr;
     pt::DevMotion* d_motion = nullptr;  // MovingSphere records (nullptr: none)
     float motion_t_lo = 0.0f, motion_t_hi = 0.0f;  // intersection of the moving spheres' [time0, time1]
@@ -183,6 +184,7 @@ int launch_update(PtScene* s, const PtParams* params, const PtCamera* cam, uint3
     a.n_spheres = (int)s->n_spheres;
     a.shade = s->d_shade;
     a.tex = s->d_tex;
+    a.images = s->d_images;
     a.perlin = s->d_perlin;
     a.prefilter = s->d_prefilter;
     a.motion = s->d_motion;
@@ -351,6 +353,8 @@ uint32_t pt_abi_struct_size(int which) {
         case 6: return sizeof(PtPartition);
         case 7: return sizeof(PtDeviceInfo);
         case 8: return sizeof(PtRenderStats);
+        case 9: return sizeof(PtMotion);
+        case 10: return sizeof(PtImage);
         default: return 0;
     }
 }
@@ -405,6 +409,19 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
     if (n > 0 && (desc->n_materials == 0 || !desc->materials)) return fail(PT_ERR_INVALID, "spheres without materials");
     if (desc->n_textures > 0 && !desc->textures) return fail(PT_ERR_INVALID, "null textures");
     if (n > (1u << 28)) return fail(PT_ERR_TOO_LARGE, "too many spheres: %u", n);
+    if (desc->n_images > 0 && !desc->images) return fail(PT_ERR_INVALID, "null images with n_images = %u", desc->n_images);
+
+    // ---- images (texture.rs:6-37): one pool of packed RGB8 pixels, each image at a 16-byte aligned offset ----
+    std::vector<size_t> image_offset(desc->n_images, 0);
+    size_t image_pool_bytes = 0;
+    for (uint32_t i = 0; i < desc->n_images; ++i) {
+        const PtImage& im = desc->images[i];
+        if (im.width == 0 || im.height == 0 || !im.data) return fail(PT_ERR_INVALID, "image %u: empty (%ux%u) or null data", i, im.width, im.height);
+        if (im.width > (1u << 20) || im.height > (1u << 20)) return fail(PT_ERR_TOO_LARGE, "image %u: %ux%u is too large", i, im.width, im.height);
+        image_offset[i] = image_pool_bytes;
+        image_pool_bytes += ((size_t)im.width * im.height * 3 + 15) & ~(size_t)15;
+        if (image_pool_bytes > 0x7fffffffULL) return fail(PT_ERR_TOO_LARGE, "image textures exceed 2 GB");
+    }
 
     // ---- validate + flatten materials/textures ----
     bool uses_noise = false;
@@ -415,8 +432,10 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
                 return fail(PT_ERR_INVALID, "texture %u: checker child index out of range", t);
         } else if (tx.kind == PT_TEX_NOISE) {
             uses_noise = true;
+        } else if (tx.kind == PT_TEX_IMAGE) {
+            if (tx.image < 0 || (uint32_t)tx.image >= desc->n_images) return fail(PT_ERR_INVALID, "texture %u: image index %d out of range", t, tx.image);
         } else if (tx.kind != PT_TEX_CONSTANT) {
-            return fail(PT_ERR_UNSUPPORTED, "texture %u: kind %d is not supported (Image textures: texture.rs:27-36, SURVEY §8f)", t, tx.kind);
+            return fail(PT_ERR_UNSUPPORTED, "texture %u: kind %d is not a Texture variant (texture.rs:40-55)", t, tx.kind);
         }
     }
     if (uses_noise && !desc->perlin) return fail(PT_ERR_INVALID, "a Noise texture is present but desc.perlin is NULL");
@@ -545,6 +564,11 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
         d.kind = tx.kind;
         d.odd = tx.odd;
         d.even = tx.even;
+        if (tx.kind == PT_TEX_IMAGE) {
+            d.odd = (int32_t)desc->images[tx.image].width;
+            d.even = (int32_t)desc->images[tx.image].height;
+            d.offset = (int32_t)image_offset[tx.image];
+        }
         tex[t] = d;
     }
 
@@ -563,6 +587,13 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
     PT_CUDA_S(cudaMemcpy(s->d_shade, shade.data(), shade.size() * sizeof(pt::DevShade), cudaMemcpyHostToDevice));
     PT_CUDA_S(cudaMalloc(&s->d_tex, tex.size() * sizeof(pt::DevTexture)));
     PT_CUDA_S(cudaMemcpy(s->d_tex, tex.data(), tex.size() * sizeof(pt::DevTexture), cudaMemcpyHostToDevice));
+    if (image_pool_bytes > 0) {
+        std::vector<uint8_t> pool(image_pool_bytes, 0);
+        for (uint32_t i = 0; i < desc->n_images; ++i)
+            std::memcpy(pool.data() + image_offset[i], desc->images[i].data, (size_t)desc->images[i].width * desc->images[i].height * 3);
+        PT_CUDA_S(cudaMalloc(&s->d_images, pool.size()));
+        PT_CUDA_S(cudaMemcpy(s->d_images, pool.data(), pool.size(), cudaMemcpyHostToDevice));
+    }
     if (any_moving) {
         std::vector<pt::DevMotion> motion(n);
         for (uint32_t i = 0; i < n; ++i) {
@@ -620,6 +651,7 @@ void pt_scene_destroy(PtScene* s) {
     cudaFree(s->d_blocks);
     cudaFree(s->d_shade);
     cudaFree(s->d_tex);
+    cudaFree(s->d_images);
     cudaFree(s->d_perlin);
     cudaFree(s->d_prefilter);
     cudaFree(s->d_motion);

@@ -12,6 +12,8 @@ LIB_DIR = os.path.join(_PKG, "lib")
 HEADER = os.path.join(_ROOT, "include", "ptgpu.h")
 
 PT_OK, PT_ERR_INVALID, PT_ERR_UNSUPPORTED, PT_ERR_NO_DEVICE, PT_ERR_CUDA, PT_ERR_TOO_LARGE = range(6)
+PT_TEX_CONSTANT, PT_TEX_CHECKER, PT_TEX_NOISE, PT_TEX_IMAGE = range(4)
+PT_MAT_LAMBERTIAN, PT_MAT_METAL, PT_MAT_DIELECTRIC, PT_MAT_DIFFUSE_LIGHT = range(4)
 
 
 class PtError(RuntimeError):
@@ -33,7 +35,11 @@ class PtCamera(C.Structure):  # src/camera.rs:8-19
 
 class PtTexture(C.Structure):
     _fields_ = [("kind", C.c_int32), ("color", C.c_float * 3), ("odd", C.c_int32), ("even", C.c_int32),
-                ("scale", C.c_float), ("_pad", C.c_int32)]
+                ("scale", C.c_float), ("image", C.c_int32)]
+
+
+class PtImage(C.Structure):  # src/texture.rs:6-10
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("data", C.POINTER(C.c_uint8))]
 
 
 class PtMaterial(C.Structure):
@@ -56,7 +62,8 @@ class PtSceneDesc(C.Structure):
                 ("radius", C.POINTER(C.c_float)), ("material_index", C.POINTER(C.c_int32)),
                 ("n_materials", C.c_uint32), ("n_textures", C.c_uint32),
                 ("materials", C.POINTER(PtMaterial)), ("textures", C.POINTER(PtTexture)), ("perlin", C.POINTER(PtPerlin)),
-                ("has_sky", C.c_uint32), ("sky", C.c_float * 3), ("motion", C.POINTER(PtMotion))]
+                ("has_sky", C.c_uint32), ("sky", C.c_float * 3), ("motion", C.POINTER(PtMotion)),
+                ("n_images", C.c_uint32), ("_pad", C.c_uint32), ("images", C.POINTER(PtImage))]
 
 
 class PtPartition(C.Structure):
@@ -156,6 +163,7 @@ def libpthost():
         L.pth_render_offline.argtypes = [C.c_char_p, C.POINTER(PthParams), C.c_char_p, C.c_int32, C.POINTER(C.c_double),
                                          C.POINTER(C.c_uint64)]
         L.pth_write_png.argtypes = [C.c_char_p, vp, C.c_uint32, C.c_uint32]
+        L.pth_image_open.argtypes = [C.c_char_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), vp, C.c_uint64]
         _pthost = L
     return _pthost
 

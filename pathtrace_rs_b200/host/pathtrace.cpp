@@ -1,8 +1,10 @@
 // pathtrace.cpp — implementation of the C++ host mirror (see pathtrace.hpp) + its C interface for ctypes.
 #include "pathtrace.hpp"
 
+#include <cctype>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <unordered_map>
@@ -100,7 +102,44 @@ namespace texture {
 Texture constant(Vec3 color) { Texture t; t.kind = Texture::Constant; t.color = color; return t; }
 Texture checker(const Texture* odd, const Texture* even) { Texture t; t.kind = Texture::Checker; t.odd = odd; t.even = even; return t; }
 Texture noise(const Perlin* n, float scale) { Texture t; t.kind = Texture::Noise; t.noise = n; t.scale = scale; return t; }
+Texture rgb_image(const RgbImage* image) { Texture t; t.kind = Texture::Image; t.image = image; return t; }
 }  // namespace texture
+
+// ---- RgbImage (src/texture.rs:12-25) ----
+RgbImage RgbImage::from_raw(uint32_t width, uint32_t height, std::vector<uint8_t> data) {
+    if (width == 0 || height == 0 || data.size() != (size_t)width * height * 3) throw std::runtime_error("RgbImage: data length != width*height*3");
+    RgbImage im;
+    im.width_ = width;
+    im.height_ = height;
+    im.data_ = std::move(data);
+    return im;
+}
+RgbImage RgbImage::open(const std::string& path) {
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) throw std::runtime_error("RgbImage::open: cannot open '" + path + "'");  // image::open(path).unwrap()
+    std::vector<uint8_t> bytes;
+    uint8_t chunk[65536];
+    size_t got;
+    while ((got = std::fread(chunk, 1, sizeof(chunk), f)) > 0) bytes.insert(bytes.end(), chunk, chunk + got);
+    std::fclose(f);
+    // binary PPM: "P6" <ws> width <ws> height <ws> maxval <single ws> pixels; '#' starts a comment up to end of line
+    size_t pos = 0;
+    auto token = [&]() -> std::string {
+        for (;;) {
+            while (pos < bytes.size() && std::isspace(bytes[pos])) ++pos;
+            if (pos < bytes.size() && bytes[pos] == '#') { while (pos < bytes.size() && bytes[pos] != '\n') ++pos; continue; }
+            break;
+        }
+        std::string t;
+        while (pos < bytes.size() && !std::isspace(bytes[pos])) t.push_back((char)bytes[pos++]);
+        return t;
+    };
+    if (token() != "P6") throw std::runtime_error("RgbImage::open: '" + path + "' is not a binary PPM (the only format this mirror decodes; the reference uses the image crate)");
+    const long w = std::atol(token().c_str()), h = std::atol(token().c_str()), maxval = std::atol(token().c_str());
+    pos += 1;  // the single whitespace byte after maxval
+    if (w <= 0 || h <= 0 || maxval != 255 || bytes.size() < pos + (size_t)w * h * 3) throw std::runtime_error("RgbImage::open: '" + path + "': bad or truncated PPM");
+    return from_raw((uint32_t)w, (uint32_t)h, std::vector<uint8_t>(bytes.begin() + pos, bytes.begin() + pos + (size_t)w * h * 3));
+}
 namespace material {
 Material lambertian(const Texture* albedo) { Material m; m.kind = Material::Lambertian; m.albedo_tex = albedo; return m; }
 Material metal(Vec3 albedo, float fuzz) { Material m; m.kind = Material::Metal; m.albedo = albedo; m.fuzz = fuzz; return m; }
@@ -119,7 +158,19 @@ struct Flattener {
     std::vector<PtTexture> textures;
     std::unordered_map<const Material*, int32_t> mat_ids;
     std::unordered_map<const Texture*, int32_t> tex_ids;
+    std::vector<PtImage> images;
+    std::unordered_map<const RgbImage*, int32_t> image_ids;
     const Perlin* perlin = nullptr;
+
+    int32_t image_id(const RgbImage* im) {
+        if (!im) throw std::runtime_error("null image reference");
+        auto it = image_ids.find(im);
+        if (it != image_ids.end()) return it->second;
+        images.push_back(PtImage{im->width(), im->height(), im->data().data()});
+        const int32_t id = (int32_t)images.size() - 1;
+        image_ids.emplace(im, id);
+        return id;
+    }
 
     int32_t texture_id(const Texture* t) {
         if (!t) throw std::runtime_error("null texture reference");
@@ -128,7 +179,10 @@ struct Flattener {
         PtTexture f{};
         f.kind = t->kind;
         f.odd = f.even = -1;
-        if (t->kind == Texture::Constant) {
+        f.image = -1;
+        if (t->kind == Texture::Image) {
+            f.image = image_id(t->image);
+        } else if (t->kind == Texture::Constant) {
             f.color[0] = t->color.x; f.color[1] = t->color.y; f.color[2] = t->color.z;
         } else if (t->kind == Texture::Checker) {
             f.odd = texture_id(t->odd);
@@ -202,6 +256,8 @@ Scene::Scene(const std::vector<Hitable>& world, std::optional<Vec3> sky, int dev
     d.textures = fl.textures.data();
     d.perlin = fl.perlin ? &fl.perlin->tables() : nullptr;
     d.motion = fl.any_moving ? fl.motion.data() : nullptr;
+    d.n_images = (uint32_t)fl.images.size();
+    d.images = fl.images.empty() ? nullptr : fl.images.data();
     d.has_sky = sky.has_value() ? 1u : 0u;
     if (sky) { d.sky[0] = sky->x; d.sky[1] = sky->y; d.sky[2] = sky->z; }
     n_spheres_ = d.n_spheres;
@@ -329,6 +385,15 @@ Preset smallpt(const Params& params, Storage& st) {  // presets.rs:853-930
     h.push_back(sphere(st, Vec3(50.0f, 81.6f - 16.5f, 81.6f), 1.5f, material::diffuse_light(constant(st, Vec3(4.0f, 4.0f, 4.0f) * 100.0f))));
     return Preset(std::move(h), camera, Vec3(0.0f, 0.0f, 0.0f));
 }
+Preset earth(const Params& params, Storage& st) {  // presets.rs:555-594
+    Camera camera = rtiow_camera(params, 0.0f, 0.0f);
+    const char* env = std::getenv("PATHTRACE_EARTHMAP");
+    const RgbImage* earth_image = st.alloc_image(RgbImage::open(env && *env ? env : "media/earthmap.jpg"));
+    const Texture* earth_texture = st.alloc_texture(texture::rgb_image(earth_image));
+    std::vector<Hitable> h;
+    h.push_back(sphere(st, Vec3(0.0f, 0.0f, 0.0f), 2.0f, material::lambertian(earth_texture)));
+    return Preset(std::move(h), camera, std::nullopt);
+}
 }  // namespace
 
 std::optional<Preset> from_name(const std::string& name, const Params& params, Xoshiro256Plus& rng, Storage& storage, bool quiet) {
@@ -340,6 +405,7 @@ std::optional<Preset> from_name(const std::string& name, const Params& params, X
     if (name == "small") return small(params, storage);
     if (name == "smallpt") return smallpt(params, storage);
     if (name == "two_perlin_spheres") return two_perlin_spheres(params, storage);
+    if (name == "earth") return earth(params, storage);
     if (name == "final") return Preset({}, rtiow_camera(params, 0.1f, 1.0f), std::nullopt);  // presets.rs:40-71: an empty stub
     return std::nullopt;
 }
@@ -566,6 +632,20 @@ int32_t pth_flatten_rejects_non_sphere(void) {
     try {
         std::vector<pathtrace::Hitable> world{pathtrace::Hitable::unsupported("Rect")};
         pathtrace::Scene s(world, std::nullopt, 0);
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+
+// RgbImage::open (texture.rs:14-25): width/height, and the pixels when rgb_out != nullptr (cap bytes available)
+int32_t pth_image_open(const char* path, uint32_t* width, uint32_t* height, uint8_t* rgb_out, uint64_t cap) {
+    try {
+        const pathtrace::RgbImage im = pathtrace::RgbImage::open(path);
+        *width = im.width();
+        *height = im.height();
+        if (rgb_out) {
+            if (cap < im.data().size()) throw std::runtime_error("buffer too small");
+            std::memcpy(rgb_out, im.data().data(), im.data().size());
+        }
         return 0;
     } catch (const std::exception& e) { g_err = e.what(); return 1; }
 }

@@ -80,19 +80,38 @@ private:
     PtPerlin t_;
 };
 
+// src/texture.rs:6-25 — width*height packed 8-bit RGB, row 0 = top (`image.to_rgb8().into_raw()`).  The lookup
+// (`RgbImage::value`, texture.rs:27-36) is device code.
+class RgbImage {
+public:
+    // RgbImage::open.  The reference decodes any format through the `image` crate; this mirror decodes binary PPM ("P6",
+    // maxval 255) whatever the file is called, and throws for a missing file (the reference `unwrap`s) or another format.
+    static RgbImage open(const std::string& path);
+    static RgbImage from_raw(uint32_t width, uint32_t height, std::vector<uint8_t> data);
+    uint32_t width() const { return width_; }
+    uint32_t height() const { return height_; }
+    const std::vector<uint8_t>& data() const { return data_; }
+
+private:
+    uint32_t width_ = 0, height_ = 0;
+    std::vector<uint8_t> data_;
+};
+
 // src/texture.rs:40-72
 struct Texture {
-    enum Kind { Constant = PT_TEX_CONSTANT, Checker = PT_TEX_CHECKER, Noise = PT_TEX_NOISE } kind = Constant;
+    enum Kind { Constant = PT_TEX_CONSTANT, Checker = PT_TEX_CHECKER, Noise = PT_TEX_NOISE, Image = PT_TEX_IMAGE } kind = Constant;
     Vec3 color;                   // Constant
     const Texture* odd = nullptr;  // Checker
     const Texture* even = nullptr;
     const Perlin* noise = nullptr;  // Noise
     float scale = 0;
+    const RgbImage* image = nullptr;  // Image
 };
 namespace texture {
 Texture constant(Vec3 color);
 Texture checker(const Texture* odd, const Texture* even);
 Texture noise(const Perlin* noise, float scale);
+Texture rgb_image(const RgbImage* image);
 }  // namespace texture
 
 // src/material.rs:13-39
@@ -159,6 +178,7 @@ public:
     const Material* alloc_material(Material m) { materials_.push_back(m); return &materials_.back(); }
     const Sphere* alloc_sphere(Sphere s) { spheres_.push_back(s); return &spheres_.back(); }
     const MovingSphere* alloc_moving_sphere(MovingSphere s) { moving_spheres_.push_back(s); return &moving_spheres_.back(); }
+    const RgbImage* alloc_image(RgbImage i) { images_.push_back(std::move(i)); return &images_.back(); }  // storage.rs: image_arena
     Perlin perlin_noise;
 
 private:
@@ -166,6 +186,7 @@ private:
     std::deque<Material> materials_;
     std::deque<Sphere> spheres_;
     std::deque<MovingSphere> moving_spheres_;
+    std::deque<RgbImage> images_;
 };
 
 struct Params;
@@ -203,8 +224,10 @@ struct Params {
 
 namespace presets {
 using Preset = std::tuple<std::vector<Hitable>, Camera, std::optional<Vec3>>;
-// presets::from_name — sphere-only presets: random (moving spheres), random_spheres, small, two_perlin_spheres, smallpt, final,
-// plus the synthetic stress100k.  Other names -> nullopt ("unrecognised preset").
+// presets::from_name — sphere-only presets: random (moving spheres), random_spheres, small, two_perlin_spheres, smallpt, earth,
+// final, plus the synthetic stress100k.  Other names -> nullopt ("unrecognised preset").
+// `earth` opens "media/earthmap.jpg" like presets.rs:583 (the asset is not part of the reference tree); the environment
+// variable PATHTRACE_EARTHMAP names another file.
 std::optional<Preset> from_name(const std::string& name, const Params& params, Xoshiro256Plus& rng, Storage& storage, bool quiet = false);
 }  // namespace presets
 

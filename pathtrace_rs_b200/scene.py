@@ -5,6 +5,7 @@ Mirrors the call sequence of ``render_offline`` (src/offline.rs:16-29):
 (GPU upload); ``.update(...)`` = ``scene.update(&params, &camera, frame_num, &mut buffer) -> ray_count``.
 """
 import ctypes as C
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -162,6 +163,26 @@ def probe_fp32_peak(device=0):
     v = C.c_double(0)
     ffi.check(ffi.libptgpu().pt_probe_fp32_peak(device, C.byref(v)))
     return v.value
+
+
+def image_open(path):
+    """RgbImage::open (src/texture.rs:14-25) through the host mirror: uint8 [height, width, 3], row 0 = top."""
+    L = ffi.libpthost()
+    w, h = C.c_uint32(), C.c_uint32()
+    if L.pth_image_open(os.fsencode(path), C.byref(w), C.byref(h), None, 0) != 0:
+        raise RuntimeError(L.pth_last_error().decode())
+    px = np.zeros((h.value, w.value, 3), np.uint8)
+    if L.pth_image_open(os.fsencode(path), C.byref(w), C.byref(h), _vp(px), px.nbytes) != 0:
+        raise RuntimeError(L.pth_last_error().decode())
+    return px
+
+
+def write_ppm(path, rgb8):
+    """Binary PPM (P6) writer — the one image format RgbImage::open decodes in this mirror."""
+    rgb8 = np.ascontiguousarray(rgb8, np.uint8)
+    with open(path, "wb") as f:
+        f.write(b"P6\n%d %d\n255\n" % (rgb8.shape[1], rgb8.shape[0]))
+        f.write(rgb8.tobytes())
 
 
 def render_offline(preset, params, output_png="", device=0):

@@ -2,13 +2,14 @@
 //! a `Hitable::List` of spheres / moving spheres and forwards `Scene::update` to the CUDA library.  NOT compiled in this repository's CI
 //! (no Rust toolchain in the build image); the identical C ABI is exercised by the C++ mirror and the ctypes tests.
 //!
-//! Needs four small `pub(crate)` accessors in the reference:
+//! Needs five small `pub(crate)` accessors in the reference:
 //!   Camera::to_ffi(&self) -> PtCamera                      (src/camera.rs, fields are private)
 //!   Scene::world(&self) -> &Hitable, Scene::sky(&self) -> Option<Vec3>      (src/scene.rs:18-22)
 //!   HitableList::hitables(&self) -> &[Hitable]             (src/collision/hitable_list.rs:9-11)
 //!   Perlin::tables(&self) -> (&[Vec3], &[u32], &[u32], &[u32])               (src/perlin.rs:7-12)
+//!   RgbImage::raw(&self) -> (u32, u32, &[u8])              (src/texture.rs:6-10, fields are private)
 #![cfg(feature = "gpu")]
-use crate::{camera::Camera, collision::Hitable, material::Material, params::Params, perlin::Perlin, scene::Scene, texture::Texture};
+use crate::{camera::Camera, collision::Hitable, material::Material, params::Params, perlin::Perlin, scene::Scene, texture::{RgbImage, Texture}};
 use std::{collections::HashMap, ffi::CStr, os::raw::{c_char, c_int, c_void}, ptr};
 
 #[repr(C)] #[derive(Copy, Clone, Default)]
@@ -16,7 +17,10 @@ pub struct PtParams { pub width: u32, pub height: u32, pub samples: u32, pub max
 #[repr(C)] #[derive(Copy, Clone, Default)]
 pub struct PtCamera { pub origin: [f32; 3], pub lower_left_corner: [f32; 3], pub horizontal: [f32; 3], pub vertical: [f32; 3], pub u: [f32; 3], pub v: [f32; 3], pub w: [f32; 3], pub time0: f32, pub time1: f32, pub lens_radius: f32 }
 #[repr(C)] #[derive(Copy, Clone, Default)]
-pub struct PtTexture { pub kind: i32, pub color: [f32; 3], pub odd: i32, pub even: i32, pub scale: f32, pub _pad: i32 }
+pub struct PtTexture { pub kind: i32, pub color: [f32; 3], pub odd: i32, pub even: i32, pub scale: f32, pub image: i32 }
+/// src/texture.rs:6-10: `image.to_rgb8().into_raw()` (copied by pt_scene_create)
+#[repr(C)] #[derive(Copy, Clone)]
+pub struct PtImage { pub width: u32, pub height: u32, pub data: *const u8 }
 #[repr(C)] #[derive(Copy, Clone, Default)]
 pub struct PtMaterial { pub kind: i32, pub texture: i32, pub albedo: [f32; 3], pub fuzz: f32, pub ref_idx: f32, pub _pad: i32 }
 #[repr(C)]
@@ -28,6 +32,7 @@ pub struct PtSceneDesc {
     pub n_materials: u32, pub n_textures: u32, pub materials: *const PtMaterial, pub textures: *const PtTexture, pub perlin: *const PtPerlin,
     pub has_sky: u32, pub sky: [f32; 3],
     pub motion: *const PtMotion, // per sphere, or null when nothing moves
+    pub n_images: u32, pub _pad: u32, pub images: *const PtImage,
 }
 /// src/collision/moving_sphere.rs:16-26 inverted to its constructor arguments (centre0/radius travel in the sphere arrays)
 #[repr(C)] #[derive(Copy, Clone, Default)]
@@ -53,7 +58,7 @@ impl GpuScene {
     /// The GPU arm of `Params::new_scene` (src/params.rs:29-46): walk `Hitable::List`, reject anything that is not a sphere
     /// (same message as the panic in src/collision/spheres_soa.rs:49-51), dedupe arena pointers into indices, upload.
     pub fn new(scene: &Scene, perlin: &Perlin, device: i32) -> GpuScene {
-        assert_eq!(unsafe { pt_abi_version() }, 2);
+        assert_eq!(unsafe { pt_abi_version() }, 3);
         assert_eq!(unsafe { pt_abi_struct_size(5) } as usize, std::mem::size_of::<PtSceneDesc>());
         let hitables = match scene.world() { Hitable::List(list) => list.hitables(), other => panic!("Expected Hitable::List, got {:?}", other) };
         let (mut cx, mut cy, mut cz, mut radius, mut mat_index) = (vec![], vec![], vec![], vec![], vec![]);
@@ -63,15 +68,28 @@ impl GpuScene {
         let mut mat_ids: HashMap<*const Material, i32> = HashMap::new();
         let mut tex_ids: HashMap<*const Texture, i32> = HashMap::new();
         let mut uses_noise = false;
-        fn texture_id(t: &Texture, textures: &mut Vec<PtTexture>, ids: &mut HashMap<*const Texture, i32>, uses_noise: &mut bool) -> i32 {
-            if let Some(id) = ids.get(&(t as *const Texture)) { return *id; }
-            let mut f = PtTexture { odd: -1, even: -1, ..Default::default() };
+        let mut images: Vec<PtImage> = vec![];
+        let mut image_ids: HashMap<*const RgbImage, i32> = HashMap::new();
+        struct Tables<'t> { textures: &'t mut Vec<PtTexture>, ids: &'t mut HashMap<*const Texture, i32>, images: &'t mut Vec<PtImage>,
+                            image_ids: &'t mut HashMap<*const RgbImage, i32>, uses_noise: &'t mut bool }
+        fn texture_id(t: &Texture, tb: &mut Tables) -> i32 {
+            if let Some(id) = tb.ids.get(&(t as *const Texture)) { return *id; }
+            let mut f = PtTexture { odd: -1, even: -1, image: -1, ..Default::default() };
             match t {
                 Texture::Constant { color } => { f.kind = 0; f.color = [color.x, color.y, color.z]; }
-                Texture::Checker { odd, even } => { f.kind = 1; f.odd = texture_id(odd, textures, ids, uses_noise); f.even = texture_id(even, textures, ids, uses_noise); }
-                Texture::Noise { scale, .. } => { f.kind = 2; f.scale = *scale; *uses_noise = true; }
-                Texture::Image { .. } => panic!("Texture::Image is not supported on the GPU path"),
+                Texture::Checker { odd, even } => { f.kind = 1; f.odd = texture_id(odd, tb); f.even = texture_id(even, tb); }
+                Texture::Noise { scale, .. } => { f.kind = 2; f.scale = *scale; *tb.uses_noise = true; }
+                Texture::Image { image } => {
+                    f.kind = 3;
+                    let images = &mut *tb.images;
+                    f.image = *tb.image_ids.entry(*image as *const RgbImage).or_insert_with(|| {
+                        let (width, height, data) = image.raw();
+                        images.push(PtImage { width, height, data: data.as_ptr() });
+                        images.len() as i32 - 1
+                    });
+                }
             }
+            let (textures, ids) = (&mut *tb.textures, &mut *tb.ids);
             textures.push(f);
             let id = textures.len() as i32 - 1;
             ids.insert(t as *const Texture, id);
@@ -100,10 +118,10 @@ impl GpuScene {
                 let id = *mat_ids.entry(key).or_insert_with(|| {
                     let mut f = PtMaterial { texture: -1, ..Default::default() };
                     match material {
-                        Material::Lambertian { albedo } => { f.kind = 0; f.texture = texture_id(albedo, &mut textures, &mut tex_ids, &mut uses_noise); }
+                        Material::Lambertian { albedo } => { f.kind = 0; f.texture = texture_id(albedo, &mut Tables { textures: &mut textures, ids: &mut tex_ids, images: &mut images, image_ids: &mut image_ids, uses_noise: &mut uses_noise }); }
                         Material::Metal { albedo, fuzz } => { f.kind = 1; f.albedo = [albedo.x, albedo.y, albedo.z]; f.fuzz = *fuzz; }
                         Material::Dielectric { ref_idx } => { f.kind = 2; f.ref_idx = *ref_idx; }
-                        Material::DiffuseLight { emit } => { f.kind = 3; f.texture = texture_id(emit, &mut textures, &mut tex_ids, &mut uses_noise); }
+                        Material::DiffuseLight { emit } => { f.kind = 3; f.texture = texture_id(emit, &mut Tables { textures: &mut textures, ids: &mut tex_ids, images: &mut images, image_ids: &mut image_ids, uses_noise: &mut uses_noise }); }
                         Material::Isotropic { .. } => panic!("Material::Isotropic is not supported on the GPU path"),
                     }
                     materials.push(f);
@@ -128,6 +146,7 @@ impl GpuScene {
             perlin: tables.as_ref().map_or(ptr::null(), |t| &**t as *const PtPerlin),
             has_sky: sky.is_some() as u32, sky: sky.map_or([0.0; 3], |s| [s.x, s.y, s.z]),
             motion: if any_moving { motion.as_ptr() } else { ptr::null() },
+            n_images: images.len() as u32, _pad: 0, images: if images.is_empty() { ptr::null() } else { images.as_ptr() },
         };
         let mut handle: *mut PtScene = ptr::null_mut();
         let rc = unsafe { pt_scene_create(&desc, device, &mut handle) };

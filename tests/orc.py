@@ -15,7 +15,7 @@ _LIB_PATH = os.path.join(_ORACLE_DIR, "_build", "liboracle.so")
 
 HIT_LIST, HIT_SOA_SCALAR, HIT_SOA_AVX2 = 0, 1, 2
 MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC, MAT_DIFFUSE_LIGHT = 0, 1, 2, 3
-TEX_CONSTANT, TEX_CHECKER, TEX_NOISE = 0, 1, 2
+TEX_CONSTANT, TEX_CHECKER, TEX_NOISE, TEX_IMAGE = 0, 1, 2, 3
 
 
 class OrcParams(C.Structure):
@@ -60,6 +60,15 @@ def lib():
         L.orc_noise.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float]
         L.orc_tex_value.argtypes = [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_void_p]
         L.orc_srgb.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+        L.orc_set_earth_image.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
+        L.orc_scene_add_image.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        L.orc_scene_add_image_texture.argtypes = [C.c_void_p, C.c_int32]
+        L.orc_scene_add_checker_texture.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+        L.orc_scene_set_sphere_texture.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+        L.orc_scene_image_count.argtypes = [C.c_void_p]
+        L.orc_scene_image.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_image_value.argtypes = [C.c_void_p, C.c_int32, C.c_float, C.c_float, C.c_void_p]
+        L.orc_sphere_uv.argtypes = [C.c_float, C.c_float, C.c_float, C.c_void_p]
         L.orc_hit.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.orc_bench_fixture_ray.argtypes = [C.POINTER(OrcParams), C.c_void_p]
         L.orc_next_f32_after_random_spheres.restype = C.c_float
@@ -80,8 +89,12 @@ def params(width, height, samples, max_depth):
 class Scene:
     """A preset built by the oracle's restatement of presets.rs (scene rng seed 0)."""
 
-    def __init__(self, preset, width, height, samples=1, max_depth=50, custom=None):
+    def __init__(self, preset, width, height, samples=1, max_depth=50, custom=None, image=None):
+        """image: uint8 [h, w, 3] (row 0 = top) — what RgbImage::open would decode for the `earth` preset."""
         self.preset = preset
+        if image is not None:
+            image = np.ascontiguousarray(image, np.uint8)
+            lib().orc_set_earth_image(image.shape[1], image.shape[0], _p(image))
         self.p = params(width, height, samples, max_depth)
         if custom is not None:
             # custom = dict(centre_radius[n,4], kind[n], params5[n,5], motion[n,6] or None, cam15[15], sky[3] or None)
@@ -105,6 +118,35 @@ class Scene:
             self.close()
         except Exception:
             pass
+
+    # ---- Image textures (texture.rs:6-37) on a custom scene ----
+    def add_image(self, image):
+        image = np.ascontiguousarray(image, np.uint8)
+        return lib().orc_scene_add_image(self.h, image.shape[1], image.shape[0], _p(image))
+
+    def add_image_texture(self, image_index):
+        return lib().orc_scene_add_image_texture(self.h, image_index)
+
+    def add_checker_texture(self, odd, even):
+        return lib().orc_scene_add_checker_texture(self.h, odd, even)
+
+    def set_sphere_texture(self, sphere, tex):
+        lib().orc_scene_set_sphere_texture(self.h, sphere, tex)
+
+    def images(self):
+        out = []
+        for i in range(lib().orc_scene_image_count(self.h)):
+            w, h = C.c_uint32(), C.c_uint32()
+            lib().orc_scene_image(self.h, i, C.byref(w), C.byref(h), None)
+            px = np.zeros((h.value, w.value, 3), np.uint8)
+            lib().orc_scene_image(self.h, i, C.byref(w), C.byref(h), _p(px))
+            out.append(px)
+        return out
+
+    def image_value(self, image_index, u, v):
+        out = np.zeros(3, np.float32)
+        lib().orc_image_value(self.h, image_index, u, v, _p(out))
+        return out
 
     def counts(self):
         a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
@@ -199,6 +241,13 @@ def srgb(rgb):
     rgb = np.ascontiguousarray(rgb, np.float32).reshape(-1, 3)
     out = np.zeros((len(rgb), 3), np.uint8)
     lib().orc_srgb(_p(rgb), _p(out), len(rgb))
+    return out
+
+
+def sphere_uv(n):
+    """material.rs:41-49 get_sphere_uv for one normal."""
+    out = np.zeros(2, np.float32)
+    lib().orc_sphere_uv(float(n[0]), float(n[1]), float(n[2]), _p(out))
     return out
 
 

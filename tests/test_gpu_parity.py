@@ -406,14 +406,21 @@ def _random_scene(seed, n, moving=False, sky=False):
     return dict(centre_radius=cr, kind=kind, params5=p5, motion=motion, cam15=cam15, sky=np.array([0.7, 0.8, 1.0], np.float32) if sky else None)
 
 
-def _gpu_render_custom(custom, cam24, w, h, spp, depth):
+def _gpu_render_custom(custom, cam24, w, h, spp, depth, images=(), sphere_tex=None):
+    """images: uint8 [h, w, 3] arrays; sphere_tex: {sphere: ("image", k)} gives the sphere's material an Image texture of
+    image k, {sphere: ("checker", k)} a Checker whose odd child is that Image and whose even child is the sphere's colour."""
     L = ffi.libptgpu()
     n = len(custom["kind"])
     cr = custom["centre_radius"]
     cols = [np.ascontiguousarray(cr[:, i]) for i in range(4)] if n else [np.zeros(1, np.float32)] * 4
+    sphere_tex = sphere_tex or {}
     mats = (ffi.PtMaterial * max(n, 1))()
-    texs = (ffi.PtTexture * max(n, 1))()
+    texs = (ffi.PtTexture * (max(n, 1) + 2 * len(sphere_tex)))()
     midx = np.arange(max(n, 1), dtype=np.int32)
+    imgs = (ffi.PtImage * max(len(images), 1))()
+    keep = [np.ascontiguousarray(im, np.uint8) for im in images]
+    for k, im in enumerate(keep):
+        imgs[k].width, imgs[k].height, imgs[k].data = im.shape[1], im.shape[0], im.ctypes.data_as(C.POINTER(C.c_uint8))
     for i in range(n):
         k, p5 = int(custom["kind"][i]), custom["params5"][i]
         mats[i].kind, mats[i].texture = k, (i if k in (0, 3) else -1)
@@ -426,8 +433,19 @@ def _gpu_render_custom(custom, cam24, w, h, spp, depth):
     fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
     d.centre_x, d.centre_y, d.centre_z, d.radius = fp(cols[0]), fp(cols[1]), fp(cols[2]), fp(cols[3])
     d.material_index = midx.ctypes.data_as(C.POINTER(C.c_int32))
-    d.n_materials = d.n_textures = n
+    n_tex = n
+    for sphere, (how, k) in sorted(sphere_tex.items()):  # same order as the oracle-side helper (_apply_sphere_tex)
+        texs[n_tex].kind, texs[n_tex].image, texs[n_tex].odd, texs[n_tex].even = ffi.PT_TEX_IMAGE, k, -1, -1
+        n_tex += 1
+        if how == "checker":
+            texs[n_tex].kind, texs[n_tex].odd, texs[n_tex].even, texs[n_tex].image = ffi.PT_TEX_CHECKER, n_tex - 1, sphere, -1
+            n_tex += 1
+        mats[sphere].texture = n_tex - 1
+    d.n_materials, d.n_textures = n, n_tex
     d.materials, d.textures = mats, texs
+    d.n_images = len(keep)
+    if keep:
+        d.images = imgs
     if custom.get("sky") is not None:
         d.has_sky = 1
         d.sky[:] = [float(x) for x in custom["sky"]]
@@ -467,6 +485,78 @@ def test_random_scenes_through_the_c_abi(n, moving, sky):
     assert abs(rays - ref_rays) <= max(2, 1e-3 * ref_rays)
     assert np.mean(np.all(np.abs(img - ref) <= 1e-5 * np.maximum(1.0, np.abs(ref)), axis=2)) > 0.99
     assert np.isfinite(img).all()
+
+
+# ---- Texture::Image (texture.rs:6-37,76; material.rs:41-49,169-180) -----------------------------------------------------
+def _test_image(seed, w, h):
+    """A smooth-ish synthetic RGB8 picture (the reference's media/earthmap.jpg is not part of its tree)."""
+    r = np.random.default_rng(seed)
+    y, x = np.mgrid[0:h, 0:w]
+    base = np.stack([127 + 120 * np.sin(x * 0.31 + 1.0), 127 + 120 * np.cos(y * 0.23), 127 + 120 * np.sin((x + y) * 0.11)], axis=2)
+    return np.clip(base + r.integers(-6, 7, (h, w, 3)), 0, 255).astype(np.uint8)
+
+
+def _apply_sphere_tex(sc, images, sphere_tex):
+    ids = [sc.add_image(im) for im in images]
+    f = sc.flat()
+    for sphere, (how, k) in sorted(sphere_tex.items()):
+        t = sc.add_image_texture(ids[k])
+        if how == "checker":
+            own = int(f["mat_kind_tex"][f["sphere_material"][sphere], 1])  # the sphere's Constant colour texture
+            t = sc.add_checker_texture(t, own)
+        sc.set_sphere_texture(sphere, t)
+
+
+def test_earth_preset_image_texture_vs_oracle(tmp_path, monkeypatch):
+    """presets.rs:555-594: one Lambertian sphere with an Image albedo, looked up at get_sphere_uv(normal) as the SoA
+    epilogue does (spheres_soa.rs:141).  The image travels host mirror -> PtImage -> device pool."""
+    im = _test_image(7, 96, 48)
+    path = tmp_path / "earthmap.ppm"
+    pt.write_ppm(path, im)
+    monkeypatch.setenv("PATHTRACE_EARTHMAP", str(path))
+    w, h, spp, depth = 120, 60, 16, 50
+    img, rays, _ = gpu_render("earth", w, h, spp, depth)
+    sc = orc.Scene("earth", w, h, image=im)
+    ref, ref_rays = sc.update(spp, depth, mode=SOA_ITER)
+    assert rays == ref_rays
+    # device atan2f/asinf are a few ulp from libm: a sample whose (u, v) sits on a texel edge may pick the neighbour
+    assert np.mean(np.all(np.abs(img - ref) < 1e-5, axis=2)) > 0.98
+    assert rel_mean_diff(img, ref).max() < 2e-3
+    # the picture is really on the sphere: the sphere's pixels are not one flat colour (the live path's u = v = 0 would be)
+    centre = img[h // 4: 3 * h // 4, w // 3: 2 * w // 3].reshape(-1, 3)
+    assert centre.std(axis=0).min() > 0.02
+
+
+@pytest.mark.parametrize("n,moving", [(6, False), (40, True)])
+def test_image_textures_through_the_c_abi(n, moving):
+    """Image albedo on the ground and on a small sphere, an Image emitter, an Image nested in a Checker (sampled at
+    u = v = 0, material.rs:169-180), an Image on a MovingSphere (u = v = 0, moving_sphere.rs:53-54); two images."""
+    w, h, spp, depth = 61, 37, 6, 12
+    custom = _random_scene(4000 + n, n, moving, sky=False)
+    custom["kind"][3] = 0
+    custom["kind"][4] = 3
+    custom["kind"][5] = 0
+    images = [_test_image(1, 64, 32), _test_image(2, 5, 9)]
+    sphere_tex = {0: ("image", 0), 3: ("image", 1), 4: ("image", 1), 5: ("checker", 0)}
+    if moving:
+        mv = [i for i in range(6, n) if custom["motion"][i, 5] != 0 and custom["kind"][i] == 0]
+        assert mv
+        sphere_tex[mv[0]] = ("image", 0)
+    sc = orc.Scene("custom", w, h, custom=custom)
+    _apply_sphere_tex(sc, images, sphere_tex)
+    ref, ref_rays = sc.update(spp, depth, mode=SOA_ITER)
+    img, rays = _gpu_render_custom(custom, sc.flat()["camera"], w, h, spp, depth, images=images, sphere_tex=sphere_tex)
+    assert abs(rays - ref_rays) <= max(2, 1e-3 * ref_rays)
+    assert np.mean(np.all(np.abs(img - ref) <= 1e-5 * np.maximum(1.0, np.abs(ref)), axis=2)) > 0.97
+    assert rel_mean_diff(img, ref).max() < 5e-3
+    assert np.isfinite(img).all()
+
+
+def test_image_texture_errors():
+    custom = _random_scene(1, 4)
+    cam = orc.Scene("custom", 8, 8, custom=custom).flat()["camera"]
+    with pytest.raises(ffi.PtError, match="image index"):
+        _gpu_render_custom(custom, cam, 8, 8, 1, 1, images=[], sphere_tex={0: ("image", 0)})
 
 
 # ---- BASELINE sizes: size-independent properties ------------------------------------------------------------------------

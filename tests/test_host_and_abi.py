@@ -27,7 +27,7 @@ def test_abi_symbols_exported():
     assert len(names) >= 15 and "pt_render" in names and "pt_scene_create" in names
     for n in names:
         assert hasattr(L, n), n
-    assert L.pt_abi_version() == 2
+    assert L.pt_abi_version() == 3
     out = subprocess.check_output(["nm", "-D", "--defined-only", os.path.join(ffi.LIB_DIR, "libptgpu.so")], text=True)
     exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
     assert set(names) <= exported
@@ -36,7 +36,7 @@ def test_abi_symbols_exported():
 def test_ctypes_layouts_match_compiled_structs():
     L = pt.libptgpu()
     structs = [ffi.PtParams, ffi.PtCamera, ffi.PtTexture, ffi.PtMaterial, ffi.PtPerlin, ffi.PtSceneDesc, ffi.PtPartition,
-               ffi.PtDeviceInfo, ffi.PtRenderStats]
+               ffi.PtDeviceInfo, ffi.PtRenderStats, ffi.PtMotion, ffi.PtImage]
     for i, s in enumerate(structs):
         assert L.pt_abi_struct_size(i) == C.sizeof(s), s.__name__
     assert L.pt_abi_struct_size(99) == 0
@@ -86,6 +86,33 @@ def test_host_mirror_builds_the_oracles_scene(preset):
         if k in (orc.MAT_LAMBERTIAN, orc.MAT_DIFFUSE_LIGHT) and o["tex_kind_odd_even"][t, 0] != orc.TEX_CONSTANT:
             continue
         assert np.array_equal(host["params5"][i], exp), (i, k)
+
+
+def test_earth_preset_and_rgb_image_open(tmp_path, monkeypatch):
+    """presets.rs:555-594 + texture.rs:14-25 through the host mirror: same sphere/camera as the oracle's preset, pixels
+    decoded from a binary PPM (the mirror's one decoder), loud errors for a missing file or another format."""
+    r = np.random.default_rng(11)
+    im = r.integers(0, 256, (6, 10, 3)).astype(np.uint8)
+    path = tmp_path / "earthmap.ppm"
+    pt.write_ppm(path, im)
+    np.testing.assert_array_equal(pt.image_open(path), im)
+    with open(tmp_path / "commented.ppm", "wb") as f:  # header comments and arbitrary whitespace are legal PPM
+        f.write(b"P6 # made by hand\n10\t6\n# maxval next\n255\n" + im.tobytes())
+    np.testing.assert_array_equal(pt.image_open(tmp_path / "commented.ppm"), im)
+    monkeypatch.setenv("PATHTRACE_EARTHMAP", str(path))
+    host = pt.Preset("earth", pt.Params(120, 80, 1, 10)).flat()
+    o = orc.Scene("earth", 120, 80, image=im).flat()
+    assert np.array_equal(host["centre_radius"], o["centre_radius"]) and np.array_equal(host["camera"], o["camera"])
+    assert host["kind"].tolist() == [orc.MAT_LAMBERTIAN] and host["has_sky"] == o["has_sky"] == 0
+    monkeypatch.setenv("PATHTRACE_EARTHMAP", str(tmp_path / "missing.jpg"))
+    with pytest.raises(ValueError, match="cannot open"):  # image::open(path).unwrap() in the reference
+        pt.Preset("earth", pt.Params(8, 8, 1, 1))
+    (tmp_path / "not_ppm.jpg").write_bytes(b"\xff\xd8\xff\xe0 not really a jpeg")
+    with pytest.raises(RuntimeError, match="binary PPM"):
+        pt.image_open(tmp_path / "not_ppm.jpg")
+    (tmp_path / "short.ppm").write_bytes(b"P6\n4 4\n255\n" + bytes(10))
+    with pytest.raises(RuntimeError, match="truncated"):
+        pt.image_open(tmp_path / "short.ppm")
 
 
 def test_host_rng_continues_like_the_reference():

@@ -17,6 +17,65 @@ import orc
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
 
+# ---- Texture::Image: closed-form pins of get_sphere_uv / RgbImage::value ---------------------------------
+def test_sphere_uv_closed_form():
+    """material.rs:41-49: phi = atan2(x, y) (the reference's argument order), theta = asin(y),
+    u = 1 - (phi + pi) / 2pi, v = (theta + pi/2) / pi."""
+    cases = {(0, 1, 0): (0.5, 1.0), (0, -1, 0): (0.0, 0.0), (1, 0, 0): (0.25, 0.5), (-1, 0, 0): (0.75, 0.5), (0, 0, 1): (0.5, 0.5)}
+    for n, (u, v) in cases.items():
+        got = orc.sphere_uv(n)
+        assert abs(got[0] - u) < 2e-7 and abs(got[1] - v) < 2e-7, (n, got)
+    r = np.random.default_rng(3)
+    for _ in range(200):
+        n = r.normal(size=3)
+        n /= np.linalg.norm(n)
+        n = n.astype(np.float32)
+        u, v = orc.sphere_uv(n)
+        assert abs(u - (1 - (np.arctan2(float(n[0]), float(n[1])) + np.pi) / (2 * np.pi))) < 1e-6
+        assert abs(v - (np.arcsin(float(n[1])) + np.pi / 2) / np.pi) < 1e-6
+    assert np.isnan(orc.sphere_uv([0.0, 1.0000001, 0.0])[1])  # |y| > 1 by rounding: asin -> NaN, which `as i32` maps to row 0
+
+
+def test_rgb_image_value_indexing():
+    """texture.rs:27-36: i = (u*w) as i32, j = ((1-v)*h - 0.001) as i32, both clamped; `as i32` saturates, NaN -> 0."""
+    r = np.random.default_rng(5)
+    im = r.integers(0, 256, (9, 5, 3)).astype(np.uint8)
+    sc = orc.Scene("earth", 8, 8, image=im)
+    h, w = im.shape[:2]
+    us = list(r.uniform(-0.5, 1.5, 300).astype(np.float32)) + [0.0, 1.0, np.float32(np.nan), np.float32(1e30), np.float32(-1e30)]
+    vs = list(r.uniform(-0.5, 1.5, 300).astype(np.float32)) + [1.0, 0.0, np.float32(np.nan), np.float32(-1e30), np.float32(1e30)]
+    for u, v in zip(us, vs):
+        fi = np.float32(u) * np.float32(w)
+        fj = np.float32(np.float32(np.float32(1.0) - np.float32(v)) * np.float32(h)) - np.float32(0.001)
+        cast = lambda x: 0 if np.isnan(x) else int(np.clip(np.trunc(np.float64(x)), -2**31, 2**31 - 1))
+        i = min(max(cast(fi), 0), w - 1)
+        j = min(max(cast(fj), 0), h - 1)
+        np.testing.assert_array_equal(sc.image_value(0, float(u), float(v)), im[j, i].astype(np.float32) / np.float32(255.0))
+
+
+def test_earth_preset_live_path_sees_one_texel():
+    """presets.rs:555-594.  Sphere::ray_hit returns u = v = 0 (sphere.rs:44-45): the LIVE list path colours the whole
+    globe with texel (0, height-1); the SoA epilogue (spheres_soa.rs:141) — the GPU path's spec — maps the picture."""
+    r = np.random.default_rng(9)
+    im = r.integers(1, 256, (16, 32, 3)).astype(np.uint8)
+    w, h = 48, 24
+    sc = orc.Scene("earth", w, h, image=im)
+    assert sc.counts() == (1, 1, 1) and sc.flat()["tex_kind_odd_even"][0, 0] == orc.TEX_IMAGE
+    np.testing.assert_array_equal(sc.images()[0], im)
+    lst, rays_l = sc.update(8, 1, mode=orc.HIT_LIST)      # depth 1: primary hit colour x sky
+    soa, rays_s = sc.update(8, 1, mode=orc.HIT_SOA_SCALAR)
+    assert rays_l == rays_s  # same hits, only the looked-up texel differs
+    centre_l = lst[h // 2 - 2: h // 2 + 2, w // 2 - 2: w // 2 + 2].reshape(-1, 3)
+    centre_s = soa[h // 2 - 2: h // 2 + 2, w // 2 - 2: w // 2 + 2].reshape(-1, 3)
+    texel = im[15, 0].astype(np.float32) / 255.0
+    ratio = centre_l / texel  # = the sky seen by the bounce, the same grey-blue ramp in all three channels' ratios
+    assert np.all(ratio <= 1.0 + 1e-6) and np.all(ratio >= 0.25)
+    assert np.abs(centre_l - centre_s).max() > 0.05  # the two paths genuinely differ on this preset
+    with pytest.raises(ValueError):
+        orc.lib().orc_set_earth_image(0, 0, None)
+        orc.Scene("earth", w, h)
+
+
 # ---- (1) RNG known answers ------------------------------------------------------------------------------
 def test_splitmix64_seed_from_u64_zero():
     # SplitMix64 from state 0 (Vigna's reference stream) == xoshiro state after seed_from_u64(0)
