@@ -31,6 +31,22 @@ __device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
     return *reinterpret_cast<float2*>(&d);
 }
 
+// same instruction, `asm volatile`: NVVM keeps volatile asm statements in source order (PT_SWEEP_GRAY relies on it)
+__device__ __forceinline__ float2 f2_fma_v(float2 a, float2 b, float2 c) {
+    u64_t d;
+    asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<u64_t*>(&a)), "l"(*reinterpret_cast<u64_t*>(&b)), "l"(*reinterpret_cast<u64_t*>(&c)));
+    return *reinterpret_cast<float2*>(&d);
+}
+#ifndef PT_SWEEP_GRAY
+#define PT_SWEEP_GRAY 0
+#endif
+#ifndef PT_SWEEP_AB
+#define PT_SWEEP_AB 0
+#endif
+#ifndef PT_AB_BLOCKS
+#define PT_AB_BLOCKS 1  // blocks of 4 spheres that advance through the chain steps together (PT_SWEEP_AB)
+#endif
+
 constexpr float kMinT = 0.001f;   // src/scene.rs:16
 constexpr float kMaxT = FLT_MAX;  // src/scene.rs:15
 
@@ -168,6 +184,58 @@ __device__ __forceinline__ void sweep_expanded(const float4* __restrict__ pf, in
         cX = lds128(addr); cY = lds128(addr + 16u); cZ = lds128(addr + 32u); cK = lds128(addr + 48u);
     }
     const uint32_t base = addr, end = addr + 64u * (uint32_t)n_blocks;
+#if PT_SWEEP_AB
+    // A/B-packed form (PT_SWEEP_AB): one packed FMA advances BOTH affine forms of ONE sphere, (A, B') += c_axis * (d_axis,
+    // 2 o_axis), so the 64-bit operand is the RAY pair — loop-invariant, the same register pair in the same slot for every
+    // sphere of a block, i.e. served by the operand reuse cache — and the sphere enters as a 32-bit broadcast scalar.
+    // 3 packed + 2 scalar instructions per test (L = A*A + B' + k) against 3.5 packed ones, but ~3.5 register words read
+    // per packed instruction instead of ~4.6 (the packed FMA is register-read bound: tools/probe_forms.cu).
+    if (!PIPE) {
+        const float2 PX = make_float2(dx, o2x), PY = make_float2(dy, o2y), PZ = make_float2(dz, o2z), P0 = make_float2(nod, 0.0f);
+#pragma unroll 1
+        for (; addr < end; addr += 64u * kLdsGroupBlocks) {
+            float Ls[4 * kLdsGroupBlocks];
+#pragma unroll
+            for (int g = 0; g < kLdsGroupBlocks; g += PT_AB_BLOCKS) {
+                float xs[4 * PT_AB_BLOCKS], ys[4 * PT_AB_BLOCKS], zs[4 * PT_AB_BLOCKS], ks[4 * PT_AB_BLOCKS];
+#pragma unroll
+                for (int b = 0; b < PT_AB_BLOCKS; ++b) {
+                    const float4 X = lds128(addr + 64u * (g + b)), Y = lds128(addr + 64u * (g + b) + 16u), Z = lds128(addr + 64u * (g + b) + 32u),
+                                 K = lds128(addr + 64u * (g + b) + 48u);
+                    xs[4 * b] = X.x; xs[4 * b + 1] = X.y; xs[4 * b + 2] = X.z; xs[4 * b + 3] = X.w;
+                    ys[4 * b] = Y.x; ys[4 * b + 1] = Y.y; ys[4 * b + 2] = Y.z; ys[4 * b + 3] = Y.w;
+                    zs[4 * b] = Z.x; zs[4 * b + 1] = Z.y; zs[4 * b + 2] = Z.z; zs[4 * b + 3] = Z.w;
+                    ks[4 * b] = K.x; ks[4 * b + 1] = K.y; ks[4 * b + 2] = K.z; ks[4 * b + 3] = K.w;
+                }
+                float2 acc[4 * PT_AB_BLOCKS];
+#pragma unroll
+                for (int e = 0; e < 4 * PT_AB_BLOCKS; ++e) acc[e] = f2_fma(make_float2(xs[e], xs[e]), PX, P0);
+#pragma unroll
+                for (int e = 0; e < 4 * PT_AB_BLOCKS; ++e) acc[e] = f2_fma(make_float2(ys[e], ys[e]), PY, acc[e]);
+#pragma unroll
+                for (int e = 0; e < 4 * PT_AB_BLOCKS; ++e) acc[e] = f2_fma(make_float2(zs[e], zs[e]), PZ, acc[e]);
+#pragma unroll
+                for (int e = 0; e < 4 * PT_AB_BLOCKS; ++e) Ls[4 * g + e] = __fadd_rn(__fmaf_rn(acc[e].x, acc[e].x, acc[e].y), ks[e]);
+            }
+            float mx = Ls[0];
+#pragma unroll
+            for (int p = 1; p < 4 * kLdsGroupBlocks; ++p) mx = fmaxf(mx, Ls[p]);
+            if (mx > oo) {
+                uint32_t mask = 0u;
+#pragma unroll
+                for (int p = 4 * kLdsGroupBlocks - 1; p >= 0; --p) mask = __funnelshift_l(__float_as_uint(__fsub_rn(oo, Ls[p])), mask, 1);
+                const uint32_t entry = ((((uint32_t)first_block + ((addr - base) >> 6)) / kLdsGroupBlocks) << kLdsMaskBits) | mask;
+                if (cnt < kQueueCap) {
+                    q[cnt * kSweepThreads] = entry;
+                    cnt += 1;
+                } else {
+                    sweep_resolve_entry<kLdsMaskBits, MOTION>(exact, mc, entry, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
+                }
+            }
+        }
+        return;
+    }
+#endif
 #pragma unroll 1
     for (; addr < end; addr += 64u * kLdsGroupBlocks) {
         // (a warp-uniform single-branch form — vote.any on the group's flag — measured 1.5 % slower: the vote serialises
@@ -175,6 +243,44 @@ __device__ __forceinline__ void sweep_expanded(const float4* __restrict__ pf, in
         float2 L[2 * kLdsGroupBlocks];
         bool any;
         {
+#if PT_SWEEP_GRAY
+            // Operand-sharing order (PT_SWEEP_GRAY): the packed FMA is bound by register-file reads (5 words for
+            // pair * scalar + pair, tools/probe_forms.cu), and an operand that the previous instruction read in the same
+            // slot comes from the reuse cache.  Two blocks (4 sphere pairs) advance through the three chain steps together;
+            // inside a step consecutive instructions share either the sphere pair (A- and B-chain of one pair) or the ray
+            // scalar (B-chains / A-chains of neighbouring pairs).
+            if (!PIPE) {
+#pragma unroll
+                for (int g = 0; g < kLdsGroupBlocks; g += 2) {
+                    float2 cx[4], cy[4], cz[4], ck[4], A[4], B[4];
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+                        const float4 X = lds128(addr + 64u * (g + b)), Y = lds128(addr + 64u * (g + b) + 16u), Z = lds128(addr + 64u * (g + b) + 32u),
+                                     K = lds128(addr + 64u * (g + b) + 48u);
+                        cx[2 * b] = make_float2(X.x, X.y); cx[2 * b + 1] = make_float2(X.z, X.w);
+                        cy[2 * b] = make_float2(Y.x, Y.y); cy[2 * b + 1] = make_float2(Y.z, Y.w);
+                        cz[2 * b] = make_float2(Z.x, Z.y); cz[2 * b + 1] = make_float2(Z.z, Z.w);
+                        ck[2 * b] = make_float2(K.x, K.y); ck[2 * b + 1] = make_float2(K.z, K.w);
+                    }
+                    const float2 vdx = make_float2(dx, dx), vdy = make_float2(dy, dy), vdz = make_float2(dz, dz), vnod = make_float2(nod, nod);
+                    const float2 vox = make_float2(o2x, o2x), voy = make_float2(o2y, o2y), voz = make_float2(o2z, o2z);
+                    A[0] = f2_fma_v(cx[0], vdx, vnod);  B[0] = f2_fma_v(cx[0], vox, ck[0]);
+                    B[1] = f2_fma_v(cx[1], vox, ck[1]); A[1] = f2_fma_v(cx[1], vdx, vnod);
+                    A[2] = f2_fma_v(cx[2], vdx, vnod);  B[2] = f2_fma_v(cx[2], vox, ck[2]);
+                    B[3] = f2_fma_v(cx[3], vox, ck[3]); A[3] = f2_fma_v(cx[3], vdx, vnod);
+                    A[0] = f2_fma_v(cy[0], vdy, A[0]);  B[0] = f2_fma_v(cy[0], voy, B[0]);
+                    B[1] = f2_fma_v(cy[1], voy, B[1]);  A[1] = f2_fma_v(cy[1], vdy, A[1]);
+                    A[2] = f2_fma_v(cy[2], vdy, A[2]);  B[2] = f2_fma_v(cy[2], voy, B[2]);
+                    B[3] = f2_fma_v(cy[3], voy, B[3]);  A[3] = f2_fma_v(cy[3], vdy, A[3]);
+                    A[0] = f2_fma_v(cz[0], vdz, A[0]);  B[0] = f2_fma_v(cz[0], voz, B[0]);
+                    B[1] = f2_fma_v(cz[1], voz, B[1]);  A[1] = f2_fma_v(cz[1], vdz, A[1]);
+                    A[2] = f2_fma_v(cz[2], vdz, A[2]);  B[2] = f2_fma_v(cz[2], voz, B[2]);
+                    B[3] = f2_fma_v(cz[3], voz, B[3]);  A[3] = f2_fma_v(cz[3], vdz, A[3]);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) L[2 * g + q] = f2_fma_v(A[q], A[q], B[q]);
+                }
+            } else
+#endif
 #pragma unroll
             for (int g = 0; g < kLdsGroupBlocks; ++g) {
                 float4 X, Y, Z, K;

@@ -8,7 +8,8 @@ import re
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-LIB_DIR = os.path.join(_PKG, "lib")
+# PTGPU_LIB_DIR: development hook — load kernel variants built by tools/build_variant.sh (lib/<variant>/) instead of lib/
+LIB_DIR = os.environ.get("PTGPU_LIB_DIR") or os.path.join(_PKG, "lib")
 HEADER = os.path.join(_ROOT, "include", "ptgpu.h")
 
 PT_OK, PT_ERR_INVALID, PT_ERR_UNSUPPORTED, PT_ERR_NO_DEVICE, PT_ERR_CUDA, PT_ERR_TOO_LARGE = range(6)
