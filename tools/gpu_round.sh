@@ -1,6 +1,6 @@
 #!/bin/bash
 # One gpurun call: GPU parity suite, variant timings, bench line, ncu launch list + one full capture.  Outputs under gpurun_out/.
-# usage: tools/gpu_round.sh <tag> [variants...]
+# usage: [PARITY_VARIANTS="v ..."] tools/gpu_round.sh <tag> [variants to time...]
 tag=$1; shift
 out=gpurun_out; mkdir -p $out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $out/smi_$tag.txt 2>&1
@@ -9,7 +9,7 @@ for v in "" "$@"; do
   echo "== variant '$v'"
   timeout 120 python tools/variant_bench.py "$v" 256 random_spheres 1200 800 3 2>&1 | tail -1 | tee -a $out/variants_$tag.txt
 done
-for v in "$@"; do
+for v in $PARITY_VARIANTS; do
   echo "== parity subset with variant $v"
   PTGPU_LIB_DIR=$PWD/pathtrace_rs_b200/lib/$v timeout 600 python -m pytest tests -m gpu -q -k "bit_exact or cfg1 or random_scenes or golden or moving or image or chunk" > $out/pytest_gpu_${tag}_$v.log 2>&1; echo "exit $?"; tail -2 $out/pytest_gpu_${tag}_$v.log
 done
