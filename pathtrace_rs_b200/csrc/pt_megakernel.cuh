@@ -466,6 +466,11 @@ __device__ __forceinline__ bool cta_regroup(const KernelArgs& a, Lane& L, float&
 // =====================================================================================================
 // Resident variant: the whole sphere SoA lives in shared memory for the life of the CTA.
 // =====================================================================================================
+#ifdef PT_RES_PIPE
+constexpr bool kResidentPipe = true;  // LDS one block ahead in the resident kernel too (needs the registers: see PT_LDS_MIN_CTAS)
+#else
+constexpr bool kResidentPipe = false;
+#endif
 #ifdef PT_LDS_MIN_CTAS
 #define PT_LDS_LAUNCH_BOUNDS __launch_bounds__(kCtaThreads, PT_LDS_MIN_CTAS)
 #else
@@ -532,7 +537,7 @@ __global__ void PT_LDS_LAUNCH_BOUNDS pt_megakernel_resident(const __grid_constan
             const float nod = -((ox * dx + oy * dy) + oz * dz);
             const float oo = ((ox * ox + oy * oy) + oz * oz) * (1.0f - 1.9073486328125e-06f);
             int cnt = 0;
-            sweep_expanded<false, MOTION>(pf, a.n_blocks, 0, a.blocks, mc, queue, cnt, ox, oy, oz, dx, dy, dz, nod, ox + ox, oy + oy, oz + oz, oo, hit_t, hit_index);
+            sweep_expanded<kResidentPipe, MOTION>(pf, a.n_blocks, 0, a.blocks, mc, queue, cnt, ox, oy, oz, dx, dy, dz, nod, ox + ox, oy + oy, oz + oz, oo, hit_t, hit_index);
             sweep_drain<MOTION>(a.blocks, mc, queue, cnt, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
         }
         __syncwarp();

@@ -579,3 +579,24 @@ def test_cfg2_full_size_properties():
     assert np.all(img[-1, :, 2] > img[-1, :, 0])
     st = pr.stats()
     assert st.kernel_launches == 1 and st.d2h_bytes == w * h * 12 + 8
+
+
+def test_cfg3_full_size_properties():
+    """two_perlin_spheres 1920x1080, 1024 spp, depth 50 (BASELINE config 3) at full size: the noise texture is grey
+    (texture.rs:88: vec3(1,1,1) * ...), so every surface tints the three channels alike and the only colour in the picture
+    is the sky's; frames blend as an equal-weight mean at this size too."""
+    w, h, spp, depth = 1920, 1080, 1024, 50
+    img, rays, pr = gpu_render("two_perlin_spheres", w, h, spp, depth)
+    n = w * h * spp
+    assert n <= rays <= n * (depth + 1) and 2.0 < rays / n < 2.6  # the oracle measures 2.27 rays/sample on this view
+    assert np.isfinite(img).all() and img.min() >= 0 and img.max() <= 1 + 1e-5
+    # sky gradient scene.rs:43-46: white -> (0.5, 0.7, 1.0) * 0.3 ... blue >= green >= red wherever light arrives
+    assert np.all(img[..., 2] >= img[..., 1] - 1e-6) and np.all(img[..., 1] >= img[..., 0] - 1e-6)
+    ref, _ = orc.Scene("two_perlin_spheres", w, h).update(4, depth, mode=orc.HIT_SOA_SCALAR)
+    assert rel_mean_diff(img, ref).max() < 5e-3
+    bm = lambda a: a.reshape(h // 60, 60, w // 60, 60, 3).mean(axis=(1, 3))
+    assert np.abs(bm(img) - bm(ref)).max() < 0.03
+    # second frame of 1024 spp: running mean of two equal-weight frames (scene.rs:86-87) stays the same picture
+    img2, rays2 = pr.update(pt.Params(w, h, spp, depth), frame_num=1, buffer=img.copy())
+    assert rays2 != rays and np.abs(bm(img2) - bm(img)).max() < 5e-3
+    assert pr.stats().h2d_bytes == w * h * 12
