@@ -31,15 +31,7 @@ __device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
     return *reinterpret_cast<float2*>(&d);
 }
 
-// same instruction, `asm volatile`: NVVM keeps volatile asm statements in source order (PT_SWEEP_GRAY relies on it)
-__device__ __forceinline__ float2 f2_fma_v(float2 a, float2 b, float2 c) {
-    u64_t d;
-    asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<u64_t*>(&a)), "l"(*reinterpret_cast<u64_t*>(&b)), "l"(*reinterpret_cast<u64_t*>(&c)));
-    return *reinterpret_cast<float2*>(&d);
-}
-#ifndef PT_SWEEP_GRAY
-#define PT_SWEEP_GRAY 0
-#endif
+// PT_SWEEP_AB=1 builds the A/B-packed variant of the pre-filter (measured slower, kept for the record: DESIGN.md §5.1)
 #ifndef PT_SWEEP_AB
 #define PT_SWEEP_AB 0
 #endif
@@ -243,44 +235,6 @@ __device__ __forceinline__ void sweep_expanded(const float4* __restrict__ pf, in
         float2 L[2 * kLdsGroupBlocks];
         bool any;
         {
-#if PT_SWEEP_GRAY
-            // Operand-sharing order (PT_SWEEP_GRAY): the packed FMA is bound by register-file reads (5 words for
-            // pair * scalar + pair, tools/probe_forms.cu), and an operand that the previous instruction read in the same
-            // slot comes from the reuse cache.  Two blocks (4 sphere pairs) advance through the three chain steps together;
-            // inside a step consecutive instructions share either the sphere pair (A- and B-chain of one pair) or the ray
-            // scalar (B-chains / A-chains of neighbouring pairs).
-            if (!PIPE) {
-#pragma unroll
-                for (int g = 0; g < kLdsGroupBlocks; g += 2) {
-                    float2 cx[4], cy[4], cz[4], ck[4], A[4], B[4];
-#pragma unroll
-                    for (int b = 0; b < 2; ++b) {
-                        const float4 X = lds128(addr + 64u * (g + b)), Y = lds128(addr + 64u * (g + b) + 16u), Z = lds128(addr + 64u * (g + b) + 32u),
-                                     K = lds128(addr + 64u * (g + b) + 48u);
-                        cx[2 * b] = make_float2(X.x, X.y); cx[2 * b + 1] = make_float2(X.z, X.w);
-                        cy[2 * b] = make_float2(Y.x, Y.y); cy[2 * b + 1] = make_float2(Y.z, Y.w);
-                        cz[2 * b] = make_float2(Z.x, Z.y); cz[2 * b + 1] = make_float2(Z.z, Z.w);
-                        ck[2 * b] = make_float2(K.x, K.y); ck[2 * b + 1] = make_float2(K.z, K.w);
-                    }
-                    const float2 vdx = make_float2(dx, dx), vdy = make_float2(dy, dy), vdz = make_float2(dz, dz), vnod = make_float2(nod, nod);
-                    const float2 vox = make_float2(o2x, o2x), voy = make_float2(o2y, o2y), voz = make_float2(o2z, o2z);
-                    A[0] = f2_fma_v(cx[0], vdx, vnod);  B[0] = f2_fma_v(cx[0], vox, ck[0]);
-                    B[1] = f2_fma_v(cx[1], vox, ck[1]); A[1] = f2_fma_v(cx[1], vdx, vnod);
-                    A[2] = f2_fma_v(cx[2], vdx, vnod);  B[2] = f2_fma_v(cx[2], vox, ck[2]);
-                    B[3] = f2_fma_v(cx[3], vox, ck[3]); A[3] = f2_fma_v(cx[3], vdx, vnod);
-                    A[0] = f2_fma_v(cy[0], vdy, A[0]);  B[0] = f2_fma_v(cy[0], voy, B[0]);
-                    B[1] = f2_fma_v(cy[1], voy, B[1]);  A[1] = f2_fma_v(cy[1], vdy, A[1]);
-                    A[2] = f2_fma_v(cy[2], vdy, A[2]);  B[2] = f2_fma_v(cy[2], voy, B[2]);
-                    B[3] = f2_fma_v(cy[3], voy, B[3]);  A[3] = f2_fma_v(cy[3], vdy, A[3]);
-                    A[0] = f2_fma_v(cz[0], vdz, A[0]);  B[0] = f2_fma_v(cz[0], voz, B[0]);
-                    B[1] = f2_fma_v(cz[1], voz, B[1]);  A[1] = f2_fma_v(cz[1], vdz, A[1]);
-                    A[2] = f2_fma_v(cz[2], vdz, A[2]);  B[2] = f2_fma_v(cz[2], voz, B[2]);
-                    B[3] = f2_fma_v(cz[3], voz, B[3]);  A[3] = f2_fma_v(cz[3], vdz, A[3]);
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) L[2 * g + q] = f2_fma_v(A[q], A[q], B[q]);
-                }
-            } else
-#endif
 #pragma unroll
             for (int g = 0; g < kLdsGroupBlocks; ++g) {
                 float4 X, Y, Z, K;
