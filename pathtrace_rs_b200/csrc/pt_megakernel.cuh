@@ -597,13 +597,12 @@ __global__ void PT_STREAM_LAUNCH_BOUNDS pt_megakernel_streamed(const __grid_cons
     *pend = 0u;
     *tslot = 0.0f;
     const MotionCtx mc{a.motion, tslot};
-    const int n_warps = kCtaThreads / 32;
 
     if (threadIdx.x == 0) {
         mbar_init(&full_bar[0], 1);
         mbar_init(&full_bar[1], 1);
-        mbar_init(&empty_bar[0], n_warps);
-        mbar_init(&empty_bar[1], n_warps);
+        mbar_init(&empty_bar[0], kCtaThreads);  // every lane releases the buffer itself (no elected lane: each thread's
+        mbar_init(&empty_bar[1], kCtaThreads);  // own reads are ordered before its own arrive)
         fence_mbar_init();
         cta_live = 0;
     }
@@ -667,8 +666,8 @@ __global__ void PT_STREAM_LAUNCH_BOUNDS pt_megakernel_streamed(const __grid_cons
             const int first = tile * a.tile_blocks;
             const int nb = min(a.tile_blocks, a.n_blocks - first);
             sweep_expanded<kStreamPipe, MOTION>(tile_buf(b), nb, first, a.blocks, mc, queue, cnt, ox, oy, oz, dx, dy, dz, nod, ox + ox, oy + oy, oz + oz, oo, hit_t, hit_index);
+            mbar_arrive(&empty_bar[b]);
             __syncwarp();
-            if (lane_id == 0) mbar_arrive(&empty_bar[b]);
             if (threadIdx.x == 0 && tile + 2 < a.n_tiles) produce(tile + 2);
             // this tile's candidates: exact re-test against the global SoA (L2), off the tile buffer's critical path
             sweep_drain<MOTION>(a.blocks, mc, queue, cnt, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
