@@ -466,6 +466,9 @@ __device__ __forceinline__ bool cta_regroup(const KernelArgs& a, Lane& L, float&
 // =====================================================================================================
 // Resident variant: the whole sphere SoA lives in shared memory for the life of the CTA.
 // =====================================================================================================
+#ifndef PT_EXACT_SMEM
+#define PT_EXACT_SMEM 0
+#endif
 #ifdef PT_RES_PIPE
 constexpr bool kResidentPipe = true;  // LDS one block ahead in the resident kernel too (needs the registers: see PT_LDS_MIN_CTAS)
 #else
@@ -481,8 +484,15 @@ template <bool MOTION>
 __global__ void PT_LDS_LAUNCH_BOUNDS pt_megakernel_resident(const __grid_constant__ KernelArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
-    float4* pf = reinterpret_cast<float4*>(smem_raw);  // pre-filter image of the whole scene; exact blocks stay in global/L2
+    float4* pf = reinterpret_cast<float4*>(smem_raw);  // pre-filter image of the whole scene
+#if PT_EXACT_SMEM
+    // exact blocks right behind it: the candidate re-tests and the hit epilogue read them with LDS instead of LDG
+    const float4* ex = reinterpret_cast<const float4*>(smem_raw + (size_t)a.n_blocks * 64);
+    PerlinSmem* P = reinterpret_cast<PerlinSmem*>(smem_raw + (size_t)a.n_blocks * 128);
+#else
+    const float4* ex = a.blocks;  // exact blocks stay in global/L2
     PerlinSmem* P = reinterpret_cast<PerlinSmem*>(smem_raw + (size_t)a.n_blocks * 64);
+#endif
     uint32_t* queue = reinterpret_cast<uint32_t*>(P + 1) + threadIdx.x;  // [kQueueCap][kCtaThreads] candidate queues
     volatile uint32_t* pend = queue + kQueueCap * kCtaThreads;
     volatile float* tslot = reinterpret_cast<volatile float*>(pend + kCtaThreads);  // [kCtaThreads] ray.time per lane
@@ -500,8 +510,14 @@ __global__ void PT_LDS_LAUNCH_BOUNDS pt_megakernel_resident(const __grid_constan
     }
     __syncthreads();
     if (threadIdx.x == 0 && bytes != 0u) {
+#if PT_EXACT_SMEM
+        mbar_arrive_expect_tx(&bar, 2u * bytes);
+        tma_bulk_g2s_chunked(pf, a.prefilter, bytes, &bar);
+        tma_bulk_g2s_chunked(const_cast<float4*>(ex), a.blocks, bytes, &bar);
+#else
         mbar_arrive_expect_tx(&bar, bytes);
         tma_bulk_g2s_chunked(pf, a.prefilter, bytes, &bar);
+#endif
     }
     stage_perlin(a, P);
     __syncthreads();
@@ -537,8 +553,8 @@ __global__ void PT_LDS_LAUNCH_BOUNDS pt_megakernel_resident(const __grid_constan
             const float nod = -((ox * dx + oy * dy) + oz * dz);
             const float oo = ((ox * ox + oy * oy) + oz * oz) * (1.0f - 1.9073486328125e-06f);
             int cnt = 0;
-            sweep_expanded<kResidentPipe, MOTION>(pf, a.n_blocks, 0, a.blocks, mc, queue, cnt, ox, oy, oz, dx, dy, dz, nod, ox + ox, oy + oy, oz + oz, oo, hit_t, hit_index);
-            sweep_drain<MOTION>(a.blocks, mc, queue, cnt, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
+            sweep_expanded<kResidentPipe, MOTION>(pf, a.n_blocks, 0, ex, mc, queue, cnt, ox, oy, oz, dx, dy, dz, nod, ox + ox, oy + oy, oz + oz, oo, hit_t, hit_index);
+            sweep_drain<MOTION, true>(ex, mc, queue, cnt, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
         }
         __syncwarp();
         PT_PROF_TOCK(pf_sweep);
@@ -547,7 +563,7 @@ __global__ void PT_LDS_LAUNCH_BOUNDS pt_megakernel_resident(const __grid_constan
 #endif
         if (L.active) {
             rays += 1ULL;  // scene.rs:57
-            lane_shade<MOTION>(a, L, a.blocks, *P, mc, hit_t, hit_index);
+            lane_shade<MOTION>(a, L, ex, *P, mc, hit_t, hit_index);
         }
 #if PT_REGROUP
         lane_refill<MOTION>(a, L, lane_id, pend, tslot);  // ended paths sit side by side now: next sample / next ticket together
@@ -670,7 +686,7 @@ __global__ void PT_STREAM_LAUNCH_BOUNDS pt_megakernel_streamed(const __grid_cons
             __syncwarp();
             if (threadIdx.x == 0 && tile + 2 < a.n_tiles) produce(tile + 2);
             // this tile's candidates: exact re-test against the global SoA (L2), off the tile buffer's critical path
-            sweep_drain<MOTION>(a.blocks, mc, queue, cnt, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
+            sweep_drain<MOTION, false>(a.blocks, mc, queue, cnt, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
         }
         if (L.active) {
             rays += 1ULL;

@@ -168,6 +168,11 @@ __device__ __forceinline__ void sweep_expanded(const float4* __restrict__ pf, in
     // explicit shared-window address, advanced by one group per trip (keeps the loop's address arithmetic to one add)
     uint32_t addr = (uint32_t)__cvta_generic_to_shared(pf);
     asm volatile("" : "+r"(addr));
+    // the lane's queue base as a pinned shared-window address: left to itself ptxas rebuilds it from %tid, the CTA's
+    // shared window and n_blocks (12 instructions incl. S2R/S2UR) inside every candidate push — 27 % of the group
+    // iterations on cfg2.  Resident kernel only: the streamed kernel (PIPE) has no register to spare for it (-3 % there).
+    uint32_t qaddr = (uint32_t)__cvta_generic_to_shared(q);
+    if (!PIPE) asm volatile("" : "+r"(qaddr));
     // PIPE: software pipeline, one block deep — block b+1 is in flight while block b is tested (LDS latency off the
     // FFMA2 chain) at the price of 16 registers; pays when the kernel is at 2 CTAs/SM anyway (streamed tiles)
     const uint32_t last = addr + 64u * (uint32_t)(n_blocks > 0 ? n_blocks - 1 : 0);
@@ -273,7 +278,8 @@ __device__ __forceinline__ void sweep_expanded(const float4* __restrict__ pf, in
             }
             const uint32_t entry = ((((uint32_t)first_block + ((addr - base) >> 6)) / kLdsGroupBlocks) << kLdsMaskBits) | mask;
             if (cnt < kQueueCap) {
-                q[cnt * kSweepThreads] = entry;
+                if (!PIPE) asm volatile("st.shared.u32 [%0], %1;" ::"r"(qaddr + (uint32_t)cnt * (uint32_t)(kSweepThreads * 4)), "r"(entry) : "memory");
+                else q[cnt * kSweepThreads] = entry;
                 cnt += 1;
             } else {  // queue full (rare): test this group now; sweep_exact's tie rule makes the visiting order irrelevant
                 sweep_resolve_entry<kLdsMaskBits, MOTION>(exact, mc, entry, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
@@ -282,12 +288,25 @@ __device__ __forceinline__ void sweep_expanded(const float4* __restrict__ pf, in
     }
 }
 
-// drain the lane's queue: exact re-test of every flagged sphere (all lanes in parallel)
-template <bool MOTION>
+// drain the lane's queue: exact re-test of every flagged sphere (all lanes in parallel).  PIN: walk the queue through a
+// pinned shared-window address (resident kernel; see the push in sweep_expanded)
+template <bool MOTION, bool PIN>
 __device__ __forceinline__ void sweep_drain(const float4* __restrict__ exact, const MotionCtx& mc, const uint32_t* __restrict__ q, int& cnt, float ox, float oy, float oz,
                                             float dx, float dy, float dz, float& hit_t, int& hit_index) {
+    if (PIN) {
+        uint32_t qaddr = (uint32_t)__cvta_generic_to_shared(q);
+        asm volatile("" : "+r"(qaddr));
+        const uint32_t qend = qaddr + (uint32_t)cnt * (uint32_t)(kSweepThreads * 4);
 #pragma unroll 1
-    for (int i = 0; i < cnt; ++i) sweep_resolve_entry<kLdsMaskBits, MOTION>(exact, mc, q[i * kSweepThreads], ox, oy, oz, dx, dy, dz, hit_t, hit_index);
+        for (; qaddr != qend; qaddr += (uint32_t)(kSweepThreads * 4)) {
+            uint32_t entry;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(entry) : "r"(qaddr) : "memory");
+            sweep_resolve_entry<kLdsMaskBits, MOTION>(exact, mc, entry, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
+        }
+    } else {
+#pragma unroll 1
+        for (int i = 0; i < cnt; ++i) sweep_resolve_entry<kLdsMaskBits, MOTION>(exact, mc, q[i * kSweepThreads], ox, oy, oz, dx, dy, dz, hit_t, hit_index);
+    }
     cnt = 0;
 }
 

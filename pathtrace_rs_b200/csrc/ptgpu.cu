@@ -127,9 +127,10 @@ int plan_launch(PtScene* s) {
         return configure_streamed(s);
     }
     const size_t regroup_bytes = (size_t)pt::kRegroupWords * pt::kCtaThreads * sizeof(uint32_t) + 64;  // path-state exchange + category counters
-    if (all + regroup_bytes <= kMaxDynSmem) {
+    const size_t exact_bytes = PT_EXACT_SMEM ? (size_t)s->n_blocks * 64 : 0;  // resident kernel: exact blocks in shared memory too
+    if (all + regroup_bytes + exact_bytes <= kMaxDynSmem) {
         s->resident = true;
-        s->smem_bytes = all + regroup_bytes;
+        s->smem_bytes = all + regroup_bytes + exact_bytes;
         s->tile_blocks = s->n_blocks;
         s->n_tiles = 1;
         return s->d_motion ? configure_kernel(pt::pt_megakernel_resident<true>, s->smem_bytes, &s->ctas_per_sm)
