@@ -35,6 +35,14 @@ __device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
 #ifndef PT_SWEEP_AB
 #define PT_SWEEP_AB 0
 #endif
+// groups per trip of the pre-filter loop.  Two in the streamed kernel (all sweep, registers to spare: cfg5 +5.6 %); one in
+// the resident kernel, where the longer body costs more around the loop than the saved back-branch gives (cfg2 -1.4 %)
+#ifndef PT_GROUP_UNROLL_STREAMED
+#define PT_GROUP_UNROLL_STREAMED 2
+#endif
+#ifndef PT_GROUP_UNROLL_RESIDENT
+#define PT_GROUP_UNROLL_RESIDENT 1
+#endif
 #ifndef PT_AB_BLOCKS
 #define PT_AB_BLOCKS 1  // blocks of 4 spheres that advance through the chain steps together (PT_SWEEP_AB)
 #endif
@@ -233,7 +241,8 @@ __device__ __forceinline__ void sweep_expanded(const float4* __restrict__ pf, in
         return;
     }
 #endif
-#pragma unroll 1
+    constexpr int kGroupUnroll = PIPE ? PT_GROUP_UNROLL_STREAMED : PT_GROUP_UNROLL_RESIDENT;
+#pragma unroll kGroupUnroll
     for (; addr < end; addr += 64u * kLdsGroupBlocks) {
         // (a warp-uniform single-branch form — vote.any on the group's flag — measured 1.5 % slower: the vote serialises
         // the back-branch behind the whole FFMA2 chain, whereas this back-branch depends on the address alone)
