@@ -153,6 +153,18 @@ def test_golden_fixtures(name):
     assert rel_mean_diff(img, g["image"]).max() < 2e-2
 
 
+def test_golden_fixture_earth_image_texture(tmp_path, monkeypatch):
+    """The SoA-mode `earth` fixture (the picture travels inside the .npz and reaches the GPU through a PPM file)."""
+    g = np.load(os.path.join(GOLDEN, "earth_40x20_s8_d50.npz"))
+    w, h, s, d = (int(g[k]) for k in ("width", "height", "samples", "max_depth"))
+    pt.write_ppm(tmp_path / "earthmap.ppm", g["picture"])
+    monkeypatch.setenv("PATHTRACE_EARTHMAP", str(tmp_path / "earthmap.ppm"))
+    img, rays, _ = gpu_render("earth", w, h, s, d)
+    assert rays == int(g["rays"])
+    assert np.mean(np.all(np.abs(img - g["image"]) < 1e-5, axis=2)) > 0.97
+    assert rel_mean_diff(img, g["image"]).max() < 5e-3
+
+
 # ---- Scene::update semantics -------------------------------------------------------------------------------------
 def test_progressive_resident_accumulation_equals_host_round_trips():
     """pt_render_progressive (the windowed worker loop, glium_window.rs:96-131) keeps the accumulation buffer on the device;

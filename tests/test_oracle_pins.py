@@ -349,3 +349,12 @@ def test_golden_regression(name):
     img, rays = orc.Scene(preset, w, h).update(s, d, mode=orc.HIT_LIST)
     assert rays == int(g["rays"])
     np.testing.assert_allclose(img, g["image"], rtol=1e-6, atol=1e-7)  # libm sin/pow may differ in the last ulp
+
+
+def test_golden_regression_earth_image_texture():
+    g = np.load(os.path.join(GOLDEN, "earth_40x20_s8_d50.npz"))
+    w, h, s, d = (int(g[k]) for k in ("width", "height", "samples", "max_depth"))
+    img, rays = orc.Scene("earth", w, h, image=g["picture"]).update(s, d, mode=int(g["mode"]))
+    assert rays == int(g["rays"])
+    # libm atan2/asin may differ in the last ulp between builds: a sample on a texel edge may then read the neighbour
+    assert np.mean(np.all(np.abs(img - g["image"]) < 1e-6, axis=2)) > 0.98
