@@ -13,9 +13,8 @@
 // = 7 packed instructions per 2 (ray, sphere) tests on the "pre-filter image" X, Y, Z, K (k = r^2 - |c|^2 + slack) of a
 // block of 4 spheres.  Stage 2 re-tests only the flagged spheres with the reference's exact unfused expression
 // (sweep_exact = spheres_soa.rs:116-129) on the exact blocks X, Y, Z, R^2, so accepted hits and their `t` round like the
-// oracle's.  Two operand paths for stage 1: sweep_const reads the image through the constant bank into uniform
-// registers (scenes <= 4000 spheres), sweep_expanded reads it with broadcast LDS.128 from a TMA-staged shared-memory
-// tile (resident up to ~13 k spheres, streamed beyond).  Padding: k = -3e38 in the image (never a candidate),
+// oracle's.  Stage 1 (sweep_expanded) reads the image with broadcast LDS.128 from a TMA-staged shared-memory tile
+// (resident up to ~13 k spheres, streamed beyond).  Padding: k = -3e38 in the image (never a candidate),
 // centre = FLT_MAX, r^2 = 0 in the exact blocks (spheres_soa.rs:53-61).
 #pragma once
 #include <stdint.h>
@@ -145,12 +144,12 @@ __device__ __forceinline__ void sweep_resolve_entry(const float4* __restrict__ b
 }
 
 // =====================================================================================================
-// Expanded pre-filter with shared-memory operands (scenes beyond the constant bank: resident and streamed kernels).
+// Expanded pre-filter with shared-memory operands (resident and streamed kernels).
 //
-// Same algebra as sweep_const (A = c.d - o.d, B = 2 c.o + k, L = A*A + B, candidate <=> L > |o|^2 (1 - 2^-19)) but the
-// sphere pairs come from the pre-filter image staged in shared memory (LDS.128 broadcast): 7 packed instructions per
-// 2 tests of the shape FFMA2 Rpair, Rpair(spheres), Rscalar(ray), Rpair — against 11 for the sphere-relative form of
-// sweep_blocks, whose packed instructions mostly read two or three register pairs (profiles/probe_forms_r1.txt).
+// A = c.d - o.d, B = 2 c.o + k, L = A*A + B, candidate <=> L > |o|^2 (1 - 2^-19); the sphere pairs come from the
+// pre-filter image staged in shared memory (LDS.128 broadcast): 7 packed instructions per 2 tests of the shape
+// FFMA2 Rpair, Rpair(spheres), Rscalar(ray), Rpair — against 11 for the sphere-relative form co = c - o, whose packed
+// instructions mostly read two or three register pairs (profiles/probe_forms_r1.txt; history in DESIGN.md §4.1).
 // `pf` holds blocks [first_block, first_block + n_blocks) of the image (n_blocks a multiple of the group size);
 // flagged groups go to the lane's queue as (absolute block << kLdsMaskBits | flags) and are re-tested by the
 // caller with the reference's exact expression against `exact` (global memory for the streamed kernel).
