@@ -203,8 +203,8 @@ __device__ __forceinline__ bool acquire_pixel_state(const KernelArgs& a, Lane& L
 // A lane whose ticket's predecessor chunk is not published yet (rare: the predecessor was handed out n_owned_pixels
 // tickets earlier) parks for a trip and asks again — it never spins, the predecessor may be a lane of the same warp.
 // `pend` is that lane's "holding an unready ticket" flag; it lives in shared memory, and the end-of-chunk test uses the
-// uniform chunk_mask rather than a per-lane bound, because extra per-lane registers carried across the sweep make ptxas
-// drop the sweep's uniform operands (tests/test_host_and_abi.py guards the SASS).
+// uniform chunk_mask rather than a per-lane bound: the kernel sits at 78 of the 80 registers that three CTAs per SM
+// allow, so nothing that can live elsewhere is carried across the sweep in a register.
 template <bool MOTION>
 __device__ __forceinline__ void lane_refill(const KernelArgs& a, Lane& L, unsigned lane_id, volatile uint32_t* pend, volatile float* tslot) {
     bool want_pixel = false;
