@@ -26,6 +26,7 @@ struct KernelArgs {
     const DevTexture* tex;
     const uint8_t* images;     // RGB8 pool of the scene's Image textures (texture.rs:6-37), nullptr when there is none
     const PerlinSmem* perlin;  // global copy, staged to shared memory when has_noise
+    const uint32_t* order;     // stored sphere index -> position in the caller's list (equal-t ties), nullptr = identity
     const DevMotion* motion;   // per-sphere MovingSphere records, nullptr when the scene has none (moving_sphere.rs)
     const float4* prefilter;   // pre-filter image X,Y,Z,K per block (global copy; staged/streamed by the LDS kernels)
     int has_noise;
@@ -501,7 +502,7 @@ __global__ void PT_LDS_LAUNCH_BOUNDS pt_megakernel_resident(const __grid_constan
     *pend = 0u;
     *tslot = 0.0f;
     if (threadIdx.x < 16) cat_count[threadIdx.x] = 0u;  // two sets of kRegroupCats counters, 8 words apart
-    const MotionCtx mc{a.motion, tslot};
+    const MotionCtx mc{a.motion, tslot, a.order};
 
     const uint32_t bytes = (uint32_t)a.n_blocks * 64u;
     if (threadIdx.x == 0) {
@@ -612,7 +613,7 @@ __global__ void PT_STREAM_LAUNCH_BOUNDS pt_megakernel_streamed(const __grid_cons
     volatile float* tslot = reinterpret_cast<volatile float*>(pend + kCtaThreads);  // [kCtaThreads] ray.time per lane
     *pend = 0u;
     *tslot = 0.0f;
-    const MotionCtx mc{a.motion, tslot};
+    const MotionCtx mc{a.motion, tslot, a.order};
 
     if (threadIdx.x == 0) {
         mbar_init(&full_bar[0], 1);

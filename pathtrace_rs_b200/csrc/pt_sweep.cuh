@@ -50,8 +50,17 @@ constexpr float kMinT = 0.001f;   // src/scene.rs:16
 constexpr float kMaxT = FLT_MAX;  // src/scene.rs:15
 
 // exact re-test of one sphere, reference expression order (spheres_soa.rs:116-129), unfused
+// `order` (may be null): the scene's spheres are stored in a spatial order (ptgpu.cu), order[i] = the sphere's position
+// in the caller's list; equal-t ties go to the lower ORIGINAL position, as the reference's in-order walk decides them
+__device__ __noinline__ bool tie_goes_to(const uint32_t* __restrict__ order, int index, int hit_index) {
+    if (order == nullptr || hit_index < 0) return index < hit_index;
+    return __ldg(order + index) < __ldg(order + hit_index);
+}
+// ORDERED: the kernel runs on a spatially ordered scene (resident kernel); otherwise stored order = list order and the
+// tie rule is the plain index comparison
+template <bool ORDERED = false>
 __device__ __forceinline__ void sweep_exact(float cox, float coy, float coz, float r2, float dx, float dy, float dz,
-                                            int index, float& hit_t, int& hit_index) {
+                                            int index, float& hit_t, int& hit_index, const uint32_t* __restrict__ order = nullptr) {
     const float nb = (cox * dx + coy * dy) + coz * dz;
     const float c = ((cox * cox + coy * coy) + coz * coz) - r2;
     const float discriminant = nb * nb - c;
@@ -61,7 +70,7 @@ __device__ __forceinline__ void sweep_exact(float cox, float coy, float coz, flo
         if (t < kMinT) t = nb + discriminant_sqrt;
         // strict `<` in ascending index order (spheres_soa.rs:126) == lowest index among equal t; written so that the
         // result does not depend on the order candidates are visited in
-        if (t > kMinT && (t < hit_t || (t == hit_t && index < hit_index))) {
+        if (t > kMinT && (t < hit_t || (t == hit_t && (ORDERED ? tie_goes_to(order, index, hit_index) : index < hit_index)))) {
             hit_t = t;
             hit_index = index;
         }
@@ -106,6 +115,7 @@ __device__ __forceinline__ float moving_sphere_hit_t(const DevMotion* __restrict
 struct MotionCtx {
     const DevMotion* table;        // nullptr when the scene has no moving sphere
     const volatile float* time;    // this lane's ray.time (shared memory slot)
+    const uint32_t* order;         // stored index -> position in the caller's sphere list (nullptr: identity)
 };
 
 #ifndef PT_CTA_THREADS
@@ -119,7 +129,7 @@ constexpr int kSweepThreads = PT_CTA_THREADS;  // == kCtaThreads (queue stride)
 // a few trips of one SIMD loop per sweep instead of a serialized branch body per (lane, sphere) event.
 constexpr int kQueueCap = 12;
 
-template <int MASK_BITS, bool MOTION>
+template <int MASK_BITS, bool MOTION, bool ORDERED>
 __device__ __forceinline__ void sweep_resolve_entry(const float4* __restrict__ blk, const MotionCtx& mc, uint32_t entry, float ox, float oy, float oz,
                                                     float dx, float dy, float dz, float& hit_t, int& hit_index) {
     const int base = (int)(entry >> MASK_BITS) * MASK_BITS;  // MASK_BITS spheres per group
@@ -133,12 +143,12 @@ __device__ __forceinline__ void sweep_resolve_entry(const float4* __restrict__ b
         if (MOTION && r2 < 0.0f) {  // MovingSphere tag (MOTION is a kernel template parameter: static scenes compile none of this)
             const float t = moving_sphere_hit_t(mc.table + index, *mc.time, bf[0], bf[4], bf[8], ox, oy, oz, dx, dy, dz);
             // nearest hit, lowest index among equal t (the strict `<` of the in-order walk, hitable_list.rs:49-54)
-            if (t > 0.0f && (t < hit_t || (t == hit_t && index < hit_index))) {
+            if (t > 0.0f && (t < hit_t || (t == hit_t && (ORDERED ? tie_goes_to(mc.order, index, hit_index) : index < hit_index)))) {
                 hit_t = t;
                 hit_index = index;
             }
         } else {
-            sweep_exact(bf[0] - ox, bf[4] - oy, bf[8] - oz, r2, dx, dy, dz, index, hit_t, hit_index);
+            sweep_exact<ORDERED>(bf[0] - ox, bf[4] - oy, bf[8] - oz, r2, dx, dy, dz, index, hit_t, hit_index, mc.order);
         }
     }
 }
@@ -233,7 +243,7 @@ __device__ __forceinline__ void sweep_expanded(const float4* __restrict__ pf, in
                     q[cnt * kSweepThreads] = entry;
                     cnt += 1;
                 } else {
-                    sweep_resolve_entry<kLdsMaskBits, MOTION>(exact, mc, entry, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
+                    sweep_resolve_entry<kLdsMaskBits, MOTION, !PIPE>(exact, mc, entry, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
                 }
             }
         }
@@ -290,7 +300,7 @@ __device__ __forceinline__ void sweep_expanded(const float4* __restrict__ pf, in
                 else q[cnt * kSweepThreads] = entry;
                 cnt += 1;
             } else {  // queue full (rare): test this group now; sweep_exact's tie rule makes the visiting order irrelevant
-                sweep_resolve_entry<kLdsMaskBits, MOTION>(exact, mc, entry, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
+                sweep_resolve_entry<kLdsMaskBits, MOTION, !PIPE>(exact, mc, entry, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
             }
         }
     }
@@ -309,11 +319,11 @@ __device__ __forceinline__ void sweep_drain(const float4* __restrict__ exact, co
         for (; qaddr != qend; qaddr += (uint32_t)(kSweepThreads * 4)) {
             uint32_t entry;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(entry) : "r"(qaddr) : "memory");
-            sweep_resolve_entry<kLdsMaskBits, MOTION>(exact, mc, entry, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
+            sweep_resolve_entry<kLdsMaskBits, MOTION, true>(exact, mc, entry, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
         }
     } else {
 #pragma unroll 1
-        for (int i = 0; i < cnt; ++i) sweep_resolve_entry<kLdsMaskBits, MOTION>(exact, mc, q[i * kSweepThreads], ox, oy, oz, dx, dy, dz, hit_t, hit_index);
+        for (int i = 0; i < cnt; ++i) sweep_resolve_entry<kLdsMaskBits, MOTION, false>(exact, mc, q[i * kSweepThreads], ox, oy, oz, dx, dy, dz, hit_t, hit_index);
     }
     cnt = 0;
 }

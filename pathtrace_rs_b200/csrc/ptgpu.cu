@@ -54,6 +54,7 @@ struct PtScene {
     pt::DevShade* d_shade = nullptr;
     pt::DevTexture* d_tex = nullptr;
     uint8_t* d_images = nullptr;  // RGB8 pool of the Image textures (nullptr: none)
+    uint32_t* d_order = nullptr;  // stored sphere index -> position in the caller's list (nullptr: stored in list order)
     pt::PerlinSmem* d_perlin = nullptr;
     pt::DevMotion* d_motion = nullptr;  // MovingSphere records (nullptr: none)
     float motion_t_lo = 0.0f, motion_t_hi = 0.0f;  // intersection of the moving spheres' [time0, time1]
@@ -111,13 +112,24 @@ int configure_streamed(PtScene* s) {
                        : configure_kernel(pt::pt_megakernel_streamed<false>, s->smem_bytes, &s->ctas_per_sm);
 }
 
+// shared-memory budget of the two kernels (one place: plan_launch and the storage-order decision both ask)
+constexpr size_t kQueueBytes = (size_t)pt::kQueueCap * pt::kCtaThreads * sizeof(uint32_t);  // per-lane candidate queues
+constexpr size_t kPerlinBytes = sizeof(pt::PerlinSmem) + 2 * pt::kCtaThreads * sizeof(uint32_t) + kQueueBytes;  // Perlin tables + `pend` words + ray.time slots + queues
+constexpr size_t kRegroupBytes = (size_t)pt::kRegroupWords * pt::kCtaThreads * sizeof(uint32_t) + 64;  // path-state exchange + category counters
+int forced_stream_tile() {  // test hook: PTGPU_FORCE_STREAM_TILE_BLOCKS=<n> runs any scene through the streamed kernel with n-block tiles
+    const char* env = std::getenv("PTGPU_FORCE_STREAM_TILE_BLOCKS");
+    return env ? std::atoi(env) : 0;
+}
+bool fits_resident(int n_blocks) {
+    if (forced_stream_tile() > 0 && n_blocks > 0) return false;
+    const size_t exact_bytes = PT_EXACT_SMEM ? (size_t)n_blocks * 64 : 0;  // resident kernel: exact blocks in shared memory too
+    return (size_t)n_blocks * 64 + kPerlinBytes + kRegroupBytes + exact_bytes <= kMaxDynSmem;
+}
+
 int plan_launch(PtScene* s) {
-    const size_t queue_bytes = (size_t)pt::kQueueCap * pt::kCtaThreads * sizeof(uint32_t);  // per-lane candidate queues
-    const size_t perlin_bytes = sizeof(pt::PerlinSmem) + 2 * pt::kCtaThreads * sizeof(uint32_t) + queue_bytes;  // Perlin tables + `pend` words + ray.time slots + queues
+    const size_t perlin_bytes = kPerlinBytes;
     const size_t all = (size_t)s->n_blocks * 64 + perlin_bytes;
-    // test hook: PTGPU_FORCE_STREAM_TILE_BLOCKS=<n> runs any scene through the streamed kernel with n-block tiles
-    int forced_tile = 0;
-    if (const char* env = std::getenv("PTGPU_FORCE_STREAM_TILE_BLOCKS")) forced_tile = std::atoi(env);
+    int forced_tile = forced_stream_tile();
     if (forced_tile > 0 && s->n_blocks > 0) {
         s->resident = false;
         forced_tile = (forced_tile + pt::kLdsGroupBlocks - 1) / pt::kLdsGroupBlocks * pt::kLdsGroupBlocks;  // whole groups
@@ -126,11 +138,9 @@ int plan_launch(PtScene* s) {
         s->smem_bytes = 2 * (size_t)s->tile_blocks * 64 + perlin_bytes;
         return configure_streamed(s);
     }
-    const size_t regroup_bytes = (size_t)pt::kRegroupWords * pt::kCtaThreads * sizeof(uint32_t) + 64;  // path-state exchange + category counters
-    const size_t exact_bytes = PT_EXACT_SMEM ? (size_t)s->n_blocks * 64 : 0;  // resident kernel: exact blocks in shared memory too
-    if (all + regroup_bytes + exact_bytes <= kMaxDynSmem) {
+    if (fits_resident(s->n_blocks)) {
         s->resident = true;
-        s->smem_bytes = all + regroup_bytes + exact_bytes;
+        s->smem_bytes = all + kRegroupBytes + (PT_EXACT_SMEM ? (size_t)s->n_blocks * 64 : 0);
         s->tile_blocks = s->n_blocks;
         s->n_tiles = 1;
         return s->d_motion ? configure_kernel(pt::pt_megakernel_resident<true>, s->smem_bytes, &s->ctas_per_sm)
@@ -186,6 +196,7 @@ int launch_update(PtScene* s, const PtParams* params, const PtCamera* cam, uint3
     a.shade = s->d_shade;
     a.tex = s->d_tex;
     a.images = s->d_images;
+    a.order = s->d_order;
     a.perlin = s->d_perlin;
     a.prefilter = s->d_prefilter;
     a.motion = s->d_motion;
@@ -462,6 +473,75 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
     }
     auto is_moving = [&](uint32_t i) { return any_moving && desc->motion[i].moving != 0; };
 
+    // ---- storage order.  The sweep flags candidates per group of 16 consecutive spheres, and a ray's candidates are
+    // spatially coherent, so spheres are stored along a Morton curve through their centres: a group becomes a compact
+    // patch instead of a strip of the caller's list, and a ray (and the 32 neighbouring rays of its warp) touches fewer
+    // groups.  order_of[j] = position in the caller's list of the sphere stored at j; hits are decided exactly as before
+    // (same expression per sphere, equal-t ties to the lower ORIGINAL position), so images do not change.
+    std::vector<uint32_t> order_of(n);
+    for (uint32_t i = 0; i < n; ++i) order_of[i] = i;
+    int order_mode = n > 64 ? 2 : 0;  // 0: the caller's order; 1: Morton; 2: large spheres first, then Morton
+    if (const char* env = std::getenv("PTGPU_SPATIAL_ORDER")) order_mode = n > 1 ? std::max(0, std::min(2, std::atoi(env))) : 0;  // tuning hook
+    // resident kernel only: the streamed kernel keeps list order and the plain index tie rule (with ~10^5 spheres few groups
+    // are flagged anyway: 66.0 -> 66.5 % on cfg5, and the out-of-line tie rule costs that kernel more than it gains)
+    const int n_blocks_planned = (int)(((n + 3) / 4 + pt::kLdsGroupBlocks - 1) / pt::kLdsGroupBlocks * pt::kLdsGroupBlocks);
+    if (!fits_resident(n_blocks_planned)) order_mode = 0;
+#ifdef PT_RES_PIPE
+    order_mode = 0;  // that experimental build instantiates the resident sweep without the ordered tie rule
+#endif
+    const bool spatial = order_mode != 0;
+    if (spatial) {
+        auto centre_of = [&](uint32_t i, int axis) -> double {
+            const float* c = axis == 0 ? desc->centre_x : (axis == 1 ? desc->centre_y : desc->centre_z);
+            double v = c[i];
+            if (is_moving(i)) v += 0.5 * ((double)desc->motion[i].centre1[axis] - v);
+            return v;
+        };
+        double lo[3], hi[3];
+        for (int ax = 0; ax < 3; ++ax) {  // robust bounds: the 2nd..98th percentile of the centres (a 1000-radius ground sphere must not stretch the grid)
+            std::vector<double> v(n);
+            for (uint32_t i = 0; i < n; ++i) v[i] = centre_of(i, ax);
+            std::sort(v.begin(), v.end());
+            lo[ax] = v[(size_t)(0.02 * (n - 1))];
+            hi[ax] = v[(size_t)(0.98 * (n - 1))];
+            if (!(hi[ax] > lo[ax])) hi[ax] = lo[ax] + 1.0;
+        }
+        auto spread = [](uint32_t v) {  // 10 bits -> every third bit
+            v &= 0x3ffu;
+            v = (v | (v << 16)) & 0x030000ffu;
+            v = (v | (v << 8)) & 0x0300f00fu;
+            v = (v | (v << 4)) & 0x030c30c3u;
+            v = (v | (v << 2)) & 0x09249249u;
+            return v;
+        };
+        std::vector<uint32_t> code(n);
+        for (uint32_t i = 0; i < n; ++i) {
+            uint32_t q[3];
+            for (int ax = 0; ax < 3; ++ax) {
+                double t = (centre_of(i, ax) - lo[ax]) / (hi[ax] - lo[ax]);
+                t = std::isfinite(t) ? std::min(1.0, std::max(0.0, t)) : 0.0;
+                q[ax] = (uint32_t)(t * 1023.0);
+            }
+            code[i] = spread(q[0]) | (spread(q[1]) << 1) | (spread(q[2]) << 2);
+        }
+        // spheres much larger than the typical one (the ground, the three big RTIOW spheres) are candidates for a large
+        // share of all rays wherever they are stored: keep them together in the leading group(s) instead of letting each
+        // of them turn another group into an "always flagged" one
+        std::vector<uint8_t> large(n, 0);
+        if (order_mode == 2) {
+            std::vector<float> radii(n);
+            for (uint32_t i = 0; i < n; ++i) radii[i] = std::fabs(desc->radius[i]);
+            std::nth_element(radii.begin(), radii.begin() + n / 2, radii.end());
+            const float median = radii[n / 2];
+            for (uint32_t i = 0; i < n; ++i) large[i] = std::fabs(desc->radius[i]) > 3.0f * median ? 1 : 0;
+        }
+        std::stable_sort(order_of.begin(), order_of.end(), [&](uint32_t a_, uint32_t b_) {
+            if (large[a_] != large[b_]) return large[a_] > large[b_];
+            if (large[a_]) return a_ < b_;
+            return code[a_] < code[b_];
+        });
+    }
+
     cudaDeviceProp prop;
     int rc = check_device(device, &prop);
     if (rc != PT_OK) return rc;
@@ -484,8 +564,8 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
     for (int j = 0; j < s->n_blocks; ++j) {
         float* f = reinterpret_cast<float*>(&blocks[(size_t)j * 4]);
         for (int e = 0; e < 4; ++e) {
-            const uint32_t i = (uint32_t)j * 4 + e;
-            const bool valid = i < n;
+            const bool valid = (uint32_t)j * 4 + e < n;
+            const uint32_t i = valid ? order_of[(uint32_t)j * 4 + e] : 0u;  // position in the caller's list
             f[0 + e] = valid ? desc->centre_x[i] : FLT_MAX;
             f[4 + e] = valid ? desc->centre_y[i] : FLT_MAX;
             f[8 + e] = valid ? desc->centre_z[i] : FLT_MAX;
@@ -500,10 +580,10 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
         for (int j = 0; j < s->n_blocks; ++j) {
             float* f = reinterpret_cast<float*>(&h_prefilter[(size_t)j * 4]);
             for (int e = 0; e < 4; ++e) {
-                const uint32_t i = (uint32_t)j * 4 + e;
                 f[0 + e] = f[4 + e] = f[8 + e] = 0.0f;
                 f[12 + e] = -3.0e38f;  // padding: never a candidate
-                if (i >= n) continue;
+                if ((uint32_t)j * 4 + e >= n) continue;
+                const uint32_t i = order_of[(uint32_t)j * 4 + e];
                 double cx = desc->centre_x[i], cy = desc->centre_y[i], cz = desc->centre_z[i], r = std::fabs((double)desc->radius[i]);
                 if (is_moving(i)) {  // static bound of the whole sweep: centre0 + delta/2, radius r + |delta|/2 (+ f32 rounding of the lerp)
                     const double ex = desc->motion[i].centre1[0] - cx, ey = desc->motion[i].centre1[1] - cy, ez = desc->motion[i].centre1[2] - cz;
@@ -523,7 +603,8 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
             }
         }
     }
-    for (uint32_t i = 0; i < n; ++i) {
+    for (uint32_t j = 0; j < n; ++j) {
+        const uint32_t i = order_of[j];
         const int32_t mi = desc->material_index[i];
         if (mi < 0 || (uint32_t)mi >= desc->n_materials) {
             delete s;
@@ -552,7 +633,7 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
         } else {
             d.param = mt.ref_idx;
         }
-        shade[i] = d;
+        shade[j] = d;
     }
     std::vector<pt::DevTexture> tex(std::max<uint32_t>(desc->n_textures, 1));
     for (uint32_t t = 0; t < desc->n_textures; ++t) {
@@ -588,6 +669,10 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
     PT_CUDA_S(cudaMemcpy(s->d_shade, shade.data(), shade.size() * sizeof(pt::DevShade), cudaMemcpyHostToDevice));
     PT_CUDA_S(cudaMalloc(&s->d_tex, tex.size() * sizeof(pt::DevTexture)));
     PT_CUDA_S(cudaMemcpy(s->d_tex, tex.data(), tex.size() * sizeof(pt::DevTexture), cudaMemcpyHostToDevice));
+    if (spatial) {
+        PT_CUDA_S(cudaMalloc(&s->d_order, order_of.size() * sizeof(uint32_t)));
+        PT_CUDA_S(cudaMemcpy(s->d_order, order_of.data(), order_of.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
     if (image_pool_bytes > 0) {
         std::vector<uint8_t> pool(image_pool_bytes, 0);
         for (uint32_t i = 0; i < desc->n_images; ++i)
@@ -597,7 +682,8 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
     }
     if (any_moving) {
         std::vector<pt::DevMotion> motion(n);
-        for (uint32_t i = 0; i < n; ++i) {
+        for (uint32_t j = 0; j < n; ++j) {
+            const uint32_t i = order_of[j];
             pt::DevMotion m{};
             if (is_moving(i)) {  // MovingSphere::new, moving_sphere.rs:16-26
                 const PtMotion& mo = desc->motion[i];
@@ -608,7 +694,7 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
                 m.inv_time_delta = 1.0f / (mo.time1 - mo.time0);
                 m.radius = desc->radius[i];
             }
-            motion[i] = m;
+            motion[j] = m;
         }
         PT_CUDA_S(cudaMalloc(&s->d_motion, motion.size() * sizeof(pt::DevMotion)));
         PT_CUDA_S(cudaMemcpy(s->d_motion, motion.data(), motion.size() * sizeof(pt::DevMotion), cudaMemcpyHostToDevice));
@@ -653,6 +739,7 @@ void pt_scene_destroy(PtScene* s) {
     cudaFree(s->d_shade);
     cudaFree(s->d_tex);
     cudaFree(s->d_images);
+    cudaFree(s->d_order);
     cudaFree(s->d_perlin);
     cudaFree(s->d_prefilter);
     cudaFree(s->d_motion);
