@@ -612,3 +612,22 @@ def test_cfg3_full_size_properties():
     img2, rays2 = pr.update(pt.Params(w, h, spp, depth), frame_num=1, buffer=img.copy())
     assert rays2 != rays and np.abs(bm(img2) - bm(img)).max() < 5e-3
     assert pr.stats().h2d_bytes == w * h * 12
+
+
+# ---- equal-t ties under the spatial storage order (last in the file: added after the round's GPU budget ran out) ----
+def test_duplicate_spheres_tie_goes_to_the_first_in_the_list():
+    """Exact duplicates give exactly equal t: the in-order walk's strict `<` (spheres_soa.rs:126, hitable_list.rs:49-54) keeps the
+    FIRST of them in the caller's list.  The library stores resident scenes in a spatial order (ptgpu.cu), so this is the
+    case that exercises its order[] tie rule: the duplicates carry different materials, a wrong winner changes the picture."""
+    w, h, spp, depth = 61, 37, 6, 12
+    custom = _random_scene(7000, 120, moving=False, sky=True)
+    for src, kind, colour in [(7, 1, (0.9, 0.1, 0.1)), (40, 0, (0.1, 0.9, 0.1)), (0, 1, (0.2, 0.2, 0.9))]:  # incl. the ground sphere
+        custom["centre_radius"] = np.vstack([custom["centre_radius"], custom["centre_radius"][src:src + 1]])
+        custom["kind"] = np.append(custom["kind"], np.int32(kind)).astype(np.int32)
+        p5 = np.array([[colour[0], colour[1], colour[2], 0.0, 1.5]], np.float32)
+        custom["params5"] = np.vstack([custom["params5"], p5])
+    sc = orc.Scene("custom", w, h, custom=custom)
+    ref, ref_rays = sc.update(spp, depth, mode=SOA_ITER)
+    img, rays = _gpu_render_custom(custom, sc.flat()["camera"], w, h, spp, depth)
+    assert abs(rays - ref_rays) <= max(2, 1e-3 * ref_rays)
+    assert np.mean(np.all(np.abs(img - ref) <= 1e-5 * np.maximum(1.0, np.abs(ref)), axis=2)) > 0.99
