@@ -46,6 +46,7 @@ extern "C" {
     fn pt_scene_create(desc: *const PtSceneDesc, device: c_int, out: *mut *mut PtScene) -> c_int;
     fn pt_scene_destroy(scene: *mut PtScene);
     fn pt_render(scene: *mut PtScene, params: *const PtParams, camera: *const PtCamera, frame_num: u32, rgb_inout: *mut f32, ray_count_out: *mut u64) -> c_int;
+    fn pt_render_progressive(scene: *mut PtScene, params: *const PtParams, camera: *const PtCamera, frame_num: u32, rgb_out: *mut f32, rgb8_out: *mut u8, ray_count_out: *mut u64) -> c_int;
 }
 
 fn last_error() -> String { unsafe { CStr::from_ptr(pt_last_error()).to_string_lossy().into_owned() } }
@@ -165,6 +166,26 @@ impl GpuScene {
         let mut rays = 0u64;
         let rc = unsafe { pt_render(self.handle, &p, &cam, frame_num, buffer.as_mut_ptr() as *mut f32, &mut rays) };
         if rc != 0 { panic!("pt_render failed: {}", last_error()); }
+        rays as usize
+    }
+}
+
+impl GpuScene {
+    /// The worker loop of the windowed mode (src/glium_window.rs:96-131) with the accumulation buffer resident on the GPU:
+    /// `frame_num == 0` restarts, `frame_num > 0` must follow the previous call.  `rgb8` receives what the window uploads
+    /// (top-down sRGB bytes, src/glium_window.rs:108-121 / src/offline.rs:43-51); pass `None` for frames that are not shown.
+    pub fn update_progressive(&self, params: &Params, camera: &Camera, frame_num: u32, rgb8: Option<&mut [u8]>) -> usize {
+        let p = PtParams { width: params.width, height: params.height, samples: params.samples, max_depth: params.max_depth,
+                           random_seed: params.random_seed as u8, use_bvh: params.use_bvh as u8, _pad: [0; 6],
+                           seed_salt: if params.random_seed { rand::random() } else { 0 } };
+        let cam = camera.to_ffi();
+        let mut rays = 0u64;
+        let out = match rgb8 {
+            Some(buf) => { assert_eq!(buf.len(), (params.width * params.height * 3) as usize); buf.as_mut_ptr() }
+            None => ptr::null_mut(),
+        };
+        let rc = unsafe { pt_render_progressive(self.handle, &p, &cam, frame_num, ptr::null_mut(), out, &mut rays) };
+        if rc != 0 { panic!("pt_render_progressive failed: {}", last_error()); }
         rays as usize
     }
 }
