@@ -228,6 +228,14 @@ int pt_scene_stats(const PtScene* scene, PtRenderStats* out);
  * multi-GPU caller needs to gather per-GPU results. */
 uint32_t pt_partition_rows(const PtPartition* part, uint32_t height, uint32_t* rows_out, uint32_t cap);
 
+/* Diagnostic, host only (no GPU needed): the order in which pt_scene_create stores the spheres of `desc` on the device.
+ * order_out[j] = position in the caller's list of the sphere stored at j (at most `cap` entries are written; order_out
+ * may be NULL).  Returns the mode: 0 = the caller's order (small scenes, and scenes that exceed shared memory), 1 = Morton
+ * order of the centres, 2 = spheres much larger than the median first, then Morton order.  The order is internal: nearest
+ * hits and equal-t ties (first in the caller's list: src/collision/spheres_soa.rs:126, hitable_list.rs:49-54) do not
+ * depend on it. */
+uint32_t pt_scene_storage_order(const PtSceneDesc* desc, uint32_t* order_out, uint32_t cap);
+
 /* Measurement helper: sustained FP32 FFMA throughput of `device` (flop/s) from a pure-FMA kernel,
  * so bench.py can print the measured ceiling beside the nominal sm_count*128*2*clock figure. */
 int pt_probe_fp32_peak(int device, double* flops_out);

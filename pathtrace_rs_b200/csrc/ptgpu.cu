@@ -347,6 +347,81 @@ int copy_owned_rows(PtScene* s, const PtParams* params, const PtPartition& part,
     return PT_OK;
 }
 
+// Storage order of a scene's spheres (see pt_scene_create).  Fills order_of[j] = position in the caller's list of the
+// sphere stored at j and returns the mode: 0 the caller's order, 1 Morton, 2 large spheres first, then Morton.
+int storage_order(const PtSceneDesc* desc, bool any_moving, std::vector<uint32_t>& order_of) {
+    const uint32_t n = desc->n_spheres;
+    auto is_moving = [&](uint32_t i) { return any_moving && desc->motion[i].moving != 0; };
+    // ---- storage order.  The sweep flags candidates per group of 16 consecutive spheres, and a ray's candidates are
+    // spatially coherent, so spheres are stored along a Morton curve through their centres: a group becomes a compact
+    // patch instead of a strip of the caller's list, and a ray (and the 32 neighbouring rays of its warp) touches fewer
+    // groups.  order_of[j] = position in the caller's list of the sphere stored at j; hits are decided exactly as before
+    // (same expression per sphere, equal-t ties to the lower ORIGINAL position), so images do not change.
+    order_of.resize(n);
+    for (uint32_t i = 0; i < n; ++i) order_of[i] = i;
+    int order_mode = n > 64 ? 2 : 0;  // 0: the caller's order; 1: Morton; 2: large spheres first, then Morton
+    if (const char* env = std::getenv("PTGPU_SPATIAL_ORDER")) order_mode = n > 1 ? std::max(0, std::min(2, std::atoi(env))) : 0;  // tuning hook
+    // resident kernel only: the streamed kernel keeps list order and the plain index tie rule (with ~10^5 spheres few groups
+    // are flagged anyway: 66.0 -> 66.5 % on cfg5, and the out-of-line tie rule costs that kernel more than it gains)
+    const int n_blocks_planned = (int)(((n + 3) / 4 + pt::kLdsGroupBlocks - 1) / pt::kLdsGroupBlocks * pt::kLdsGroupBlocks);
+    if (!fits_resident(n_blocks_planned)) order_mode = 0;
+#ifdef PT_RES_PIPE
+    order_mode = 0;  // that experimental build instantiates the resident sweep without the ordered tie rule
+#endif
+    if (order_mode != 0) {
+        auto centre_of = [&](uint32_t i, int axis) -> double {
+            const float* c = axis == 0 ? desc->centre_x : (axis == 1 ? desc->centre_y : desc->centre_z);
+            double v = c[i];
+            if (is_moving(i)) v += 0.5 * ((double)desc->motion[i].centre1[axis] - v);
+            return v;
+        };
+        double lo[3], hi[3];
+        for (int ax = 0; ax < 3; ++ax) {  // robust bounds: the 2nd..98th percentile of the centres (a 1000-radius ground sphere must not stretch the grid)
+            std::vector<double> v(n);
+            for (uint32_t i = 0; i < n; ++i) v[i] = centre_of(i, ax);
+            std::sort(v.begin(), v.end());
+            lo[ax] = v[(size_t)(0.02 * (n - 1))];
+            hi[ax] = v[(size_t)(0.98 * (n - 1))];
+            if (!(hi[ax] > lo[ax])) hi[ax] = lo[ax] + 1.0;
+        }
+        auto spread = [](uint32_t v) {  // 10 bits -> every third bit
+            v &= 0x3ffu;
+            v = (v | (v << 16)) & 0x030000ffu;
+            v = (v | (v << 8)) & 0x0300f00fu;
+            v = (v | (v << 4)) & 0x030c30c3u;
+            v = (v | (v << 2)) & 0x09249249u;
+            return v;
+        };
+        std::vector<uint32_t> code(n);
+        for (uint32_t i = 0; i < n; ++i) {
+            uint32_t q[3];
+            for (int ax = 0; ax < 3; ++ax) {
+                double t = (centre_of(i, ax) - lo[ax]) / (hi[ax] - lo[ax]);
+                t = std::isfinite(t) ? std::min(1.0, std::max(0.0, t)) : 0.0;
+                q[ax] = (uint32_t)(t * 1023.0);
+            }
+            code[i] = spread(q[0]) | (spread(q[1]) << 1) | (spread(q[2]) << 2);
+        }
+        // spheres much larger than the typical one (the ground, the three big RTIOW spheres) are candidates for a large
+        // share of all rays wherever they are stored: keep them together in the leading group(s) instead of letting each
+        // of them turn another group into an "always flagged" one
+        std::vector<uint8_t> large(n, 0);
+        if (order_mode == 2) {
+            std::vector<float> radii(n);
+            for (uint32_t i = 0; i < n; ++i) radii[i] = std::fabs(desc->radius[i]);
+            std::nth_element(radii.begin(), radii.begin() + n / 2, radii.end());
+            const float median = radii[n / 2];
+            for (uint32_t i = 0; i < n; ++i) large[i] = std::fabs(desc->radius[i]) > 3.0f * median ? 1 : 0;
+        }
+        std::stable_sort(order_of.begin(), order_of.end(), [&](uint32_t a_, uint32_t b_) {
+            if (large[a_] != large[b_]) return large[a_] > large[b_];
+            if (large[a_]) return a_ < b_;
+            return code[a_] < code[b_];
+        });
+    }
+    return order_mode;
+}
+
 }  // namespace
 
 extern "C" {
@@ -385,6 +460,19 @@ uint32_t pt_partition_rows(const PtPartition* part_in, uint32_t height, uint32_t
         }
     }
     return count;
+}
+
+uint32_t pt_scene_storage_order(const PtSceneDesc* desc, uint32_t* order_out, uint32_t cap) {
+    if (!desc || desc->struct_size != sizeof(PtSceneDesc)) return 0;
+    const uint32_t n = desc->n_spheres;
+    if (n > 0 && (!desc->centre_x || !desc->centre_y || !desc->centre_z || !desc->radius)) return 0;
+    bool any_moving = false;
+    if (desc->motion)
+        for (uint32_t i = 0; i < n; ++i) any_moving = any_moving || desc->motion[i].moving != 0;
+    std::vector<uint32_t> order_of;
+    const int mode = storage_order(desc, any_moving, order_of);
+    for (uint32_t j = 0; j < n && j < cap && order_out; ++j) order_out[j] = order_of[j];
+    return (uint32_t)mode;
 }
 
 int pt_device_count(void) {
@@ -473,74 +561,8 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
     }
     auto is_moving = [&](uint32_t i) { return any_moving && desc->motion[i].moving != 0; };
 
-    // ---- storage order.  The sweep flags candidates per group of 16 consecutive spheres, and a ray's candidates are
-    // spatially coherent, so spheres are stored along a Morton curve through their centres: a group becomes a compact
-    // patch instead of a strip of the caller's list, and a ray (and the 32 neighbouring rays of its warp) touches fewer
-    // groups.  order_of[j] = position in the caller's list of the sphere stored at j; hits are decided exactly as before
-    // (same expression per sphere, equal-t ties to the lower ORIGINAL position), so images do not change.
-    std::vector<uint32_t> order_of(n);
-    for (uint32_t i = 0; i < n; ++i) order_of[i] = i;
-    int order_mode = n > 64 ? 2 : 0;  // 0: the caller's order; 1: Morton; 2: large spheres first, then Morton
-    if (const char* env = std::getenv("PTGPU_SPATIAL_ORDER")) order_mode = n > 1 ? std::max(0, std::min(2, std::atoi(env))) : 0;  // tuning hook
-    // resident kernel only: the streamed kernel keeps list order and the plain index tie rule (with ~10^5 spheres few groups
-    // are flagged anyway: 66.0 -> 66.5 % on cfg5, and the out-of-line tie rule costs that kernel more than it gains)
-    const int n_blocks_planned = (int)(((n + 3) / 4 + pt::kLdsGroupBlocks - 1) / pt::kLdsGroupBlocks * pt::kLdsGroupBlocks);
-    if (!fits_resident(n_blocks_planned)) order_mode = 0;
-#ifdef PT_RES_PIPE
-    order_mode = 0;  // that experimental build instantiates the resident sweep without the ordered tie rule
-#endif
-    const bool spatial = order_mode != 0;
-    if (spatial) {
-        auto centre_of = [&](uint32_t i, int axis) -> double {
-            const float* c = axis == 0 ? desc->centre_x : (axis == 1 ? desc->centre_y : desc->centre_z);
-            double v = c[i];
-            if (is_moving(i)) v += 0.5 * ((double)desc->motion[i].centre1[axis] - v);
-            return v;
-        };
-        double lo[3], hi[3];
-        for (int ax = 0; ax < 3; ++ax) {  // robust bounds: the 2nd..98th percentile of the centres (a 1000-radius ground sphere must not stretch the grid)
-            std::vector<double> v(n);
-            for (uint32_t i = 0; i < n; ++i) v[i] = centre_of(i, ax);
-            std::sort(v.begin(), v.end());
-            lo[ax] = v[(size_t)(0.02 * (n - 1))];
-            hi[ax] = v[(size_t)(0.98 * (n - 1))];
-            if (!(hi[ax] > lo[ax])) hi[ax] = lo[ax] + 1.0;
-        }
-        auto spread = [](uint32_t v) {  // 10 bits -> every third bit
-            v &= 0x3ffu;
-            v = (v | (v << 16)) & 0x030000ffu;
-            v = (v | (v << 8)) & 0x0300f00fu;
-            v = (v | (v << 4)) & 0x030c30c3u;
-            v = (v | (v << 2)) & 0x09249249u;
-            return v;
-        };
-        std::vector<uint32_t> code(n);
-        for (uint32_t i = 0; i < n; ++i) {
-            uint32_t q[3];
-            for (int ax = 0; ax < 3; ++ax) {
-                double t = (centre_of(i, ax) - lo[ax]) / (hi[ax] - lo[ax]);
-                t = std::isfinite(t) ? std::min(1.0, std::max(0.0, t)) : 0.0;
-                q[ax] = (uint32_t)(t * 1023.0);
-            }
-            code[i] = spread(q[0]) | (spread(q[1]) << 1) | (spread(q[2]) << 2);
-        }
-        // spheres much larger than the typical one (the ground, the three big RTIOW spheres) are candidates for a large
-        // share of all rays wherever they are stored: keep them together in the leading group(s) instead of letting each
-        // of them turn another group into an "always flagged" one
-        std::vector<uint8_t> large(n, 0);
-        if (order_mode == 2) {
-            std::vector<float> radii(n);
-            for (uint32_t i = 0; i < n; ++i) radii[i] = std::fabs(desc->radius[i]);
-            std::nth_element(radii.begin(), radii.begin() + n / 2, radii.end());
-            const float median = radii[n / 2];
-            for (uint32_t i = 0; i < n; ++i) large[i] = std::fabs(desc->radius[i]) > 3.0f * median ? 1 : 0;
-        }
-        std::stable_sort(order_of.begin(), order_of.end(), [&](uint32_t a_, uint32_t b_) {
-            if (large[a_] != large[b_]) return large[a_] > large[b_];
-            if (large[a_]) return a_ < b_;
-            return code[a_] < code[b_];
-        });
-    }
+    std::vector<uint32_t> order_of;
+    const bool spatial = storage_order(desc, any_moving, order_of) != 0;
 
     cudaDeviceProp prop;
     int rc = check_device(device, &prop);

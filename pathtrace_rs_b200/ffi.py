@@ -133,6 +133,8 @@ def libptgpu():
         L.pt_srgb8_device.argtypes = [vp, vp, C.c_uint32, C.c_uint32, vp, vp]
         L.pt_scene_stats.argtypes = [vp, C.POINTER(PtRenderStats)]
         L.pt_probe_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
+        L.pt_scene_storage_order.restype = C.c_uint32
+        L.pt_scene_storage_order.argtypes = [C.POINTER(PtSceneDesc), vp, C.c_uint32]
         _ptgpu = L
     return _ptgpu
 

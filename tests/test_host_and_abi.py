@@ -115,6 +115,81 @@ def test_earth_preset_and_rgb_image_open(tmp_path, monkeypatch):
         pt.image_open(tmp_path / "short.ppm")
 
 
+def _desc_from_flat(cr, motion=None):
+    """A PtSceneDesc good enough for the host-only entry points (sphere arrays + optional motion)."""
+    n = len(cr)
+    cols = [np.ascontiguousarray(cr[:, i], np.float32) for i in range(4)]
+    d = ffi.PtSceneDesc()
+    d.struct_size, d.n_spheres = C.sizeof(ffi.PtSceneDesc), n
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    d.centre_x, d.centre_y, d.centre_z, d.radius = fp(cols[0]), fp(cols[1]), fp(cols[2]), fp(cols[3])
+    keep = [cols]
+    if motion is not None:
+        mot = (ffi.PtMotion * n)()
+        for i in range(n):
+            mot[i].centre1[:] = [float(x) for x in motion[i, :3]]
+            mot[i].time0, mot[i].time1, mot[i].moving = float(motion[i, 3]), float(motion[i, 4]), int(motion[i, 5])
+        d.motion = mot
+        keep.append(mot)
+    return d, keep
+
+
+def _storage_order(cr, motion=None):
+    d, keep = _desc_from_flat(cr, motion)
+    out = np.zeros(max(len(cr), 1), np.uint32)
+    mode = pt.libptgpu().pt_scene_storage_order(C.byref(d), out.ctypes.data_as(C.c_void_p), len(cr))
+    return int(mode), out[: len(cr)]
+
+
+def test_storage_order_is_a_permutation_with_large_spheres_first(monkeypatch):
+    """pt_scene_storage_order (host only): what pt_scene_create does to the sphere list of a resident scene — large spheres
+    first in list order, the rest along a Morton curve, exact duplicates in list order (equal-t ties stay with the first)."""
+    monkeypatch.delenv("PTGPU_SPATIAL_ORDER", raising=False)
+    monkeypatch.delenv("PTGPU_FORCE_STREAM_TILE_BLOCKS", raising=False)
+    cr = orc.Scene("random_spheres", 200, 100).flat()["centre_radius"]
+    n = len(cr)
+    mode, order = _storage_order(cr)
+    assert mode == 2 and sorted(order.tolist()) == list(range(n))
+    assert order[:4].tolist() == [0, n - 3, n - 2, n - 1]  # ground + the three unit spheres (presets.rs:195-213), in list order
+    # independent restatement of the Morton part
+    c = cr[:, :3].astype(np.float64)
+    lo = np.array([np.sort(c[:, a])[int(0.02 * (n - 1))] for a in range(3)])
+    hi = np.array([np.sort(c[:, a])[int(0.98 * (n - 1))] for a in range(3)])
+    hi = np.where(hi > lo, hi, lo + 1)
+    q = (np.clip((c - lo) / (hi - lo), 0, 1) * 1023).astype(np.uint32)
+
+    def spread(v):
+        v = v & 0x3ff; v = (v | (v << 16)) & 0x030000ff; v = (v | (v << 8)) & 0x0300f00f
+        v = (v | (v << 4)) & 0x030c30c3; v = (v | (v << 2)) & 0x09249249
+        return v
+    code = spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2)
+    small = [i for i in range(n) if i not in (0, n - 3, n - 2, n - 1)]
+    assert order[4:].tolist() == sorted(small, key=lambda i: (int(code[i]), i))
+    # compactness is the point: a 16-sphere group spans far less ground than a strip of the list
+    extent = lambda o: np.mean([np.ptp(c[o[g:g + 16], 0]) + np.ptp(c[o[g:g + 16], 2]) for g in range(16, n - 15, 16)])
+    assert extent(order) < 0.6 * extent(np.arange(n))
+    # duplicates keep their list order; tuning hook and the small-scene / streamed-scene rules
+    dup = np.vstack([cr, cr[7:8], cr[0:1]])
+    _, o2 = _storage_order(dup)
+    pos = {int(v): j for j, v in enumerate(o2)}
+    assert pos[7] < pos[n] and pos[0] < pos[n + 1]
+    assert _storage_order(cr[:40])[0] == 0 and _storage_order(cr[:40])[1].tolist() == list(range(40))
+    monkeypatch.setenv("PTGPU_SPATIAL_ORDER", "0")
+    assert _storage_order(cr)[0] == 0 and _storage_order(cr)[1].tolist() == list(range(n))
+    monkeypatch.setenv("PTGPU_SPATIAL_ORDER", "1")
+    assert _storage_order(cr)[0] == 1
+    monkeypatch.delenv("PTGPU_SPATIAL_ORDER")
+    monkeypatch.setenv("PTGPU_FORCE_STREAM_TILE_BLOCKS", "16")
+    assert _storage_order(cr)[0] == 0  # streamed scenes keep the caller's order
+    monkeypatch.delenv("PTGPU_FORCE_STREAM_TILE_BLOCKS")
+    big = orc.Scene("stress100k", 64, 36).flat()["centre_radius"]
+    assert _storage_order(big)[0] == 0
+    # moving spheres are placed by the middle of their path
+    fr = orc.Scene("random", 200, 100).flat()
+    m, o3 = _storage_order(fr["centre_radius"], fr["motion"])
+    assert m == 2 and sorted(o3.tolist()) == list(range(len(o3)))
+
+
 def test_host_rng_continues_like_the_reference():
     p = pt.Preset("random_spheres", pt.Params(200, 100, 10, 10))
     assert abs(p.flat()["next_f32"] - 0.17442238) < 1e-8
