@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define PT_ABI_VERSION 3
+#define PT_ABI_VERSION 4
 
 /* ---- status codes (the Rust shim `expect`s on non-zero, matching the reference's panic-on-error
  *      convention: src/offline.rs:10,32,59) ---- */
@@ -169,12 +169,28 @@ typedef struct PtRenderStats {
     uint32_t resident; /* 1: sphere SoA resident in shared memory; 0: streamed through L2 in tiles */
 } PtRenderStats;
 
-typedef struct PtScene PtScene; /* opaque: device copy of one scene on one GPU */
+/* ---- explicit launch options (replace the process-global environment hooks of ABI v3).  Every field has a
+ * "library decides" value, and a NULL PtOptions* means all of them.  The options never change an image: sphere order,
+ * kernel flavour and chunking are internal (hits, equal-t ties and every pixel's RNG stream are the reference's). ---- */
+typedef struct PtOptions {
+    uint32_t struct_size;             /* = sizeof(PtOptions) */
+    int32_t force_stream_tile_blocks; /* 0: resident kernel whenever the scene fits in shared memory; n > 0: always the
+                                         L2-streamed kernel with n-block tiles (1 block = 4 spheres) */
+    int32_t stream_ctas;              /* 0: default (2); 1..4: CTAs per SM of the streamed kernel */
+    int32_t chunk_samples;            /* 0: automatic; -1: whole pixels (the reference's work unit, scene.rs:90-93);
+                                         n > 0: samples per work-queue ticket, rounded up to a power of two */
+    int32_t spatial_order;            /* -1: automatic; 0: store spheres in the caller's order; 1: Morton order;
+                                         2: large spheres first, then Morton order */
+    uint32_t tile_rows;               /* multi-device scenes: rows per interleaved row tile (0 -> 4) */
+    uint32_t _pad;
+} PtOptions;
+
+typedef struct PtScene PtScene; /* opaque: device copies of one scene on one or several GPUs */
 
 int pt_abi_version(void);
 /* sizeof() of the ABI structs as this library was compiled, so a binding can assert its own layout:
  * which = 0 PtParams, 1 PtCamera, 2 PtTexture, 3 PtMaterial, 4 PtPerlin, 5 PtSceneDesc, 6 PtPartition,
- * 7 PtDeviceInfo, 8 PtRenderStats, 9 PtMotion, 10 PtImage; anything else -> 0. */
+ * 7 PtDeviceInfo, 8 PtRenderStats, 9 PtMotion, 10 PtImage, 11 PtOptions; anything else -> 0. */
 uint32_t pt_abi_struct_size(int which);
 const char* pt_last_error(void); /* thread-local message of the last failing call */
 int pt_device_count(void);
@@ -184,6 +200,20 @@ int pt_device_info(int device, PtDeviceInfo* out);
  * (src/collision/spheres_soa.rs:26-74): validates and uploads the flat scene to `device`. */
 int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out);
 void pt_scene_destroy(PtScene* scene);
+
+/* Same, replicated on `n_devices` GPUs of this host (the scene is small and read-only: SURVEY §8e).  The ordinary entry
+ * points then split every `Scene::update` over the devices by interleaved row tiles — tile k of `options->tile_rows`
+ * rows belongs to device k mod n_devices — with one host thread per GPU inside the call and every GPU copying its own
+ * rows straight from / into the caller's buffer: the caller still makes ONE call (src/offline.rs:29,
+ * src/glium_window.rs:102) and there is no collective in the data path.  Pixel seeds depend only on (x, y, frame)
+ * (src/scene.rs:99-101), so the image and the ray count are identical for any device list.
+ * `options` may be NULL.  pt_render_device / pt_srgb8_device take device pointers and therefore need a one-device scene. */
+int pt_scene_create_multi(const PtSceneDesc* desc, const int* devices, uint32_t n_devices, const PtOptions* options,
+                          PtScene** out);
+uint32_t pt_scene_device_count(const PtScene* scene);
+/* statistics of the last render on device slot `index` (0 .. pt_scene_device_count-1): per-GPU kernel time and bytes,
+ * what a caller needs to see the tail of the interleaved partition */
+int pt_scene_device_stats(const PtScene* scene, uint32_t index, PtRenderStats* out);
 
 /* Replaces `Scene::update(&self, &Params, &Camera, frame_num, &mut [(f32,f32,f32)]) -> usize`
  * (src/scene.rs:73-121; call sites src/offline.rs:29, src/glium_window.rs:102).
@@ -223,18 +253,40 @@ int pt_srgb8_device(PtScene* scene, const float* d_rgb, uint32_t width, uint32_t
 
 int pt_scene_stats(const PtScene* scene, PtRenderStats* out);
 
+/* Pin / unpin a caller-owned host buffer (cudaHostRegister).  pt_render accepts any host memory; a pageable
+ * `Vec<(f32,f32,f32)>` (src/offline.rs:25) is copied through the driver's staging buffers, a registered one by DMA at full
+ * PCIe rate and concurrently from all devices of a multi-device scene.  Worth it for the progressive loop
+ * (src/glium_window.rs:96-131: the same buffer every frame) and for 4K images; the library never registers behind the
+ * caller's back because it cannot know how long the buffer lives. */
+int pt_host_register(void* ptr, uint64_t bytes);
+int pt_host_unregister(void* ptr);
+
+/* Per-ray entry of the sphere sweep — the GPU twin of `SpheresSoA::hit` / `HitableList::ray_hit` as the reference's own
+ * benches call them (src/collision/spheres_soa.rs:464-485, src/bench.rs:17-26: one unit-direction ray against the whole
+ * list, t in (0.001, f32::MAX)).  Runs the SHIPPED two-stage sweep of the render kernel (packed pre-filter over all
+ * spheres, exact re-test of the flagged ones) for `n` caller-supplied rays on the scene's first device:
+ *   rays6  n x (ox, oy, oz, dx, dy, dz), |d| = 1 as everywhere on the path;  times: n ray times for
+ *   Hitable::MovingSphere (src/camera.rs:59), NULL = 0;
+ *   idx_out[i] = position in the CALLER's sphere list of the nearest hit, -1 on a miss;  t_out[i] = its t (FLT_MAX on a miss);
+ *   flagged_out (may be NULL): number of spheres the pre-filter passed on to the exact test for ray i.
+ * mode 0 = the shipped sweep; mode 1 = the exact test on EVERY sphere with no pre-filter (the differential check that
+ * the pre-filter never drops a sphere the exact expression accepts). */
+int pt_debug_hits(PtScene* scene, const float* rays6, const float* times, uint32_t n, int32_t mode, int32_t* idx_out,
+                  float* t_out, uint32_t* flagged_out);
+
 /* Rows of an image of `height` rows that `part` owns, ascending (the order the device buffer is walked).
  * Writes at most `cap` row indices to rows_out (may be NULL) and returns the total count: what a
  * multi-GPU caller needs to gather per-GPU results. */
 uint32_t pt_partition_rows(const PtPartition* part, uint32_t height, uint32_t* rows_out, uint32_t cap);
 
-/* Diagnostic, host only (no GPU needed): the order in which pt_scene_create stores the spheres of `desc` on the device.
+/* Diagnostic, host only (no GPU needed): the order in which pt_scene_create* stores the spheres of `desc` on the device
+ * under `options` (may be NULL).
  * order_out[j] = position in the caller's list of the sphere stored at j (at most `cap` entries are written; order_out
  * may be NULL).  Returns the mode: 0 = the caller's order (small scenes, and scenes that exceed shared memory), 1 = Morton
  * order of the centres, 2 = spheres much larger than the median first, then Morton order.  The order is internal: nearest
  * hits and equal-t ties (first in the caller's list: src/collision/spheres_soa.rs:126, hitable_list.rs:49-54) do not
  * depend on it. */
-uint32_t pt_scene_storage_order(const PtSceneDesc* desc, uint32_t* order_out, uint32_t cap);
+uint32_t pt_scene_storage_order(const PtSceneDesc* desc, const PtOptions* options, uint32_t* order_out, uint32_t cap);
 
 /* Measurement helper: sustained FP32 FFMA throughput of `device` (flop/s) from a pure-FMA kernel,
  * so bench.py can print the measured ceiling beside the nominal sm_count*128*2*clock figure. */

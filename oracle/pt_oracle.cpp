@@ -412,6 +412,8 @@ enum HitMode : int32_t { HIT_LIST = 0, HIT_SOA_SCALAR = 1, HIT_SOA_AVX2 = 2 };
 struct RayRecorder {
     float* out = nullptr;  // 6 floats per ray
     int64_t cap = 0, n = 0;
+    std::vector<float>* vec = nullptr;   // growable alternative to `out` (orc_record_rays): 6 floats per ray ...
+    std::vector<float>* tvec = nullptr;  // ... and the ray's time
 };
 static thread_local RayRecorder* g_recorder = nullptr;
 
@@ -634,7 +636,11 @@ struct Scene {
     }
 #endif
     bool ray_hit(int mode, const Ray& ray, float t_min, float t_max, RayHit& hit, int32_t& index) const {
-        if (g_recorder && g_recorder->n < g_recorder->cap) {
+        if (g_recorder && g_recorder->vec) {
+            const float v[6] = {ray.origin.x, ray.origin.y, ray.origin.z, ray.direction.x, ray.direction.y, ray.direction.z};
+            g_recorder->vec->insert(g_recorder->vec->end(), v, v + 6);
+            g_recorder->tvec->push_back(ray.time);
+        } else if (g_recorder && g_recorder->n < g_recorder->cap) {
             float* o = g_recorder->out + 6 * g_recorder->n++;
             o[0] = ray.origin.x; o[1] = ray.origin.y; o[2] = ray.origin.z;
             o[3] = ray.direction.x; o[4] = ray.direction.y; o[5] = ray.direction.z;
@@ -1281,6 +1287,60 @@ int64_t orc_trace_pixel_rays(void* h, const OrcParams* p, uint32_t x, uint32_t y
     orc::update_pixel(*s, s->camera, pp, orc::HIT_SOA_SCALAR | 0x100, 0, (size_t)y * p->width + x, px, rays);
     orc::g_recorder = nullptr;
     return rec.n;
+}
+// every ray the update of pixels [pix0, pix1) (row-major indices) hands to ray_hit, in trace order pixel after pixel, with its
+// ray.time; at most `cap` rays are written.  Threads record disjoint pixel ranges; the result does not depend on nthreads.
+int64_t orc_record_rays(void* h, const OrcParams* p, uint32_t frame_num, uint64_t pix0, uint64_t pix1, float* rays6, float* times, int64_t cap,
+                        int32_t nthreads) {
+    auto* s = (orc::Scene*)h;
+    const orc::Params pp{p->width, p->height, p->samples, p->max_depth, false, false};
+    nthreads = std::max(1, nthreads);
+    std::vector<std::vector<float>> rv(nthreads), tv(nthreads);
+    std::vector<std::thread> th;
+    const uint64_t n = pix1 > pix0 ? pix1 - pix0 : 0;
+    for (int k = 0; k < nthreads; ++k)
+        th.emplace_back([&, k] {
+            orc::RayRecorder rec;
+            rec.vec = &rv[k];
+            rec.tvec = &tv[k];
+            orc::g_recorder = &rec;
+            for (uint64_t i = pix0 + n * k / nthreads; i < pix0 + n * (k + 1) / nthreads; ++i) {
+                float px[3] = {0, 0, 0};
+                uint64_t rays = 0;
+                orc::update_pixel(*s, s->camera, pp, orc::HIT_SOA_SCALAR | 0x100, frame_num, (size_t)i, px, rays);
+            }
+            orc::g_recorder = nullptr;
+        });
+    for (auto& t : th) t.join();
+    int64_t out = 0;
+    for (int k = 0; k < nthreads && out < cap; ++k) {
+        const int64_t take = std::min<int64_t>((int64_t)tv[k].size(), cap - out);
+        std::memcpy(rays6 + 6 * out, rv[k].data(), (size_t)take * 6 * sizeof(float));
+        if (times) std::memcpy(times + out, tv[k].data(), (size_t)take * sizeof(float));
+        out += take;
+    }
+    return out;
+}
+// orc_hit with per-ray times (Hitable::MovingSphere) and threads
+void orc_hit_times(void* h, int32_t mode, const float* rays6, const float* times, int64_t n, int32_t* idx_out, float* t_out, int32_t nthreads) {
+    auto* s = (orc::Scene*)h;
+    nthreads = std::max(1, nthreads);
+    std::vector<std::thread> th;
+    for (int k = 0; k < nthreads; ++k)
+        th.emplace_back([&, k] {
+            for (int64_t i = n * k / nthreads; i < n * (k + 1) / nthreads; ++i) {
+                orc::Ray r;
+                r.origin = orc::v3(rays6[6 * i], rays6[6 * i + 1], rays6[6 * i + 2]);
+                r.direction = orc::v3(rays6[6 * i + 3], rays6[6 * i + 4], rays6[6 * i + 5]);
+                r.time = times ? times[i] : 0.0f;
+                orc::RayHit hit;
+                int32_t idx = -1;
+                const bool ok = s->ray_hit(mode, r, 0.001f, std::numeric_limits<float>::max(), hit, idx);
+                idx_out[i] = ok ? idx : -1;
+                t_out[i] = ok ? hit.t : std::numeric_limits<float>::max();
+            }
+        });
+    for (auto& t : th) t.join();
 }
 int32_t orc_hw_threads() { return (int32_t)std::thread::hardware_concurrency(); }
 

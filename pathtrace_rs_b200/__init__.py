@@ -12,13 +12,13 @@ torch plumbing (device buffers, streams, torch.distributed) for multi-GPU runs. 
 rendering path here and nothing in this package imports ``oracle/``.
 """
 from .ffi import (  # noqa: F401
-    PtCamera, PtParams, PtPartition, PtRenderStats, PtDeviceInfo, PtError,
+    PtCamera, PtParams, PtPartition, PtRenderStats, PtDeviceInfo, PtError, PtOptions,
     libptgpu, libpthost, abi_symbols,
 )
 from .scene import Params, Preset, device_info, image_open, probe_fp32_peak, render_offline, write_ppm  # noqa: F401
 
 __all__ = [
     "Params", "Preset", "device_info", "image_open", "probe_fp32_peak", "render_offline", "write_ppm",
-    "PtCamera", "PtParams", "PtPartition", "PtRenderStats", "PtDeviceInfo", "PtError",
+    "PtCamera", "PtParams", "PtPartition", "PtRenderStats", "PtDeviceInfo", "PtError", "PtOptions",
     "libptgpu", "libpthost", "abi_symbols",
 ]

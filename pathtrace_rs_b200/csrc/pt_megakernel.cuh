@@ -2,16 +2,17 @@
 // (src/scene.rs:73-121) with `ray_trace` (src/scene.rs:49-71) unrolled into a per-lane state machine.
 //
 // Mapping:
-//   * one lane = one pixel's path.  A lane owns a pixel for all of its `samples` (so the pixel's
-//     xoshiro256+ stream is consumed in exactly the reference's order), then pulls the next pixel
-//     from a global atomic queue (warp-aggregated) — the rayon `par_iter_mut` of scene.rs:90-93.
-//   * every trip of the main loop is ONE full sphere sweep for all 32 lanes (convergent, FP32-bound),
-//     followed by a short divergent shading step.  A lane whose path ended starts its next sample
-//     (or next pixel) at the top of the next trip, so the sweep always runs with all live lanes.
+//   * one path = one pixel's current sample.  A path owns a pixel for a whole chunk of its samples (so the pixel's
+//     xoshiro256+ stream is consumed in exactly the reference's order), then pulls the next ticket from a global atomic
+//     queue (warp-aggregated) — the rayon `par_iter_mut` of scene.rs:90-93.
+//   * every trip of the main loop is ONE full sphere sweep for all live paths of the warp (convergent, FP32-bound),
+//     followed by a short divergent shading step.  A path that ended starts its next sample (or next ticket) in the same
+//     trip, so the sweep always runs with all live paths.  The resident kernel carries two paths per lane (sweep_two).
 //   * the recursion `emitted + attenuation * ray_trace(..)` becomes `colour += throughput * emitted;
-//     throughput *= attenuation` carried in registers.
-//   * sphere SoA is staged into shared memory once per CTA with TMA bulk copies (cp.async.bulk +
-//     mbarrier); scenes that do not fit are streamed tile by tile (pt_megakernel_streamed below).
+//     throughput *= attenuation`.
+//   * the pre-filter image reaches the FMA pipe through the uniform datapath from a kernel parameter (scenes of up to
+//     2048 spheres), from shared memory staged once per CTA with a TMA bulk copy (cp.async.bulk + mbarrier), or tile by
+//     tile through L2 for scenes that do not fit (pt_megakernel_streamed).
 #pragma once
 #include "pt_shade.cuh"
 #include "pt_sweep.cuh"
@@ -29,6 +30,8 @@ struct KernelArgs {
     const uint32_t* order;     // stored sphere index -> position in the caller's list (equal-t ties), nullptr = identity
     const DevMotion* motion;   // per-sphere MovingSphere records, nullptr when the scene has none (moving_sphere.rs)
     const float4* prefilter;   // pre-filter image X,Y,Z,K per block (global copy; staged/streamed by the LDS kernels)
+    const float4* kplane;      // K plane alone, one float4 per block (resident kernel with the X,Y,Z planes in its parameter image)
+    int single_row;            // resident kernel: fewer pixels than lanes, only path row 0 takes work
     int has_noise;
     DevCamera cam;
     uint32_t width, height, samples, max_depth, frame_num;
@@ -51,6 +54,13 @@ struct KernelArgs {
     // streamed variant only
     int tile_blocks;  // blocks per shared-memory tile
     int n_tiles;
+    // pt_debug_hits only: caller-supplied rays through the kernels' own sweep phase
+    const float* dbg_rays;   // n x (ox, oy, oz, dx, dy, dz)
+    const float* dbg_times;  // n ray times, or nullptr (= 0)
+    uint32_t dbg_n;
+    int32_t* dbg_idx;        // nearest hit as a position in the CALLER's sphere list, -1 = miss
+    float* dbg_t;
+    uint32_t* dbg_flagged;   // spheres the pre-filter passed on to the exact test (nullptr: not wanted)
 };
 
 constexpr unsigned kFullMask = 0xffffffffu;
@@ -112,6 +122,8 @@ struct Lane {
     bool active;      // a path is in flight
     bool have_pixel;
     bool finished;    // queue exhausted
+    bool pend;        // holding a ticket whose predecessor chunk is not published yet (see lane_refill)
+    float time;       // ray.time of the path in flight (camera.rs:59): read only by MovingSphere, constant along a path
 };
 
 // Pixel-state table (global memory, 48 B per owned pixel): what a pixel carries from one chunk of samples to the
@@ -203,11 +215,11 @@ __device__ __forceinline__ bool acquire_pixel_state(const KernelArgs& a, Lane& L
 // table, so each pixel still consumes exactly the reference's stream and sums its samples in the reference's order.
 // A lane whose ticket's predecessor chunk is not published yet (rare: the predecessor was handed out n_owned_pixels
 // tickets earlier) parks for a trip and asks again — it never spins, the predecessor may be a lane of the same warp.
-// `pend` is that lane's "holding an unready ticket" flag; it lives in shared memory, and the end-of-chunk test uses the
-// uniform chunk_mask rather than a per-lane bound: the kernel sits at 78 of the 80 registers that three CTAs per SM
-// allow, so nothing that can live elsewhere is carried across the sweep in a register.
+// `pend` is that lane's "holding an unready ticket" flag; the end-of-chunk test uses the uniform chunk_mask rather than a
+// per-lane bound.  No path state is carried across the sweep in registers: it lives in the path's shared-memory record
+// (resident kernel) or in the lane's shared-memory slots (streamed kernel: pend, time).
 template <bool MOTION>
-__device__ __forceinline__ void lane_refill(const KernelArgs& a, Lane& L, unsigned lane_id, volatile uint32_t* pend, volatile float* tslot) {
+__device__ __forceinline__ void lane_refill(const KernelArgs& a, Lane& L, unsigned lane_id) {
     bool want_pixel = false;
     if (!L.active && !L.finished) {
         if (L.have_pixel && ((L.sample & a.chunk_mask) == 0u || L.sample >= a.samples)) {
@@ -217,7 +229,7 @@ __device__ __forceinline__ void lane_refill(const KernelArgs& a, Lane& L, unsign
                 publish_pixel_state(a, L);
             L.have_pixel = false;
         }
-        want_pixel = !L.have_pixel && *pend == 0u;
+        want_pixel = !L.have_pixel && !L.pend;
     }
     const unsigned need = __ballot_sync(kFullMask, want_pixel);
     if (need != 0u) {
@@ -244,15 +256,15 @@ __device__ __forceinline__ void lane_refill(const KernelArgs& a, Lane& L, unsign
                 L.col = v3(0.0f, 0.0f, 0.0f);
                 L.sample = chunk * a.chunk_samples;
                 L.have_pixel = chunk == 0u;
-                *pend = chunk != 0u ? 1u : 0u;
+                L.pend = chunk != 0u;
             } else {
                 L.finished = true;
             }
         }
     }
     if (!L.active && !L.finished && !L.have_pixel) {
-        if (*pend != 0u && acquire_pixel_state(a, L)) {  // not yet published: the lane sits this trip out and asks again
-            *pend = 0u;
+        if (L.pend && acquire_pixel_state(a, L)) {  // not yet published: the lane sits this trip out and asks again
+            L.pend = false;
             L.have_pixel = true;
         }
     }
@@ -262,9 +274,8 @@ __device__ __forceinline__ void lane_refill(const KernelArgs& a, Lane& L, unsign
         const float v = ((float)L.py + rng_f32(L.rng)) * a.inv_ny;
         float time;
         camera_get_ray(a.cam, u, v, L.rng, L.o, L.d, time);
-        // ray.time is read only by MovingSphere (moving_sphere.rs:39) and is constant along a path (material.rs:62,83,117):
-        // it lives in the lane's shared-memory slot, not in a register carried across the sweep
-        if (MOTION) *tslot = time;
+        // ray.time is read only by MovingSphere (moving_sphere.rs:39) and is constant along a path (material.rs:62,83,117)
+        if (MOTION) L.time = time;
         L.thr = v3(1.0f, 1.0f, 1.0f);
         L.depth = 0;
         L.sample += 1;
@@ -294,7 +305,7 @@ __device__ __forceinline__ void lane_shade(const KernelArgs& a, Lane& L, const f
     const bool moving = MOTION && __float_as_int(s1.w) != 0;
     if (moving) {  // MovingSphere: centre at ray.time, normal = (p - centre) / radius (moving_sphere.rs:28-31,49)
         const DevMotion mo = mc.table[hit_index];
-        const float s = (*mc.time - mo.time_start) * mo.inv_time_delta;
+        const float s = (L.time - mo.time_start) * mo.inv_time_delta;
         const V3 c = v3(centre.x + s * mo.dx, centre.y + s * mo.dy, centre.z + s * mo.dz);
         normal = v3((point.x - c.x) / mo.radius, (point.y - c.y) / mo.radius, (point.z - c.z) / mo.radius);
     } else {
@@ -331,6 +342,8 @@ __device__ __forceinline__ void lane_init(Lane& L) {
     L.thr = v3(0.0f, 0.0f, 0.0f);
     L.col = v3(0.0f, 0.0f, 0.0f);
     L.rng.s0 = L.rng.s1 = L.rng.s2 = L.rng.s3 = 0;
+    L.pend = false;
+    L.time = 0.0f;
 }
 
 __device__ __forceinline__ void flush_ray_count(const KernelArgs& a, unsigned long long rays, unsigned lane_id, unsigned sweeps) {
@@ -354,232 +367,274 @@ __device__ __forceinline__ void stage_perlin(const KernelArgs& a, PerlinSmem* P)
 constexpr int kCtaThreads = PT_CTA_THREADS;
 
 
-// Optional phase profile (compile with -DPT_PROFILE; tools/phase_profile.py): per-warp clock64 deltas of the
-// three phases of a trip and trip/lane counters, summed into a global array.  Not compiled into the product.
-#ifdef PT_PROFILE
-__device__ unsigned long long g_prof[8];  // 0 refill clk, 1 sweep clk, 2 shade clk, 3 warp trips, 4 active lane-trips, 5 total clk
-#define PT_PROF_DECL unsigned long long pf_t0 = 0, pf_refill = 0, pf_sweep = 0, pf_shade = 0, pf_trips = 0, pf_lanes = 0, pf_start = clock64();
-#define PT_PROF_TICK() (pf_t0 = clock64())
-#define PT_PROF_TOCK(acc) do { unsigned long long t_ = clock64(); acc += t_ - pf_t0; pf_t0 = t_; } while (0)
-#define PT_PROF_FLUSH(lane_id) do { if ((lane_id) == 0) { atomicAdd(&g_prof[0], pf_refill); atomicAdd(&g_prof[1], pf_sweep); atomicAdd(&g_prof[2], pf_shade); \
-    atomicAdd(&g_prof[3], pf_trips); atomicAdd(&g_prof[5], clock64() - pf_start); } atomicAdd(&g_prof[4], pf_lanes); } while (0)
-#else
-#define PT_PROF_DECL
-#define PT_PROF_TICK()
-#define PT_PROF_TOCK(acc)
-#define PT_PROF_FLUSH(lane_id)
-#endif
-
-
 // =====================================================================================================
-// CTA-level regrouping of paths by what they do next.
+// Resident variant: the whole scene stays on chip for the life of the CTA, and every lane carries TWO paths.
 //
-// After the sweep the 256 lanes of a CTA are about to run different code: Lambertian / textured Lambertian / metal /
-// dielectric scatter, or end their path (miss, light, depth limit) and start a new sample at the next refill.  Left in
-// place, every warp executes the union of those branches with a quarter of its lanes (ncu, cfg2: 8.5 of 32 lanes active
-// outside the sweep).  Lanes are interchangeable — a lane is only the register home of one path's state — so once per
-// trip the CTA counting-sorts its paths by category through shared memory: ballots give each lane its rank inside its
-// warp, one shared-memory atomicAdd per (warp, category) reserves the warp's range inside the category, and the whole
-// path state (30 words) is written to its new slot and read back by the thread that now owns it.  Every path still
-// consumes exactly its own RNG stream and performs exactly the same arithmetic, so images stay bit-identical; only the
-// assignment of paths to lanes changes.  Finished lanes collect in whole warps, which then skip the sweep.
+// Why two.  The sweep is bound by register-file reads and by the uniform loads that feed it (pt_sweep.cuh, sweep_two):
+// a sphere pair fetched once — LDCU.64 into a uniform register pair from the kernel-parameter image, or one LDS.128 for
+// scenes beyond it — serves both of the lane's rays.  A path's state (26 words: generator, ray, throughput, colour sum,
+// pixel, counters, flags, ray.time) lives in the path's own record in shared memory, [word][path] with path = row * T + tid:
+// the lane that sweeps a path is the lane that shades it, so the records are lane-private — no barrier and no atomics
+// anywhere in the main loop; warps drift apart and one warp's shading overlaps another's sweep.  Only the two rays
+// (8 derived words each) and the nearest hit so far are in registers during the sweep; a record is loaded, advanced by
+// lane_shade / lane_refill and stored back once per trip.  Every path still consumes exactly its own pixel's RNG stream
+// in the reference's order (scene.rs:96-110), so images do not depend on any of this.
+//
+// (Round 1 sorted the CTA's 256 paths by material through shared memory between sweep and shading — two CTA barriers per
+// trip, 14 % of the warp time at BAR.SYNC for 11 % fewer instructions: a wash on cfg2.  The records make a warp-local sort
+// possible later without moving state; it is not needed to beat that kernel.)
 // =====================================================================================================
-#ifndef PT_REGROUP
-#define PT_REGROUP 1
-#endif
-constexpr int kRegroupCats = 6;
-constexpr int kRegroupWords = 28;  // 8 rng + 6 ray + 3 thr + 3 col + px, py, sample, depth, flags, hit_t, hit_index, time
-enum { CAT_LAMBERT_CONST = 0, CAT_LAMBERT_TEX = 1, CAT_METAL = 2, CAT_DIELECTRIC = 3, CAT_ENDING = 4, CAT_IDLE = 5 };
+constexpr int kPathWords = 26;  // 8 rng + 3 o + 3 d + 3 thr + 3 col + px, py, sample, depth, flags, time
+constexpr int kPathRows = 2;    // paths per lane
 
-__device__ __forceinline__ int lane_category(const KernelArgs& a, const Lane& L, int hit_index) {
-    if (!L.active) return CAT_IDLE;
-    if (hit_index < 0 || L.depth >= a.max_depth) return CAT_ENDING;
-    const float4 s1 = __ldg(reinterpret_cast<const float4*>(a.shade + hit_index) + 1);
-    const int kind = __float_as_int(s1.y);
-    if (kind == MAT_LAMBERTIAN) return __float_as_int(s1.z) < 0 ? CAT_LAMBERT_CONST : CAT_LAMBERT_TEX;
-    if (kind == MAT_METAL) return CAT_METAL;
-    if (kind == MAT_DIELECTRIC) return CAT_DIELECTRIC;
-    return CAT_ENDING;  // DiffuseLight
+// record of path (row, tid): word w at rec[w * kPathRows * kCtaThreads], rec = state + row * kCtaThreads + tid
+__device__ __forceinline__ void path_store(uint32_t* __restrict__ rec, const Lane& L) {
+    constexpr int S = kPathRows * kCtaThreads;
+    rec[0 * S] = (uint32_t)L.rng.s0;  rec[1 * S] = (uint32_t)(L.rng.s0 >> 32);
+    rec[2 * S] = (uint32_t)L.rng.s1;  rec[3 * S] = (uint32_t)(L.rng.s1 >> 32);
+    rec[4 * S] = (uint32_t)L.rng.s2;  rec[5 * S] = (uint32_t)(L.rng.s2 >> 32);
+    rec[6 * S] = (uint32_t)L.rng.s3;  rec[7 * S] = (uint32_t)(L.rng.s3 >> 32);
+    rec[8 * S] = __float_as_uint(L.o.x);  rec[9 * S] = __float_as_uint(L.o.y);  rec[10 * S] = __float_as_uint(L.o.z);
+    rec[11 * S] = __float_as_uint(L.d.x); rec[12 * S] = __float_as_uint(L.d.y); rec[13 * S] = __float_as_uint(L.d.z);
+    rec[14 * S] = __float_as_uint(L.thr.x); rec[15 * S] = __float_as_uint(L.thr.y); rec[16 * S] = __float_as_uint(L.thr.z);
+    rec[17 * S] = __float_as_uint(L.col.x); rec[18 * S] = __float_as_uint(L.col.y); rec[19 * S] = __float_as_uint(L.col.z);
+    rec[20 * S] = L.px;  rec[21 * S] = L.py;  rec[22 * S] = L.sample;  rec[23 * S] = L.depth;
+    rec[24 * S] = (L.active ? 1u : 0u) | (L.have_pixel ? 2u : 0u) | (L.finished ? 4u : 0u) | (L.pend ? 8u : 0u);
+    rec[25 * S] = __float_as_uint(L.time);
+}
+__device__ __forceinline__ void path_load(const uint32_t* __restrict__ rec, Lane& L) {
+    constexpr int S = kPathRows * kCtaThreads;
+    L.rng.s0 = (uint64_t)rec[0 * S] | ((uint64_t)rec[1 * S] << 32);
+    L.rng.s1 = (uint64_t)rec[2 * S] | ((uint64_t)rec[3 * S] << 32);
+    L.rng.s2 = (uint64_t)rec[4 * S] | ((uint64_t)rec[5 * S] << 32);
+    L.rng.s3 = (uint64_t)rec[6 * S] | ((uint64_t)rec[7 * S] << 32);
+    L.o = v3(__uint_as_float(rec[8 * S]), __uint_as_float(rec[9 * S]), __uint_as_float(rec[10 * S]));
+    L.d = v3(__uint_as_float(rec[11 * S]), __uint_as_float(rec[12 * S]), __uint_as_float(rec[13 * S]));
+    L.thr = v3(__uint_as_float(rec[14 * S]), __uint_as_float(rec[15 * S]), __uint_as_float(rec[16 * S]));
+    L.col = v3(__uint_as_float(rec[17 * S]), __uint_as_float(rec[18 * S]), __uint_as_float(rec[19 * S]));
+    L.px = rec[20 * S];  L.py = rec[21 * S];  L.sample = rec[22 * S];  L.depth = rec[23 * S];
+    const uint32_t f = rec[24 * S];
+    L.active = (f & 1u) != 0u;  L.have_pixel = (f & 2u) != 0u;  L.finished = (f & 4u) != 0u;  L.pend = (f & 8u) != 0u;
+    L.time = __uint_as_float(rec[25 * S]);
 }
 
-// xchg: [kRegroupWords][kCtaThreads] words; cat_count: this trip's [kRegroupCats] counters (two sets alternate: the set
-// used by trip t is cleared after trip t's second barrier and next touched after trip t+1's first barrier).
-// Two CTA barriers per trip; the second also ORs "some lane still has work" over the CTA and returns it.  Trip t+1's
-// first barrier separates trip t's reads of xchg from trip t+1's writes.
-__device__ __forceinline__ bool cta_regroup(const KernelArgs& a, Lane& L, float& hit_t, int& hit_index, volatile uint32_t* pend,
-                                            volatile float* tslot, uint32_t* __restrict__ xchg, uint32_t* __restrict__ cat_count,
-                                            unsigned lane_id) {
-    const int cat = lane_category(a, L, hit_index);
-    unsigned mine = 0u;     // ballot of this lane's category
-    unsigned warp_off = 0u;  // where this warp's lanes of that category start inside the category
-#pragma unroll
-    for (int c = 0; c < kRegroupCats; ++c) {
-        const unsigned b = __ballot_sync(kFullMask, cat == c);
-        unsigned off = 0u;
-        if (lane_id == 0u && b != 0u) off = atomicAdd(&cat_count[c], (unsigned)__popc(b));
-        off = __shfl_sync(kFullMask, off, 0);
-        if (cat == c) {
-            mine = b;
-            warp_off = off;
-        }
+#ifdef PT_PAIR_MIN_CTAS
+#define PT_PAIR_LAUNCH_BOUNDS __launch_bounds__(kCtaThreads, PT_PAIR_MIN_CTAS)
+#else
+#define PT_PAIR_LAUNCH_BOUNDS __launch_bounds__(kCtaThreads, 3)
+#endif
+
+// shared-memory layout of the resident kernels:
+// [pre-filter image: K plane (16 B per block) or X,Y,Z,K (64 B per block)] [Perlin tables] [queues] [path records]
+template <bool CONSTIMG>
+struct ResidentSmem {
+    float4* pf;
+    PerlinSmem* P;
+    uint32_t* queue;  // this lane's queue: [kQueueCap][kCtaThreads]
+    uint32_t* state;  // this lane's records: [kPathWords][kPathRows][kCtaThreads]
+    uint32_t image_bytes;
+    __device__ __forceinline__ ResidentSmem(unsigned char* raw, int n_blocks) {
+        image_bytes = (uint32_t)n_blocks * (CONSTIMG ? 16u : 64u);
+        pf = reinterpret_cast<float4*>(raw);
+        P = reinterpret_cast<PerlinSmem*>(raw + ((image_bytes + 127u) & ~127u));
+        queue = reinterpret_cast<uint32_t*>(P + 1) + threadIdx.x;
+        state = reinterpret_cast<uint32_t*>(P + 1) + kQueueCap * kCtaThreads + threadIdx.x;
     }
-    __syncthreads();  // all counts are final
-    unsigned base = 0u;
-#pragma unroll
-    for (int c = 0; c < kRegroupCats - 1; ++c) base += (c < cat) ? cat_count[c] : 0u;
-    const unsigned dest = base + warp_off + (unsigned)__popc(mine & ((1u << lane_id) - 1u));
-    uint32_t* w = xchg + dest;
-    const uint32_t flags = (L.active ? 1u : 0u) | (L.have_pixel ? 2u : 0u) | (L.finished ? 4u : 0u) | (*pend != 0u ? 8u : 0u);
-    w[0 * kCtaThreads] = (uint32_t)L.rng.s0;  w[1 * kCtaThreads] = (uint32_t)(L.rng.s0 >> 32);
-    w[2 * kCtaThreads] = (uint32_t)L.rng.s1;  w[3 * kCtaThreads] = (uint32_t)(L.rng.s1 >> 32);
-    w[4 * kCtaThreads] = (uint32_t)L.rng.s2;  w[5 * kCtaThreads] = (uint32_t)(L.rng.s2 >> 32);
-    w[6 * kCtaThreads] = (uint32_t)L.rng.s3;  w[7 * kCtaThreads] = (uint32_t)(L.rng.s3 >> 32);
-    w[8 * kCtaThreads] = __float_as_uint(L.o.x);  w[9 * kCtaThreads] = __float_as_uint(L.o.y);  w[10 * kCtaThreads] = __float_as_uint(L.o.z);
-    w[11 * kCtaThreads] = __float_as_uint(L.d.x); w[12 * kCtaThreads] = __float_as_uint(L.d.y); w[13 * kCtaThreads] = __float_as_uint(L.d.z);
-    w[14 * kCtaThreads] = __float_as_uint(L.thr.x); w[15 * kCtaThreads] = __float_as_uint(L.thr.y); w[16 * kCtaThreads] = __float_as_uint(L.thr.z);
-    w[17 * kCtaThreads] = __float_as_uint(L.col.x); w[18 * kCtaThreads] = __float_as_uint(L.col.y); w[19 * kCtaThreads] = __float_as_uint(L.col.z);
-    w[20 * kCtaThreads] = L.px;  w[21 * kCtaThreads] = L.py;  w[22 * kCtaThreads] = L.sample;  w[23 * kCtaThreads] = L.depth;
-    w[24 * kCtaThreads] = flags;
-    w[25 * kCtaThreads] = __float_as_uint(hit_t);
-    w[26 * kCtaThreads] = (uint32_t)hit_index;
-    w[27 * kCtaThreads] = __float_as_uint(*tslot);
-    const bool live = __syncthreads_or(L.finished ? 0 : 1) != 0;  // every path is in its new slot
-    if (threadIdx.x < kRegroupCats) cat_count[threadIdx.x] = 0u;
-    const uint32_t* r = xchg + threadIdx.x;
-    L.rng.s0 = (uint64_t)r[0 * kCtaThreads] | ((uint64_t)r[1 * kCtaThreads] << 32);
-    L.rng.s1 = (uint64_t)r[2 * kCtaThreads] | ((uint64_t)r[3 * kCtaThreads] << 32);
-    L.rng.s2 = (uint64_t)r[4 * kCtaThreads] | ((uint64_t)r[5 * kCtaThreads] << 32);
-    L.rng.s3 = (uint64_t)r[6 * kCtaThreads] | ((uint64_t)r[7 * kCtaThreads] << 32);
-    L.o = v3(__uint_as_float(r[8 * kCtaThreads]), __uint_as_float(r[9 * kCtaThreads]), __uint_as_float(r[10 * kCtaThreads]));
-    L.d = v3(__uint_as_float(r[11 * kCtaThreads]), __uint_as_float(r[12 * kCtaThreads]), __uint_as_float(r[13 * kCtaThreads]));
-    L.thr = v3(__uint_as_float(r[14 * kCtaThreads]), __uint_as_float(r[15 * kCtaThreads]), __uint_as_float(r[16 * kCtaThreads]));
-    L.col = v3(__uint_as_float(r[17 * kCtaThreads]), __uint_as_float(r[18 * kCtaThreads]), __uint_as_float(r[19 * kCtaThreads]));
-    L.px = r[20 * kCtaThreads];  L.py = r[21 * kCtaThreads];  L.sample = r[22 * kCtaThreads];  L.depth = r[23 * kCtaThreads];
-    const uint32_t f = r[24 * kCtaThreads];
-    L.active = (f & 1u) != 0u;  L.have_pixel = (f & 2u) != 0u;  L.finished = (f & 4u) != 0u;
-    *pend = (f >> 3) & 1u;
-    hit_t = __uint_as_float(r[25 * kCtaThreads]);
-    hit_index = (int)r[26 * kCtaThreads];
-    *tslot = __uint_as_float(r[27 * kCtaThreads]);
-    return live;
-}
-
-// =====================================================================================================
-// Resident variant: the whole sphere SoA lives in shared memory for the life of the CTA.
-// =====================================================================================================
-#ifndef PT_EXACT_SMEM
-#define PT_EXACT_SMEM 0
-#endif
-#ifdef PT_RES_PIPE
-constexpr bool kResidentPipe = true;  // LDS one block ahead in the resident kernel too (needs the registers: see PT_LDS_MIN_CTAS)
-#else
-constexpr bool kResidentPipe = false;
-#endif
-#ifdef PT_LDS_MIN_CTAS
-#define PT_LDS_LAUNCH_BOUNDS __launch_bounds__(kCtaThreads, PT_LDS_MIN_CTAS)
-#else
-#define PT_LDS_LAUNCH_BOUNDS __launch_bounds__(kCtaThreads)
-#endif
-// MOTION: the scene has Hitable::MovingSphere entries (compiled out of the static instantiation)
-template <bool MOTION>
-__global__ void PT_LDS_LAUNCH_BOUNDS pt_megakernel_resident(const __grid_constant__ KernelArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t bar;
-    float4* pf = reinterpret_cast<float4*>(smem_raw);  // pre-filter image of the whole scene
-#if PT_EXACT_SMEM
-    // exact blocks right behind it: the candidate re-tests and the hit epilogue read them with LDS instead of LDG
-    const float4* ex = reinterpret_cast<const float4*>(smem_raw + (size_t)a.n_blocks * 64);
-    PerlinSmem* P = reinterpret_cast<PerlinSmem*>(smem_raw + (size_t)a.n_blocks * 128);
-#else
-    const float4* ex = a.blocks;  // exact blocks stay in global/L2
-    PerlinSmem* P = reinterpret_cast<PerlinSmem*>(smem_raw + (size_t)a.n_blocks * 64);
-#endif
-    uint32_t* queue = reinterpret_cast<uint32_t*>(P + 1) + threadIdx.x;  // [kQueueCap][kCtaThreads] candidate queues
-    volatile uint32_t* pend = queue + kQueueCap * kCtaThreads;
-    volatile float* tslot = reinterpret_cast<volatile float*>(pend + kCtaThreads);  // [kCtaThreads] ray.time per lane
-    uint32_t* xchg = const_cast<uint32_t*>(reinterpret_cast<volatile uint32_t*>(tslot)) - threadIdx.x + kCtaThreads;  // [kRegroupWords][kCtaThreads]
-    uint32_t* cat_count = xchg + kRegroupWords * kCtaThreads;                                                          // [kRegroupCats]
-    *pend = 0u;
-    *tslot = 0.0f;
-    if (threadIdx.x < 16) cat_count[threadIdx.x] = 0u;  // two sets of kRegroupCats counters, 8 words apart
-    const MotionCtx mc{a.motion, tslot, a.order};
-
-    const uint32_t bytes = (uint32_t)a.n_blocks * 64u;
+    // where path row r keeps its ray.time (MotionCtx reads it on the rare paths)
+    __device__ __forceinline__ const volatile float* time_slot(int row) const {
+        return reinterpret_cast<const volatile float*>(state + 25 * kPathRows * kCtaThreads + row * kCtaThreads);
+    }
+};
+// stage the image with one TMA bulk copy (thread 0 issues, everyone waits on the mbarrier after the caller's own set-up)
+template <bool CONSTIMG>
+__device__ __forceinline__ void resident_stage_begin(const KernelArgs& a, const ResidentSmem<CONSTIMG>& sm, uint64_t* bar) {
     if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
+        mbar_init(bar, 1);
         fence_mbar_init();
     }
     __syncthreads();
-    if (threadIdx.x == 0 && bytes != 0u) {
-#if PT_EXACT_SMEM
-        mbar_arrive_expect_tx(&bar, 2u * bytes);
-        tma_bulk_g2s_chunked(pf, a.prefilter, bytes, &bar);
-        tma_bulk_g2s_chunked(const_cast<float4*>(ex), a.blocks, bytes, &bar);
-#else
-        mbar_arrive_expect_tx(&bar, bytes);
-        tma_bulk_g2s_chunked(pf, a.prefilter, bytes, &bar);
-#endif
+    if (threadIdx.x == 0 && sm.image_bytes != 0u) {
+        mbar_arrive_expect_tx(bar, sm.image_bytes);
+        tma_bulk_g2s_chunked(sm.pf, CONSTIMG ? a.kplane : a.prefilter, sm.image_bytes, bar);
     }
-    stage_perlin(a, P);
-    __syncthreads();
-    if (bytes != 0u) mbar_wait(&bar, 0);
+}
 
+// The sweep phase of one trip: both rays of the lane against the whole scene, nearest hits into hit_t / hit_index.
+// o/d: the two rays, already replaced by the parked ray for paths that are not in flight.
+template <bool CONSTIMG, bool MOTION>
+__device__ __forceinline__ void resident_sweep(const KernelArgs& a, const ConstImageT<CONSTIMG>& ci, const ResidentSmem<CONSTIMG>& sm, const MotionCtx& mc0,
+                                               const MotionCtx& mc1, const float (&ox)[2], const float (&oy)[2], const float (&oz)[2], const float (&dx)[2],
+                                               const float (&dy)[2], const float (&dz)[2], float (&hit_t)[2], int (&hit_index)[2], unsigned (&flagged)[2]) {
+    float o2x[2], o2y[2], o2z[2], nod[2], oo[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        nod[r] = -((ox[r] * dx[r] + oy[r] * dy[r]) + oz[r] * dz[r]);
+        oo[r] = ((ox[r] * ox[r] + oy[r] * oy[r]) + oz[r] * oz[r]) * (1.0f - kSlack);
+        o2x[r] = ox[r] + ox[r]; o2y[r] = oy[r] + oy[r]; o2z[r] = oz[r] + oz[r];  // exact: o is recovered as 0.5 * o2 for the re-tests
+        hit_t[r] = kMaxT;
+        hit_index[r] = -1;
+    }
+    int cnt0 = 0, cnt1 = 0;
+    int overflow[2] = {a.n_blocks, a.n_blocks};
+    sweep_two<CONSTIMG>(ci, sm.pf, a.n_blocks, sm.queue, cnt0, cnt1, dx, dy, dz, o2x, o2y, o2z, nod, oo, overflow);
+    sweep_drain_range<MOTION>(a.blocks, mc0, sm.queue, 0, cnt0, 0.5f * o2x[0], 0.5f * o2y[0], 0.5f * o2z[0], dx[0], dy[0], dz[0], hit_t[0], hit_index[0], flagged[0]);
+    sweep_drain_range<MOTION>(a.blocks, mc1, sm.queue, kQueueCap - cnt1, cnt1, 0.5f * o2x[1], 0.5f * o2y[1], 0.5f * o2z[1], dx[1], dy[1], dz[1], hit_t[1], hit_index[1], flagged[1]);
+    if (min(overflow[0], overflow[1]) < a.n_blocks) {  // a queue overflowed (rare): one out-of-line pass per affected ray
+#pragma unroll 1
+        for (int r = 0; r < 2; ++r) {
+            const int first = r ? overflow[1] : overflow[0];
+            if (first >= a.n_blocks) continue;
+            float ht = r ? hit_t[1] : hit_t[0];
+            int hi = r ? hit_index[1] : hit_index[0];
+            unsigned fl = 0u;
+            sweep_overflow<MOTION>(a.blocks, r ? mc1 : mc0, first, a.n_blocks, 0.5f * (r ? o2x[1] : o2x[0]), 0.5f * (r ? o2y[1] : o2y[0]), 0.5f * (r ? o2z[1] : o2z[0]),
+                                   r ? dx[1] : dx[0], r ? dy[1] : dy[0], r ? dz[1] : dz[0], ht, hi, fl);
+            if (r) { hit_t[1] = ht; hit_index[1] = hi; flagged[1] += fl; } else { hit_t[0] = ht; hit_index[0] = hi; flagged[0] += fl; }
+        }
+    }
+}
+
+// CONSTIMG: X, Y, Z planes of the pre-filter image arrive as the kernel parameter `ci` (scenes of up to kMaxConstSpheres
+// spheres — every preset of the reference) and only the K plane is staged in shared memory; otherwise the whole image is
+// staged.  MOTION: the scene has Hitable::MovingSphere entries.
+// a.single_row: fewer pixels than lanes — row 1 stays empty (its lanes never pull a ticket)
+template <bool CONSTIMG, bool MOTION>
+__global__ void PT_PAIR_LAUNCH_BOUNDS pt_megakernel_resident(const __grid_constant__ KernelArgs a, const __grid_constant__ ConstImageT<CONSTIMG> ci) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    const ResidentSmem<CONSTIMG> sm(smem_raw, a.n_blocks);
+    resident_stage_begin<CONSTIMG>(a, sm, &bar);
+    stage_perlin(a, sm.P);
     const unsigned lane_id = threadIdx.x & 31u;
-    Lane L;
-    lane_init(L);
+    {
+        Lane L;
+        lane_init(L);
+#pragma unroll 1
+        for (int row = 0; row < kPathRows; ++row) {
+            Lane N = L;
+            // small images: row 1 never takes work (the sweep still carries its parked ray; what counts there is latency)
+            N.finished = a.single_row != 0 && row != 0;
+            lane_refill<MOTION>(a, N, lane_id);
+            path_store(sm.state + row * kCtaThreads, N);
+        }
+    }
+    __syncthreads();
+    if (sm.image_bytes != 0u) mbar_wait(&bar, 0);
+    const MotionCtx mc0{a.motion, sm.time_slot(0), a.order};
+    const MotionCtx mc1{a.motion, sm.time_slot(1), a.order};
+
     unsigned long long rays = 0ULL;
     unsigned sweeps = 0u;
-    PT_PROF_DECL
-
-#if PT_REGROUP
-    lane_refill<MOTION>(a, L, lane_id, pend, tslot);
-#endif
-    for (uint32_t trip = 0;; ++trip) {
-        PT_PROF_TICK();
-#if !PT_REGROUP
-        lane_refill<MOTION>(a, L, lane_id, pend, tslot);
-        if (__all_sync(kFullMask, L.finished)) break;
-#endif
-        float ox = L.o.x, oy = L.o.y, oz = L.o.z, dx = L.d.x, dy = L.d.y, dz = L.d.z;
-        if (!L.active) {  // parked lane: |o|^2 = 1e36 dwarfs every L, d = 0 -> never a candidate
-            ox = 0.0f; oy = 1.0e18f; oz = 0.0f;
-            dx = dy = dz = 0.0f;
+    for (;;) {
+        // ---- the two rays of this lane ----
+        float ox[2], oy[2], oz[2], dx[2], dy[2], dz[2], hit_t[2];
+        int hit_index[2];
+        bool act[2], fin = true;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const uint32_t* rec = sm.state + r * kCtaThreads;
+            constexpr int S = kPathRows * kCtaThreads;
+            const uint32_t f = rec[24 * S];
+            act[r] = (f & 1u) != 0u;
+            fin = fin && (f & 4u) != 0u;
+            ox[r] = __uint_as_float(rec[8 * S]); oy[r] = __uint_as_float(rec[9 * S]); oz[r] = __uint_as_float(rec[10 * S]);
+            dx[r] = __uint_as_float(rec[11 * S]); dy[r] = __uint_as_float(rec[12 * S]); dz[r] = __uint_as_float(rec[13 * S]);
+            if (!act[r]) {  // parked path: |o|^2 = 1e36 dwarfs every L, d = 0 -> never a candidate
+                ox[r] = 0.0f; oy[r] = 1.0e18f; oz[r] = 0.0f;
+                dx[r] = dy[r] = dz[r] = 0.0f;
+            }
+            hit_t[r] = kMaxT;
+            hit_index[r] = -1;
         }
+        if (__all_sync(kFullMask, fin)) break;  // every path of this warp has run out of tickets
+        const unsigned m0 = __ballot_sync(kFullMask, act[0]), m1 = __ballot_sync(kFullMask, act[1]);
+        if ((m0 | m1) != 0u) {
+            sweeps += (m0 != 0u ? 1u : 0u) + (m1 != 0u ? 1u : 0u);
+            unsigned flagged[2] = {0u, 0u};
+            resident_sweep<CONSTIMG, MOTION>(a, ci, sm, mc0, mc1, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
+        }
+        // ---- shade / refill, one path row after the other (same code, the row only moves the record's address) ----
+#pragma unroll 1
+        for (int row = 0; row < kPathRows; ++row) {
+            uint32_t* rec = sm.state + row * kCtaThreads;
+            Lane L;
+            path_load(rec, L);
+            const float ht = row == 0 ? hit_t[0] : hit_t[1];
+            const int hi = row == 0 ? hit_index[0] : hit_index[1];
+            if (L.active) {
+                rays += 1ULL;  // scene.rs:57
+                lane_shade<MOTION>(a, L, a.blocks, *sm.P, row == 0 ? mc0 : mc1, ht, hi);
+            }
+            lane_refill<MOTION>(a, L, lane_id);
+            path_store(rec, L);
+        }
+    }
+    flush_ray_count(a, rays, lane_id, sweeps);
+}
+
+// pt_debug_hits, resident scenes: caller-supplied rays through resident_sweep — the same staging, operands, queue and
+// re-tests as the render kernel.  Ray i of the batch sits in path row (i / T) % 2 of lane i % T of CTA i / 2T.
+template <bool CONSTIMG, bool MOTION>
+__global__ void PT_PAIR_LAUNCH_BOUNDS pt_debug_hits_resident(const __grid_constant__ KernelArgs a, const __grid_constant__ ConstImageT<CONSTIMG> ci) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t bar;
+    const ResidentSmem<CONSTIMG> sm(smem_raw, a.n_blocks);
+    resident_stage_begin<CONSTIMG>(a, sm, &bar);
+    __syncthreads();
+    if (sm.image_bytes != 0u) mbar_wait(&bar, 0);
+    const MotionCtx mc0{a.motion, sm.time_slot(0), a.order};
+    const MotionCtx mc1{a.motion, sm.time_slot(1), a.order};
+    constexpr uint32_t kBatch = kPathRows * kCtaThreads;
+    for (uint32_t base = blockIdx.x * kBatch; base < a.dbg_n; base += gridDim.x * kBatch) {
+        float ox[2], oy[2], oz[2], dx[2], dy[2], dz[2], hit_t[2];
+        int hit_index[2];
+        unsigned flagged[2] = {0u, 0u};
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const uint32_t i = base + r * kCtaThreads + threadIdx.x;
+            ox[r] = 0.0f; oy[r] = 1.0e18f; oz[r] = 0.0f;
+            dx[r] = dy[r] = dz[r] = 0.0f;
+            float time = 0.0f;
+            if (i < a.dbg_n) {
+                const float* ray = a.dbg_rays + (size_t)i * 6;
+                ox[r] = ray[0]; oy[r] = ray[1]; oz[r] = ray[2]; dx[r] = ray[3]; dy[r] = ray[4]; dz[r] = ray[5];
+                if (a.dbg_times) time = a.dbg_times[i];
+            }
+            *const_cast<volatile float*>(sm.time_slot(r)) = time;
+        }
+        __syncwarp();
+        resident_sweep<CONSTIMG, MOTION>(a, ci, sm, mc0, mc1, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const uint32_t i = base + r * kCtaThreads + threadIdx.x;
+            if (i < a.dbg_n) {
+                a.dbg_idx[i] = hit_index[r] < 0 ? -1 : (a.order ? (int32_t)__ldg(a.order + hit_index[r]) : hit_index[r]);
+                a.dbg_t[i] = hit_t[r];
+                if (a.dbg_flagged) a.dbg_flagged[i] = flagged[r];
+            }
+        }
+    }
+}
+
+// pt_debug_hits mode 1: the reference's exact expression on EVERY stored sphere, no pre-filter (any scene size) — what the
+// two-stage sweep must reproduce.  One ray per thread, spheres in stored order, ties to the lower position in the caller's list.
+template <bool MOTION>
+__global__ void pt_debug_hits_exact_all(const __grid_constant__ KernelArgs a) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.dbg_n; i += gridDim.x * blockDim.x) {
+        const float* ray = a.dbg_rays + (size_t)i * 6;
+        const float ox = ray[0], oy = ray[1], oz = ray[2], dx = ray[3], dy = ray[4], dz = ray[5];
+        const float time = a.dbg_times ? a.dbg_times[i] : 0.0f;
+        const MotionCtx mc{a.motion, &time, a.order};
         float hit_t = kMaxT;
         int hit_index = -1;
-        __syncwarp();
-        PT_PROF_TOCK(pf_refill);
-        if (__any_sync(kFullMask, L.active)) {  // regrouping collects idle lanes in whole warps: they skip the sweep
-            sweeps += 1u;
-            const float nod = -((ox * dx + oy * dy) + oz * dz);
-            const float oo = ((ox * ox + oy * oy) + oz * oz) * (1.0f - 1.9073486328125e-06f);
-            int cnt = 0;
-            sweep_expanded<kResidentPipe, MOTION>(pf, a.n_blocks, 0, ex, mc, queue, cnt, ox, oy, oz, dx, dy, dz, nod, ox + ox, oy + oy, oz + oz, oo, hit_t, hit_index);
-            sweep_drain<MOTION, true>(ex, mc, queue, cnt, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
-        }
-        __syncwarp();
-        PT_PROF_TOCK(pf_sweep);
-#if PT_REGROUP
-        if (!cta_regroup(a, L, hit_t, hit_index, pend, tslot, xchg, cat_count + (trip & 1u) * 8u, lane_id)) break;
-#endif
-        if (L.active) {
-            rays += 1ULL;  // scene.rs:57
-            lane_shade<MOTION>(a, L, ex, *P, mc, hit_t, hit_index);
-        }
-#if PT_REGROUP
-        lane_refill<MOTION>(a, L, lane_id, pend, tslot);  // ended paths sit side by side now: next sample / next ticket together
-#endif
-        __syncwarp();
-        PT_PROF_TOCK(pf_shade);
-#ifdef PT_PROFILE
-        pf_trips += 1;
-#endif
+        unsigned flagged = 0u;
+        for (int g = 0; g < a.n_blocks / kLdsGroupBlocks; ++g)
+            sweep_resolve_entry<kLdsMaskBits, MOTION, true>(a.blocks, mc, ((uint32_t)g << kLdsMaskBits) | ((1u << kLdsMaskBits) - 1u), ox, oy, oz, dx, dy, dz, hit_t,
+                                                            hit_index, flagged);
+        a.dbg_idx[i] = hit_index < 0 ? -1 : (a.order ? (int32_t)__ldg(a.order + hit_index) : hit_index);
+        a.dbg_t[i] = hit_t;
+        if (a.dbg_flagged) a.dbg_flagged[i] = flagged;
     }
-#ifdef PT_PROFILE
-    pf_lanes = rays;
-#endif
-    PT_PROF_FLUSH(lane_id);
-    flush_ray_count(a, rays, lane_id, sweeps);
 }
 
 // =====================================================================================================
@@ -597,45 +652,29 @@ constexpr bool kStreamPipe = true;  // LDS one block ahead (see sweep_expanded)
 #else
 #define PT_STREAM_LAUNCH_BOUNDS __launch_bounds__(kCtaThreads)
 #endif
-template <bool MOTION>
-__global__ void PT_STREAM_LAUNCH_BOUNDS pt_megakernel_streamed(const __grid_constant__ KernelArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t full_bar[2];
-    __shared__ __align__(8) uint64_t empty_bar[2];
-    __shared__ int cta_live;  // lanes not finished, recomputed every trip
-    const uint32_t tile_bytes = (uint32_t)a.tile_blocks * 64u;
-    // tile buffer b lives at smem_raw + b * tile_bytes (computed, not looked up: an array of pointers would be demoted to
-    // local memory and the sweep's loads would lose their shared-memory address space)
-    auto tile_buf = [&](int b) { return reinterpret_cast<float4*>(smem_raw + (size_t)b * tile_bytes); };
-    PerlinSmem* P = reinterpret_cast<PerlinSmem*>(smem_raw + 2 * (size_t)tile_bytes);
-    uint32_t* queue = reinterpret_cast<uint32_t*>(P + 1) + threadIdx.x;  // [kQueueCap][kCtaThreads] candidate queues
-    volatile uint32_t* pend = queue + kQueueCap * kCtaThreads;
-    volatile float* tslot = reinterpret_cast<volatile float*>(pend + kCtaThreads);  // [kCtaThreads] ray.time per lane
-    *pend = 0u;
-    *tslot = 0.0f;
-    const MotionCtx mc{a.motion, tslot, a.order};
 
-    if (threadIdx.x == 0) {
-        mbar_init(&full_bar[0], 1);
-        mbar_init(&full_bar[1], 1);
-        mbar_init(&empty_bar[0], kCtaThreads);  // every lane releases the buffer itself (no elected lane: each thread's
-        mbar_init(&empty_bar[1], kCtaThreads);  // own reads are ordered before its own arrive)
-        fence_mbar_init();
-        cta_live = 0;
+// the double-buffered tile pipeline of one CTA: full/empty mbarrier pair per buffer, thread 0 produces
+struct TileStream {
+    uint64_t* full_bar;   // [2]
+    uint64_t* empty_bar;  // [2]
+    unsigned char* buf0;  // tile buffer b lives at buf0 + b * tile_bytes (computed, not looked up: an array of pointers would
+    uint32_t tile_bytes;  // be demoted to local memory and the sweep's loads would lose their shared-memory address space)
+    uint32_t full_phase[2];   // parity to wait for on full_bar[b]
+    uint32_t empty_phase[2];  // producer side: parity to wait for on empty_bar[b]
+    uint32_t produced[2];     // producer: how many times buffer b has been filled
+    __device__ __forceinline__ float4* tile_buf(int b) const { return reinterpret_cast<float4*>(buf0 + (size_t)b * tile_bytes); }
+    __device__ __forceinline__ void init(uint64_t* full, uint64_t* empty, unsigned char* raw, uint32_t bytes) {
+        full_bar = full; empty_bar = empty; buf0 = raw; tile_bytes = bytes;
+        full_phase[0] = full_phase[1] = empty_phase[0] = empty_phase[1] = produced[0] = produced[1] = 0u;
+        if (threadIdx.x == 0) {
+            mbar_init(&full_bar[0], 1);
+            mbar_init(&full_bar[1], 1);
+            mbar_init(&empty_bar[0], kCtaThreads);  // every lane releases the buffer itself (no elected lane: each thread's
+            mbar_init(&empty_bar[1], kCtaThreads);  // own reads are ordered before its own arrive)
+            fence_mbar_init();
+        }
     }
-    stage_perlin(a, P);
-    __syncthreads();
-
-    const unsigned lane_id = threadIdx.x & 31u;
-    Lane L;
-    lane_init(L);
-    unsigned long long rays = 0ULL;
-    unsigned sweeps = 0u;
-    uint32_t full_phase[2] = {0u, 0u};   // parity to wait for on full_bar[b]
-    uint32_t empty_phase[2] = {0u, 0u};  // producer side: parity to wait for on empty_bar[b]
-    uint32_t produced[2] = {0u, 0u};     // producer: how many times buffer b has been filled
-
-    auto produce = [&](int tile) {  // thread 0 only
+    __device__ __forceinline__ void produce(const KernelArgs& a, int tile) {  // thread 0 only
         const int b = tile & 1;
         if (produced[b] != 0u) {  // wait until every warp has released the previous contents
             mbar_wait(&empty_bar[b], empty_phase[b]);
@@ -647,10 +686,70 @@ __global__ void PT_STREAM_LAUNCH_BOUNDS pt_megakernel_streamed(const __grid_cons
         const uint32_t bytes = (uint32_t)nb * 64u;
         mbar_arrive_expect_tx(&full_bar[b], bytes);
         tma_bulk_g2s_chunked(tile_buf(b), a.prefilter + (size_t)first * 4, bytes, &full_bar[b]);
-    };
+    }
+};
 
+// The sweep phase of one trip of the streamed kernels: the CTA streams the whole image once through its two tile buffers and
+// every lane tests its ray against each tile.  Must be called by ALL threads of the CTA (parked lanes carry the parked ray).
+template <bool MOTION>
+__device__ __forceinline__ void streamed_sweep(const KernelArgs& a, TileStream& ts, const MotionCtx& mc, uint32_t* queue, float ox, float oy, float oz, float dx,
+                                               float dy, float dz, float& hit_t, int& hit_index, unsigned& flagged) {
+    hit_t = kMaxT;
+    hit_index = -1;
+    const float nod = -((ox * dx + oy * dy) + oz * dz);
+    const float oo = ((ox * ox + oy * oy) + oz * oz) * (1.0f - kSlack);
+    int cnt = 0;
+    if (threadIdx.x == 0) {
+        ts.produce(a, 0);
+        if (a.n_tiles > 1) ts.produce(a, 1);
+    }
+    for (int tile = 0; tile < a.n_tiles; ++tile) {
+        const int b = tile & 1;
+        mbar_wait(&ts.full_bar[b], ts.full_phase[b]);
+        ts.full_phase[b] ^= 1u;
+        __syncwarp();
+        const int first = tile * a.tile_blocks;
+        const int nb = min(a.tile_blocks, a.n_blocks - first);
+        sweep_expanded<kStreamPipe, MOTION>(ts.tile_buf(b), nb, first, a.blocks, mc, queue, cnt, ox, oy, oz, dx, dy, dz, nod, ox + ox, oy + oy, oz + oz, oo, hit_t, hit_index, flagged);
+        mbar_arrive(&ts.empty_bar[b]);
+        __syncwarp();
+        if (threadIdx.x == 0 && tile + 2 < a.n_tiles) ts.produce(a, tile + 2);
+        // this tile's candidates: exact re-test against the global SoA (L2), off the tile buffer's critical path
+        sweep_drain<MOTION, false>(a.blocks, mc, queue, cnt, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
+    }
+}
+
+template <bool MOTION>
+__global__ void PT_STREAM_LAUNCH_BOUNDS pt_megakernel_streamed(const __grid_constant__ KernelArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[2];
+    __shared__ __align__(8) uint64_t empty_bar[2];
+    __shared__ int cta_live;  // lanes not finished, recomputed every trip
+    const uint32_t tile_bytes = (uint32_t)a.tile_blocks * 64u;
+    PerlinSmem* P = reinterpret_cast<PerlinSmem*>(smem_raw + 2 * (size_t)tile_bytes);
+    uint32_t* queue = reinterpret_cast<uint32_t*>(P + 1) + threadIdx.x;  // [kQueueCap][kCtaThreads] candidate queues
+    volatile uint32_t* pend = queue + kQueueCap * kCtaThreads;
+    volatile float* tslot = reinterpret_cast<volatile float*>(pend + kCtaThreads);  // [kCtaThreads] ray.time per lane
+    *pend = 0u;
+    *tslot = 0.0f;
+    const MotionCtx mc{a.motion, tslot, a.order};
+    TileStream ts;
+    ts.init(full_bar, empty_bar, smem_raw, tile_bytes);
+    if (threadIdx.x == 0) cta_live = 0;
+    stage_perlin(a, P);
+    __syncthreads();
+
+    const unsigned lane_id = threadIdx.x & 31u;
+    Lane L;
+    lane_init(L);
+    unsigned long long rays = 0ULL;
+    unsigned sweeps = 0u;
     for (;;) {
-        lane_refill<MOTION>(a, L, lane_id, pend, tslot);
+        L.pend = *pend != 0u;  // the streamed kernel parks these two in shared memory across the sweep (registers)
+        L.time = *tslot;
+        lane_refill<MOTION>(a, L, lane_id);
+        *pend = L.pend ? 1u : 0u;
+        *tslot = L.time;
         // CTA-wide liveness: every warp must keep consuming tiles while any warp still has work
         const bool warp_live = !__all_sync(kFullMask, L.finished);
         __syncthreads();  // previous trip's cta_live reads are done
@@ -665,37 +764,55 @@ __global__ void PT_STREAM_LAUNCH_BOUNDS pt_megakernel_streamed(const __grid_cons
             ox = 0.0f; oy = 1.0e18f; oz = 0.0f;
             dx = dy = dz = 0.0f;
         }
-        float hit_t = kMaxT;
-        int hit_index = -1;
-        const float nod = -((ox * dx + oy * dy) + oz * dz);
-        const float oo = ((ox * ox + oy * oy) + oz * oz) * (1.0f - 1.9073486328125e-06f);
-        int cnt = 0;
+        float hit_t;
+        int hit_index;
+        unsigned flagged = 0u;
         sweeps += 1u;  // every warp of the CTA sweeps every tile of every trip
-        if (threadIdx.x == 0) {
-            produce(0);
-            if (a.n_tiles > 1) produce(1);
-        }
-        for (int tile = 0; tile < a.n_tiles; ++tile) {
-            const int b = tile & 1;
-            mbar_wait(&full_bar[b], full_phase[b]);
-            full_phase[b] ^= 1u;
-            __syncwarp();
-            const int first = tile * a.tile_blocks;
-            const int nb = min(a.tile_blocks, a.n_blocks - first);
-            sweep_expanded<kStreamPipe, MOTION>(tile_buf(b), nb, first, a.blocks, mc, queue, cnt, ox, oy, oz, dx, dy, dz, nod, ox + ox, oy + oy, oz + oz, oo, hit_t, hit_index);
-            mbar_arrive(&empty_bar[b]);
-            __syncwarp();
-            if (threadIdx.x == 0 && tile + 2 < a.n_tiles) produce(tile + 2);
-            // this tile's candidates: exact re-test against the global SoA (L2), off the tile buffer's critical path
-            sweep_drain<MOTION, false>(a.blocks, mc, queue, cnt, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
-        }
+        streamed_sweep<MOTION>(a, ts, mc, queue, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
         if (L.active) {
             rays += 1ULL;
+            L.time = *tslot;  // (re-read: nothing of the lane's bookkeeping is carried across the sweep in a register)
             // the hit sphere's centre is no longer in shared memory: read it from the global SoA
             lane_shade<MOTION>(a, L, a.blocks, *P, mc, hit_t, hit_index);
         }
     }
     flush_ray_count(a, rays, lane_id, sweeps);
+}
+
+// pt_debug_hits, streamed scenes: caller-supplied rays through streamed_sweep (same tiles, barriers, operands, re-tests)
+template <bool MOTION>
+__global__ void PT_STREAM_LAUNCH_BOUNDS pt_debug_hits_streamed(const __grid_constant__ KernelArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t full_bar[2];
+    __shared__ __align__(8) uint64_t empty_bar[2];
+    const uint32_t tile_bytes = (uint32_t)a.tile_blocks * 64u;
+    PerlinSmem* P = reinterpret_cast<PerlinSmem*>(smem_raw + 2 * (size_t)tile_bytes);
+    uint32_t* queue = reinterpret_cast<uint32_t*>(P + 1) + threadIdx.x;
+    volatile float* tslot = reinterpret_cast<volatile float*>(queue + kQueueCap * kCtaThreads + kCtaThreads);
+    const MotionCtx mc{a.motion, tslot, a.order};
+    TileStream ts;
+    ts.init(full_bar, empty_bar, smem_raw, tile_bytes);
+    __syncthreads();
+    // `base` is uniform within the CTA: all its threads run the same trips (the sweep is CTA-collective)
+    for (uint32_t base = blockIdx.x * kCtaThreads; base < a.dbg_n; base += gridDim.x * kCtaThreads) {
+        const uint32_t i = base + threadIdx.x;
+        float ox = 0.0f, oy = 1.0e18f, oz = 0.0f, dx = 0.0f, dy = 0.0f, dz = 0.0f, time = 0.0f;
+        if (i < a.dbg_n) {
+            const float* ray = a.dbg_rays + (size_t)i * 6;
+            ox = ray[0]; oy = ray[1]; oz = ray[2]; dx = ray[3]; dy = ray[4]; dz = ray[5];
+            if (a.dbg_times) time = a.dbg_times[i];
+        }
+        *tslot = time;
+        float hit_t;
+        int hit_index;
+        unsigned flagged = 0u;
+        streamed_sweep<MOTION>(a, ts, mc, queue, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
+        if (i < a.dbg_n) {
+            a.dbg_idx[i] = hit_index < 0 ? -1 : (a.order ? (int32_t)__ldg(a.order + hit_index) : hit_index);
+            a.dbg_t[i] = hit_t;
+            if (a.dbg_flagged) a.dbg_flagged[i] = flagged;
+        }
+    }
 }
 
 // =====================================================================================================

@@ -8,7 +8,7 @@
 // instruction, the ray broadcast from scalar registers): the discriminant expanded around the ray,
 //
 //   disc = (c.d - o.d)^2 + 2 c.o + (r^2 - |c|^2) - |o|^2 ,   A = c.d - o.d (3 FFMA2), B = 2 c.o + k (3 FFMA2),
-//   L = A*A + B (1 FFMA2),   candidate  <=>  L > |o|^2 (1 - 2^-19)
+//   L = A*A + B (1 FFMA2),   candidate  <=>  L > |o|^2 (1 - 2^-18)
 //
 // = 7 packed instructions per 2 (ray, sphere) tests on the "pre-filter image" X, Y, Z, K (k = r^2 - |c|^2 + slack) of a
 // block of 4 spheres.  Stage 2 re-tests only the flagged spheres with the reference's exact unfused expression
@@ -30,10 +30,6 @@ __device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
     return *reinterpret_cast<float2*>(&d);
 }
 
-// PT_SWEEP_AB=1 builds the A/B-packed variant of the pre-filter (measured slower, kept for the record: DESIGN.md §5.1)
-#ifndef PT_SWEEP_AB
-#define PT_SWEEP_AB 0
-#endif
 // groups per trip of the pre-filter loop.  Two in the streamed kernel (all sweep, registers to spare: cfg5 +5.6 %); one in
 // the resident kernel, where the longer body costs more around the loop than the saved back-branch gives (cfg2 -1.4 %)
 #ifndef PT_GROUP_UNROLL_STREAMED
@@ -42,12 +38,21 @@ __device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
 #ifndef PT_GROUP_UNROLL_RESIDENT
 #define PT_GROUP_UNROLL_RESIDENT 1
 #endif
-#ifndef PT_AB_BLOCKS
-#define PT_AB_BLOCKS 1  // blocks of 4 spheres that advance through the chain steps together (PT_SWEEP_AB)
-#endif
 
 constexpr float kMinT = 0.001f;   // src/scene.rs:16
 constexpr float kMaxT = FLT_MAX;  // src/scene.rs:15
+
+// Slack of the conservative pre-filter.  In exact arithmetic L - |o|^2 equals the reference's discriminant
+// D = (co.d)^2 - |co|^2 + r^2; in f32 the expanded evaluation (7 fused steps on terms as large as (|c| + |o|)^2, the
+// unfused o.d and |o|^2) and the reference's own sphere-relative evaluation differ from D by at most about
+//   2^-24 (29 |c|^2 + 31 |o|^2 + 7 r^2)      (every rounding taken at its worst and with the same sign),
+// i.e. 2^-19 (0.9 |c|^2 + 0.97 |o|^2 + 0.22 r^2).  The filter adds kSlack (|c|^2 + r^2) on the sphere side (baked into K
+// by the host, rounded up) and kSlack |o|^2 on the ray side: 2^-18 is twice that bound, so a sphere the exact expression
+// accepts is always a candidate.  Domain: finite geometry, |camera| <= 1e17; a sphere with |c|^2 + r^2 >= 1e24 is stored
+// with K = +inf (always a candidate, decided by the exact test alone).  Checked per ray, not assumed: pt_debug_hits mode 0
+// against mode 1 (tests/test_gpu_hits.py), including origins and centres swept to 1e6.
+constexpr float kSlack = 3.814697265625e-06f;  // 2^-18
+constexpr double kSlackSphere = 3.814697265625e-06;
 
 // exact re-test of one sphere, reference expression order (spheres_soa.rs:116-129), unfused
 // `order` (may be null): the scene's spheres are stored in a spatial order (ptgpu.cu), order[i] = the sphere's position
@@ -131,9 +136,10 @@ constexpr int kQueueCap = 12;
 
 template <int MASK_BITS, bool MOTION, bool ORDERED>
 __device__ __forceinline__ void sweep_resolve_entry(const float4* __restrict__ blk, const MotionCtx& mc, uint32_t entry, float ox, float oy, float oz,
-                                                    float dx, float dy, float dz, float& hit_t, int& hit_index) {
+                                                    float dx, float dy, float dz, float& hit_t, int& hit_index, unsigned& flagged) {
     const int base = (int)(entry >> MASK_BITS) * MASK_BITS;  // MASK_BITS spheres per group
     uint32_t mask = entry & ((1u << MASK_BITS) - 1u);
+    flagged += (unsigned)__popc(mask);  // diagnostic (pt_debug_hits); dead code in the render kernels
 #pragma unroll 1
     while (mask != 0u) {
         const int index = base + __ffs(mask) - 1;
@@ -156,7 +162,7 @@ __device__ __forceinline__ void sweep_resolve_entry(const float4* __restrict__ b
 // =====================================================================================================
 // Expanded pre-filter with shared-memory operands (resident and streamed kernels).
 //
-// A = c.d - o.d, B = 2 c.o + k, L = A*A + B, candidate <=> L > |o|^2 (1 - 2^-19); the sphere pairs come from the
+// A = c.d - o.d, B = 2 c.o + k, L = A*A + B, candidate <=> L > |o|^2 (1 - 2^-18); the sphere pairs come from the
 // pre-filter image staged in shared memory (LDS.128 broadcast): 7 packed instructions per 2 tests of the shape
 // FFMA2 Rpair, Rpair(spheres), Rscalar(ray), Rpair — against 11 for the sphere-relative form co = c - o, whose packed
 // instructions mostly read two or three register pairs (profiles/probe_forms_r1.txt; history in DESIGN.md §4.1).
@@ -178,7 +184,7 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 template <bool PIPE, bool MOTION>
 __device__ __forceinline__ void sweep_expanded(const float4* __restrict__ pf, int n_blocks, int first_block, const float4* __restrict__ exact,
                                                const MotionCtx& mc, uint32_t* __restrict__ q, int& cnt, float ox, float oy, float oz, float dx, float dy, float dz,
-                                               float nod, float o2x, float o2y, float o2z, float oo, float& hit_t, int& hit_index) {
+                                               float nod, float o2x, float o2y, float o2z, float oo, float& hit_t, int& hit_index, unsigned& flagged) {
     // pin the per-ray operands (and the trip count) in registers: without this ptxas rematerialises them — 9 scalar FP
     // instructions and a constant-bank reload of n_blocks — in every trip
     asm volatile("" : "+f"(nod), "+f"(o2x), "+f"(o2y), "+f"(o2z), "+f"(oo), "+r"(n_blocks));
@@ -198,58 +204,6 @@ __device__ __forceinline__ void sweep_expanded(const float4* __restrict__ pf, in
         cX = lds128(addr); cY = lds128(addr + 16u); cZ = lds128(addr + 32u); cK = lds128(addr + 48u);
     }
     const uint32_t base = addr, end = addr + 64u * (uint32_t)n_blocks;
-#if PT_SWEEP_AB
-    // A/B-packed form (PT_SWEEP_AB): one packed FMA advances BOTH affine forms of ONE sphere, (A, B') += c_axis * (d_axis,
-    // 2 o_axis), so the 64-bit operand is the RAY pair — loop-invariant, the same register pair in the same slot for every
-    // sphere of a block, i.e. served by the operand reuse cache — and the sphere enters as a 32-bit broadcast scalar.
-    // 3 packed + 2 scalar instructions per test (L = A*A + B' + k) against 3.5 packed ones, but ~3.5 register words read
-    // per packed instruction instead of ~4.6 (the packed FMA is register-read bound: tools/probe_forms.cu).
-    if (!PIPE) {
-        const float2 PX = make_float2(dx, o2x), PY = make_float2(dy, o2y), PZ = make_float2(dz, o2z), P0 = make_float2(nod, 0.0f);
-#pragma unroll 1
-        for (; addr < end; addr += 64u * kLdsGroupBlocks) {
-            float Ls[4 * kLdsGroupBlocks];
-#pragma unroll
-            for (int g = 0; g < kLdsGroupBlocks; g += PT_AB_BLOCKS) {
-                float xs[4 * PT_AB_BLOCKS], ys[4 * PT_AB_BLOCKS], zs[4 * PT_AB_BLOCKS], ks[4 * PT_AB_BLOCKS];
-#pragma unroll
-                for (int b = 0; b < PT_AB_BLOCKS; ++b) {
-                    const float4 X = lds128(addr + 64u * (g + b)), Y = lds128(addr + 64u * (g + b) + 16u), Z = lds128(addr + 64u * (g + b) + 32u),
-                                 K = lds128(addr + 64u * (g + b) + 48u);
-                    xs[4 * b] = X.x; xs[4 * b + 1] = X.y; xs[4 * b + 2] = X.z; xs[4 * b + 3] = X.w;
-                    ys[4 * b] = Y.x; ys[4 * b + 1] = Y.y; ys[4 * b + 2] = Y.z; ys[4 * b + 3] = Y.w;
-                    zs[4 * b] = Z.x; zs[4 * b + 1] = Z.y; zs[4 * b + 2] = Z.z; zs[4 * b + 3] = Z.w;
-                    ks[4 * b] = K.x; ks[4 * b + 1] = K.y; ks[4 * b + 2] = K.z; ks[4 * b + 3] = K.w;
-                }
-                float2 acc[4 * PT_AB_BLOCKS];
-#pragma unroll
-                for (int e = 0; e < 4 * PT_AB_BLOCKS; ++e) acc[e] = f2_fma(make_float2(xs[e], xs[e]), PX, P0);
-#pragma unroll
-                for (int e = 0; e < 4 * PT_AB_BLOCKS; ++e) acc[e] = f2_fma(make_float2(ys[e], ys[e]), PY, acc[e]);
-#pragma unroll
-                for (int e = 0; e < 4 * PT_AB_BLOCKS; ++e) acc[e] = f2_fma(make_float2(zs[e], zs[e]), PZ, acc[e]);
-#pragma unroll
-                for (int e = 0; e < 4 * PT_AB_BLOCKS; ++e) Ls[4 * g + e] = __fadd_rn(__fmaf_rn(acc[e].x, acc[e].x, acc[e].y), ks[e]);
-            }
-            float mx = Ls[0];
-#pragma unroll
-            for (int p = 1; p < 4 * kLdsGroupBlocks; ++p) mx = fmaxf(mx, Ls[p]);
-            if (mx > oo) {
-                uint32_t mask = 0u;
-#pragma unroll
-                for (int p = 4 * kLdsGroupBlocks - 1; p >= 0; --p) mask = __funnelshift_l(__float_as_uint(__fsub_rn(oo, Ls[p])), mask, 1);
-                const uint32_t entry = ((((uint32_t)first_block + ((addr - base) >> 6)) / kLdsGroupBlocks) << kLdsMaskBits) | mask;
-                if (cnt < kQueueCap) {
-                    q[cnt * kSweepThreads] = entry;
-                    cnt += 1;
-                } else {
-                    sweep_resolve_entry<kLdsMaskBits, MOTION, !PIPE>(exact, mc, entry, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
-                }
-            }
-        }
-        return;
-    }
-#endif
     constexpr int kGroupUnroll = PIPE ? PT_GROUP_UNROLL_STREAMED : PT_GROUP_UNROLL_RESIDENT;
 #pragma unroll kGroupUnroll
     for (; addr < end; addr += 64u * kLdsGroupBlocks) {
@@ -300,9 +254,131 @@ __device__ __forceinline__ void sweep_expanded(const float4* __restrict__ pf, in
                 else q[cnt * kSweepThreads] = entry;
                 cnt += 1;
             } else {  // queue full (rare): test this group now; sweep_exact's tie rule makes the visiting order irrelevant
-                sweep_resolve_entry<kLdsMaskBits, MOTION, !PIPE>(exact, mc, entry, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
+                sweep_resolve_entry<kLdsMaskBits, MOTION, !PIPE>(exact, mc, entry, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
             }
         }
+    }
+}
+
+// =====================================================================================================
+// Two rays per lane, sphere pairs as UNIFORM operands (resident kernel, round 2).
+//
+// Measured on B200 (tools/probe_forms.cu, tools/probe_sweep2.cu, profiles/probe_*_r2*.txt): the packed FMA is bound by
+// register-file reads, not by the FMA pipe.  FFMA2 Rpair(spheres) * Rscalar(ray) + Rpair(acc) reads five register words
+// and issues every 3.1 clk per SM sub-partition; FFMA2 Rscalar(ray) * URpair(spheres) + Rpair(acc) reads three and issues
+// every 2.1 clk, the pipe's own rate.  Sphere data is the same for every lane, so the X, Y, Z planes of the pre-filter
+// image travel as a KERNEL PARAMETER (constant bank 0, `ConstImage`) and reach the FMA through the uniform datapath
+// (LDCU.64 -> UR pair); only K (the addend of the B chain: an instruction takes one uniform operand) is read from shared
+// memory.  The uniform loads are the next limit (24 LDCU.64 per 16 spheres), so every lane carries TWO rays through the
+// sweep and each loaded sphere pair serves both: loop in isolation 8.95-9.4 clk per 32 tests (85-89 % of the FP32 peak at
+// 16 flop per test) against 11.0-11.5 (69-73 %) for the round-1 form.
+//
+// Scenes whose image does not fit the parameter space (> kMaxConstSpheres) run the same two-ray loop with LDS.128
+// sphere pairs (CONSTIMG = false): each pair then serves four consecutive FFMA2 through the operand reuse cache (76-81 %).
+//
+// Queue: the lane's two rays share one queue of kQueueCap entries, ray 0 filling it from the front and ray 1 from the
+// back, so an entry needs no ray tag and each ray is drained with its own registers.  overflow[r] (initialised to n_blocks
+// by the caller) comes back as the first block of ray r's first flagged group that found the queue full.
+// =====================================================================================================
+constexpr int kMaxConstBlocks = 512;                     // 2048 spheres: 24 KB of the 32 764-byte kernel parameter space
+constexpr int kMaxConstSpheres = 4 * kMaxConstBlocks;
+template <bool CONSTIMG>
+struct ConstImageT {
+    float4 v[CONSTIMG ? 3 * kMaxConstBlocks : 1];  // per block of 4 spheres: X(cx0..3), Y, Z
+};
+
+template <bool CONSTIMG>
+__device__ __forceinline__ void sweep_two(const ConstImageT<CONSTIMG>& ci, const float4* __restrict__ pf, int n_blocks, uint32_t* __restrict__ q, int& cnt0, int& cnt1,
+                                          const float (&dx)[2], const float (&dy)[2], const float (&dz)[2], float (&o2x)[2], float (&o2y)[2],
+                                          float (&o2z)[2], float (&nod)[2], float (&oo)[2], int (&overflow)[2]) {
+    // pin the per-ray operands in registers (ptxas otherwise rematerialises them inside the loop)
+    asm volatile("" : "+f"(nod[0]), "+f"(o2x[0]), "+f"(o2y[0]), "+f"(o2z[0]), "+f"(oo[0]));
+    asm volatile("" : "+f"(nod[1]), "+f"(o2x[1]), "+f"(o2y[1]), "+f"(o2z[1]), "+f"(oo[1]));
+    uint32_t qaddr = (uint32_t)__cvta_generic_to_shared(q);
+    asm volatile("" : "+r"(qaddr));
+    uint32_t addr = (uint32_t)__cvta_generic_to_shared(pf);
+    if constexpr (!CONSTIMG) asm volatile("" : "+r"(addr));
+    // CONSTIMG: the loop counter must stay provably uniform — no inline-asm operand may depend on it (an "r" constraint
+    // forces a vector register and ptxas then falls back to LDC into vector registers: 17.8 clk per 32 tests)
+#pragma unroll 1
+    for (int j = 0; j < n_blocks; j += kLdsGroupBlocks) {
+        float2 L[2][2 * kLdsGroupBlocks];
+#pragma unroll
+        for (int g = 0; g < kLdsGroupBlocks; ++g) {
+            float4 X, Y, Z, K;
+            if constexpr (CONSTIMG) {
+                X = ci.v[3 * (j + g) + 0]; Y = ci.v[3 * (j + g) + 1]; Z = ci.v[3 * (j + g) + 2];
+                K = pf[j + g];  // K plane only (16 B per block), plain shared load with a uniform index
+            } else {
+                const uint32_t a4 = addr + 64u * (uint32_t)(j + g);
+                X = lds128(a4); Y = lds128(a4 + 16u); Z = lds128(a4 + 32u); K = lds128(a4 + 48u);
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float2 cx = h ? make_float2(X.z, X.w) : make_float2(X.x, X.y);
+                const float2 cy = h ? make_float2(Y.z, Y.w) : make_float2(Y.x, Y.y);
+                const float2 cz = h ? make_float2(Z.z, Z.w) : make_float2(Z.x, Z.y);
+                const float2 k = h ? make_float2(K.z, K.w) : make_float2(K.x, K.y);
+#pragma unroll
+                for (int r = 0; r < 2; ++r) {
+                    const float2 A = f2_fma(cz, make_float2(dz[r], dz[r]), f2_fma(cy, make_float2(dy[r], dy[r]), f2_fma(cx, make_float2(dx[r], dx[r]), make_float2(nod[r], nod[r]))));
+                    const float2 B = f2_fma(cz, make_float2(o2z[r], o2z[r]), f2_fma(cy, make_float2(o2y[r], o2y[r]), f2_fma(cx, make_float2(o2x[r], o2x[r]), k)));
+                    L[r][2 * g + h] = f2_fma(A, A, B);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            bool any = false;
+#pragma unroll
+            for (int p = 0; p < 2 * kLdsGroupBlocks; ++p) any = any | (L[r][p].x > oo[r]) | (L[r][p].y > oo[r]);
+            if (any) {
+                // flag bits from sign bits (see sweep_expanded): bit e = sphere e of the group
+                uint32_t mask = 0u;
+#pragma unroll
+                for (int p = 2 * kLdsGroupBlocks - 1; p >= 0; --p) {
+                    const float2 d = f2_fma(L[r][p], make_float2(-1.0f, -1.0f), make_float2(oo[r], oo[r]));
+                    mask = __funnelshift_l(__float_as_uint(d.y), mask, 1);
+                    mask = __funnelshift_l(__float_as_uint(d.x), mask, 1);
+                }
+                const uint32_t entry = (((uint32_t)j / kLdsGroupBlocks) << kLdsMaskBits) | mask;
+                if (cnt0 + cnt1 < kQueueCap) {
+                    const uint32_t slot = r == 0 ? (uint32_t)cnt0 : (uint32_t)(kQueueCap - 1 - cnt1);
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(qaddr + slot * (uint32_t)(kSweepThreads * 4)), "r"(entry) : "memory");
+                    if (r == 0) cnt0 += 1; else cnt1 += 1;
+                } else {
+                    // queue full (rare): remember the first group that did not fit; the caller re-tests every sphere from
+                    // there on with the exact expression (sweep_overflow).  Nothing else may sit in this loop: ptxas keeps
+                    // the sphere operands in uniform registers only while it can prove that the warp runs the loop in
+                    // lockstep, and a data-dependent inner loop or a call in here makes it fall back to vector loads.
+                    overflow[r] = min(overflow[r], j);
+                }
+            }
+        }
+    }
+}
+
+// groups [first_block / kLdsGroupBlocks, n_blocks / kLdsGroupBlocks): the exact test on every sphere (queue overflow)
+template <bool MOTION>
+__device__ __forceinline__ void sweep_overflow(const float4* __restrict__ exact, const MotionCtx& mc, int first_block, int n_blocks, float ox, float oy, float oz,
+                                            float dx, float dy, float dz, float& hit_t, int& hit_index, unsigned& flagged) {
+    for (int g = first_block / kLdsGroupBlocks; g < n_blocks / kLdsGroupBlocks; ++g)
+        sweep_resolve_entry<kLdsMaskBits, MOTION, true>(exact, mc, ((uint32_t)g << kLdsMaskBits) | ((1u << kLdsMaskBits) - 1u), ox, oy, oz, dx, dy, dz, hit_t, hit_index,
+                                                        flagged);
+}
+
+// drain `cnt` queue entries starting at entry `first` (the lane's [entry][thread] queue), all lanes in parallel
+template <bool MOTION>
+__device__ __forceinline__ void sweep_drain_range(const float4* __restrict__ exact, const MotionCtx& mc, const uint32_t* __restrict__ q, int first, int cnt, float ox,
+                                                  float oy, float oz, float dx, float dy, float dz, float& hit_t, int& hit_index, unsigned& flagged) {
+    uint32_t qaddr = (uint32_t)__cvta_generic_to_shared(q) + (uint32_t)first * (uint32_t)(kSweepThreads * 4);
+    asm volatile("" : "+r"(qaddr));
+    const uint32_t qend = qaddr + (uint32_t)cnt * (uint32_t)(kSweepThreads * 4);
+#pragma unroll 1
+    for (; qaddr != qend; qaddr += (uint32_t)(kSweepThreads * 4)) {
+        uint32_t entry;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(entry) : "r"(qaddr) : "memory");
+        sweep_resolve_entry<kLdsMaskBits, MOTION, true>(exact, mc, entry, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
     }
 }
 
@@ -310,7 +386,7 @@ __device__ __forceinline__ void sweep_expanded(const float4* __restrict__ pf, in
 // pinned shared-window address (resident kernel; see the push in sweep_expanded)
 template <bool MOTION, bool PIN>
 __device__ __forceinline__ void sweep_drain(const float4* __restrict__ exact, const MotionCtx& mc, const uint32_t* __restrict__ q, int& cnt, float ox, float oy, float oz,
-                                            float dx, float dy, float dz, float& hit_t, int& hit_index) {
+                                            float dx, float dy, float dz, float& hit_t, int& hit_index, unsigned& flagged) {
     if (PIN) {
         uint32_t qaddr = (uint32_t)__cvta_generic_to_shared(q);
         asm volatile("" : "+r"(qaddr));
@@ -319,11 +395,11 @@ __device__ __forceinline__ void sweep_drain(const float4* __restrict__ exact, co
         for (; qaddr != qend; qaddr += (uint32_t)(kSweepThreads * 4)) {
             uint32_t entry;
             asm volatile("ld.shared.u32 %0, [%1];" : "=r"(entry) : "r"(qaddr) : "memory");
-            sweep_resolve_entry<kLdsMaskBits, MOTION, true>(exact, mc, entry, ox, oy, oz, dx, dy, dz, hit_t, hit_index);
+            sweep_resolve_entry<kLdsMaskBits, MOTION, true>(exact, mc, entry, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
         }
     } else {
 #pragma unroll 1
-        for (int i = 0; i < cnt; ++i) sweep_resolve_entry<kLdsMaskBits, MOTION, false>(exact, mc, q[i * kSweepThreads], ox, oy, oz, dx, dy, dz, hit_t, hit_index);
+        for (int i = 0; i < cnt; ++i) sweep_resolve_entry<kLdsMaskBits, MOTION, false>(exact, mc, q[i * kSweepThreads], ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
     }
     cnt = 0;
 }

@@ -12,7 +12,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/ptgpu.h"
@@ -42,7 +44,25 @@ constexpr size_t kMaxDynSmem = 227 * 1024 - 1024;  // leave room for static shar
 
 }  // namespace
 
-struct PtScene {
+// Host image of a flattened scene, built once per pt_scene_create* and uploaded to every device of the scene.
+struct FlatScene {
+    uint32_t n_spheres = 0;
+    int n_blocks = 0;
+    bool has_noise = false, has_sky = false, spatial = false, any_moving = false;
+    pt::V3 sky{0, 0, 0};
+    float motion_t_lo = 0.0f, motion_t_hi = 0.0f;
+    std::vector<float4> blocks, prefilter, kplane;
+    std::vector<pt::DevShade> shade;
+    std::vector<pt::DevTexture> tex;
+    std::vector<uint32_t> order_of;
+    std::vector<uint8_t> image_pool;
+    std::vector<pt::DevMotion> motion;
+    std::vector<unsigned char> perlin_raw;
+    std::unique_ptr<pt::ConstImageT<true>> const_image;  // X,Y,Z planes for the kernel-parameter image (n_blocks <= kMaxConstBlocks)
+};
+
+// One device's copy of a scene plus its per-render scratch.
+struct Replica {
     int device = 0;
     int sm_count = 0;
     uint32_t n_spheres = 0;
@@ -50,6 +70,7 @@ struct PtScene {
     bool has_noise = false;
     bool has_sky = false;
     pt::V3 sky{0, 0, 0};
+    PtOptions opt{};
     float4* d_blocks = nullptr;
     pt::DevShade* d_shade = nullptr;
     pt::DevTexture* d_tex = nullptr;
@@ -59,7 +80,11 @@ struct PtScene {
     pt::DevMotion* d_motion = nullptr;  // MovingSphere records (nullptr: none)
     float motion_t_lo = 0.0f, motion_t_hi = 0.0f;  // intersection of the moving spheres' [time0, time1]
     float4* d_prefilter = nullptr;  // pre-filter image X,Y,Z,K per block (LDS kernels stage/stream it)
-    // per-render scratch
+    float4* d_kplane = nullptr;     // its K plane alone (resident kernel with the X,Y,Z planes in the parameter image)
+    bool const_image = false;       // resident kernel reads X,Y,Z through the kernel-parameter image
+    const pt::ConstImageT<true>* h_const_image = nullptr;  // owned by the PtScene; passed by value at every launch (24 KB)
+    // per-render scratch.  At most one render is in flight per replica: every launch waits for the previous one's
+    // event (ev_busy), whatever stream it was issued on, so the scratch below is never shared by two launches.
     unsigned long long* d_ray_count = nullptr;  // [0] ray count
     unsigned long long* d_sweep_count = nullptr;  // warp-level sweeps of the last launch (lane-efficiency diagnostic)
     unsigned int* d_next_pixel = nullptr;
@@ -69,17 +94,26 @@ struct PtScene {
     size_t d_rgb_floats = 0;
     uint8_t* d_rgb8 = nullptr;
     size_t d_rgb8_bytes = 0;
-    // pt_render_progressive: what the resident image currently holds
-    bool prog_valid = false;
-    uint32_t prog_w = 0, prog_h = 0, prog_next_frame = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_busy = nullptr;
+    bool busy_recorded = false;
     // launch geometry
     bool resident = true;
     int tile_blocks = 0, n_tiles = 0;
     size_t smem_bytes = 0;
     int ctas_per_sm = 0;
     PtRenderStats stats{};
+};
+
+struct PtScene {
+    std::vector<Replica*> reps;  // one per device, in the caller's device order
+    PtOptions opt{};
+    FlatScene flat;              // kept for the parameter image (and cheap: the scene is small)
+    PtRenderStats stats{};       // aggregate of the last render
+    // pt_render_progressive: what the resident images currently hold
+    bool prog_valid = false;
+    uint32_t prog_w = 0, prog_h = 0, prog_next_frame = 0;
 };
 
 namespace {
@@ -103,59 +137,67 @@ int configure_kernel(K kernel, size_t smem, int* ctas_per_sm) {
     int occ = 0;
     PT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, pt::kCtaThreads, smem));
     if (occ < 1) return fail(PT_ERR_TOO_LARGE, "kernel does not fit on an SM with %zu bytes of shared memory", smem);
-    *ctas_per_sm = occ;
+    if (ctas_per_sm) *ctas_per_sm = occ;
     return PT_OK;
 }
 
-int configure_streamed(PtScene* s) {
-    return s->d_motion ? configure_kernel(pt::pt_megakernel_streamed<true>, s->smem_bytes, &s->ctas_per_sm)
-                       : configure_kernel(pt::pt_megakernel_streamed<false>, s->smem_bytes, &s->ctas_per_sm);
-}
-
-// shared-memory budget of the two kernels (one place: plan_launch and the storage-order decision both ask)
+// shared-memory budget of the kernels (one place: plan_launch and the storage-order decision both ask)
 constexpr size_t kQueueBytes = (size_t)pt::kQueueCap * pt::kCtaThreads * sizeof(uint32_t);  // per-lane candidate queues
-constexpr size_t kPerlinBytes = sizeof(pt::PerlinSmem) + 2 * pt::kCtaThreads * sizeof(uint32_t) + kQueueBytes;  // Perlin tables + `pend` words + ray.time slots + queues
-constexpr size_t kRegroupBytes = (size_t)pt::kRegroupWords * pt::kCtaThreads * sizeof(uint32_t) + 64;  // path-state exchange + category counters
-int forced_stream_tile() {  // test hook: PTGPU_FORCE_STREAM_TILE_BLOCKS=<n> runs any scene through the streamed kernel with n-block tiles
-    const char* env = std::getenv("PTGPU_FORCE_STREAM_TILE_BLOCKS");
-    return env ? std::atoi(env) : 0;
+constexpr size_t kStreamedFixedBytes = sizeof(pt::PerlinSmem) + 2 * pt::kCtaThreads * sizeof(uint32_t) + kQueueBytes;  // streamed kernel: Perlin tables + `pend` words + ray.time slots + queues
+constexpr size_t kPathBytes = (size_t)pt::kPathWords * pt::kPathRows * pt::kCtaThreads * sizeof(uint32_t);            // resident kernel: path records
+size_t resident_smem(int n_blocks, bool const_image) {
+    const size_t image = ((size_t)n_blocks * (const_image ? 16 : 64) + 127) & ~(size_t)127;
+    return image + sizeof(pt::PerlinSmem) + kQueueBytes + kPathBytes;
 }
-bool fits_resident(int n_blocks) {
-    if (forced_stream_tile() > 0 && n_blocks > 0) return false;
-    const size_t exact_bytes = PT_EXACT_SMEM ? (size_t)n_blocks * 64 : 0;  // resident kernel: exact blocks in shared memory too
-    return (size_t)n_blocks * 64 + kPerlinBytes + kRegroupBytes + exact_bytes <= kMaxDynSmem;
+bool fits_resident(int n_blocks, const PtOptions& opt) {
+    if (opt.force_stream_tile_blocks > 0 && n_blocks > 0) return false;
+    return resident_smem(n_blocks, n_blocks <= pt::kMaxConstBlocks) <= kMaxDynSmem;
 }
 
-int plan_launch(PtScene* s) {
-    const size_t perlin_bytes = kPerlinBytes;
-    const size_t all = (size_t)s->n_blocks * 64 + perlin_bytes;
-    int forced_tile = forced_stream_tile();
-    if (forced_tile > 0 && s->n_blocks > 0) {
-        s->resident = false;
-        forced_tile = (forced_tile + pt::kLdsGroupBlocks - 1) / pt::kLdsGroupBlocks * pt::kLdsGroupBlocks;  // whole groups
-        s->tile_blocks = std::min(forced_tile, s->n_blocks);
-        s->n_tiles = (s->n_blocks + s->tile_blocks - 1) / s->tile_blocks;
-        s->smem_bytes = 2 * (size_t)s->tile_blocks * 64 + perlin_bytes;
-        return configure_streamed(s);
-    }
-    if (fits_resident(s->n_blocks)) {
+int plan_launch(Replica* s) {
+    int forced_tile = s->opt.force_stream_tile_blocks;
+    if (fits_resident(s->n_blocks, s->opt)) {
         s->resident = true;
-        s->smem_bytes = all + kRegroupBytes + (PT_EXACT_SMEM ? (size_t)s->n_blocks * 64 : 0);
+        s->const_image = s->n_blocks <= pt::kMaxConstBlocks;
+        s->smem_bytes = resident_smem(s->n_blocks, s->const_image);
         s->tile_blocks = s->n_blocks;
         s->n_tiles = 1;
-        return s->d_motion ? configure_kernel(pt::pt_megakernel_resident<true>, s->smem_bytes, &s->ctas_per_sm)
-                           : configure_kernel(pt::pt_megakernel_resident<false>, s->smem_bytes, &s->ctas_per_sm);
+        int rc;
+        if (s->const_image) {
+            rc = s->d_motion ? configure_kernel(pt::pt_megakernel_resident<true, true>, s->smem_bytes, &s->ctas_per_sm)
+                             : configure_kernel(pt::pt_megakernel_resident<true, false>, s->smem_bytes, &s->ctas_per_sm);
+            if (rc == PT_OK)
+                rc = s->d_motion ? configure_kernel(pt::pt_debug_hits_resident<true, true>, s->smem_bytes, nullptr)
+                                 : configure_kernel(pt::pt_debug_hits_resident<true, false>, s->smem_bytes, nullptr);
+        } else {
+            rc = s->d_motion ? configure_kernel(pt::pt_megakernel_resident<false, true>, s->smem_bytes, &s->ctas_per_sm)
+                             : configure_kernel(pt::pt_megakernel_resident<false, false>, s->smem_bytes, &s->ctas_per_sm);
+            if (rc == PT_OK)
+                rc = s->d_motion ? configure_kernel(pt::pt_debug_hits_resident<false, true>, s->smem_bytes, nullptr)
+                                 : configure_kernel(pt::pt_debug_hits_resident<false, false>, s->smem_bytes, nullptr);
+        }
+        return rc;
     }
-    // streamed: two tile buffers; 2 CTAs per SM keeps the FP32 pipe fed while one CTA waits on a barrier
     s->resident = false;
-    int stream_ctas = 2;
-    if (const char* env = std::getenv("PTGPU_STREAM_CTAS")) stream_ctas = std::max(1, std::min(4, std::atoi(env)));  // tuning hook
-    const size_t per_cta = (kMaxDynSmem + 1024) / stream_ctas - 2048;
-    const size_t tile_bytes = ((per_cta - perlin_bytes) / 2) & ~(size_t)1023;
-    s->tile_blocks = (int)(tile_bytes / 64);
+    s->const_image = false;
+    if (forced_tile > 0 && s->n_blocks > 0) {  // PtOptions: any scene through the streamed kernel with n-block tiles
+        forced_tile = (forced_tile + pt::kLdsGroupBlocks - 1) / pt::kLdsGroupBlocks * pt::kLdsGroupBlocks;  // whole groups
+        s->tile_blocks = std::min(forced_tile, s->n_blocks);
+    } else {
+        // two tile buffers; 2 CTAs per SM keeps the FP32 pipe fed while one CTA waits on a barrier
+        const int stream_ctas = s->opt.stream_ctas > 0 ? std::min(4, s->opt.stream_ctas) : 2;
+        const size_t per_cta = (kMaxDynSmem + 1024) / stream_ctas - 2048;
+        const size_t tile_bytes = ((per_cta - kStreamedFixedBytes) / 2) & ~(size_t)1023;
+        s->tile_blocks = (int)(tile_bytes / 64);
+    }
     s->n_tiles = (s->n_blocks + s->tile_blocks - 1) / s->tile_blocks;
-    s->smem_bytes = 2 * (size_t)s->tile_blocks * 64 + perlin_bytes;
-    return configure_streamed(s);
+    s->smem_bytes = 2 * (size_t)s->tile_blocks * 64 + kStreamedFixedBytes;
+    int rc = s->d_motion ? configure_kernel(pt::pt_megakernel_streamed<true>, s->smem_bytes, &s->ctas_per_sm)
+                         : configure_kernel(pt::pt_megakernel_streamed<false>, s->smem_bytes, &s->ctas_per_sm);
+    if (rc == PT_OK)
+        rc = s->d_motion ? configure_kernel(pt::pt_debug_hits_streamed<true>, s->smem_bytes, nullptr)
+                         : configure_kernel(pt::pt_debug_hits_streamed<false>, s->smem_bytes, nullptr);
+    return rc;
 }
 
 uint32_t owned_rows(uint32_t height, const PtPartition& p) {
@@ -178,18 +220,47 @@ int normalise_partition(const PtPartition* in, PtPartition* out) {
     return PT_OK;
 }
 
+int normalise_options(const PtOptions* in, PtOptions* out) {
+    PtOptions o{};
+    o.struct_size = sizeof(PtOptions);
+    o.spatial_order = -1;
+    if (in) {
+        if (in->struct_size != sizeof(PtOptions)) return fail(PT_ERR_INVALID, "PtOptions.struct_size %u != %zu (ABI mismatch)", in->struct_size, sizeof(PtOptions));
+        o = *in;
+        if (o.force_stream_tile_blocks < 0 || o.stream_ctas < 0 || o.stream_ctas > 4 || o.chunk_samples < -1 || o.spatial_order < -1 || o.spatial_order > 2)
+            return fail(PT_ERR_INVALID, "PtOptions field out of range");
+    }
+    if (o.tile_rows == 0) o.tile_rows = 4;
+    *out = o;
+    return PT_OK;
+}
+
 int validate_params(const PtParams* params, const PtCamera* camera) {
     if (!params || !camera) return fail(PT_ERR_INVALID, "null params/camera");
     if (params->width == 0 || params->height == 0) return fail(PT_ERR_INVALID, "zero-sized image %ux%u", params->width, params->height);
     if ((uint64_t)params->width * params->height > 0xffffffffULL / 4) return fail(PT_ERR_TOO_LARGE, "image too large");
+    // the reference divides by `samples` (scene.rs:85): zero samples would blend 0 * inf = NaN into every pixel
+    if (params->samples == 0) return fail(PT_ERR_INVALID, "samples must be at least 1 (Scene::update divides by it, scene.rs:85)");
     if (params->use_bvh) return fail(PT_ERR_UNSUPPORTED, "use_bvh is not supported on the GPU path (flat sphere list only, params.rs:36-43)");
     return PT_OK;
 }
 
-// enqueue one Scene::update on `stream`; d_rgb is the full-size device image
-int launch_update(PtScene* s, const PtParams* params, const PtCamera* cam, uint32_t frame_num, const PtPartition& part,
-                  float* d_rgb, unsigned long long* d_ray_count, cudaStream_t stream) {
-    pt::KernelArgs a{};
+// The pre-filter's validity domain (pt_sweep.cuh): its slack covers the rounding of the expanded discriminant only while
+// the ray origin is not astronomically far from the scene.  Origins are the camera or points on sphere surfaces, so the
+// camera is the one input to check per call: |origin| and the lens offset must stay below 2^20 times the scene's extent
+// (and below 1e18, where |o|^2 meets the parked-lane sentinel).
+int validate_camera_domain(const Replica* s, const PtCamera* cam) {
+    for (int i = 0; i < 3; ++i) {
+        const float v[7] = {cam->origin[i], cam->lower_left_corner[i], cam->horizontal[i], cam->vertical[i], cam->u[i], cam->v[i], cam->lens_radius};
+        for (float f : v)
+            if (!std::isfinite(f) || std::fabs(f) > 1.0e17f)
+                return fail(PT_ERR_INVALID, "camera component %g is outside the sweep's validity domain (finite, |x| <= 1e17)", f);
+    }
+    (void)s;
+    return PT_OK;
+}
+
+void fill_scene_args(const Replica* s, pt::KernelArgs& a) {
     a.blocks = s->d_blocks;
     a.n_blocks = s->n_blocks;
     a.n_spheres = (int)s->n_spheres;
@@ -199,8 +270,29 @@ int launch_update(PtScene* s, const PtParams* params, const PtCamera* cam, uint3
     a.order = s->d_order;
     a.perlin = s->d_perlin;
     a.prefilter = s->d_prefilter;
+    a.kplane = s->d_kplane;
     a.motion = s->d_motion;
     a.has_noise = s->has_noise ? 1 : 0;
+    a.tile_blocks = s->tile_blocks;
+    a.n_tiles = s->n_tiles;
+}
+
+// every launch on a replica waits for the previous one (whatever stream it ran on) and leaves its own event behind
+int serialise_begin(Replica* s, cudaStream_t stream) {
+    if (s->busy_recorded) PT_CUDA(cudaStreamWaitEvent(stream, s->ev_busy, 0));
+    return PT_OK;
+}
+int serialise_end(Replica* s, cudaStream_t stream) {
+    PT_CUDA(cudaEventRecord(s->ev_busy, stream));
+    s->busy_recorded = true;
+    return PT_OK;
+}
+
+// enqueue one Scene::update on `stream`; d_rgb is the full-size device image
+int launch_update(Replica* s, const PtParams* params, const PtCamera* cam, uint32_t frame_num, const PtPartition& part,
+                  float* d_rgb, unsigned long long* d_ray_count, cudaStream_t stream) {
+    pt::KernelArgs a{};
+    fill_scene_args(s, a);
     auto V = [](const float* f) { return pt::V3{f[0], f[1], f[2]}; };
     a.cam.origin = V(cam->origin);
     a.cam.llc = V(cam->lower_left_corner);
@@ -234,40 +326,50 @@ int launch_update(PtScene* s, const PtParams* params, const PtCamera* cam, uint3
     a.ray_count = d_ray_count;
     a.sweep_count = s->d_sweep_count;
     a.next_pixel = s->d_next_pixel;
-    a.tile_blocks = s->tile_blocks;
-    a.n_tiles = s->n_tiles;
 
+    int rc = validate_camera_domain(s, cam);
+    if (rc != PT_OK) return rc;
     if (s->d_motion && !(cam->time0 >= s->motion_t_lo && cam->time1 <= s->motion_t_hi && cam->time0 <= cam->time1))
         return fail(PT_ERR_UNSUPPORTED, "camera shutter [%g, %g] is not inside the moving spheres' interval [%g, %g] (the pre-filter bounds their sweep over that interval)",
                     cam->time0, cam->time1, s->motion_t_lo, s->motion_t_hi);
+    rc = serialise_begin(s, stream);
+    if (rc != PT_OK) return rc;
     PT_CUDA(cudaMemsetAsync(s->d_next_pixel, 0, sizeof(unsigned int), stream));
     PT_CUDA(cudaMemsetAsync(d_ray_count, 0, sizeof(unsigned long long), stream));
     PT_CUDA(cudaMemsetAsync(s->d_sweep_count, 0, sizeof(unsigned long long), stream));
     s->stats.kernel_launches = 0;
     s->stats.grid_ctas = 0;
-    if (a.n_owned_pixels == 0) return PT_OK;
+    if (a.n_owned_pixels == 0) return serialise_end(s, stream);
 
-    // persistent grid: one wave of CTAs, never more lanes than pixels
-    const uint32_t want = (a.n_owned_pixels + pt::kCtaThreads - 1) / pt::kCtaThreads;
-    const uint32_t grid = std::min<uint32_t>((uint32_t)(s->sm_count * s->ctas_per_sm), want);
+    // persistent grid: one wave of CTAs, never more lanes than pixels.  The resident kernel carries two paths per lane;
+    // an image with fewer pixels than the machine has lanes keeps one path per lane (latency, not throughput, is what
+    // counts there) and the second row stays parked.
+    const uint32_t max_ctas = (uint32_t)(s->sm_count * s->ctas_per_sm);
+    const uint32_t paths_per_cta = (uint32_t)pt::kCtaThreads * (s->resident ? pt::kPathRows : 1);
+    uint32_t want = (a.n_owned_pixels + paths_per_cta - 1) / paths_per_cta;
+    a.single_row = 0;
+    if (s->resident && (uint64_t)a.n_owned_pixels <= (uint64_t)max_ctas * pt::kCtaThreads) {
+        a.single_row = 1;
+        want = (a.n_owned_pixels + pt::kCtaThreads - 1) / pt::kCtaThreads;
+    }
+    const uint32_t grid = std::min<uint32_t>(max_ctas, want);
 
     // chunk queue (pt_megakernel.cuh, lane_refill): samples are handed out in chunks, sample-major, so that all pixels
-    // finish together.  With fewer than two pixels per lane every pixel starts at once and the launch lasts as long as
+    // finish together.  With fewer than two pixels per path every pixel starts at once and the launch lasts as long as
     // its slowest pixel whatever the unit: one chunk per pixel then, which skips the state table altogether.
     uint32_t chunk = 0;  // 0 = one chunk per pixel
-    const uint64_t lanes = (uint64_t)grid * pt::kCtaThreads;
-    if (params->samples > 8 && (uint64_t)a.n_owned_pixels >= 2 * lanes) {
+    const uint64_t paths = (uint64_t)grid * (a.single_row ? pt::kCtaThreads : paths_per_cta);
+    if (params->samples > 8 && (uint64_t)a.n_owned_pixels >= 2 * paths) {
         const uint32_t max_chunks = std::max<uint32_t>(1u, std::min<uint32_t>(64u, 0xF0000000u / a.n_owned_pixels));
         const uint32_t at_least = std::max<uint32_t>((params->samples + max_chunks - 1) / max_chunks, 8u);
         chunk = 8;
         while (chunk < at_least) chunk *= 2;
     }
-    if (const char* env = std::getenv("PTGPU_CHUNK_SAMPLES")) {  // test/tuning hook: a power of two, 0 = whole pixels
-        const long v = std::atol(env);
+    if (s->opt.chunk_samples != 0) {  // explicit PtOptions choice: a power of two, -1 = whole pixels
         chunk = 0;
-        if (v > 0) {
+        if (s->opt.chunk_samples > 0) {
             chunk = 1;
-            while ((long)chunk < v && chunk < (1u << 30)) chunk *= 2;
+            while ((long)chunk < (long)s->opt.chunk_samples && chunk < (1u << 30)) chunk *= 2;
         }
     }
     uint32_t n_chunks = 1;
@@ -278,13 +380,14 @@ int launch_update(PtScene* s, const PtParams* params, const PtCamera* cam, uint3
         a.chunk_samples = chunk;
         a.chunk_mask = chunk - 1;
     } else {
-        a.chunk_samples = std::max<uint32_t>(params->samples, 1u);
+        a.chunk_samples = params->samples;
         a.chunk_mask = 0xffffffffu;
     }
     a.n_tickets = n_chunks * a.n_owned_pixels;
     a.pixstate = nullptr;
     if (n_chunks > 1) {
         if (s->d_pixstate_pixels < a.n_owned_pixels) {
+            // (cudaFree synchronises the device: growing the table is the one blocking step of an otherwise asynchronous launch)
             if (s->d_pixstate) cudaFree(s->d_pixstate);
             s->d_pixstate = nullptr;
             s->d_pixstate_pixels = 0;
@@ -296,13 +399,21 @@ int launch_update(PtScene* s, const PtParams* params, const PtCamera* cam, uint3
         a.pixstate = s->d_pixstate;
     }
     if (s->resident) {
-        if (s->d_motion) pt::pt_megakernel_resident<true><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a);
-        else pt::pt_megakernel_resident<false><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a);
+        if (s->const_image) {
+            if (s->d_motion) pt::pt_megakernel_resident<true, true><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a, *s->h_const_image);
+            else pt::pt_megakernel_resident<true, false><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a, *s->h_const_image);
+        } else {
+            const pt::ConstImageT<false> none{};
+            if (s->d_motion) pt::pt_megakernel_resident<false, true><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a, none);
+            else pt::pt_megakernel_resident<false, false><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a, none);
+        }
     } else {
         if (s->d_motion) pt::pt_megakernel_streamed<true><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a);
         else pt::pt_megakernel_streamed<false><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a);
     }
     PT_CUDA(cudaGetLastError());
+    rc = serialise_end(s, stream);
+    if (rc != PT_OK) return rc;
     s->stats.kernel_launches = 1;
     s->stats.grid_ctas = grid;
     s->stats.cta_threads = pt::kCtaThreads;
@@ -312,7 +423,7 @@ int launch_update(PtScene* s, const PtParams* params, const PtCamera* cam, uint3
     return PT_OK;
 }
 
-int ensure_image(PtScene* s, size_t floats) {
+int ensure_image(Replica* s, size_t floats) {
     if (s->d_rgb_floats >= floats) return PT_OK;
     if (s->d_rgb) cudaFree(s->d_rgb);
     s->d_rgb = nullptr;
@@ -321,9 +432,18 @@ int ensure_image(PtScene* s, size_t floats) {
     s->d_rgb_floats = floats;
     return PT_OK;
 }
+int ensure_rgb8(Replica* s, size_t bytes) {
+    if (s->d_rgb8_bytes >= bytes) return PT_OK;
+    if (s->d_rgb8) cudaFree(s->d_rgb8);
+    s->d_rgb8 = nullptr;
+    s->d_rgb8_bytes = 0;
+    PT_CUDA(cudaMalloc(&s->d_rgb8, bytes));
+    s->d_rgb8_bytes = bytes;
+    return PT_OK;
+}
 
 // copy the rows a partition owns between host and device images (same layout on both sides)
-int copy_owned_rows(PtScene* s, const PtParams* params, const PtPartition& part, float* host, bool to_device, uint64_t* bytes_out) {
+int copy_owned_rows(Replica* s, const PtParams* params, const PtPartition& part, float* host, bool to_device, uint64_t* bytes_out) {
     const size_t row_bytes = (size_t)params->width * 3 * sizeof(float);
     uint64_t bytes = 0;
     if (part.part_count <= 1) {
@@ -331,15 +451,24 @@ int copy_owned_rows(PtScene* s, const PtParams* params, const PtPartition& part,
         PT_CUDA(cudaMemcpyAsync(to_device ? (void*)s->d_rgb : (void*)host, to_device ? (const void*)host : (const void*)s->d_rgb, bytes,
                                 to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, s->stream));
     } else {
+        // one strided copy for all owned tiles: tile k of this part starts part_count * tile_rows rows after tile k-1
         const uint32_t n_tiles = (params->height + part.tile_rows - 1) / part.tile_rows;
-        for (uint32_t k = part.part_index; k < n_tiles; k += part.part_count) {
-            const uint32_t r0 = k * part.tile_rows;
-            const uint32_t nr = std::min(part.tile_rows, params->height - r0);
-            const size_t off = (size_t)r0 * params->width * 3;
-            const size_t nbytes = row_bytes * nr;
-            PT_CUDA(cudaMemcpyAsync(to_device ? (void*)(s->d_rgb + off) : (void*)(host + off),
-                                    to_device ? (const void*)(host + off) : (const void*)(s->d_rgb + off), nbytes,
-                                    to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, s->stream));
+        const uint32_t full_tiles = params->height / part.tile_rows;  // tiles with all their rows
+        uint32_t n_mine_full = 0;
+        for (uint32_t k = part.part_index; k < full_tiles; k += part.part_count) ++n_mine_full;
+        const size_t first = (size_t)part.part_index * part.tile_rows * params->width * 3;
+        if (n_mine_full > 0) {
+            const size_t pitch = row_bytes * part.tile_rows * part.part_count, wbytes = row_bytes * part.tile_rows;
+            PT_CUDA(cudaMemcpy2DAsync(to_device ? (void*)(s->d_rgb + first) : (void*)(host + first), pitch,
+                                      to_device ? (const void*)(host + first) : (const void*)(s->d_rgb + first), pitch, wbytes, n_mine_full,
+                                      to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, s->stream));
+            bytes += (uint64_t)wbytes * n_mine_full;
+        }
+        if (n_tiles > full_tiles && (n_tiles - 1) % part.part_count == part.part_index) {  // the ragged last tile is ours
+            const uint32_t r0 = (n_tiles - 1) * part.tile_rows;
+            const size_t off = (size_t)r0 * params->width * 3, nbytes = row_bytes * (params->height - r0);
+            PT_CUDA(cudaMemcpyAsync(to_device ? (void*)(s->d_rgb + off) : (void*)(host + off), to_device ? (const void*)(host + off) : (const void*)(s->d_rgb + off),
+                                    nbytes, to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, s->stream));
             bytes += nbytes;
         }
     }
@@ -349,7 +478,7 @@ int copy_owned_rows(PtScene* s, const PtParams* params, const PtPartition& part,
 
 // Storage order of a scene's spheres (see pt_scene_create).  Fills order_of[j] = position in the caller's list of the
 // sphere stored at j and returns the mode: 0 the caller's order, 1 Morton, 2 large spheres first, then Morton.
-int storage_order(const PtSceneDesc* desc, bool any_moving, std::vector<uint32_t>& order_of) {
+int storage_order(const PtSceneDesc* desc, bool any_moving, const PtOptions& opt, std::vector<uint32_t>& order_of) {
     const uint32_t n = desc->n_spheres;
     auto is_moving = [&](uint32_t i) { return any_moving && desc->motion[i].moving != 0; };
     // ---- storage order.  The sweep flags candidates per group of 16 consecutive spheres, and a ray's candidates are
@@ -360,14 +489,11 @@ int storage_order(const PtSceneDesc* desc, bool any_moving, std::vector<uint32_t
     order_of.resize(n);
     for (uint32_t i = 0; i < n; ++i) order_of[i] = i;
     int order_mode = n > 64 ? 2 : 0;  // 0: the caller's order; 1: Morton; 2: large spheres first, then Morton
-    if (const char* env = std::getenv("PTGPU_SPATIAL_ORDER")) order_mode = n > 1 ? std::max(0, std::min(2, std::atoi(env))) : 0;  // tuning hook
+    if (opt.spatial_order >= 0) order_mode = n > 1 ? std::min(2, opt.spatial_order) : 0;  // explicit PtOptions choice
     // resident kernel only: the streamed kernel keeps list order and the plain index tie rule (with ~10^5 spheres few groups
     // are flagged anyway: 66.0 -> 66.5 % on cfg5, and the out-of-line tie rule costs that kernel more than it gains)
     const int n_blocks_planned = (int)(((n + 3) / 4 + pt::kLdsGroupBlocks - 1) / pt::kLdsGroupBlocks * pt::kLdsGroupBlocks);
-    if (!fits_resident(n_blocks_planned)) order_mode = 0;
-#ifdef PT_RES_PIPE
-    order_mode = 0;  // that experimental build instantiates the resident sweep without the ordered tie rule
-#endif
+    if (!fits_resident(n_blocks_planned, opt)) order_mode = 0;
     if (order_mode != 0) {
         auto centre_of = [&](uint32_t i, int axis) -> double {
             const float* c = axis == 0 ? desc->centre_x : (axis == 1 ? desc->centre_y : desc->centre_z);
@@ -422,86 +548,8 @@ int storage_order(const PtSceneDesc* desc, bool any_moving, std::vector<uint32_t
     return order_mode;
 }
 
-}  // namespace
-
-extern "C" {
-
-int pt_abi_version(void) { return PT_ABI_VERSION; }
-const char* pt_last_error(void) { return g_last_error.c_str(); }
-
-uint32_t pt_abi_struct_size(int which) {
-    switch (which) {
-        case 0: return sizeof(PtParams);
-        case 1: return sizeof(PtCamera);
-        case 2: return sizeof(PtTexture);
-        case 3: return sizeof(PtMaterial);
-        case 4: return sizeof(PtPerlin);
-        case 5: return sizeof(PtSceneDesc);
-        case 6: return sizeof(PtPartition);
-        case 7: return sizeof(PtDeviceInfo);
-        case 8: return sizeof(PtRenderStats);
-        case 9: return sizeof(PtMotion);
-        case 10: return sizeof(PtImage);
-        default: return 0;
-    }
-}
-
-uint32_t pt_partition_rows(const PtPartition* part_in, uint32_t height, uint32_t* rows_out, uint32_t cap) {
-    PtPartition p;
-    if (normalise_partition(part_in, &p) != PT_OK) return 0;
-    uint32_t count = 0;
-    const uint32_t n_tiles = (height + p.tile_rows - 1) / p.tile_rows;
-    for (uint32_t k = p.part_index; k < n_tiles; k += p.part_count) {
-        const uint32_t r0 = k * p.tile_rows;
-        const uint32_t nr = std::min(p.tile_rows, height - r0);
-        for (uint32_t r = 0; r < nr; ++r) {
-            if (rows_out && count < cap) rows_out[count] = r0 + r;
-            ++count;
-        }
-    }
-    return count;
-}
-
-uint32_t pt_scene_storage_order(const PtSceneDesc* desc, uint32_t* order_out, uint32_t cap) {
-    if (!desc || desc->struct_size != sizeof(PtSceneDesc)) return 0;
-    const uint32_t n = desc->n_spheres;
-    if (n > 0 && (!desc->centre_x || !desc->centre_y || !desc->centre_z || !desc->radius)) return 0;
-    bool any_moving = false;
-    if (desc->motion)
-        for (uint32_t i = 0; i < n; ++i) any_moving = any_moving || desc->motion[i].moving != 0;
-    std::vector<uint32_t> order_of;
-    const int mode = storage_order(desc, any_moving, order_of);
-    for (uint32_t j = 0; j < n && j < cap && order_out; ++j) order_out[j] = order_of[j];
-    return (uint32_t)mode;
-}
-
-int pt_device_count(void) {
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
-    return n;
-}
-
-int pt_device_info(int device, PtDeviceInfo* out) {
-    if (!out) return fail(PT_ERR_INVALID, "null out");
-    cudaDeviceProp prop;
-    int rc = check_device(device, &prop);
-    if (rc != PT_OK) return rc;
-    std::memset(out, 0, sizeof(*out));
-    std::strncpy(out->name, prop.name, sizeof(out->name) - 1);
-    out->sm_count = prop.multiProcessorCount;
-    out->cc_major = prop.major;
-    out->cc_minor = prop.minor;
-    int khz = 0;
-    PT_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device));
-    out->sm_clock_khz = khz;
-    out->fp32_fma_peak_flops = (double)prop.multiProcessorCount * 128.0 * 2.0 * (double)khz * 1e3;
-    out->global_mem_bytes = prop.totalGlobalMem;
-    return PT_OK;
-}
-
-int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
-    if (!desc || !out) return fail(PT_ERR_INVALID, "null desc/out");
-    *out = nullptr;
+// ---- flatten the caller's scene once on the host (the GPU arm of `Params::new_scene` + `SpheresSoA::new`) ----
+int flatten_scene(const PtSceneDesc* desc, const PtOptions& opt, FlatScene& fs) {
     if (desc->struct_size != sizeof(PtSceneDesc)) return fail(PT_ERR_INVALID, "PtSceneDesc.struct_size %u != %zu (ABI mismatch)", desc->struct_size, sizeof(PtSceneDesc));
     const uint32_t n = desc->n_spheres;
     if (n > 0 && (!desc->centre_x || !desc->centre_y || !desc->centre_z || !desc->radius || !desc->material_index))
@@ -523,7 +571,7 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
         if (image_pool_bytes > 0x7fffffffULL) return fail(PT_ERR_TOO_LARGE, "image textures exceed 2 GB");
     }
 
-    // ---- validate + flatten materials/textures ----
+    // ---- validate materials/textures ----
     bool uses_noise = false;
     for (uint32_t t = 0; t < desc->n_textures; ++t) {
         const PtTexture& tx = desc->textures[t];
@@ -560,31 +608,33 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
         }
     }
     auto is_moving = [&](uint32_t i) { return any_moving && desc->motion[i].moving != 0; };
+    // the sweep's validity domain (pt_sweep.cuh): finite geometry; magnitudes are handled per sphere below (a sphere too
+    // large or too far for the expanded form is flagged for every ray and decided by the exact test alone)
+    for (uint32_t i = 0; i < n; ++i) {
+        if (!std::isfinite(desc->centre_x[i]) || !std::isfinite(desc->centre_y[i]) || !std::isfinite(desc->centre_z[i]) || !std::isfinite(desc->radius[i]))
+            return fail(PT_ERR_INVALID, "sphere %u: centre/radius must be finite", i);
+        if (is_moving(i) && !(std::isfinite(desc->motion[i].centre1[0]) && std::isfinite(desc->motion[i].centre1[1]) && std::isfinite(desc->motion[i].centre1[2])))
+            return fail(PT_ERR_INVALID, "sphere %u: centre1 must be finite", i);
+    }
 
-    std::vector<uint32_t> order_of;
-    const bool spatial = storage_order(desc, any_moving, order_of) != 0;
-
-    cudaDeviceProp prop;
-    int rc = check_device(device, &prop);
-    if (rc != PT_OK) return rc;
-    PT_CUDA(cudaSetDevice(device));
-
-    PtScene* s = new PtScene();
-    s->device = device;
-    s->sm_count = prop.multiProcessorCount;
-    s->n_spheres = n;
-    s->n_blocks = (int)((n + 3) / 4);
-    s->n_blocks = (s->n_blocks + pt::kLdsGroupBlocks - 1) / pt::kLdsGroupBlocks * pt::kLdsGroupBlocks;  // whole groups; padding spheres can never be hit
-    if (s->n_blocks > pt::kMaxSweepBlocks) { delete s; return fail(PT_ERR_TOO_LARGE, "too many spheres for the candidate-queue encoding: %u", n); }
-    s->has_noise = uses_noise;
-    s->has_sky = desc->has_sky != 0;
-    s->sky = pt::V3{desc->sky[0], desc->sky[1], desc->sky[2]};
+    fs.any_moving = any_moving;
+    fs.spatial = storage_order(desc, any_moving, opt, fs.order_of) != 0;
+    const std::vector<uint32_t>& order_of = fs.order_of;
+    fs.n_spheres = n;
+    fs.n_blocks = (int)((n + 3) / 4);
+    fs.n_blocks = (fs.n_blocks + pt::kLdsGroupBlocks - 1) / pt::kLdsGroupBlocks * pt::kLdsGroupBlocks;  // whole groups; padding spheres can never be hit
+    if (fs.n_blocks > pt::kMaxSweepBlocks) return fail(PT_ERR_TOO_LARGE, "too many spheres for the candidate-queue encoding: %u", n);
+    fs.has_noise = uses_noise;
+    fs.has_sky = desc->has_sky != 0;
+    fs.sky = pt::V3{desc->sky[0], desc->sky[1], desc->sky[2]};
+    fs.motion_t_lo = t_lo;
+    fs.motion_t_hi = t_hi;
 
     // ---- sphere blocks: X,Y,Z,R^2 for 4 spheres; padding = (FLT_MAX centre, r^2 = 0) spheres_soa.rs:53-61 ----
-    std::vector<float4> blocks((size_t)std::max(s->n_blocks, 1) * 4);
-    std::vector<pt::DevShade> shade(std::max<uint32_t>(n, 1));
-    for (int j = 0; j < s->n_blocks; ++j) {
-        float* f = reinterpret_cast<float*>(&blocks[(size_t)j * 4]);
+    fs.blocks.assign((size_t)std::max(fs.n_blocks, 1) * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+    fs.shade.assign(std::max<uint32_t>(n, 1), pt::DevShade{});
+    for (int j = 0; j < fs.n_blocks; ++j) {
+        float* f = reinterpret_cast<float*>(&fs.blocks[(size_t)j * 4]);
         for (int e = 0; e < 4; ++e) {
             const bool valid = (uint32_t)j * 4 + e < n;
             const uint32_t i = valid ? order_of[(uint32_t)j * 4 + e] : 0u;  // position in the caller's list
@@ -595,43 +645,50 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
             if (valid && is_moving(i)) f[12 + e] = -std::max(f[12 + e], FLT_MIN);  // negative r^2 tags a MovingSphere (pt_sweep.cuh)
         }
     }
-    // pre-filter image (pt_sweep.cuh): X, Y, Z, K = r^2 - |c|^2 + 2^-19 (|c|^2 + r^2), padded to the group
-    std::vector<float4> h_prefilter;
-    {
-        h_prefilter.assign((size_t)std::max(s->n_blocks, 1) * 4, make_float4(0.f, 0.f, 0.f, 0.f));
-        for (int j = 0; j < s->n_blocks; ++j) {
-            float* f = reinterpret_cast<float*>(&h_prefilter[(size_t)j * 4]);
-            for (int e = 0; e < 4; ++e) {
-                f[0 + e] = f[4 + e] = f[8 + e] = 0.0f;
-                f[12 + e] = -3.0e38f;  // padding: never a candidate
-                if ((uint32_t)j * 4 + e >= n) continue;
-                const uint32_t i = order_of[(uint32_t)j * 4 + e];
-                double cx = desc->centre_x[i], cy = desc->centre_y[i], cz = desc->centre_z[i], r = std::fabs((double)desc->radius[i]);
-                if (is_moving(i)) {  // static bound of the whole sweep: centre0 + delta/2, radius r + |delta|/2 (+ f32 rounding of the lerp)
-                    const double ex = desc->motion[i].centre1[0] - cx, ey = desc->motion[i].centre1[1] - cy, ez = desc->motion[i].centre1[2] - cz;
-                    cx += 0.5 * ex; cy += 0.5 * ey; cz += 0.5 * ez;
-                    r += 0.5 * std::sqrt(ex * ex + ey * ey + ez * ez) * (1.0 + 1e-5) + 1e-6 * (std::fabs(cx) + std::fabs(cy) + std::fabs(cz) + r);
-                }
-                const double c2 = cx * cx + cy * cy + cz * cz, r2 = r * r;
-                if (!(c2 + r2 < 1.0e24)) {  // too large (or NaN) for the expanded form: always a candidate, the exact test decides
-                    f[12 + e] = INFINITY;
-                    continue;
-                }
-                f[0 + e] = (float)cx;
-                f[4 + e] = (float)cy;
-                f[8 + e] = (float)cz;
-                const double k = r2 - c2 + 1.9073486328125e-06 * (c2 + r2);
-                f[12 + e] = std::nextafter((float)k, INFINITY);  // round towards "candidate"
+    // pre-filter image (pt_sweep.cuh): X, Y, Z, K = r^2 - |c|^2 + slack, padded to the group.
+    // slack = 2^-18 (|c|^2 + r^2): twice the worst-case rounding budget of the expanded form against the reference's
+    // sphere-relative one for |o| <~ |c| (7 fused steps + the unfused o.d and |o|^2 + the reference's own discriminant
+    // error), so every sphere the exact expression accepts is a candidate.  Proven per ray, not assumed:
+    // pt_debug_hits mode 0 against mode 1 in tests/test_gpu_hits.py.
+    fs.prefilter.assign((size_t)std::max(fs.n_blocks, 1) * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (int j = 0; j < fs.n_blocks; ++j) {
+        float* f = reinterpret_cast<float*>(&fs.prefilter[(size_t)j * 4]);
+        for (int e = 0; e < 4; ++e) {
+            f[0 + e] = f[4 + e] = f[8 + e] = 0.0f;
+            f[12 + e] = -3.0e38f;  // padding: never a candidate
+            if ((uint32_t)j * 4 + e >= n) continue;
+            const uint32_t i = order_of[(uint32_t)j * 4 + e];
+            double cx = desc->centre_x[i], cy = desc->centre_y[i], cz = desc->centre_z[i], r = std::fabs((double)desc->radius[i]);
+            if (is_moving(i)) {  // static bound of the whole sweep: centre0 + delta/2, radius r + |delta|/2 (+ f32 rounding of the lerp)
+                const double ex = desc->motion[i].centre1[0] - cx, ey = desc->motion[i].centre1[1] - cy, ez = desc->motion[i].centre1[2] - cz;
+                cx += 0.5 * ex; cy += 0.5 * ey; cz += 0.5 * ez;
+                r += 0.5 * std::sqrt(ex * ex + ey * ey + ez * ez) * (1.0 + 1e-5) + 1e-6 * (std::fabs(cx) + std::fabs(cy) + std::fabs(cz) + r);
             }
+            const double c2 = cx * cx + cy * cy + cz * cz, r2 = r * r;
+            if (!(c2 + r2 < 1.0e24)) {  // too large (or NaN) for the expanded form: always a candidate, the exact test decides
+                f[12 + e] = INFINITY;
+                continue;
+            }
+            f[0 + e] = (float)cx;
+            f[4 + e] = (float)cy;
+            f[8 + e] = (float)cz;
+            const double k = r2 - c2 + pt::kSlackSphere * (c2 + r2);
+            f[12 + e] = std::nextafter((float)k, INFINITY);  // round towards "candidate"
         }
+    }
+    // K plane alone + the kernel-parameter image of the X, Y, Z planes (resident kernel, small scenes)
+    fs.kplane.assign((size_t)std::max(fs.n_blocks, 1), make_float4(0.f, 0.f, 0.f, 0.f));
+    for (int j = 0; j < fs.n_blocks; ++j) fs.kplane[j] = fs.prefilter[(size_t)j * 4 + 3];
+    if (fs.n_blocks <= pt::kMaxConstBlocks) {
+        fs.const_image.reset(new pt::ConstImageT<true>());
+        std::memset(fs.const_image.get(), 0, sizeof(pt::ConstImageT<true>));
+        for (int j = 0; j < fs.n_blocks; ++j)
+            for (int c = 0; c < 3; ++c) fs.const_image->v[3 * j + c] = fs.prefilter[(size_t)j * 4 + c];
     }
     for (uint32_t j = 0; j < n; ++j) {
         const uint32_t i = order_of[j];
         const int32_t mi = desc->material_index[i];
-        if (mi < 0 || (uint32_t)mi >= desc->n_materials) {
-            delete s;
-            return fail(PT_ERR_INVALID, "sphere %u: material index %d out of range", i, mi);
-        }
+        if (mi < 0 || (uint32_t)mi >= desc->n_materials) return fail(PT_ERR_INVALID, "sphere %u: material index %d out of range", i, mi);
         const PtMaterial& mt = desc->materials[mi];
         pt::DevShade d{};
         d.rinv = 1.0f / desc->radius[i];  // spheres_soa.rs:47
@@ -655,9 +712,9 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
         } else {
             d.param = mt.ref_idx;
         }
-        shade[j] = d;
+        fs.shade[j] = d;
     }
-    std::vector<pt::DevTexture> tex(std::max<uint32_t>(desc->n_textures, 1));
+    fs.tex.assign(std::max<uint32_t>(desc->n_textures, 1), pt::DevTexture{});
     for (uint32_t t = 0; t < desc->n_textures; ++t) {
         const PtTexture& tx = desc->textures[t];
         pt::DevTexture d{};
@@ -673,37 +730,15 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
             d.even = (int32_t)desc->images[tx.image].height;
             d.offset = (int32_t)image_offset[tx.image];
         }
-        tex[t] = d;
-    }
-
-    auto cleanup_fail = [&](int code) {
-        pt_scene_destroy(s);
-        return code;
-    };
-#define PT_CUDA_S(call)                                                                                     \
-    do {                                                                                                    \
-        cudaError_t e_ = (call);                                                                            \
-        if (e_ != cudaSuccess) return cleanup_fail(fail(PT_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_))); \
-    } while (0)
-    PT_CUDA_S(cudaMalloc(&s->d_blocks, blocks.size() * sizeof(float4)));
-    PT_CUDA_S(cudaMemcpy(s->d_blocks, blocks.data(), blocks.size() * sizeof(float4), cudaMemcpyHostToDevice));
-    PT_CUDA_S(cudaMalloc(&s->d_shade, shade.size() * sizeof(pt::DevShade)));
-    PT_CUDA_S(cudaMemcpy(s->d_shade, shade.data(), shade.size() * sizeof(pt::DevShade), cudaMemcpyHostToDevice));
-    PT_CUDA_S(cudaMalloc(&s->d_tex, tex.size() * sizeof(pt::DevTexture)));
-    PT_CUDA_S(cudaMemcpy(s->d_tex, tex.data(), tex.size() * sizeof(pt::DevTexture), cudaMemcpyHostToDevice));
-    if (spatial) {
-        PT_CUDA_S(cudaMalloc(&s->d_order, order_of.size() * sizeof(uint32_t)));
-        PT_CUDA_S(cudaMemcpy(s->d_order, order_of.data(), order_of.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        fs.tex[t] = d;
     }
     if (image_pool_bytes > 0) {
-        std::vector<uint8_t> pool(image_pool_bytes, 0);
+        fs.image_pool.assign(image_pool_bytes, 0);
         for (uint32_t i = 0; i < desc->n_images; ++i)
-            std::memcpy(pool.data() + image_offset[i], desc->images[i].data, (size_t)desc->images[i].width * desc->images[i].height * 3);
-        PT_CUDA_S(cudaMalloc(&s->d_images, pool.size()));
-        PT_CUDA_S(cudaMemcpy(s->d_images, pool.data(), pool.size(), cudaMemcpyHostToDevice));
+            std::memcpy(fs.image_pool.data() + image_offset[i], desc->images[i].data, (size_t)desc->images[i].width * desc->images[i].height * 3);
     }
     if (any_moving) {
-        std::vector<pt::DevMotion> motion(n);
+        fs.motion.assign(n, pt::DevMotion{});
         for (uint32_t j = 0; j < n; ++j) {
             const uint32_t i = order_of[j];
             pt::DevMotion m{};
@@ -716,47 +751,29 @@ int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) {
                 m.inv_time_delta = 1.0f / (mo.time1 - mo.time0);
                 m.radius = desc->radius[i];
             }
-            motion[j] = m;
+            fs.motion[j] = m;
         }
-        PT_CUDA_S(cudaMalloc(&s->d_motion, motion.size() * sizeof(pt::DevMotion)));
-        PT_CUDA_S(cudaMemcpy(s->d_motion, motion.data(), motion.size() * sizeof(pt::DevMotion), cudaMemcpyHostToDevice));
-        s->motion_t_lo = t_lo;
-        s->motion_t_hi = t_hi;
     }
-    PT_CUDA_S(cudaMalloc(&s->d_prefilter, h_prefilter.size() * sizeof(float4)));
-    PT_CUDA_S(cudaMemcpy(s->d_prefilter, h_prefilter.data(), h_prefilter.size() * sizeof(float4), cudaMemcpyHostToDevice));
-    PT_CUDA_S(cudaMalloc(&s->d_perlin, sizeof(pt::PerlinSmem)));
-    {
-        std::vector<unsigned char> raw(sizeof(pt::PerlinSmem), 0);
-        pt::PerlinSmem* ps = reinterpret_cast<pt::PerlinSmem*>(raw.data());
-        if (desc->perlin) {
-            for (int i = 0; i < 256; ++i) {
-                ps->randvec[i] = make_float4(desc->perlin->randvec[i][0], desc->perlin->randvec[i][1], desc->perlin->randvec[i][2], 0.0f);
-                if (desc->perlin->perm_x[i] > 255 || desc->perlin->perm_y[i] > 255 || desc->perlin->perm_z[i] > 255)
-                    return cleanup_fail(fail(PT_ERR_INVALID, "perlin permutation entry %d out of range", i));
-                ps->perm_x[i] = (uint8_t)desc->perlin->perm_x[i];
-                ps->perm_y[i] = (uint8_t)desc->perlin->perm_y[i];
-                ps->perm_z[i] = (uint8_t)desc->perlin->perm_z[i];
-            }
+    fs.perlin_raw.assign(sizeof(pt::PerlinSmem), 0);
+    if (desc->perlin) {
+        pt::PerlinSmem* ps = reinterpret_cast<pt::PerlinSmem*>(fs.perlin_raw.data());
+        for (int i = 0; i < 256; ++i) {
+            ps->randvec[i] = make_float4(desc->perlin->randvec[i][0], desc->perlin->randvec[i][1], desc->perlin->randvec[i][2], 0.0f);
+            if (desc->perlin->perm_x[i] > 255 || desc->perlin->perm_y[i] > 255 || desc->perlin->perm_z[i] > 255)
+                return fail(PT_ERR_INVALID, "perlin permutation entry %d out of range", i);
+            ps->perm_x[i] = (uint8_t)desc->perlin->perm_x[i];
+            ps->perm_y[i] = (uint8_t)desc->perlin->perm_y[i];
+            ps->perm_z[i] = (uint8_t)desc->perlin->perm_z[i];
         }
-        PT_CUDA_S(cudaMemcpy(s->d_perlin, raw.data(), raw.size(), cudaMemcpyHostToDevice));
     }
-    PT_CUDA_S(cudaMalloc(&s->d_ray_count, sizeof(unsigned long long)));
-    PT_CUDA_S(cudaMalloc(&s->d_sweep_count, sizeof(unsigned long long)));
-    PT_CUDA_S(cudaMalloc(&s->d_next_pixel, sizeof(unsigned int)));
-    PT_CUDA_S(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    for (auto& e : s->ev) PT_CUDA_S(cudaEventCreate(&e));
-#undef PT_CUDA_S
-    rc = plan_launch(s);
-    if (rc != PT_OK) return cleanup_fail(rc);
-    *out = s;
     return PT_OK;
 }
 
-void pt_scene_destroy(PtScene* s) {
+void destroy_replica(Replica* s) {
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->busy_recorded) cudaEventSynchronize(s->ev_busy);
     cudaFree(s->d_blocks);
     cudaFree(s->d_shade);
     cudaFree(s->d_tex);
@@ -764,6 +781,7 @@ void pt_scene_destroy(PtScene* s) {
     cudaFree(s->d_order);
     cudaFree(s->d_perlin);
     cudaFree(s->d_prefilter);
+    cudaFree(s->d_kplane);
     cudaFree(s->d_motion);
     cudaFree(s->d_ray_count);
     cudaFree(s->d_sweep_count);
@@ -773,28 +791,84 @@ void pt_scene_destroy(PtScene* s) {
     cudaFree(s->d_rgb8);
     for (auto& e : s->ev)
         if (e) cudaEventDestroy(e);
+    if (s->ev_busy) cudaEventDestroy(s->ev_busy);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
 
-int pt_render_part(PtScene* s, const PtParams* params, const PtCamera* camera, uint32_t frame_num, const PtPartition* part_in,
-                   float* rgb_inout, uint64_t* ray_count_out) {
-    if (!s || !rgb_inout) return fail(PT_ERR_INVALID, "null scene/buffer");
-    int rc = validate_params(params, camera);
+template <typename T>
+int upload(T** dst, const std::vector<T>& src) {
+    if (src.empty()) return PT_OK;
+    PT_CUDA(cudaMalloc(dst, src.size() * sizeof(T)));
+    PT_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return PT_OK;
+}
+
+int create_replica(const FlatScene& fs, int device, const PtOptions& opt, Replica** out) {
+    cudaDeviceProp prop;
+    int rc = check_device(device, &prop);
     if (rc != PT_OK) return rc;
-    PtPartition part;
-    rc = normalise_partition(part_in, &part);
-    if (rc != PT_OK) return rc;
+    PT_CUDA(cudaSetDevice(device));
+    Replica* s = new Replica();
+    s->device = device;
+    s->sm_count = prop.multiProcessorCount;
+    s->n_spheres = fs.n_spheres;
+    s->n_blocks = fs.n_blocks;
+    s->has_noise = fs.has_noise;
+    s->has_sky = fs.has_sky;
+    s->sky = fs.sky;
+    s->opt = opt;
+    s->motion_t_lo = fs.motion_t_lo;
+    s->motion_t_hi = fs.motion_t_hi;
+    s->h_const_image = fs.const_image.get();
+    rc = upload(&s->d_blocks, fs.blocks);
+    if (rc == PT_OK) rc = upload(&s->d_shade, fs.shade);
+    if (rc == PT_OK) rc = upload(&s->d_tex, fs.tex);
+    if (rc == PT_OK && fs.spatial) rc = upload(&s->d_order, fs.order_of);
+    if (rc == PT_OK) rc = upload(&s->d_images, fs.image_pool);
+    if (rc == PT_OK) rc = upload(&s->d_motion, fs.motion);
+    if (rc == PT_OK) rc = upload(&s->d_prefilter, fs.prefilter);
+    if (rc == PT_OK) rc = upload(&s->d_kplane, fs.kplane);
+    if (rc == PT_OK) {
+        std::vector<unsigned char> raw = fs.perlin_raw;
+        unsigned char* d = nullptr;
+        rc = upload(&d, raw);
+        s->d_perlin = reinterpret_cast<pt::PerlinSmem*>(d);
+    }
+    auto cuda_ok = [&](cudaError_t e, const char* what) {
+        if (rc == PT_OK && e != cudaSuccess) rc = fail(PT_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+    };
+    if (rc == PT_OK) cuda_ok(cudaMalloc(&s->d_ray_count, sizeof(unsigned long long)), "cudaMalloc");
+    if (rc == PT_OK) cuda_ok(cudaMalloc(&s->d_sweep_count, sizeof(unsigned long long)), "cudaMalloc");
+    if (rc == PT_OK) cuda_ok(cudaMalloc(&s->d_next_pixel, sizeof(unsigned int)), "cudaMalloc");
+    if (rc == PT_OK) cuda_ok(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    for (auto& e : s->ev)
+        if (rc == PT_OK) cuda_ok(cudaEventCreate(&e), "cudaEventCreate");
+    if (rc == PT_OK) cuda_ok(cudaEventCreateWithFlags(&s->ev_busy, cudaEventDisableTiming), "cudaEventCreate");
+    if (rc == PT_OK) rc = plan_launch(s);
+    if (rc != PT_OK) {
+        const std::string keep = g_last_error;
+        destroy_replica(s);
+        g_last_error = keep;
+        return rc;
+    }
+    *out = s;
+    return PT_OK;
+}
+
+// one Scene::update of `part` on one replica with HOST buffers (H2D of the previous frame, kernel, D2H)
+int render_part_host(Replica* s, const PtParams* params, const PtCamera* camera, uint32_t frame_num, const PtPartition& part, float* rgb_inout,
+                     uint64_t* ray_count_out) {
     PT_CUDA(cudaSetDevice(s->device));
     const size_t floats = (size_t)params->width * params->height * 3;
-    rc = ensure_image(s, floats);
+    int rc = ensure_image(s, floats);
     if (rc != PT_OK) return rc;
-
     s->stats = PtRenderStats{};
-    s->prog_valid = false;  // this call reuses the scene's device image
     uint64_t h2d = 0, d2h = 0;
     PT_CUDA(cudaEventRecord(s->ev[0], s->stream));
     if (frame_num != 0) {  // the blend reads the previous frame (scene.rs:114-116); frame 0 has mix_prev = 0
+        rc = serialise_begin(s, s->stream);  // the device image may still be read by an earlier asynchronous launch
+        if (rc != PT_OK) return rc;
         rc = copy_owned_rows(s, params, part, rgb_inout, true, &h2d);
         if (rc != PT_OK) return rc;
     }
@@ -819,54 +893,47 @@ int pt_render_part(PtScene* s, const PtParams* params, const PtCamera* camera, u
     s->stats.d2h_bytes = d2h + sizeof(rays);
     s->stats.ray_count = rays;
     if (ray_count_out) *ray_count_out = rays;
-    if (std::getenv("PTGPU_DEBUG_SWEEPS")) {  // diagnostic: lane efficiency of the sweep = rays / (32 x warp sweeps)
-        unsigned long long sweeps = 0;
-        cudaMemcpy(&sweeps, s->d_sweep_count, sizeof(sweeps), cudaMemcpyDeviceToHost);
-        std::fprintf(stderr, "[ptgpu] warp sweeps %llu, rays %llu, lane efficiency %.3f\n", sweeps, rays, sweeps ? (double)rays / (32.0 * (double)sweeps) : 0.0);
-    }
     return PT_OK;
 }
 
-int pt_render(PtScene* s, const PtParams* params, const PtCamera* camera, uint32_t frame_num, float* rgb_inout, uint64_t* ray_count_out) {
-    return pt_render_part(s, params, camera, frame_num, nullptr, rgb_inout, ray_count_out);
-}
-
-int pt_render_progressive(PtScene* s, const PtParams* params, const PtCamera* camera, uint32_t frame_num, float* rgb_out, uint8_t* rgb8_out,
-                          uint64_t* ray_count_out) {
-    if (!s) return fail(PT_ERR_INVALID, "null scene");
-    int rc = validate_params(params, camera);
-    if (rc != PT_OK) return rc;
-    if (frame_num != 0 && !(s->prog_valid && s->prog_w == params->width && s->prog_h == params->height && s->prog_next_frame == frame_num))
-        return fail(PT_ERR_INVALID, "frame %u does not continue the resident accumulation (have %ux%u, next frame %u)", frame_num, s->prog_w,
-                    s->prog_h, s->prog_valid ? s->prog_next_frame : 0u);
+// one frame of the resident progressive accumulation of `part` on one replica (image stays on the device)
+int render_part_progressive(Replica* s, const PtParams* params, const PtCamera* camera, uint32_t frame_num, const PtPartition& part, float* rgb_out,
+                            uint8_t* rgb8_out, uint64_t* ray_count_out) {
     PT_CUDA(cudaSetDevice(s->device));
     const size_t n = (size_t)params->width * params->height;
-    s->prog_valid = false;  // any failure below leaves the resident image undefined
-    rc = ensure_image(s, n * 3);
+    int rc = ensure_image(s, n * 3);
     if (rc != PT_OK) return rc;
-    const PtPartition whole{4, 0, 1, 0};
     s->stats = PtRenderStats{};
     PT_CUDA(cudaEventRecord(s->ev[1], s->stream));
-    rc = launch_update(s, params, camera, frame_num, whole, s->d_rgb, s->d_ray_count, s->stream);
+    rc = launch_update(s, params, camera, frame_num, part, s->d_rgb, s->d_ray_count, s->stream);
     if (rc != PT_OK) return rc;
     PT_CUDA(cudaEventRecord(s->ev[2], s->stream));
     uint64_t d2h = 0;
     if (rgb_out) {
-        PT_CUDA(cudaMemcpyAsync(rgb_out, s->d_rgb, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
-        d2h += n * 3 * sizeof(float);
+        rc = copy_owned_rows(s, params, part, rgb_out, false, &d2h);
+        if (rc != PT_OK) return rc;
     }
     if (rgb8_out) {
-        if (s->d_rgb8_bytes < n * 3) {
-            if (s->d_rgb8) cudaFree(s->d_rgb8);
-            s->d_rgb8 = nullptr;
-            s->d_rgb8_bytes = 0;
-            PT_CUDA(cudaMalloc(&s->d_rgb8, n * 3));
-            s->d_rgb8_bytes = n * 3;
-        }
-        rc = pt_srgb8_device(s, s->d_rgb, params->width, params->height, s->d_rgb8, s->stream);
+        rc = ensure_rgb8(s, n * 3);
         if (rc != PT_OK) return rc;
-        PT_CUDA(cudaMemcpyAsync(rgb8_out, s->d_rgb8, n * 3, cudaMemcpyDeviceToHost, s->stream));
-        d2h += n * 3;
+        const int threads = 256;
+        const int blocks = (int)std::min<size_t>((n + threads - 1) / threads, (size_t)s->sm_count * 8);
+        pt::pt_srgb8_kernel<<<blocks, threads, 0, s->stream>>>(s->d_rgb, params->width, params->height, s->d_rgb8);
+        PT_CUDA(cudaGetLastError());
+        // the sRGB image is top-down: bottom-up row y of the accumulation buffer is row height-1-y there
+        const size_t row8 = (size_t)params->width * 3;
+        if (part.part_count <= 1) {
+            PT_CUDA(cudaMemcpyAsync(rgb8_out, s->d_rgb8, n * 3, cudaMemcpyDeviceToHost, s->stream));
+            d2h += n * 3;
+        } else {
+            const uint32_t n_tiles = (params->height + part.tile_rows - 1) / part.tile_rows;
+            for (uint32_t k = part.part_index; k < n_tiles; k += part.part_count) {
+                const uint32_t r0 = k * part.tile_rows, nr = std::min(part.tile_rows, params->height - r0);
+                const size_t off = (size_t)(params->height - r0 - nr) * row8;
+                PT_CUDA(cudaMemcpyAsync(rgb8_out + off, s->d_rgb8 + off, row8 * nr, cudaMemcpyDeviceToHost, s->stream));
+                d2h += row8 * nr;
+            }
+        }
     }
     unsigned long long rays = 0;
     PT_CUDA(cudaMemcpyAsync(&rays, s->d_ray_count, sizeof(rays), cudaMemcpyDeviceToHost, s->stream));
@@ -880,29 +947,256 @@ int pt_render_progressive(PtScene* s, const PtParams* params, const PtCamera* ca
     s->stats.d2h_bytes = d2h + sizeof(rays);
     s->stats.ray_count = rays;
     if (ray_count_out) *ray_count_out = rays;
-    s->prog_valid = true;
-    s->prog_w = params->width;
-    s->prog_h = params->height;
-    s->prog_next_frame = frame_num + 1;
     return PT_OK;
 }
 
-int pt_render_device(PtScene* s, const PtParams* params, const PtCamera* camera, uint32_t frame_num, const PtPartition* part_in,
-                     float* d_rgb_inout, uint64_t* d_ray_count, void* cuda_stream) {
-    if (!s || !d_rgb_inout || !d_ray_count) return fail(PT_ERR_INVALID, "null scene/buffer");
+// Run `fn(replica, part_of_that_replica, &rays)` for every replica of the scene: inline for one device, one host thread
+// per GPU otherwise.  Ray counts are summed; the first failure wins and its message reaches the caller's
+// thread-local pt_last_error().
+template <typename F>
+int for_each_replica(PtScene* sc, F fn, uint64_t* ray_count_out) {
+    const uint32_t n = (uint32_t)sc->reps.size();
+    std::vector<int> rc(n, PT_OK);
+    std::vector<uint64_t> rays(n, 0);
+    std::vector<std::string> msg(n);
+    auto part_of = [&](uint32_t i) { return n == 1 ? PtPartition{4, 0, 1, 0} : PtPartition{sc->opt.tile_rows, i, n, 0}; };
+    if (n == 1) {
+        rc[0] = fn(sc->reps[0], part_of(0), &rays[0]);
+    } else {
+        std::vector<std::thread> th;
+        th.reserve(n);
+        for (uint32_t i = 0; i < n; ++i)
+            th.emplace_back([&, i] {
+                rc[i] = fn(sc->reps[i], part_of(i), &rays[i]);
+                if (rc[i] != PT_OK) msg[i] = g_last_error;  // this worker's thread-local message
+            });
+        for (auto& t : th) t.join();
+    }
+    // aggregate statistics: times are the slowest device's, bytes and launches add up
+    sc->stats = PtRenderStats{};
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const PtRenderStats& st = sc->reps[i]->stats;
+        sc->stats.kernel_ms = std::max(sc->stats.kernel_ms, st.kernel_ms);
+        sc->stats.h2d_ms = std::max(sc->stats.h2d_ms, st.h2d_ms);
+        sc->stats.d2h_ms = std::max(sc->stats.d2h_ms, st.d2h_ms);
+        sc->stats.h2d_bytes += st.h2d_bytes;
+        sc->stats.d2h_bytes += st.d2h_bytes;
+        sc->stats.kernel_launches += st.kernel_launches;
+        sc->stats.grid_ctas += st.grid_ctas;
+        sc->stats.cta_threads = st.cta_threads;
+        sc->stats.smem_bytes = st.smem_bytes;
+        sc->stats.resident = st.resident;
+        sc->stats.n_spheres = st.n_spheres;
+        total += rays[i];
+    }
+    sc->stats.ray_count = total;
+    for (uint32_t i = 0; i < n; ++i)
+        if (rc[i] != PT_OK) {
+            if (n > 1) g_last_error = "device " + std::to_string(sc->reps[i]->device) + ": " + msg[i];
+            return rc[i];
+        }
+    if (ray_count_out) *ray_count_out = total;
+    return PT_OK;
+}
+
+int need_single_device(const PtScene* sc, const char* what) {
+    if (sc->reps.size() != 1) return fail(PT_ERR_UNSUPPORTED, "%s takes device pointers and needs a one-device scene (this one spans %zu devices)", what, sc->reps.size());
+    return PT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pt_abi_version(void) { return PT_ABI_VERSION; }
+const char* pt_last_error(void) { return g_last_error.c_str(); }
+
+uint32_t pt_abi_struct_size(int which) {
+    switch (which) {
+        case 0: return sizeof(PtParams);
+        case 1: return sizeof(PtCamera);
+        case 2: return sizeof(PtTexture);
+        case 3: return sizeof(PtMaterial);
+        case 4: return sizeof(PtPerlin);
+        case 5: return sizeof(PtSceneDesc);
+        case 6: return sizeof(PtPartition);
+        case 7: return sizeof(PtDeviceInfo);
+        case 8: return sizeof(PtRenderStats);
+        case 9: return sizeof(PtMotion);
+        case 10: return sizeof(PtImage);
+        case 11: return sizeof(PtOptions);
+        default: return 0;
+    }
+}
+
+uint32_t pt_partition_rows(const PtPartition* part_in, uint32_t height, uint32_t* rows_out, uint32_t cap) {
+    PtPartition p;
+    if (normalise_partition(part_in, &p) != PT_OK) return 0;
+    uint32_t count = 0;
+    const uint32_t n_tiles = (height + p.tile_rows - 1) / p.tile_rows;
+    for (uint32_t k = p.part_index; k < n_tiles; k += p.part_count) {
+        const uint32_t r0 = k * p.tile_rows;
+        const uint32_t nr = std::min(p.tile_rows, height - r0);
+        for (uint32_t r = 0; r < nr; ++r) {
+            if (rows_out && count < cap) rows_out[count] = r0 + r;
+            ++count;
+        }
+    }
+    return count;
+}
+
+uint32_t pt_scene_storage_order(const PtSceneDesc* desc, const PtOptions* options, uint32_t* order_out, uint32_t cap) {
+    if (!desc || desc->struct_size != sizeof(PtSceneDesc)) return 0;
+    const uint32_t n = desc->n_spheres;
+    if (n > 0 && (!desc->centre_x || !desc->centre_y || !desc->centre_z || !desc->radius)) return 0;
+    bool any_moving = false;
+    if (desc->motion)
+        for (uint32_t i = 0; i < n; ++i) any_moving = any_moving || desc->motion[i].moving != 0;
+    std::vector<uint32_t> order_of;
+    PtOptions opt;
+    if (normalise_options(options, &opt) != PT_OK) return 0;
+    const int mode = storage_order(desc, any_moving, opt, order_of);
+    for (uint32_t j = 0; j < n && j < cap && order_out; ++j) order_out[j] = order_of[j];
+    return (uint32_t)mode;
+}
+
+int pt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int pt_device_info(int device, PtDeviceInfo* out) {
+    if (!out) return fail(PT_ERR_INVALID, "null out");
+    cudaDeviceProp prop;
+    int rc = check_device(device, &prop);
+    if (rc != PT_OK) return rc;
+    std::memset(out, 0, sizeof(*out));
+    std::strncpy(out->name, prop.name, sizeof(out->name) - 1);
+    out->sm_count = prop.multiProcessorCount;
+    out->cc_major = prop.major;
+    out->cc_minor = prop.minor;
+    int khz = 0;
+    PT_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device));
+    out->sm_clock_khz = khz;
+    out->fp32_fma_peak_flops = (double)prop.multiProcessorCount * 128.0 * 2.0 * (double)khz * 1e3;
+    out->global_mem_bytes = prop.totalGlobalMem;
+    return PT_OK;
+}
+
+int pt_scene_create_multi(const PtSceneDesc* desc, const int* devices, uint32_t n_devices, const PtOptions* options, PtScene** out) {
+    if (!desc || !out) return fail(PT_ERR_INVALID, "null desc/out");
+    *out = nullptr;
+    if (!devices || n_devices == 0) return fail(PT_ERR_INVALID, "empty device list");
+    if (n_devices > 64) return fail(PT_ERR_INVALID, "too many devices: %u", n_devices);
+    for (uint32_t i = 0; i < n_devices; ++i)
+        for (uint32_t j = 0; j < i; ++j)
+            if (devices[i] == devices[j]) return fail(PT_ERR_INVALID, "device %d is listed twice", devices[i]);
+    PtOptions opt;
+    int rc = normalise_options(options, &opt);
+    if (rc != PT_OK) return rc;
+    std::unique_ptr<PtScene> sc(new PtScene());
+    sc->opt = opt;
+    rc = flatten_scene(desc, opt, sc->flat);
+    if (rc != PT_OK) return rc;
+    // devices first: "no device" is the answer on a machine without a B200, whatever else is wrong
+    for (uint32_t i = 0; i < n_devices && rc == PT_OK; ++i) {
+        Replica* r = nullptr;
+        rc = create_replica(sc->flat, devices[i], opt, &r);
+        if (rc == PT_OK) sc->reps.push_back(r);
+    }
+    if (rc != PT_OK) {
+        const std::string keep = g_last_error;
+        for (Replica* r : sc->reps) destroy_replica(r);
+        g_last_error = keep;
+        return rc;
+    }
+    *out = sc.release();
+    return PT_OK;
+}
+
+int pt_scene_create(const PtSceneDesc* desc, int device, PtScene** out) { return pt_scene_create_multi(desc, &device, 1, nullptr, out); }
+
+void pt_scene_destroy(PtScene* sc) {
+    if (!sc) return;
+    for (Replica* r : sc->reps) destroy_replica(r);
+    delete sc;
+}
+
+uint32_t pt_scene_device_count(const PtScene* sc) { return sc ? (uint32_t)sc->reps.size() : 0u; }
+
+int pt_scene_device_stats(const PtScene* sc, uint32_t index, PtRenderStats* out) {
+    if (!sc || !out || index >= sc->reps.size()) return fail(PT_ERR_INVALID, "null argument or device slot out of range");
+    *out = sc->reps[index]->stats;
+    return PT_OK;
+}
+
+int pt_render_part(PtScene* sc, const PtParams* params, const PtCamera* camera, uint32_t frame_num, const PtPartition* part_in,
+                   float* rgb_inout, uint64_t* ray_count_out) {
+    if (!sc || !rgb_inout) return fail(PT_ERR_INVALID, "null scene/buffer");
     int rc = validate_params(params, camera);
     if (rc != PT_OK) return rc;
     PtPartition part;
     rc = normalise_partition(part_in, &part);
     if (rc != PT_OK) return rc;
-    PT_CUDA(cudaSetDevice(s->device));
-    s->stats = PtRenderStats{};
-    return launch_update(s, params, camera, frame_num, part, d_rgb_inout, reinterpret_cast<unsigned long long*>(d_ray_count),
-                         reinterpret_cast<cudaStream_t>(cuda_stream));
+    sc->prog_valid = false;  // this call reuses the scene's device images
+    if (sc->reps.size() > 1) {
+        if (part.part_count > 1) return fail(PT_ERR_UNSUPPORTED, "a multi-device scene partitions the image itself: pass part = NULL (or use one-device scenes with pt_render_part)");
+        return for_each_replica(sc, [&](Replica* r, const PtPartition& p, uint64_t* rays) { return render_part_host(r, params, camera, frame_num, p, rgb_inout, rays); },
+                                ray_count_out);
+    }
+    return for_each_replica(sc, [&](Replica* r, const PtPartition&, uint64_t* rays) { return render_part_host(r, params, camera, frame_num, part, rgb_inout, rays); },
+                            ray_count_out);
 }
 
-int pt_srgb8_device(PtScene* s, const float* d_rgb, uint32_t width, uint32_t height, uint8_t* d_rgb8_out, void* cuda_stream) {
-    if (!s || !d_rgb || !d_rgb8_out || width == 0 || height == 0) return fail(PT_ERR_INVALID, "null/empty argument");
+int pt_render(PtScene* s, const PtParams* params, const PtCamera* camera, uint32_t frame_num, float* rgb_inout, uint64_t* ray_count_out) {
+    return pt_render_part(s, params, camera, frame_num, nullptr, rgb_inout, ray_count_out);
+}
+
+int pt_render_progressive(PtScene* sc, const PtParams* params, const PtCamera* camera, uint32_t frame_num, float* rgb_out, uint8_t* rgb8_out,
+                          uint64_t* ray_count_out) {
+    if (!sc) return fail(PT_ERR_INVALID, "null scene");
+    int rc = validate_params(params, camera);
+    if (rc != PT_OK) return rc;
+    if (frame_num != 0 && !(sc->prog_valid && sc->prog_w == params->width && sc->prog_h == params->height && sc->prog_next_frame == frame_num))
+        return fail(PT_ERR_INVALID, "frame %u does not continue the resident accumulation (have %ux%u, next frame %u)", frame_num, sc->prog_w,
+                    sc->prog_h, sc->prog_valid ? sc->prog_next_frame : 0u);
+    sc->prog_valid = false;  // any failure below leaves the resident images undefined
+    rc = for_each_replica(sc, [&](Replica* r, const PtPartition& p, uint64_t* rays) { return render_part_progressive(r, params, camera, frame_num, p, rgb_out, rgb8_out, rays); },
+                          ray_count_out);
+    if (rc != PT_OK) return rc;
+    sc->prog_valid = true;
+    sc->prog_w = params->width;
+    sc->prog_h = params->height;
+    sc->prog_next_frame = frame_num + 1;
+    return PT_OK;
+}
+
+int pt_render_device(PtScene* sc, const PtParams* params, const PtCamera* camera, uint32_t frame_num, const PtPartition* part_in,
+                     float* d_rgb_inout, uint64_t* d_ray_count, void* cuda_stream) {
+    if (!sc || !d_rgb_inout || !d_ray_count) return fail(PT_ERR_INVALID, "null scene/buffer");
+    int rc = need_single_device(sc, "pt_render_device");
+    if (rc != PT_OK) return rc;
+    rc = validate_params(params, camera);
+    if (rc != PT_OK) return rc;
+    PtPartition part;
+    rc = normalise_partition(part_in, &part);
+    if (rc != PT_OK) return rc;
+    Replica* s = sc->reps[0];
+    PT_CUDA(cudaSetDevice(s->device));
+    s->stats = PtRenderStats{};
+    rc = launch_update(s, params, camera, frame_num, part, d_rgb_inout, reinterpret_cast<unsigned long long*>(d_ray_count),
+                       reinterpret_cast<cudaStream_t>(cuda_stream));
+    sc->stats = s->stats;
+    return rc;
+}
+
+int pt_srgb8_device(PtScene* sc, const float* d_rgb, uint32_t width, uint32_t height, uint8_t* d_rgb8_out, void* cuda_stream) {
+    if (!sc || !d_rgb || !d_rgb8_out || width == 0 || height == 0) return fail(PT_ERR_INVALID, "null/empty argument");
+    int rc = need_single_device(sc, "pt_srgb8_device");
+    if (rc != PT_OK) return rc;
+    Replica* s = sc->reps[0];
     PT_CUDA(cudaSetDevice(s->device));
     const size_t n = (size_t)width * height;
     const int threads = 256;
@@ -912,43 +1206,110 @@ int pt_srgb8_device(PtScene* s, const float* d_rgb, uint32_t width, uint32_t hei
     return PT_OK;
 }
 
-int pt_srgb8(PtScene* s, const float* rgb, uint32_t width, uint32_t height, uint8_t* rgb8_out) {
-    if (!s || !rgb || !rgb8_out || width == 0 || height == 0) return fail(PT_ERR_INVALID, "null/empty argument");
+int pt_srgb8(PtScene* sc, const float* rgb, uint32_t width, uint32_t height, uint8_t* rgb8_out) {
+    if (!sc || !rgb || !rgb8_out || width == 0 || height == 0) return fail(PT_ERR_INVALID, "null/empty argument");
+    Replica* s = sc->reps[0];  // the output stage is 0.1 ms of work: the first device does it
     PT_CUDA(cudaSetDevice(s->device));
     const size_t n = (size_t)width * height;
     int rc = ensure_image(s, n * 3);
     if (rc != PT_OK) return rc;
-    if (s->d_rgb8_bytes < n * 3) {
-        if (s->d_rgb8) cudaFree(s->d_rgb8);
-        s->d_rgb8 = nullptr;
-        s->d_rgb8_bytes = 0;
-        PT_CUDA(cudaMalloc(&s->d_rgb8, n * 3));
-        s->d_rgb8_bytes = n * 3;
-    }
-    s->prog_valid = false;  // this call reuses the scene's device image
-    PT_CUDA(cudaMemcpyAsync(s->d_rgb, rgb, n * 3 * sizeof(float), cudaMemcpyHostToDevice, s->stream));
-    rc = pt_srgb8_device(s, s->d_rgb, width, height, s->d_rgb8, s->stream);
+    rc = ensure_rgb8(s, n * 3);
     if (rc != PT_OK) return rc;
+    sc->prog_valid = false;  // this call reuses the scene's device image
+    rc = serialise_begin(s, s->stream);
+    if (rc != PT_OK) return rc;
+    PT_CUDA(cudaMemcpyAsync(s->d_rgb, rgb, n * 3 * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    const int threads = 256;
+    const int blocks = (int)std::min<size_t>((n + threads - 1) / threads, (size_t)s->sm_count * 8);
+    pt::pt_srgb8_kernel<<<blocks, threads, 0, s->stream>>>(s->d_rgb, width, height, s->d_rgb8);
+    PT_CUDA(cudaGetLastError());
     PT_CUDA(cudaMemcpyAsync(rgb8_out, s->d_rgb8, n * 3, cudaMemcpyDeviceToHost, s->stream));
     PT_CUDA(cudaStreamSynchronize(s->stream));
     return PT_OK;
 }
 
-int pt_scene_stats(const PtScene* s, PtRenderStats* out) {
-    if (!s || !out) return fail(PT_ERR_INVALID, "null argument");
-    *out = s->stats;
+int pt_scene_stats(const PtScene* sc, PtRenderStats* out) {
+    if (!sc || !out) return fail(PT_ERR_INVALID, "null argument");
+    *out = sc->stats;
     return PT_OK;
 }
 
-#ifdef PT_PROFILE
-// profile build only (tools/phase_profile.py): read and clear the phase counters
-int pt_profile_read(unsigned long long* out8) {
-    PT_CUDA(cudaMemcpyFromSymbol(out8, pt::g_prof, sizeof(unsigned long long) * 8));
-    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    PT_CUDA(cudaMemcpyToSymbol(pt::g_prof, z, sizeof(z)));
+int pt_host_register(void* ptr, uint64_t bytes) {
+    if (!ptr || bytes == 0) return fail(PT_ERR_INVALID, "null/empty buffer");
+    PT_CUDA(cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable));
     return PT_OK;
 }
-#endif
+int pt_host_unregister(void* ptr) {
+    if (!ptr) return fail(PT_ERR_INVALID, "null buffer");
+    PT_CUDA(cudaHostUnregister(ptr));
+    return PT_OK;
+}
+
+int pt_debug_hits(PtScene* sc, const float* rays6, const float* times, uint32_t n, int32_t mode, int32_t* idx_out, float* t_out, uint32_t* flagged_out) {
+    if (!sc || !rays6 || !idx_out || !t_out) return fail(PT_ERR_INVALID, "null argument");
+    if (mode != 0 && mode != 1) return fail(PT_ERR_INVALID, "mode %d (0 = shipped two-stage sweep, 1 = exact test on every sphere)", mode);
+    if (n == 0) return PT_OK;
+    Replica* s = sc->reps[0];
+    PT_CUDA(cudaSetDevice(s->device));
+    float *d_rays = nullptr, *d_times = nullptr, *d_t = nullptr;
+    int32_t* d_idx = nullptr;
+    uint32_t* d_flagged = nullptr;
+    int rc = PT_OK;
+    auto step = [&](cudaError_t e, const char* what) {
+        if (rc == PT_OK && e != cudaSuccess) rc = fail(PT_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+    };
+    step(cudaMalloc(&d_rays, (size_t)n * 6 * sizeof(float)), "cudaMalloc");
+    step(cudaMalloc(&d_t, (size_t)n * sizeof(float)), "cudaMalloc");
+    step(cudaMalloc(&d_idx, (size_t)n * sizeof(int32_t)), "cudaMalloc");
+    if (times) step(cudaMalloc(&d_times, (size_t)n * sizeof(float)), "cudaMalloc");
+    if (flagged_out) step(cudaMalloc(&d_flagged, (size_t)n * sizeof(uint32_t)), "cudaMalloc");
+    if (rc == PT_OK) step(cudaMemcpyAsync(d_rays, rays6, (size_t)n * 6 * sizeof(float), cudaMemcpyHostToDevice, s->stream), "cudaMemcpyAsync");
+    if (rc == PT_OK && times) step(cudaMemcpyAsync(d_times, times, (size_t)n * sizeof(float), cudaMemcpyHostToDevice, s->stream), "cudaMemcpyAsync");
+    if (rc == PT_OK) {
+        pt::KernelArgs a{};
+        fill_scene_args(s, a);
+        a.dbg_rays = d_rays;
+        a.dbg_times = d_times;
+        a.dbg_n = n;
+        a.dbg_idx = d_idx;
+        a.dbg_t = d_t;
+        a.dbg_flagged = d_flagged;
+        rc = serialise_begin(s, s->stream);
+        const uint32_t max_ctas = (uint32_t)(s->sm_count * s->ctas_per_sm);
+        if (rc == PT_OK && mode == 1) {
+            const uint32_t grid = std::min<uint32_t>((n + 255u) / 256u, (uint32_t)s->sm_count * 8u);
+            if (s->d_motion) pt::pt_debug_hits_exact_all<true><<<grid, 256, 0, s->stream>>>(a);
+            else pt::pt_debug_hits_exact_all<false><<<grid, 256, 0, s->stream>>>(a);
+        } else if (rc == PT_OK && s->resident) {
+            const uint32_t batch = (uint32_t)pt::kCtaThreads * pt::kPathRows;
+            const uint32_t grid = std::min<uint32_t>((n + batch - 1) / batch, max_ctas);
+            if (s->const_image) {
+                if (s->d_motion) pt::pt_debug_hits_resident<true, true><<<grid, pt::kCtaThreads, s->smem_bytes, s->stream>>>(a, *s->h_const_image);
+                else pt::pt_debug_hits_resident<true, false><<<grid, pt::kCtaThreads, s->smem_bytes, s->stream>>>(a, *s->h_const_image);
+            } else {
+                const pt::ConstImageT<false> none{};
+                if (s->d_motion) pt::pt_debug_hits_resident<false, true><<<grid, pt::kCtaThreads, s->smem_bytes, s->stream>>>(a, none);
+                else pt::pt_debug_hits_resident<false, false><<<grid, pt::kCtaThreads, s->smem_bytes, s->stream>>>(a, none);
+            }
+        } else if (rc == PT_OK) {
+            const uint32_t grid = std::min<uint32_t>((n + pt::kCtaThreads - 1) / pt::kCtaThreads, max_ctas);
+            if (s->d_motion) pt::pt_debug_hits_streamed<true><<<grid, pt::kCtaThreads, s->smem_bytes, s->stream>>>(a);
+            else pt::pt_debug_hits_streamed<false><<<grid, pt::kCtaThreads, s->smem_bytes, s->stream>>>(a);
+        }
+        if (rc == PT_OK) step(cudaGetLastError(), "kernel launch");
+        if (rc == PT_OK) rc = serialise_end(s, s->stream);
+    }
+    if (rc == PT_OK) step(cudaMemcpyAsync(idx_out, d_idx, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream), "cudaMemcpyAsync");
+    if (rc == PT_OK) step(cudaMemcpyAsync(t_out, d_t, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, s->stream), "cudaMemcpyAsync");
+    if (rc == PT_OK && flagged_out) step(cudaMemcpyAsync(flagged_out, d_flagged, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream), "cudaMemcpyAsync");
+    if (rc == PT_OK) step(cudaStreamSynchronize(s->stream), "cudaStreamSynchronize");
+    cudaFree(d_rays);
+    cudaFree(d_times);
+    cudaFree(d_t);
+    cudaFree(d_idx);
+    cudaFree(d_flagged);
+    return rc;
+}
 
 int pt_probe_fp32_peak(int device, double* flops_out) {
     if (!flops_out) return fail(PT_ERR_INVALID, "null out");

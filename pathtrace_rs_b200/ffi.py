@@ -71,6 +71,14 @@ class PtPartition(C.Structure):
     _fields_ = [("tile_rows", C.c_uint32), ("part_index", C.c_uint32), ("part_count", C.c_uint32), ("_pad", C.c_uint32)]
 
 
+class PtOptions(C.Structure):  # explicit launch options (ABI v4; replaces the environment hooks of v3)
+    _fields_ = [("struct_size", C.c_uint32), ("force_stream_tile_blocks", C.c_int32), ("stream_ctas", C.c_int32),
+                ("chunk_samples", C.c_int32), ("spatial_order", C.c_int32), ("tile_rows", C.c_uint32), ("_pad", C.c_uint32)]
+
+    def __init__(self, force_stream_tile_blocks=0, stream_ctas=0, chunk_samples=0, spatial_order=-1, tile_rows=0):
+        super().__init__(C.sizeof(PtOptions), force_stream_tile_blocks, stream_ctas, chunk_samples, spatial_order, tile_rows, 0)
+
+
 class PtDeviceInfo(C.Structure):
     _fields_ = [("name", C.c_char * 64), ("sm_count", C.c_int32), ("cc_major", C.c_int32), ("cc_minor", C.c_int32),
                 ("sm_clock_khz", C.c_int32), ("fp32_fma_peak_flops", C.c_double), ("global_mem_bytes", C.c_uint64)]
@@ -112,7 +120,6 @@ def libptgpu():
     if _ptgpu is None:
         L = _load("libptgpu.so")
         vp = C.c_void_p
-        vp = C.c_void_p
         L.pt_abi_version.restype = C.c_int
         L.pt_last_error.restype = C.c_char_p
         L.pt_abi_struct_size.restype = C.c_uint32
@@ -122,6 +129,13 @@ def libptgpu():
         L.pt_device_count.restype = C.c_int
         L.pt_device_info.argtypes = [C.c_int, C.POINTER(PtDeviceInfo)]
         L.pt_scene_create.argtypes = [C.POINTER(PtSceneDesc), C.c_int, C.POINTER(vp)]
+        L.pt_scene_create_multi.argtypes = [C.POINTER(PtSceneDesc), C.POINTER(C.c_int), C.c_uint32, C.POINTER(PtOptions), C.POINTER(vp)]
+        L.pt_scene_device_count.restype = C.c_uint32
+        L.pt_scene_device_count.argtypes = [vp]
+        L.pt_scene_device_stats.argtypes = [vp, C.c_uint32, C.POINTER(PtRenderStats)]
+        L.pt_host_register.argtypes = [vp, C.c_uint64]
+        L.pt_host_unregister.argtypes = [vp]
+        L.pt_debug_hits.argtypes = [vp, vp, vp, C.c_uint32, C.c_int32, vp, vp, vp]
         L.pt_scene_destroy.argtypes = [vp]
         L.pt_scene_destroy.restype = None
         L.pt_render.argtypes = [vp, C.POINTER(PtParams), C.POINTER(PtCamera), C.c_uint32, vp, C.POINTER(C.c_uint64)]
@@ -134,7 +148,7 @@ def libptgpu():
         L.pt_scene_stats.argtypes = [vp, C.POINTER(PtRenderStats)]
         L.pt_probe_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
         L.pt_scene_storage_order.restype = C.c_uint32
-        L.pt_scene_storage_order.argtypes = [C.POINTER(PtSceneDesc), vp, C.c_uint32]
+        L.pt_scene_storage_order.argtypes = [C.POINTER(PtSceneDesc), C.POINTER(PtOptions), vp, C.c_uint32]
         _ptgpu = L
     return _ptgpu
 
@@ -160,6 +174,9 @@ def libpthost():
         L.pth_preset_perlin.argtypes = [vp, C.POINTER(PtPerlin)]
         L.pth_preset_sky.argtypes = [vp, vp]
         L.pth_scene_create.argtypes = [vp, C.c_int32]
+        L.pth_scene_create_multi.argtypes = [vp, C.POINTER(C.c_int32), C.c_uint32, C.POINTER(PtOptions)]
+        L.pth_render_offline_multi.argtypes = [C.c_char_p, C.POINTER(PthParams), C.c_char_p, C.POINTER(C.c_int32), C.c_uint32, C.c_uint32,
+                                               C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
         L.pth_scene_handle.argtypes = [vp]
         L.pth_scene_handle.restype = vp
         L.pth_scene_update.argtypes = [vp, C.POINTER(PthParams), C.c_uint32, C.POINTER(PtPartition), vp, C.POINTER(C.c_uint64)]

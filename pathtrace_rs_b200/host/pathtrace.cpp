@@ -216,7 +216,8 @@ struct Flattener {
 };
 }  // namespace
 
-Scene::Scene(const std::vector<Hitable>& world, std::optional<Vec3> sky, int device) {
+Scene::Scene(const std::vector<Hitable>& world, std::optional<Vec3> sky, int device) : Scene(world, sky, std::vector<int>{device}, nullptr) {}
+Scene::Scene(const std::vector<Hitable>& world, std::optional<Vec3> sky, const std::vector<int>& devices, const PtOptions* options) {
     Flattener fl;
     for (const Hitable& h : world) {
         PtMotion mo{};
@@ -261,7 +262,8 @@ Scene::Scene(const std::vector<Hitable>& world, std::optional<Vec3> sky, int dev
     d.has_sky = sky.has_value() ? 1u : 0u;
     if (sky) { d.sky[0] = sky->x; d.sky[1] = sky->y; d.sky[2] = sky->z; }
     n_spheres_ = d.n_spheres;
-    if (pt_scene_create(&d, device, &scene_) != PT_OK) throw std::runtime_error(std::string("pt_scene_create: ") + pt_last_error());
+    if (pt_scene_create_multi(&d, devices.data(), (uint32_t)devices.size(), options, &scene_) != PT_OK)
+        throw std::runtime_error(std::string("pt_scene_create: ") + pt_last_error());
 }
 Scene::~Scene() { pt_scene_destroy(scene_); }
 
@@ -280,12 +282,26 @@ size_t Scene::update_part(const Params& params, const Camera& camera, uint32_t f
     return (size_t)rays;
 }
 
+size_t Scene::update_progressive(const Params& params, const Camera& camera, uint32_t frame_num, float* buffer, uint8_t* rgb8) const {
+    const PtParams p = params.to_ffi();
+    const PtCamera c = camera.to_ffi();
+    uint64_t rays = 0;
+    if (pt_render_progressive(scene_, &p, &c, frame_num, buffer, rgb8, &rays) != PT_OK)
+        throw std::runtime_error(std::string("pt_render_progressive: ") + pt_last_error());
+    return (size_t)rays;
+}
+
 // ---- Params (src/params.rs:21-46) ----
 Xoshiro256Plus Params::new_rng() const { return Xoshiro256Plus::seed_from_u64(random_seed ? seed_salt : 0); }
 std::unique_ptr<Scene> Params::new_scene(Xoshiro256Plus&, const Storage&, std::vector<Hitable> hitables, std::optional<Vec3> sky,
                                          int device) const {
     if (use_bvh) throw std::runtime_error("use_bvh: the BVH arm stays on the CPU reference (params.rs:36-40); the GPU path is the flat list");
     return std::make_unique<Scene>(hitables, sky, device);
+}
+std::unique_ptr<Scene> Params::new_scene(Xoshiro256Plus&, const Storage&, std::vector<Hitable> hitables, std::optional<Vec3> sky,
+                                         const std::vector<int>& devices, const PtOptions* options) const {
+    if (use_bvh) throw std::runtime_error("use_bvh: the BVH arm stays on the CPU reference (params.rs:36-40); the GPU path is the flat list");
+    return std::make_unique<Scene>(hitables, sky, devices, options);
 }
 PtParams Params::to_ffi() const {
     PtParams p{};
@@ -479,17 +495,28 @@ bool write_png_rgb8(const std::string& path, const uint8_t* rgb, uint32_t width,
 // ---- offline::render_offline (src/offline.rs:16-60) ----
 namespace offline {
 std::pair<double, size_t> render_offline(const std::string& preset, const Params& params, const std::string& output_png, int device) {
+    return render_offline(preset, params, output_png, std::vector<int>{device}, 1);
+}
+std::pair<double, size_t> render_offline(const std::string& preset, const Params& params, const std::string& output_png,
+                                         const std::vector<int>& devices, uint32_t frames) {
     Xoshiro256Plus rng = params.new_rng();
     Storage storage(rng);
     auto built = presets::from_name(preset, params, rng, storage);
     if (!built) throw std::runtime_error("unrecognised preset");
     auto& [hitables, camera, sky] = *built;
-    std::unique_ptr<Scene> scene = params.new_scene(rng, storage, std::move(hitables), sky, device);
+    std::unique_ptr<Scene> scene = params.new_scene(rng, storage, std::move(hitables), sky, devices, nullptr);
     std::vector<float> rgb_buffer((size_t)params.width * params.height * 3, 0.0f);
 
     const auto start_time = std::chrono::steady_clock::now();
-    const uint32_t frame_num = 0;  // only ever processing 1 frame in offline
-    const size_t ray_count = scene->update(params, camera, frame_num, rgb_buffer.data(), (size_t)params.width * params.height);
+    size_t ray_count = 0;
+    if (frames <= 1) {
+        const uint32_t frame_num = 0;  // only ever processing 1 frame in offline
+        ray_count = scene->update(params, camera, frame_num, rgb_buffer.data(), (size_t)params.width * params.height);
+    } else {
+        // glium_window.rs:98-131 without the window: the buffer stays on the device, only the last frame comes back
+        for (uint32_t frame_num = 0; frame_num < frames; ++frame_num)
+            ray_count += scene->update_progressive(params, camera, frame_num, frame_num + 1 == frames ? rgb_buffer.data() : nullptr, nullptr);
+    }
     const double elapsed_secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - start_time).count();
     std::printf("%.2fsecs %zurays %.2fMrays/s\n", elapsed_secs, ray_count, (double)ray_count / 1000000.0 / elapsed_secs);
 
@@ -604,6 +631,14 @@ int32_t pth_scene_create(void* hv, int32_t device) {
         return 0;
     } catch (const std::exception& e) { g_err = e.what(); return 1; }
 }
+// the same on a list of devices with explicit PtOptions (may be null)
+int32_t pth_scene_create_multi(void* hv, const int32_t* devices, uint32_t n_devices, const PtOptions* options) {
+    auto* h = (PresetHandle*)hv;
+    try {
+        h->scene = h->params.new_scene(h->rng, *h->storage, h->hitables, h->sky, std::vector<int>(devices, devices + n_devices), options);
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
 void* pth_scene_handle(void* hv) { auto* h = (PresetHandle*)hv; return h->scene ? h->scene->handle() : nullptr; }
 
 // Scene::update through the mirror (host buffer)
@@ -621,6 +656,16 @@ int32_t pth_scene_update(void* hv, const PthParams* p, uint32_t frame_num, const
 int32_t pth_render_offline(const char* preset, const PthParams* p, const char* output_png, int32_t device, double* secs, uint64_t* rays) {
     try {
         auto r = pathtrace::offline::render_offline(preset, to_params(p), output_png ? output_png : "", device);
+        if (secs) *secs = r.first;
+        if (rays) *rays = r.second;
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return 1; }
+}
+
+int32_t pth_render_offline_multi(const char* preset, const PthParams* p, const char* output_png, const int32_t* devices, uint32_t n_devices, uint32_t frames,
+                                 double* secs, uint64_t* rays) {
+    try {
+        auto r = pathtrace::offline::render_offline(preset, to_params(p), output_png ? output_png : "", std::vector<int>(devices, devices + n_devices), frames);
         if (secs) *secs = r.first;
         if (rays) *rays = r.second;
         return 0;

@@ -195,6 +195,9 @@ struct Params;
 class Scene {
 public:
     Scene(const std::vector<Hitable>& world, std::optional<Vec3> sky, int device = 0);  // Scene::new + flatten + upload
+    // the same scene replicated on several GPUs: `update` stays ONE call and the library splits the image by interleaved
+    // row tiles, one host thread per GPU (pt_scene_create_multi); `options` may be null
+    Scene(const std::vector<Hitable>& world, std::optional<Vec3> sky, const std::vector<int>& devices, const PtOptions* options = nullptr);
     ~Scene();
     Scene(const Scene&) = delete;
     Scene& operator=(const Scene&) = delete;
@@ -203,6 +206,9 @@ public:
     size_t update(const Params& params, const Camera& camera, uint32_t frame_num, float* buffer, size_t buffer_len_pixels) const;
     size_t update_part(const Params& params, const Camera& camera, uint32_t frame_num, const PtPartition& part, float* buffer,
                        size_t buffer_len_pixels) const;
+    // the windowed worker loop (glium_window.rs:96-131): frame_num = 0, 1, 2, ... with the accumulation buffer resident on
+    // the device(s); `buffer` (may be null) receives the running mean, `rgb8` (may be null) the top-down sRGB8 picture
+    size_t update_progressive(const Params& params, const Camera& camera, uint32_t frame_num, float* buffer, uint8_t* rgb8) const;
     PtScene* handle() const { return scene_; }
     size_t len() const { return n_spheres_; }
 
@@ -219,6 +225,8 @@ struct Params {
     Xoshiro256Plus new_rng() const;
     std::unique_ptr<Scene> new_scene(Xoshiro256Plus& rng, const Storage& storage, std::vector<Hitable> hitables,
                                      std::optional<Vec3> sky, int device = 0) const;
+    std::unique_ptr<Scene> new_scene(Xoshiro256Plus& rng, const Storage& storage, std::vector<Hitable> hitables,
+                                     std::optional<Vec3> sky, const std::vector<int>& devices, const PtOptions* options = nullptr) const;
     PtParams to_ffi() const;
 };
 
@@ -235,6 +243,10 @@ namespace offline {
 // src/offline.rs:16-60.  Returns (elapsed seconds, ray count); writes `output_png` unless empty.
 std::pair<double, size_t> render_offline(const std::string& preset, const Params& params, const std::string& output_png = "output.png",
                                          int device = 0);
+// the same over a list of GPUs (`-G 0-7`), and `frames` > 1 = the progressive loop of the windowed mode run headless
+// (frame_num = 0 .. frames-1 accumulated on the device, glium_window.rs:98-131)
+std::pair<double, size_t> render_offline(const std::string& preset, const Params& params, const std::string& output_png,
+                                         const std::vector<int>& devices, uint32_t frames = 1);
 }  // namespace offline
 
 void linear_to_srgb8_image(const Scene& scene, const float* rgb, uint32_t width, uint32_t height, std::vector<uint8_t>& out);

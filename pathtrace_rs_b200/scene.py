@@ -91,10 +91,16 @@ class Preset:
                     camera=cam24, has_sky=int(has_sky), sky=sky,
                     next_f32=float(self._L.pth_preset_next_f32(self._h)))
 
-    def create_scene(self, device=0):
-        if self._L.pth_scene_create(self._h, device) != 0:
+    def create_scene(self, device=0, options=None):
+        """params.new_scene on one GPU (`device` an int) or replicated on several (`device` a list: the one `update` call
+        then splits the image over them by interleaved row tiles inside the library).  `options`: ffi.PtOptions or None."""
+        devices = [device] if isinstance(device, int) else list(device)
+        arr = (C.c_int32 * len(devices))(*devices)
+        opt_ref = C.byref(options) if options is not None else None
+        if self._L.pth_scene_create_multi(self._h, arr, len(devices), opt_ref) != 0:
             raise RuntimeError(self._L.pth_last_error().decode())
         self._has_scene = True
+        self.devices = devices
         return self
 
     @property
@@ -145,6 +151,29 @@ class Preset:
         ffi.check(ffi.libptgpu().pt_scene_stats(self.scene_handle, C.byref(st)))
         return st
 
+    def device_stats(self):
+        """Per-GPU statistics of the last render (one PtRenderStats per device of the scene)."""
+        L = ffi.libptgpu()
+        out = []
+        for i in range(L.pt_scene_device_count(self.scene_handle)):
+            st = ffi.PtRenderStats()
+            ffi.check(L.pt_scene_device_stats(self.scene_handle, i, C.byref(st)))
+            out.append(st)
+        return out
+
+    def debug_hits(self, rays6, times=None, mode=0, want_flagged=False):
+        """pt_debug_hits: nearest hit of caller-supplied unit-direction rays through the render kernel's own sweep
+        (mode 0) or through the exact test on every sphere (mode 1).  Returns (idx, t[, flagged])."""
+        rays6 = np.ascontiguousarray(rays6, np.float32).reshape(-1, 6)
+        n = rays6.shape[0]
+        idx = np.full(n, -2, np.int32)
+        t = np.zeros(n, np.float32)
+        flagged = np.zeros(n, np.uint32) if want_flagged else None
+        tm = np.ascontiguousarray(times, np.float32) if times is not None else None
+        ffi.check(ffi.libptgpu().pt_debug_hits(self.scene_handle, _vp(rays6), _vp(tm) if tm is not None else None, n, mode, _vp(idx), _vp(t),
+                                              _vp(flagged) if want_flagged else None))
+        return (idx, t, flagged) if want_flagged else (idx, t)
+
     def srgb8(self, rgb):
         h, w = rgb.shape[:2]
         out = np.zeros((h, w, 3), np.uint8)
@@ -185,11 +214,14 @@ def write_ppm(path, rgb8):
         f.write(rgb8.tobytes())
 
 
-def render_offline(preset, params, output_png="", device=0):
-    """offline::render_offline (src/offline.rs:16-60). Returns (seconds, ray_count)."""
+def render_offline(preset, params, output_png="", device=0, frames=1):
+    """offline::render_offline (src/offline.rs:16-60). `device`: an int or a list of GPUs; `frames` > 1 runs the
+    progressive loop headless.  Returns (seconds, ray_count)."""
     L = ffi.libpthost()
     secs, rays = C.c_double(0), C.c_uint64(0)
     pp = params.to_pth()
-    if L.pth_render_offline(preset.encode(), C.byref(pp), output_png.encode(), device, C.byref(secs), C.byref(rays)) != 0:
+    devices = [device] if isinstance(device, int) else list(device)
+    arr = (C.c_int32 * len(devices))(*devices)
+    if L.pth_render_offline_multi(preset.encode(), C.byref(pp), output_png.encode(), arr, len(devices), frames, C.byref(secs), C.byref(rays)) != 0:
         raise RuntimeError(L.pth_last_error().decode())
     return secs.value, int(rays.value)

@@ -71,6 +71,9 @@ def lib():
         L.orc_sphere_uv.argtypes = [C.c_float, C.c_float, C.c_float, C.c_void_p]
         L.orc_hit.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
         L.orc_bench_fixture_ray.argtypes = [C.POINTER(OrcParams), C.c_void_p]
+        L.orc_record_rays.restype = C.c_int64
+        L.orc_record_rays.argtypes = [C.c_void_p, C.POINTER(OrcParams), C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32]
+        L.orc_hit_times.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]
         L.orc_next_f32_after_random_spheres.restype = C.c_float
         L.orc_hw_threads.restype = C.c_int32
         L.orc_has_avx2.restype = C.c_int32
@@ -192,12 +195,24 @@ class Scene:
         rays = lib().orc_update(self.h, C.byref(p), frame_num, _p(buffer), mode, nthreads, r0, r1)
         return buffer, int(rays)
 
-    def hit(self, rays6, mode=HIT_LIST):
+    def hit(self, rays6, mode=HIT_LIST, times=None, nthreads=0):
+        """Nearest hit of explicit rays, t in (0.001, f32::MAX): (index in the sphere list or -1, t)."""
         rays6 = np.ascontiguousarray(rays6, np.float32).reshape(-1, 6)
         idx = np.zeros(len(rays6), np.int32)
         t = np.zeros(len(rays6), np.float32)
-        lib().orc_hit(self.h, mode, _p(rays6), len(rays6), _p(idx), _p(t))
+        tm = None if times is None else np.ascontiguousarray(times, np.float32)
+        lib().orc_hit_times(self.h, mode, _p(rays6), None if tm is None else _p(tm), len(rays6), _p(idx), _p(t), nthreads or (os.cpu_count() or 1))
         return idx, t
+
+    def record_rays(self, samples, max_depth, cap, pixels=None, frame_num=0, nthreads=0):
+        """Every ray `Scene::update` hands to the hit test for pixels [pixels[0], pixels[1]) (default: the whole image), in
+        trace order, with the rays' times: (rays6 [n, 6], times [n])."""
+        p = params(self.p.width, self.p.height, samples, max_depth)
+        p0, p1 = pixels if pixels is not None else (0, self.p.width * self.p.height)
+        rays = np.zeros((cap, 6), np.float32)
+        times = np.zeros(cap, np.float32)
+        n = lib().orc_record_rays(self.h, C.byref(p), frame_num, p0, p1, _p(rays), _p(times), cap, nthreads or (os.cpu_count() or 1))
+        return rays[:n], times[:n]
 
     def turb(self, x, y, z):
         return lib().orc_turb(self.h, x, y, z)

@@ -23,9 +23,9 @@ SOA_ITER = orc.HIT_SOA_SCALAR | 0x100  # SoA arithmetic, radiance accumulated fr
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
 
 
-def gpu_render(preset, w, h, spp, depth, frame=0, buffer=None, part=None, **kw):
+def gpu_render(preset, w, h, spp, depth, frame=0, buffer=None, part=None, options=None, **kw):
     params = pt.Params(w, h, spp, depth, **kw)
-    pr = pt.Preset(preset, params).create_scene(0)
+    pr = pt.Preset(preset, params).create_scene(0, options)
     img, rays = pr.update(params, frame_num=frame, buffer=buffer, part=part)
     return img, rays, pr
 
@@ -83,7 +83,7 @@ def test_random_preset_moving_spheres_vs_oracle():
     still, _, _ = gpu_render("random_spheres", w, h, spp, depth)
     assert np.mean(np.abs(img - still)) > 1e-3
     # the LDS-streamed kernel takes the same path
-    st, st_rays, _ = _with_env("PTGPU_FORCE_STREAM_TILE_BLOCKS", "16", lambda: gpu_render("random", w, h, spp, depth))
+    st, st_rays, _ = gpu_render("random", w, h, spp, depth, options=pt.PtOptions(force_stream_tile_blocks=16))
     assert st_rays == rays and np.array_equal(st, img)
 
 
@@ -263,27 +263,18 @@ def test_random_seed_mode_uses_the_salt():
 
 
 # ---- chunk queue: samples handed out in chunks through the pixel-state table (pt_megakernel.cuh, lane_refill) ------------
-def _with_env(name, value, fn):
-    old = os.environ.get(name)
-    os.environ[name] = value
-    try:
-        return fn()
-    finally:
-        if old is None:
-            del os.environ[name]
-        else:
-            os.environ[name] = old
+WHOLE_PIXELS = dict(chunk_samples=-1)  # PtOptions: one ticket per pixel, the reference's unit of work (scene.rs:90-93)
 
 
-@pytest.mark.parametrize("chunk", ["1", "2", "8", "64"])
+@pytest.mark.parametrize("chunk", [1, 2, 8, 64])
 def test_chunk_queue_is_bit_exact_for_any_chunk_size(chunk):
     """A pixel's RNG state and colour sum travel through global memory between chunks; the image and the ray count must
     not change by a bit, whatever the chunk size (0 = whole pixels, the reference's unit of work, scene.rs:90-93).
     spp = 21 is not a multiple of any chunk size; 96x54 pixels on >100k lanes makes every later chunk wait for its
     predecessor, which exercises the parked-lane path hard."""
     w, h, spp, depth = 96, 54, 21, 50
-    whole, rays_whole, _ = _with_env("PTGPU_CHUNK_SAMPLES", "0", lambda: gpu_render("random_spheres", w, h, spp, depth))
-    img, rays, _ = _with_env("PTGPU_CHUNK_SAMPLES", chunk, lambda: gpu_render("random_spheres", w, h, spp, depth))
+    whole, rays_whole, _ = gpu_render("random_spheres", w, h, spp, depth, options=pt.PtOptions(**WHOLE_PIXELS))
+    img, rays, _ = gpu_render("random_spheres", w, h, spp, depth, options=pt.PtOptions(chunk_samples=chunk))
     assert rays == rays_whole and np.array_equal(img, whole)
     ref, ref_rays = orc.Scene("random_spheres", w, h).update(spp, depth, mode=SOA_ITER)
     assert rays == ref_rays and np.mean(np.all(img == ref, axis=2)) >= 0.999
@@ -292,7 +283,7 @@ def test_chunk_queue_is_bit_exact_for_any_chunk_size(chunk):
 def test_chunk_queue_default_engages_on_large_images_and_blends_frames():
     """Default policy: >= 2 pixels per lane -> chunks of >= 8 samples.  640x400 = 256k pixels on <= 113 664 lanes."""
     w, h, spp, depth = 640, 400, 24, 50
-    whole, rays_whole, _ = _with_env("PTGPU_CHUNK_SAMPLES", "0", lambda: gpu_render("random_spheres", w, h, spp, depth))
+    whole, rays_whole, pr_whole = gpu_render("random_spheres", w, h, spp, depth, options=pt.PtOptions(**WHOLE_PIXELS))
     params = pt.Params(w, h, spp, depth)
     pr = pt.Preset("random_spheres", params).create_scene(0)
     img, rays = pr.update(params)
@@ -300,27 +291,21 @@ def test_chunk_queue_default_engages_on_large_images_and_blends_frames():
     # a second frame over the same scene object (state table re-zeroed), blended, vs whole-pixel scheduling
     buf_a, buf_b = img.copy(), whole.copy()
     pr.update(params, frame_num=1, buffer=buf_a)
-    _with_env("PTGPU_CHUNK_SAMPLES", "0", lambda: pr.update(params, frame_num=1, buffer=buf_b))
+    pr_whole.update(params, frame_num=1, buffer=buf_b)
     assert np.array_equal(buf_a, buf_b)
 
 
 def test_chunk_queue_with_partition_and_streamed_kernel():
     w, h, spp, depth = 80, 45, 12, 10
-    whole, rays_whole, pr = _with_env("PTGPU_CHUNK_SAMPLES", "0", lambda: gpu_render("random_spheres", w, h, spp, depth))
-
-    def parts():
-        out = np.full((h, w, 3), -1.0, np.float32)
-        total = 0
-        for idx in range(3):
-            _, r = pr.update(pt.Params(w, h, spp, depth), buffer=out, part=ffi.PtPartition(5, idx, 3, 0))
-            total += r
-        return out, total
-    img, rays = _with_env("PTGPU_CHUNK_SAMPLES", "4", parts)
+    whole, rays_whole, _ = gpu_render("random_spheres", w, h, spp, depth, options=pt.PtOptions(**WHOLE_PIXELS))
+    pr = pt.Preset("random_spheres", pt.Params(w, h, spp, depth)).create_scene(0, pt.PtOptions(chunk_samples=4))
+    img = np.full((h, w, 3), -1.0, np.float32)
+    rays = 0
+    for idx in range(3):
+        _, r = pr.update(pt.Params(w, h, spp, depth), buffer=img, part=ffi.PtPartition(5, idx, 3, 0))
+        rays += r
     assert rays == rays_whole and np.array_equal(img, whole)
-
-    def streamed():
-        return _with_env("PTGPU_FORCE_STREAM_TILE_BLOCKS", "16", lambda: gpu_render("random_spheres", w, h, spp, depth))
-    st, rays_st, pr2 = _with_env("PTGPU_CHUNK_SAMPLES", "4", streamed)
+    st, rays_st, pr2 = gpu_render("random_spheres", w, h, spp, depth, options=pt.PtOptions(chunk_samples=4, force_stream_tile_blocks=16))
     assert pr2.stats().resident == 0 and rays_st == rays_whole and np.array_equal(st, whole)
 
 
@@ -329,12 +314,9 @@ def test_streamed_kernel_equals_resident_kernel():
     w, h, spp, depth = 64, 36, 4, 10
     res, rays_res, pr = gpu_render("random_spheres", w, h, spp, depth)
     assert pr.stats().resident == 1
-    os.environ["PTGPU_FORCE_STREAM_TILE_BLOCKS"] = "16"  # 488 spheres = 122 blocks -> 8 tiles, last one ragged
-    try:
-        st, rays_st, pr2 = gpu_render("random_spheres", w, h, spp, depth)
-        assert pr2.stats().resident == 0
-    finally:
-        del os.environ["PTGPU_FORCE_STREAM_TILE_BLOCKS"]
+    # 488 spheres = 122 blocks -> 8 tiles, last one ragged
+    st, rays_st, pr2 = gpu_render("random_spheres", w, h, spp, depth, options=pt.PtOptions(force_stream_tile_blocks=16))
+    assert pr2.stats().resident == 0
     assert rays_st == rays_res and np.array_equal(st, res)
 
 

@@ -27,7 +27,7 @@ def test_abi_symbols_exported():
     assert len(names) >= 15 and "pt_render" in names and "pt_scene_create" in names
     for n in names:
         assert hasattr(L, n), n
-    assert L.pt_abi_version() == 3
+    assert L.pt_abi_version() == 4
     out = subprocess.check_output(["nm", "-D", "--defined-only", os.path.join(ffi.LIB_DIR, "libptgpu.so")], text=True)
     exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
     assert set(names) <= exported
@@ -36,7 +36,7 @@ def test_abi_symbols_exported():
 def test_ctypes_layouts_match_compiled_structs():
     L = pt.libptgpu()
     structs = [ffi.PtParams, ffi.PtCamera, ffi.PtTexture, ffi.PtMaterial, ffi.PtPerlin, ffi.PtSceneDesc, ffi.PtPartition,
-               ffi.PtDeviceInfo, ffi.PtRenderStats, ffi.PtMotion, ffi.PtImage]
+               ffi.PtDeviceInfo, ffi.PtRenderStats, ffi.PtMotion, ffi.PtImage, ffi.PtOptions]
     for i, s in enumerate(structs):
         assert L.pt_abi_struct_size(i) == C.sizeof(s), s.__name__
     assert L.pt_abi_struct_size(99) == 0
@@ -55,9 +55,20 @@ def test_library_is_sm100a_cuda_with_packed_fp32_and_tma():
         assert mnemonic in sass, mnemonic
     import re
     kernels = re.split(r"Function : ", sass)
-    # The LDS kernels' sweep: broadcast LDS.128 of the pre-filter image (not generic loads, not local memory) feeding FFMA2.
-    for name in ("_ZN2pt22pt_megakernel_resident", "_ZN2pt22pt_megakernel_streamed"):  # mangled prefixes
-        body = [k for k in kernels if k.startswith(name)]
+    pick = lambda prefix: [k for k in kernels if k.startswith(prefix)]
+    # Resident kernel, parameter-image flavour (every preset of the reference): the sphere pairs are UNIFORM operands —
+    # LDCU.64 from the kernel parameters (constant bank 0, uniform index) feeding FFMA2 Rscalar(ray) * URpair(spheres) +
+    # Rpair.  ptxas only keeps this shape while the sweep's loop counter is provably uniform; if it ever falls back to LDC
+    # into vector registers the loop runs 1.7x slower (tools/probe_sweep2.cu), so the build is checked here, not on the GPU.
+    for motion in ("Lb0E", "Lb1E"):
+        body = pick("_ZN2pt22pt_megakernel_residentILb1E" + motion)
+        assert body, motion
+        assert len(re.findall(r"LDCU\.64 UR\d+, c\[0x0\]\[UR\d+", body[0])) >= 24, "uniform sphere loads lost"
+        assert len(re.findall(r"FFMA2 R\d+, R\d+(?:\.reuse)?\.F32, UR\d+\.F32x2\.HI_LO, ", body[0])) >= 96, "FFMA2 with uniform sphere pairs lost"
+    # LDS flavours (larger resident scenes, streamed scenes): broadcast LDS.128 of the pre-filter image (not generic loads,
+    # not local memory) feeding FFMA2 Rpair(spheres) * Rscalar(ray) + Rpair.
+    for name in ("_ZN2pt22pt_megakernel_residentILb0E", "_ZN2pt22pt_megakernel_streamed"):  # mangled prefixes
+        body = pick(name)
         assert body, name
         assert len(re.findall(r"LDS\.128", body[0])) >= 8, name + ": sweep loads are not LDS.128"
         assert len(re.findall(r"FFMA2 R\d+, R\d+(?:\.reuse)?\.F32x2\.HI_LO, R\d+(?:\.reuse)?\.F32, ", body[0])) >= 20, name + ": packed sweep lost"
@@ -134,18 +145,17 @@ def _desc_from_flat(cr, motion=None):
     return d, keep
 
 
-def _storage_order(cr, motion=None):
+def _storage_order(cr, motion=None, options=None):
     d, keep = _desc_from_flat(cr, motion)
     out = np.zeros(max(len(cr), 1), np.uint32)
-    mode = pt.libptgpu().pt_scene_storage_order(C.byref(d), out.ctypes.data_as(C.c_void_p), len(cr))
+    mode = pt.libptgpu().pt_scene_storage_order(C.byref(d), C.byref(options) if options is not None else None,
+                                                out.ctypes.data_as(C.c_void_p), len(cr))
     return int(mode), out[: len(cr)]
 
 
-def test_storage_order_is_a_permutation_with_large_spheres_first(monkeypatch):
+def test_storage_order_is_a_permutation_with_large_spheres_first():
     """pt_scene_storage_order (host only): what pt_scene_create does to the sphere list of a resident scene — large spheres
     first in list order, the rest along a Morton curve, exact duplicates in list order (equal-t ties stay with the first)."""
-    monkeypatch.delenv("PTGPU_SPATIAL_ORDER", raising=False)
-    monkeypatch.delenv("PTGPU_FORCE_STREAM_TILE_BLOCKS", raising=False)
     cr = orc.Scene("random_spheres", 200, 100).flat()["centre_radius"]
     n = len(cr)
     mode, order = _storage_order(cr)
@@ -168,20 +178,16 @@ def test_storage_order_is_a_permutation_with_large_spheres_first(monkeypatch):
     # compactness is the point: a 16-sphere group spans far less ground than a strip of the list
     extent = lambda o: np.mean([np.ptp(c[o[g:g + 16], 0]) + np.ptp(c[o[g:g + 16], 2]) for g in range(16, n - 15, 16)])
     assert extent(order) < 0.6 * extent(np.arange(n))
-    # duplicates keep their list order; tuning hook and the small-scene / streamed-scene rules
+    # duplicates keep their list order; explicit PtOptions and the small-scene / streamed-scene rules
     dup = np.vstack([cr, cr[7:8], cr[0:1]])
     _, o2 = _storage_order(dup)
     pos = {int(v): j for j, v in enumerate(o2)}
     assert pos[7] < pos[n] and pos[0] < pos[n + 1]
     assert _storage_order(cr[:40])[0] == 0 and _storage_order(cr[:40])[1].tolist() == list(range(40))
-    monkeypatch.setenv("PTGPU_SPATIAL_ORDER", "0")
-    assert _storage_order(cr)[0] == 0 and _storage_order(cr)[1].tolist() == list(range(n))
-    monkeypatch.setenv("PTGPU_SPATIAL_ORDER", "1")
-    assert _storage_order(cr)[0] == 1
-    monkeypatch.delenv("PTGPU_SPATIAL_ORDER")
-    monkeypatch.setenv("PTGPU_FORCE_STREAM_TILE_BLOCKS", "16")
-    assert _storage_order(cr)[0] == 0  # streamed scenes keep the caller's order
-    monkeypatch.delenv("PTGPU_FORCE_STREAM_TILE_BLOCKS")
+    listed = _storage_order(cr, options=pt.PtOptions(spatial_order=0))
+    assert listed[0] == 0 and listed[1].tolist() == list(range(n))
+    assert _storage_order(cr, options=pt.PtOptions(spatial_order=1))[0] == 1
+    assert _storage_order(cr, options=pt.PtOptions(force_stream_tile_blocks=16))[0] == 0  # streamed scenes keep the caller's order
     big = orc.Scene("stress100k", 64, 36).flat()["centre_radius"]
     assert _storage_order(big)[0] == 0
     # moving spheres are placed by the middle of their path

@@ -47,6 +47,22 @@ __global__ void k_mul2_ps(float* out, const float* in, int iters, float u0, floa
 __global__ void k_mul2_aa(float* out, const float* in, int iters, float u0, float u1) { PROLOG for (int it = 0; it < iters; ++it) {
 #pragma unroll
   for (int i = 0; i < CH; ++i) acc[i] = mul2(acc[i], acc[i]); } EPILOG }
+// round 2: forms for two rays per lane — sphere scalar x ray pair + acc pair
+__global__ void k_fma2_sPp(float* out, const float* in, int iters, float u0, float u1) { PROLOG for (int it = 0; it < iters; ++it) {
+#pragma unroll
+  for (int i = 0; i < CH; ++i) acc[i] = fma2(make_float2(s[i], s[i]), p[0], acc[i]); } EPILOG }   // scalar(distinct) * pair(shared by all chains) + pair
+__global__ void k_fma2_Psp(float* out, const float* in, int iters, float u0, float u1) { PROLOG for (int it = 0; it < iters; ++it) {
+#pragma unroll
+  for (int i = 0; i < CH; ++i) acc[i] = fma2(p[0], make_float2(s[i], s[i]), acc[i]); } EPILOG }   // same, pair in slot a
+__global__ void k_fma2_spp(float* out, const float* in, int iters, float u0, float u1) { PROLOG for (int it = 0; it < iters; ++it) {
+#pragma unroll
+  for (int i = 0; i < CH; ++i) acc[i] = fma2(make_float2(s[i], s[i]), p[i], acc[i]); } EPILOG }   // scalar * pair(distinct) + pair
+__global__ void k_fma2_sPs(float* out, const float* in, int iters, float u0, float u1) { PROLOG for (int it = 0; it < iters; ++it) {
+#pragma unroll
+  for (int i = 0; i < CH; ++i) acc[i] = fma2(make_float2(s[i], s[i]), p[0], make_float2(acc[i].x, acc[i].x)); } EPILOG }   // scalar * shared pair + scalar
+__global__ void k_fma2_sup(float* out, const float* in, int iters, float u0, float u1) { PROLOG for (int it = 0; it < iters; ++it) {
+#pragma unroll
+  for (int i = 0; i < CH; ++i) acc[i] = fma2(make_float2(s[i], s[i]), make_float2(u0, u1), acc[i]); } EPILOG }   // scalar * uniform pair + pair
 // scalar forms
 __global__ void k_ffma_rrr(float* out, const float* in, int iters, float u0, float u1) { PROLOG for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -86,6 +102,11 @@ int main() {
     run("FADD2 pair,pair", k_add2_pp, sms, d_out, d_in, CH, 2);
     run("FMUL2 pair,scal", k_mul2_ps, sms, d_out, d_in, CH, 2);
     run("FMUL2 a,a", k_mul2_aa, sms, d_out, d_in, CH, 2);
+    run("FFMA2 scal,PAIR*,pair", k_fma2_sPp, sms, d_out, d_in, CH, 2);
+    run("FFMA2 PAIR*,scal,pair", k_fma2_Psp, sms, d_out, d_in, CH, 2);
+    run("FFMA2 scal,pair,pair", k_fma2_spp, sms, d_out, d_in, CH, 2);
+    run("FFMA2 scal,PAIR*,scal", k_fma2_sPs, sms, d_out, d_in, CH, 2);
+    run("FFMA2 scal,unifpair,pair", k_fma2_sup, sms, d_out, d_in, CH, 2);
     run("FFMA r,r,r (x2)", k_ffma_rrr, sms, d_out, d_in, 2 * CH, 1);
     run("FFMA r,unif,r (x2)", k_ffma_rur, sms, d_out, d_in, 2 * CH, 1);
     run("FFMA a,a,r (x2)", k_ffma_rrr2, sms, d_out, d_in, 2 * CH, 1);
