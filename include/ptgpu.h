@@ -182,7 +182,8 @@ typedef struct PtOptions {
     int32_t spatial_order;            /* -1: automatic; 0: store spheres in the caller's order; 1: Morton order;
                                          2: large spheres first, then Morton order */
     uint32_t tile_rows;               /* multi-device scenes: rows per interleaved row tile (0 -> 4) */
-    uint32_t _pad;
+    uint32_t resident_kernel;         /* scenes of up to 2048 spheres: 0 automatic; 1 wavefront kernel (path pool + job
+                                         queues in shared memory); 2 two paths per lane in lockstep */
 } PtOptions;
 
 typedef struct PtScene PtScene; /* opaque: device copies of one scene on one or several GPUs */

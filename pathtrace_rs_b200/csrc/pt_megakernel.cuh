@@ -32,6 +32,7 @@ struct KernelArgs {
     const float4* prefilter;   // pre-filter image X,Y,Z,K per block (global copy; staged/streamed by the LDS kernels)
     const float4* kplane;      // K plane alone, one float4 per block (resident kernel with the X,Y,Z planes in its parameter image)
     int single_row;            // resident kernel: fewer pixels than lanes, only path row 0 takes work
+    int wave_pool;             // wavefront kernel: paths in the CTA's shared-memory pool
     int has_noise;
     DevCamera cam;
     uint32_t width, height, samples, max_depth, frame_num;
@@ -421,7 +422,11 @@ __device__ __forceinline__ void path_load(const uint32_t* __restrict__ rec, Lane
 #ifdef PT_PAIR_MIN_CTAS
 #define PT_PAIR_LAUNCH_BOUNDS __launch_bounds__(kCtaThreads, PT_PAIR_MIN_CTAS)
 #else
-#define PT_PAIR_LAUNCH_BOUNDS __launch_bounds__(kCtaThreads, 3)
+#define PT_PAIR_LAUNCH_BOUNDS __launch_bounds__(kCtaThreads, 768 / kCtaThreads)  // 24 warps per SM at 80 registers
+#endif
+// PT_TRIP_SYNC=1: the warps of a CTA start every trip together (one CTA barrier per trip)
+#ifndef PT_TRIP_SYNC
+#define PT_TRIP_SYNC 0
 #endif
 
 // shared-memory layout of the resident kernels:
@@ -441,8 +446,8 @@ struct ResidentSmem {
         state = reinterpret_cast<uint32_t*>(P + 1) + kQueueCap * kCtaThreads + threadIdx.x;
     }
     // where path row r keeps its ray.time (MotionCtx reads it on the rare paths)
-    __device__ __forceinline__ const volatile float* time_slot(int row) const {
-        return reinterpret_cast<const volatile float*>(state + 25 * kPathRows * kCtaThreads + row * kCtaThreads);
+    __device__ __forceinline__ const float* time_slot(int row) const {
+        return reinterpret_cast<const float*>(state + 25 * kPathRows * kCtaThreads + row * kCtaThreads);
     }
 };
 // stage the image with one TMA bulk copy (thread 0 issues, everyone waits on the mbarrier after the caller's own set-up)
@@ -460,11 +465,13 @@ __device__ __forceinline__ void resident_stage_begin(const KernelArgs& a, const 
 }
 
 // The sweep phase of one trip: both rays of the lane against the whole scene, nearest hits into hit_t / hit_index.
-// o/d: the two rays, already replaced by the parked ray for paths that are not in flight.
-template <bool CONSTIMG, bool MOTION>
-__device__ __forceinline__ void resident_sweep(const KernelArgs& a, const ConstImageT<CONSTIMG>& ci, const ResidentSmem<CONSTIMG>& sm, const MotionCtx& mc0,
-                                               const MotionCtx& mc1, const float (&ox)[2], const float (&oy)[2], const float (&oz)[2], const float (&dx)[2],
-                                               const float (&dy)[2], const float (&dz)[2], float (&hit_t)[2], int (&hit_index)[2], unsigned (&flagged)[2]) {
+// o/d: the two rays, already replaced by the parked ray for paths that are not in flight.  pf: the staged image (K plane
+// for CONSTIMG); queue: this lane's candidate queue, [QCAP][QSTRIDE threads].
+template <bool CONSTIMG, bool MOTION, int QSTRIDE, int QCAP>
+__device__ __forceinline__ void resident_sweep_core(const KernelArgs& a, const ConstImageT<CONSTIMG>& ci, const float4* __restrict__ pf, uint32_t* __restrict__ queue,
+                                                    const MotionCtx& mc0, const MotionCtx& mc1, const float (&ox)[2], const float (&oy)[2], const float (&oz)[2],
+                                                    const float (&dx)[2], const float (&dy)[2], const float (&dz)[2], float (&hit_t)[2], int (&hit_index)[2],
+                                                    unsigned (&flagged)[2]) {
     float o2x[2], o2y[2], o2z[2], nod[2], oo[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
@@ -476,9 +483,9 @@ __device__ __forceinline__ void resident_sweep(const KernelArgs& a, const ConstI
     }
     int cnt0 = 0, cnt1 = 0;
     int overflow[2] = {a.n_blocks, a.n_blocks};
-    sweep_two<CONSTIMG>(ci, sm.pf, a.n_blocks, sm.queue, cnt0, cnt1, dx, dy, dz, o2x, o2y, o2z, nod, oo, overflow);
-    sweep_drain_range<MOTION>(a.blocks, mc0, sm.queue, 0, cnt0, 0.5f * o2x[0], 0.5f * o2y[0], 0.5f * o2z[0], dx[0], dy[0], dz[0], hit_t[0], hit_index[0], flagged[0]);
-    sweep_drain_range<MOTION>(a.blocks, mc1, sm.queue, kQueueCap - cnt1, cnt1, 0.5f * o2x[1], 0.5f * o2y[1], 0.5f * o2z[1], dx[1], dy[1], dz[1], hit_t[1], hit_index[1], flagged[1]);
+    sweep_two<CONSTIMG, QSTRIDE, QCAP>(ci, pf, a.n_blocks, queue, cnt0, cnt1, dx, dy, dz, o2x, o2y, o2z, nod, oo, overflow);
+    sweep_drain_range<MOTION, QSTRIDE>(a.blocks, mc0, queue, 0, cnt0, 0.5f * o2x[0], 0.5f * o2y[0], 0.5f * o2z[0], dx[0], dy[0], dz[0], hit_t[0], hit_index[0], flagged[0]);
+    sweep_drain_range<MOTION, QSTRIDE>(a.blocks, mc1, queue, QCAP - cnt1, cnt1, 0.5f * o2x[1], 0.5f * o2y[1], 0.5f * o2z[1], dx[1], dy[1], dz[1], hit_t[1], hit_index[1], flagged[1]);
     if (min(overflow[0], overflow[1]) < a.n_blocks) {  // a queue overflowed (rare): one out-of-line pass per affected ray
 #pragma unroll 1
         for (int r = 0; r < 2; ++r) {
@@ -492,6 +499,12 @@ __device__ __forceinline__ void resident_sweep(const KernelArgs& a, const ConstI
             if (r) { hit_t[1] = ht; hit_index[1] = hi; flagged[1] += fl; } else { hit_t[0] = ht; hit_index[0] = hi; flagged[0] += fl; }
         }
     }
+}
+template <bool CONSTIMG, bool MOTION>
+__device__ __forceinline__ void resident_sweep(const KernelArgs& a, const ConstImageT<CONSTIMG>& ci, const ResidentSmem<CONSTIMG>& sm, const MotionCtx& mc0,
+                                               const MotionCtx& mc1, const float (&ox)[2], const float (&oy)[2], const float (&oz)[2], const float (&dx)[2],
+                                               const float (&dy)[2], const float (&dz)[2], float (&hit_t)[2], int (&hit_index)[2], unsigned (&flagged)[2]) {
+    resident_sweep_core<CONSTIMG, MOTION, kCtaThreads, kQueueCap>(a, ci, sm.pf, sm.queue, mc0, mc1, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
 }
 
 // CONSTIMG: X, Y, Z planes of the pre-filter image arrive as the kernel parameter `ci` (scenes of up to kMaxConstSpheres
@@ -546,7 +559,11 @@ __global__ void PT_PAIR_LAUNCH_BOUNDS pt_megakernel_resident(const __grid_consta
             hit_t[r] = kMaxT;
             hit_index[r] = -1;
         }
+#if PT_TRIP_SYNC
+        if (__syncthreads_and(fin ? 1 : 0)) break;  // every path of this CTA has run out of tickets
+#else
         if (__all_sync(kFullMask, fin)) break;  // every path of this warp has run out of tickets
+#endif
         const unsigned m0 = __ballot_sync(kFullMask, act[0]), m1 = __ballot_sync(kFullMask, act[1]);
         if ((m0 | m1) != 0u) {
             sweeps += (m0 != 0u ? 1u : 0u) + (m1 != 0u ? 1u : 0u);
@@ -600,7 +617,7 @@ __global__ void PT_PAIR_LAUNCH_BOUNDS pt_debug_hits_resident(const __grid_consta
                 ox[r] = ray[0]; oy[r] = ray[1]; oz[r] = ray[2]; dx[r] = ray[3]; dy[r] = ray[4]; dz[r] = ray[5];
                 if (a.dbg_times) time = a.dbg_times[i];
             }
-            *const_cast<volatile float*>(sm.time_slot(r)) = time;
+            *const_cast<float*>(sm.time_slot(r)) = time;
         }
         __syncwarp();
         resident_sweep<CONSTIMG, MOTION>(a, ci, sm, mc0, mc1, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
@@ -732,7 +749,7 @@ __global__ void PT_STREAM_LAUNCH_BOUNDS pt_megakernel_streamed(const __grid_cons
     volatile float* tslot = reinterpret_cast<volatile float*>(pend + kCtaThreads);  // [kCtaThreads] ray.time per lane
     *pend = 0u;
     *tslot = 0.0f;
-    const MotionCtx mc{a.motion, tslot, a.order};
+    const MotionCtx mc{a.motion, const_cast<const float*>(tslot), a.order};
     TileStream ts;
     ts.init(full_bar, empty_bar, smem_raw, tile_bytes);
     if (threadIdx.x == 0) cta_live = 0;
@@ -789,7 +806,7 @@ __global__ void PT_STREAM_LAUNCH_BOUNDS pt_debug_hits_streamed(const __grid_cons
     PerlinSmem* P = reinterpret_cast<PerlinSmem*>(smem_raw + 2 * (size_t)tile_bytes);
     uint32_t* queue = reinterpret_cast<uint32_t*>(P + 1) + threadIdx.x;
     volatile float* tslot = reinterpret_cast<volatile float*>(queue + kQueueCap * kCtaThreads + kCtaThreads);
-    const MotionCtx mc{a.motion, tslot, a.order};
+    const MotionCtx mc{a.motion, const_cast<const float*>(tslot), a.order};
     TileStream ts;
     ts.init(full_bar, empty_bar, smem_raw, tile_bytes);
     __syncthreads();

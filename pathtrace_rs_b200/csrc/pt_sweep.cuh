@@ -119,7 +119,8 @@ __device__ __forceinline__ float moving_sphere_hit_t(const DevMotion* __restrict
 // what the rare paths need to know about motion: the table and where this lane keeps its ray's time
 struct MotionCtx {
     const DevMotion* table;        // nullptr when the scene has no moving sphere
-    const volatile float* time;    // this lane's ray.time (shared memory slot)
+    const float* time;             // this path's ray.time (a shared-memory slot; NOT volatile: a volatile shared load in the
+                                   // re-test path makes ptxas drop the sweep's uniform operands, see pt_wave.cuh)
     const uint32_t* order;         // stored index -> position in the caller's sphere list (nullptr: identity)
 };
 
@@ -276,7 +277,7 @@ __device__ __forceinline__ void sweep_expanded(const float4* __restrict__ pf, in
 // Scenes whose image does not fit the parameter space (> kMaxConstSpheres) run the same two-ray loop with LDS.128
 // sphere pairs (CONSTIMG = false): each pair then serves four consecutive FFMA2 through the operand reuse cache (76-81 %).
 //
-// Queue: the lane's two rays share one queue of kQueueCap entries, ray 0 filling it from the front and ray 1 from the
+// Queue: the lane's two rays share one queue of QCAP entries ([entry][QSTRIDE threads]), ray 0 filling it from the front and ray 1 from the
 // back, so an entry needs no ray tag and each ray is drained with its own registers.  overflow[r] (initialised to n_blocks
 // by the caller) comes back as the first block of ray r's first flagged group that found the queue full.
 // =====================================================================================================
@@ -287,7 +288,7 @@ struct ConstImageT {
     float4 v[CONSTIMG ? 3 * kMaxConstBlocks : 1];  // per block of 4 spheres: X(cx0..3), Y, Z
 };
 
-template <bool CONSTIMG>
+template <bool CONSTIMG, int QSTRIDE, int QCAP>
 __device__ __forceinline__ void sweep_two(const ConstImageT<CONSTIMG>& ci, const float4* __restrict__ pf, int n_blocks, uint32_t* __restrict__ q, int& cnt0, int& cnt1,
                                           const float (&dx)[2], const float (&dy)[2], const float (&dz)[2], float (&o2x)[2], float (&o2y)[2],
                                           float (&o2z)[2], float (&nod)[2], float (&oo)[2], int (&overflow)[2]) {
@@ -342,9 +343,9 @@ __device__ __forceinline__ void sweep_two(const ConstImageT<CONSTIMG>& ci, const
                     mask = __funnelshift_l(__float_as_uint(d.x), mask, 1);
                 }
                 const uint32_t entry = (((uint32_t)j / kLdsGroupBlocks) << kLdsMaskBits) | mask;
-                if (cnt0 + cnt1 < kQueueCap) {
-                    const uint32_t slot = r == 0 ? (uint32_t)cnt0 : (uint32_t)(kQueueCap - 1 - cnt1);
-                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(qaddr + slot * (uint32_t)(kSweepThreads * 4)), "r"(entry) : "memory");
+                if (cnt0 + cnt1 < QCAP) {
+                    const uint32_t slot = r == 0 ? (uint32_t)cnt0 : (uint32_t)(QCAP - 1 - cnt1);
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(qaddr + slot * (uint32_t)(QSTRIDE * 4)), "r"(entry) : "memory");
                     if (r == 0) cnt0 += 1; else cnt1 += 1;
                 } else {
                     // queue full (rare): remember the first group that did not fit; the caller re-tests every sphere from
@@ -367,15 +368,15 @@ __device__ __forceinline__ void sweep_overflow(const float4* __restrict__ exact,
                                                         flagged);
 }
 
-// drain `cnt` queue entries starting at entry `first` (the lane's [entry][thread] queue), all lanes in parallel
-template <bool MOTION>
+// drain `cnt` queue entries starting at entry `first` (the lane's [entry][QSTRIDE threads] queue), all lanes in parallel
+template <bool MOTION, int QSTRIDE>
 __device__ __forceinline__ void sweep_drain_range(const float4* __restrict__ exact, const MotionCtx& mc, const uint32_t* __restrict__ q, int first, int cnt, float ox,
                                                   float oy, float oz, float dx, float dy, float dz, float& hit_t, int& hit_index, unsigned& flagged) {
-    uint32_t qaddr = (uint32_t)__cvta_generic_to_shared(q) + (uint32_t)first * (uint32_t)(kSweepThreads * 4);
+    uint32_t qaddr = (uint32_t)__cvta_generic_to_shared(q) + (uint32_t)first * (uint32_t)(QSTRIDE * 4);
     asm volatile("" : "+r"(qaddr));
-    const uint32_t qend = qaddr + (uint32_t)cnt * (uint32_t)(kSweepThreads * 4);
+    const uint32_t qend = qaddr + (uint32_t)cnt * (uint32_t)(QSTRIDE * 4);
 #pragma unroll 1
-    for (; qaddr != qend; qaddr += (uint32_t)(kSweepThreads * 4)) {
+    for (; qaddr != qend; qaddr += (uint32_t)(QSTRIDE * 4)) {
         uint32_t entry;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(entry) : "r"(qaddr) : "memory");
         sweep_resolve_entry<kLdsMaskBits, MOTION, true>(exact, mc, entry, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);

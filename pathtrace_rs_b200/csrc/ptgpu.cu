@@ -18,7 +18,7 @@
 #include <vector>
 
 #include "../../include/ptgpu.h"
-#include "pt_megakernel.cuh"
+#include "pt_wave.cuh"
 
 namespace {
 
@@ -82,6 +82,8 @@ struct Replica {
     float4* d_prefilter = nullptr;  // pre-filter image X,Y,Z,K per block (LDS kernels stage/stream it)
     float4* d_kplane = nullptr;     // its K plane alone (resident kernel with the X,Y,Z planes in the parameter image)
     bool const_image = false;       // resident kernel reads X,Y,Z through the kernel-parameter image
+    bool wave = false;              // ... in its wavefront form (pt_wave.cuh): one CTA per SM, wave_pool paths in shared memory
+    int wave_pool = 0;
     const pt::ConstImageT<true>* h_const_image = nullptr;  // owned by the PtScene; passed by value at every launch (24 KB)
     // per-render scratch.  At most one render is in flight per replica: every launch waits for the previous one's
     // event (ev_busy), whatever stream it was issued on, so the scratch below is never shared by two launches.
@@ -163,6 +165,25 @@ int plan_launch(Replica* s) {
         s->tile_blocks = s->n_blocks;
         s->n_tiles = 1;
         int rc;
+        if (s->const_image && s->opt.resident_kernel != 2) {
+            // wavefront kernel: everything that is left of the SM's shared memory becomes the path pool
+            const size_t fixed = (((size_t)s->n_blocks * 16 + 127) & ~(size_t)127) + sizeof(pt::PerlinSmem) + (size_t)pt::kWaveCandCap * pt::kWaveThreads * sizeof(uint32_t) + 64;
+            const size_t per_path = (size_t)pt::kWaveRecWords * 4 + pt::kWaveQueues * sizeof(uint16_t);
+            long pool = ((long)kMaxDynSmem - (long)fixed - (long)(pt::kWaveQueues * 64 * sizeof(uint16_t))) / (long)per_path;
+            pool = std::min<long>(pool / 64 * 64, pt::kWaveMaxPool / 64 * 64);
+            if (pool >= 2 * 64 * pt::kWaveWarps / 2) {  // at least 64 paths per warp
+                s->wave = true;
+                s->wave_pool = (int)pool;
+                s->smem_bytes = fixed + (size_t)pt::kWaveQueues * ((size_t)pool + 64) * sizeof(uint16_t) + (size_t)pool * pt::kWaveRecWords * 4;
+                PT_CUDA(cudaFuncSetAttribute(pt::pt_megakernel_wave<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+                PT_CUDA(cudaFuncSetAttribute(pt::pt_megakernel_wave<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes));
+                s->ctas_per_sm = 1;
+                // pt_debug_hits runs the lockstep kernel's sweep phase (same sweep_two / re-test code)
+                const size_t dbg_smem = resident_smem(s->n_blocks, true);
+                return s->d_motion ? configure_kernel(pt::pt_debug_hits_resident<true, true>, dbg_smem, nullptr)
+                                   : configure_kernel(pt::pt_debug_hits_resident<true, false>, dbg_smem, nullptr);
+            }
+        }
         if (s->const_image) {
             rc = s->d_motion ? configure_kernel(pt::pt_megakernel_resident<true, true>, s->smem_bytes, &s->ctas_per_sm)
                              : configure_kernel(pt::pt_megakernel_resident<true, false>, s->smem_bytes, &s->ctas_per_sm);
@@ -227,7 +248,7 @@ int normalise_options(const PtOptions* in, PtOptions* out) {
     if (in) {
         if (in->struct_size != sizeof(PtOptions)) return fail(PT_ERR_INVALID, "PtOptions.struct_size %u != %zu (ABI mismatch)", in->struct_size, sizeof(PtOptions));
         o = *in;
-        if (o.force_stream_tile_blocks < 0 || o.stream_ctas < 0 || o.stream_ctas > 4 || o.chunk_samples < -1 || o.spatial_order < -1 || o.spatial_order > 2)
+        if (o.force_stream_tile_blocks < 0 || o.stream_ctas < 0 || o.stream_ctas > 4 || o.chunk_samples < -1 || o.spatial_order < -1 || o.spatial_order > 2 || o.resident_kernel > 2)
             return fail(PT_ERR_INVALID, "PtOptions field out of range");
     }
     if (o.tile_rows == 0) o.tile_rows = 4;
@@ -345,10 +366,11 @@ int launch_update(Replica* s, const PtParams* params, const PtCamera* cam, uint3
     // an image with fewer pixels than the machine has lanes keeps one path per lane (latency, not throughput, is what
     // counts there) and the second row stays parked.
     const uint32_t max_ctas = (uint32_t)(s->sm_count * s->ctas_per_sm);
-    const uint32_t paths_per_cta = (uint32_t)pt::kCtaThreads * (s->resident ? pt::kPathRows : 1);
+    const uint32_t paths_per_cta = s->wave ? (uint32_t)s->wave_pool : (uint32_t)pt::kCtaThreads * (s->resident ? pt::kPathRows : 1);
+    a.wave_pool = s->wave_pool;
     uint32_t want = (a.n_owned_pixels + paths_per_cta - 1) / paths_per_cta;
     a.single_row = 0;
-    if (s->resident && (uint64_t)a.n_owned_pixels <= (uint64_t)max_ctas * pt::kCtaThreads) {
+    if (s->resident && !s->wave && (uint64_t)a.n_owned_pixels <= (uint64_t)max_ctas * pt::kCtaThreads) {
         a.single_row = 1;
         want = (a.n_owned_pixels + pt::kCtaThreads - 1) / pt::kCtaThreads;
     }
@@ -398,7 +420,10 @@ int launch_update(Replica* s, const PtParams* params, const PtCamera* cam, uint3
         PT_CUDA(cudaMemsetAsync(s->d_pixstate, 0, (size_t)a.n_owned_pixels * pt::kPixStateWords * sizeof(uint32_t), stream));
         a.pixstate = s->d_pixstate;
     }
-    if (s->resident) {
+    if (s->wave) {
+        if (s->d_motion) pt::pt_megakernel_wave<true><<<grid, pt::kWaveThreads, s->smem_bytes, stream>>>(a, *s->h_const_image);
+        else pt::pt_megakernel_wave<false><<<grid, pt::kWaveThreads, s->smem_bytes, stream>>>(a, *s->h_const_image);
+    } else if (s->resident) {
         if (s->const_image) {
             if (s->d_motion) pt::pt_megakernel_resident<true, true><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a, *s->h_const_image);
             else pt::pt_megakernel_resident<true, false><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a, *s->h_const_image);
@@ -416,7 +441,7 @@ int launch_update(Replica* s, const PtParams* params, const PtCamera* cam, uint3
     if (rc != PT_OK) return rc;
     s->stats.kernel_launches = 1;
     s->stats.grid_ctas = grid;
-    s->stats.cta_threads = pt::kCtaThreads;
+    s->stats.cta_threads = s->wave ? pt::kWaveThreads : pt::kCtaThreads;
     s->stats.smem_bytes = (uint32_t)s->smem_bytes;
     s->stats.resident = s->resident ? 1u : 0u;
     s->stats.n_spheres = s->n_spheres;
@@ -1282,10 +1307,11 @@ int pt_debug_hits(PtScene* sc, const float* rays6, const float* times, uint32_t 
             else pt::pt_debug_hits_exact_all<false><<<grid, 256, 0, s->stream>>>(a);
         } else if (rc == PT_OK && s->resident) {
             const uint32_t batch = (uint32_t)pt::kCtaThreads * pt::kPathRows;
-            const uint32_t grid = std::min<uint32_t>((n + batch - 1) / batch, max_ctas);
+            const uint32_t grid = std::min<uint32_t>((n + batch - 1) / batch, (uint32_t)s->sm_count * 2u);
             if (s->const_image) {
-                if (s->d_motion) pt::pt_debug_hits_resident<true, true><<<grid, pt::kCtaThreads, s->smem_bytes, s->stream>>>(a, *s->h_const_image);
-                else pt::pt_debug_hits_resident<true, false><<<grid, pt::kCtaThreads, s->smem_bytes, s->stream>>>(a, *s->h_const_image);
+                const size_t dbg_smem = resident_smem(s->n_blocks, true);
+                if (s->d_motion) pt::pt_debug_hits_resident<true, true><<<grid, pt::kCtaThreads, dbg_smem, s->stream>>>(a, *s->h_const_image);
+                else pt::pt_debug_hits_resident<true, false><<<grid, pt::kCtaThreads, dbg_smem, s->stream>>>(a, *s->h_const_image);
             } else {
                 const pt::ConstImageT<false> none{};
                 if (s->d_motion) pt::pt_debug_hits_resident<false, true><<<grid, pt::kCtaThreads, s->smem_bytes, s->stream>>>(a, none);

@@ -73,10 +73,10 @@ class PtPartition(C.Structure):
 
 class PtOptions(C.Structure):  # explicit launch options (ABI v4; replaces the environment hooks of v3)
     _fields_ = [("struct_size", C.c_uint32), ("force_stream_tile_blocks", C.c_int32), ("stream_ctas", C.c_int32),
-                ("chunk_samples", C.c_int32), ("spatial_order", C.c_int32), ("tile_rows", C.c_uint32), ("_pad", C.c_uint32)]
+                ("chunk_samples", C.c_int32), ("spatial_order", C.c_int32), ("tile_rows", C.c_uint32), ("resident_kernel", C.c_uint32)]
 
-    def __init__(self, force_stream_tile_blocks=0, stream_ctas=0, chunk_samples=0, spatial_order=-1, tile_rows=0):
-        super().__init__(C.sizeof(PtOptions), force_stream_tile_blocks, stream_ctas, chunk_samples, spatial_order, tile_rows, 0)
+    def __init__(self, force_stream_tile_blocks=0, stream_ctas=0, chunk_samples=0, spatial_order=-1, tile_rows=0, resident_kernel=0):
+        super().__init__(C.sizeof(PtOptions), force_stream_tile_blocks, stream_ctas, chunk_samples, spatial_order, tile_rows, resident_kernel)
 
 
 class PtDeviceInfo(C.Structure):

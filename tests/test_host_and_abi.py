@@ -60,9 +60,10 @@ def test_library_is_sm100a_cuda_with_packed_fp32_and_tma():
     # LDCU.64 from the kernel parameters (constant bank 0, uniform index) feeding FFMA2 Rscalar(ray) * URpair(spheres) +
     # Rpair.  ptxas only keeps this shape while the sweep's loop counter is provably uniform; if it ever falls back to LDC
     # into vector registers the loop runs 1.7x slower (tools/probe_sweep2.cu), so the build is checked here, not on the GPU.
-    for motion in ("Lb0E", "Lb1E"):
-        body = pick("_ZN2pt22pt_megakernel_residentILb1E" + motion)
-        assert body, motion
+    for name in ("_ZN2pt22pt_megakernel_residentILb1ELb0E", "_ZN2pt22pt_megakernel_residentILb1ELb1E",
+                 "_ZN2pt18pt_megakernel_waveILb0E", "_ZN2pt18pt_megakernel_waveILb1E"):
+        body = pick(name)
+        assert body, name
         assert len(re.findall(r"LDCU\.64 UR\d+, c\[0x0\]\[UR\d+", body[0])) >= 24, "uniform sphere loads lost"
         assert len(re.findall(r"FFMA2 R\d+, R\d+(?:\.reuse)?\.F32, UR\d+\.F32x2\.HI_LO, ", body[0])) >= 96, "FFMA2 with uniform sphere pairs lost"
     # LDS flavours (larger resident scenes, streamed scenes): broadcast LDS.128 of the pre-filter image (not generic loads,
