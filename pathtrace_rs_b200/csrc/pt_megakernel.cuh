@@ -33,6 +33,7 @@ struct KernelArgs {
     const float4* kplane;      // K plane alone, one float4 per block (resident kernel with the X,Y,Z planes in its parameter image)
     int single_row;            // resident kernel: fewer pixels than lanes, only path row 0 takes work
     int wave_pool;             // wavefront kernel: paths in the CTA's shared-memory pool
+    unsigned int* status;      // wavefront kernel: watchdog report (0 = clean), see pt_wave.cuh
     int has_noise;
     DevCamera cam;
     uint32_t width, height, samples, max_depth, frame_num;

@@ -1,5 +1,5 @@
 // pt_wave.cuh — the wavefront form of the resident kernel: one persistent CTA per SM, a pool of paths in shared memory,
-// warps as asynchronous workers that pull JOBS from per-category queues.
+// warps that trade paths through per-material queues so that every warp SHADES 32 paths of one kind.
 //
 // Why.  ncu of the two-paths-per-lane kernel (profiles/ncu_r2_v1_cfg2_*): the sweep loop is 58 % of the executed
 // instructions and runs with 32 of 32 lanes, everything else runs with 12.5 of 32 — after the sweep the 32 paths of a warp
@@ -9,14 +9,15 @@
 // barriers what the sort won; one barrier per trip in the two-path kernel costs 14 % (variant `sync1`).
 //
 // Here nothing waits for anything.  A path is a 112-byte record in the CTA's pool; a queue entry is a 16-bit slot index.
-//   SWEEP job   64 paths from the needs-sweep queue: sweep_two (uniform sphere operands, two rays per lane), exact re-tests,
-//               nearest hit into the record, then every path is filed under what it does next —
-//   SHADE job   32 paths of ONE category: lane_shade + lane_refill run convergent; paths with a new ray go back to the
-//               needs-sweep queue, paths whose pixel/ticket supply ended retire.
-// Queues are rings in shared memory guarded by one CTA-wide spin lock that lane 0 of a warp holds for a few dozen
-// instructions per job (a 64-ray sweep is ~10 000 clk).  A warp that finds no full batch takes the fullest partial one
-// unless other warps are still busy (they will refill the queues), so the CTA can never stall with work outstanding.
-// Every path still consumes exactly its own pixel's RNG stream and the same arithmetic: images are bit-identical.
+// A warp's cycle:
+//   SWEEP     its hand of <= 64 paths (two per lane): sweep_two with uniform sphere operands, exact re-tests, nearest hit
+//             into the record, every path classified by what it does next;
+//   EXCHANGE  one critical section: the 64 classified paths go into the category queues, two batches of <= 32 paths of ONE
+//             category each come out (round-robin over the categories that have a full batch);
+//   SHADE     each batch runs lane_shade + lane_refill convergent; the paths that have a ray afterwards are the next hand.
+// The pool holds 64 paths per warp plus a few hundred in the queues, which is what makes full single-category batches
+// available; one lock acquisition per warp per ~10 000-clk cycle keeps the lock idle.  Every path still consumes exactly its
+// own pixel's RNG stream and the same arithmetic: images are bit-identical to the lockstep kernels'.
 #pragma once
 #include "pt_megakernel.cuh"
 
@@ -30,18 +31,35 @@ constexpr int kWaveWarps = kWaveThreads / 32;
 constexpr int kWaveRecWords = 28;  // 7 x 16 bytes: the 112-byte stride spreads LDS.128 of random slots over all banks
 constexpr int kWaveMaxPool = 2048 - 64;
 constexpr int kWaveCandCap = 8;    // candidate-queue entries per lane, shared by its two rays (overflow: sweep_overflow)
-enum { WQ_SWEEP = 0, WQ_END = 1, WQ_LAMBERT = 2, WQ_LAMBERT_TEX = 3, WQ_METAL = 4, WQ_DIELECTRIC = 5, kWaveQueues = 6 };
-enum { WJ_NONE = -1, WJ_EXIT = -2 };
+enum { WQ_END = 0, WQ_LAMBERT = 1, WQ_LAMBERT_TEX = 2, WQ_METAL = 3, WQ_DIELECTRIC = 4, kWaveQueues = 5 };
 
 // record: r0,r1 = generator | r2 = origin, hit_t | r3 = direction, hit_index | r4 = throughput, ray.time |
 //         r5 = colour sum, px | r6 = py, sample, depth, flags
 struct WaveCtl {
-    unsigned lock;
-    unsigned head[kWaveQueues];
-    unsigned count[kWaveQueues];
-    int live;  // paths that have not retired
-    int busy;  // warps currently holding a job
+    unsigned tail[kWaveQueues];   // ring positions handed to producers (reserved with atomicAdd, monotone, taken modulo cap)
+    unsigned head[kWaveQueues];   // ring positions handed to consumers
+    int avail[kWaveQueues];       // published entries not yet claimed (a consumer claims by subtracting; may dip below 0 briefly)
+    unsigned rr;                  // round-robin start of the batch selection (racy on purpose: a hint)
+    int live;                     // paths that have not retired
+    unsigned abort;               // a watchdog fired: every warp leaves its loop, the host reports the launch as failed
+    unsigned int* status;         // global words the watchdog reports to (KernelArgs.status)
+    unsigned scratch[32];         // where lanes 1..31 aim their share of every atomic (see wave_atomic_add)
 };
+// Watchdogs.  The queues cannot deadlock by construction (a path is always in exactly one queue or in a warp's hand), but a
+// bug here would hang the GPU, so every wait is bounded: after ~seconds the warp records why, raises `abort`, and the whole
+// CTA drains out; the host turns a non-zero status word into PT_ERR_CUDA.
+enum { WAVE_LOST_ENTRY = 1, WAVE_STARVED = 2 };
+__device__ __forceinline__ void wave_abort(volatile WaveCtl* ctl, unsigned code) {
+    if (atomicOr(ctl->status, code) == 0u) {  // first report: a snapshot of the queue state for the host's error message
+        unsigned int* dbg = ctl->status;
+        dbg[1] = (unsigned)ctl->live;
+        dbg[2] = 0u;
+        for (int q = 0; q < kWaveQueues; ++q) dbg[3 + q] = (unsigned)ctl->avail[q];
+        dbg[8] = blockIdx.x;
+        dbg[9] = threadIdx.x;
+    }
+    ctl->abort = 1u;
+}
 
 struct WaveSmem {
     float4* kplane;
@@ -49,7 +67,7 @@ struct WaveSmem {
     uint32_t* cand;    // this lane's candidate queue: [kWaveCandCap][kWaveThreads]
     uint16_t* queues;  // [kWaveQueues][cap]
     uint4* pool;       // [pool_paths][7]
-    uint32_t cap;      // ring capacity of every job queue (>= pool_paths + 64)
+    uint32_t cap;      // ring capacity of every queue (>= pool_paths + 64)
     __device__ __forceinline__ WaveSmem(unsigned char* raw, const KernelArgs& a) {
         const uint32_t image_bytes = ((uint32_t)a.n_blocks * 16u + 127u) & ~127u;
         kplane = reinterpret_cast<float4*>(raw);
@@ -64,26 +82,16 @@ struct WaveSmem {
     __device__ __forceinline__ uint16_t* queue(int q) const { return queues + (size_t)q * cap; }
 };
 
-// The lock is taken by the WARP, and no lane does anything the others do not.  ptxas keeps the sweep's sphere operands in
-// uniform registers only while it can prove that the warp reaches the sweep converged, and (measured, CUDA 12.9) it gives
-// that up as soon as a lane-dependent branch with a side effect — `if (lane == 0) atomicCAS(..)`, `if (lane == 0) ctl->x = ..`
-// — sits on the path from the top of the job loop to the sweep; the loop then falls back to LDC into vector registers and
-// runs 1.7x slower.  So every lane executes the same instructions: the compare-and-swap of lanes 1..31 compares against a
-// value the lock never holds, the release is an AND with all ones for them, and the queue bookkeeping inside the critical
-// section is computed and stored redundantly by all 32 lanes (same values, same addresses).
-__device__ __forceinline__ void wave_lock(volatile WaveCtl* ctl, unsigned lane_id) {
-    for (unsigned spins = 0u;; ++spins) {
-        const unsigned old = atomicCAS(const_cast<unsigned*>(&ctl->lock), lane_id == 0u ? 0u : 0xffffffffu, 1u);
-        if (__ballot_sync(kFullMask, lane_id == 0u && old == 0u) != 0u) break;
-        if (spins > (1u << 26)) __trap();  // watchdog: a lost lock must end the launch with an error, not hang the GPU
-        __nanosleep(32);
-    }
-    __threadfence_block();
-}
-__device__ __forceinline__ void wave_unlock(volatile WaveCtl* ctl, unsigned lane_id) {
-    __threadfence_block();
-    __syncwarp();
-    atomicAnd(const_cast<unsigned*>(&ctl->lock), lane_id == 0u ? 0u : 0xffffffffu);
+// One atomic add on a control word on behalf of the warp; returns the old value to every lane.  No lane does anything the
+// others do not: ptxas keeps the sweep's sphere operands in uniform registers only while it can prove that the warp reaches
+// the sweep converged, and (measured, CUDA 12.9) it gives that up as soon as a lane-dependent branch with a side effect —
+// `if (lane == 0) atomicAdd(..)` — or a spin loop that a single lane executes is reachable in the warp's loop, even inside
+// an out-of-line callee; the sweep then falls back to LDC into vector registers and runs 1.7x slower.  So lanes 1..31 execute
+// the same atomic on a scratch word of their own with an increment of zero.
+__device__ __forceinline__ int wave_atomic_add(volatile WaveCtl* ctl, volatile void* word, int inc, unsigned lane_id) {
+    int* p = const_cast<int*>(lane_id == 0u ? reinterpret_cast<volatile int*>(word) : reinterpret_cast<volatile int*>(&ctl->scratch[lane_id]));
+    const int old = atomicAdd(p, lane_id == 0u ? inc : 0);
+    return __shfl_sync(kFullMask, old, 0);
 }
 
 __device__ __forceinline__ void wave_store(uint4* r, const Lane& L) {
@@ -124,95 +132,114 @@ __device__ __forceinline__ int wave_category(const KernelArgs& a, int hit_index,
     return WQ_END;  // DiffuseLight
 }
 
-// Take a job (warp-uniform result: every lane computes it): .x = queue to serve (or WJ_EXIT), .y = entries taken, .z = ring
-// position of the first one.  OUT OF LINE on purpose: with these spin loops inlined into the job loop ptxas stops keeping the
-// sweep's sphere operands in uniform registers (it can no longer prove that the warp reaches the sweep converged; measured
-// with CUDA 12.9: LDC into vector registers instead of LDCU, the loop 1.7x slower — tests/test_host_and_abi.py checks the
-// SASS).  A call is a convergence point it does understand.
-__device__ __noinline__ int4 wave_get_job(volatile WaveCtl* ctl, unsigned cap, unsigned lane_id, bool was_busy) {
-    unsigned tries = 0u;
-    int4 job = make_int4(WJ_NONE, 0, 0, 0);
-    for (unsigned spins = 0;; ++spins) {
-        const unsigned old = atomicCAS(const_cast<unsigned*>(&ctl->lock), lane_id == 0u ? 0u : 0xffffffffu, 1u);
-        if (__ballot_sync(kFullMask, lane_id == 0u && old == 0u) != 0u) {
-            __threadfence_block();
-            // fullest shading queue
-            int best = WQ_END;
-            unsigned best_n = ctl->count[WQ_END];
+// EXCHANGE: file the warp's hand (lane-level (slot, category) pairs, two per lane; category < 0: nothing) and take two
+// batches of up to 32 paths of one category each.  Returns {category A, n A, ring head A} in .x .y .z and B packed in .w as
+// category | n << 8 | head << 16 (the rings hold fewer than 65 536 entries); .x = -2: everything has retired, leave.
+//
+// Lock-free.  A queue is a ring of 16-bit slot indices (0xFFFF = empty) with three counters.  A producer reserves ring
+// positions with one atomicAdd on `tail`, writes its entries, fences, and publishes their NUMBER with an atomicAdd on
+// `avail`.  A consumer claims a number with an atomicAdd(-n) on `avail` (giving it back if it overdrew), takes the positions
+// with an atomicAdd on `head`, and — because two producers may publish out of order — waits for each of its positions to
+// turn non-empty before reading it and marking it empty again; that wait is a handful of instructions of another warp.
+// The ring is larger than the pool, so a reserved position has always been consumed.
+//
+// OUT OF LINE on purpose: with these loops inlined into the warp's loop ptxas stops keeping the sweep's sphere operands in
+// uniform registers (measured with CUDA 12.9: LDC into vector registers instead of LDCU, the sweep 1.7x slower —
+// tests/test_host_and_abi.py checks the SASS).  A call is a convergence point it does understand.
+constexpr uint16_t kWaveEmpty = 0xFFFFu;
+__device__ __noinline__ int4 wave_exchange(volatile WaveCtl* ctl, uint16_t* queues, unsigned cap, unsigned lane_id, int q0, uint32_t slot0, int q1, uint32_t slot1,
+                                           int retired) {
+    const unsigned below = (1u << lane_id) - 1u;
+    // ---- push ----
 #pragma unroll
-            for (int q = WQ_END + 1; q < kWaveQueues; ++q) {
-                const unsigned c = ctl->count[q];
-                if (c > best_n) {
-                    best_n = c;
-                    best = q;
+    for (int q = 0; q < kWaveQueues; ++q) {
+        const unsigned b0 = __ballot_sync(kFullMask, q0 == q), b1 = __ballot_sync(kFullMask, q1 == q);
+        const unsigned n0 = (unsigned)__popc(b0), n1 = (unsigned)__popc(b1);
+        if (n0 + n1 == 0u) continue;  // (a vote: warp-uniform)
+        const unsigned t = (unsigned)wave_atomic_add(ctl, &ctl->tail[q], (int)(n0 + n1), lane_id);
+        volatile uint16_t* ring = queues + (size_t)q * cap;
+        volatile uint16_t* e0 = ring + (t + (unsigned)__popc(b0 & below)) % cap;
+        volatile uint16_t* e1 = ring + (t + n0 + (unsigned)__popc(b1 & below)) % cap;
+        // a reserved position is normally long free (the ring is larger than the pool); if its last consumer has claimed it
+        // but not emptied it yet, wait for that
+        for (unsigned spins = 0u;; ++spins) {
+            const bool busy = (q0 == q && *e0 != kWaveEmpty) || (q1 == q && *e1 != kWaveEmpty);
+            if (__ballot_sync(kFullMask, busy) == 0u) break;
+            if (spins > (1u << 24)) wave_abort(ctl, WAVE_LOST_ENTRY);
+            if (ctl->abort != 0u) break;
+        }
+        if (q0 == q) *e0 = (uint16_t)slot0;
+        if (q1 == q) *e1 = (uint16_t)slot1;
+        __threadfence_block();
+        __syncwarp();
+        wave_atomic_add(ctl, &ctl->avail[q], (int)(n0 + n1), lane_id);
+    }
+    if (retired != 0) wave_atomic_add(ctl, &ctl->live, -retired, lane_id);
+    // ---- pop two batches: a category with a full batch, round-robin; else the fullest one ----
+    int cat[2] = {-1, -1};
+    unsigned n[2] = {0u, 0u}, h[2] = {0u, 0u};
+    unsigned rr = ctl->rr;
+    for (unsigned tries = 0u;; ++tries) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            if (n[k] != 0u) continue;
+            int pick = -1, best = 0;
+#pragma unroll
+            for (int i = 0; i < kWaveQueues; ++i) {
+                const int q = (int)((rr + (unsigned)i) % (unsigned)kWaveQueues);
+                const int c = ctl->avail[q];
+                const int score = c >= 32 ? 1000 - i : c;  // first full batch in round-robin order, else the fullest
+                if (score > best) {
+                    best = score;
+                    pick = q;
                 }
             }
-            const unsigned ns = ctl->count[WQ_SWEEP];
-            int busy = ctl->busy - (was_busy ? 1 : 0);
-            was_busy = false;
-            int pick = WJ_NONE;
-            if (best_n >= 32u) pick = best;                 // a full, convergent shading batch: short, and it feeds the sweep queue
-            else if (ns >= 64u) pick = WQ_SWEEP;            // a full sweep
-            else if (ns + best_n != 0u && (busy == 0 || tries >= 4u)) pick = (ns * 32u >= best_n * 64u) ? WQ_SWEEP : best;  // nobody will add to the queues, or waited long enough: the fuller partial batch
-            else if (ns + best_n == 0u && busy == 0 && ctl->live == 0) pick = WJ_EXIT;
-            // (unconditional stores: `pick` is warp-uniform, but ptxas cannot know that, and a store under a branch it takes
-            // for divergent costs the sweep its uniform registers)
-            const int qi = pick >= 0 ? pick : 0;
-            const unsigned have = ctl->count[qi];
-            const unsigned h = ctl->head[qi];
-            const int cnt = pick >= 0 ? (int)min(have, pick == WQ_SWEEP ? 64u : 32u) : 0;
-            busy += pick >= 0 ? 1 : 0;
-            __syncwarp();  // all lanes have read the old values
-            ctl->head[qi] = (h + (unsigned)cnt) % cap;
-            ctl->count[qi] = have - (unsigned)cnt;
-            ctl->busy = busy;
-            wave_unlock(ctl, lane_id);
-            job = make_int4(pick, cnt, (int)h, 0);
-            tries += 1u;
-            if (__ballot_sync(kFullMask, pick != WJ_NONE) != 0u) break;
-            __nanosleep(200);
-        } else {
-            __nanosleep(32);
+            if (__ballot_sync(kFullMask, pick >= 0) == 0u) continue;
+            const int seen = ctl->avail[pick];
+            const int want = min(max(seen, 1), 32);
+            const int old = wave_atomic_add(ctl, &ctl->avail[pick], -want, lane_id);
+            if (old < want) {  // somebody else was faster: give it back and look again
+                wave_atomic_add(ctl, &ctl->avail[pick], want, lane_id);
+                continue;
+            }
+            cat[k] = pick;
+            n[k] = (unsigned)want;
+            h[k] = (unsigned)wave_atomic_add(ctl, &ctl->head[pick], want, lane_id) % cap;
+            rr = (unsigned)pick + 1u;
         }
-        if (spins > (1u << 26)) __trap();  // watchdog (seconds): a lost lock, or queues empty with nobody busy and paths still alive
+        if (__ballot_sync(kFullMask, n[0] + n[1] != 0u) != 0u) break;
+        // empty-handed: either everything has retired, or the remaining paths are in other warps' hands — wait for them
+        if (ctl->live == 0 || ctl->abort != 0u) {  // (`live` only ever falls: 0 is final)
+            cat[0] = -2;
+            break;
+        }
+        if (tries > (1u << 21)) wave_abort(ctl, WAVE_STARVED);
+        __nanosleep(1000);
     }
-    return job;
+    ctl->rr = rr % (unsigned)kWaveQueues;
+    return make_int4(cat[0], (int)n[0], (int)h[0], (cat[1] & 0xff) | (int)(n[1] << 8) | (int)(h[1] << 16));
 }
 
-// File this warp's paths: lane-level (slot, queue) pairs, up to two per lane (queue < 0: nothing).  One critical section.
-// Out of line for the same reason as wave_get_job.
-__device__ __noinline__ void wave_push2(volatile WaveCtl* ctl, const WaveSmem& sm, unsigned lane_id, int q0, uint32_t slot0, int q1, uint32_t slot1, int retired) {
-    unsigned b0[kWaveQueues], b1[kWaveQueues];
-#pragma unroll
-    for (int q = 0; q < kWaveQueues; ++q) {
-        b0[q] = __ballot_sync(kFullMask, q0 == q);
-        b1[q] = __ballot_sync(kFullMask, q1 == q);
+// the slot index in ring position (head + lane) of queue `cat`: waits for the producer's write, then frees the position
+__device__ __forceinline__ uint32_t wave_take_entry(volatile WaveCtl* ctl, uint16_t* queues, unsigned cap, int cat, unsigned head, bool valid, unsigned lane_id) {
+    volatile uint16_t* e = queues + (size_t)cat * cap + (head + lane_id) % cap;
+    uint16_t v = kWaveEmpty;
+    for (unsigned spins = 0u;; ++spins) {
+        if (valid && v == kWaveEmpty) v = *e;
+        if (__ballot_sync(kFullMask, valid && v == kWaveEmpty) == 0u) break;
+        if (spins > (1u << 24)) wave_abort(ctl, WAVE_LOST_ENTRY);
+        if (ctl->abort != 0u) break;
     }
-    wave_lock(ctl, lane_id);
-    unsigned tail = 0u;
-    if (lane_id < (unsigned)kWaveQueues) tail = (ctl->head[lane_id] + ctl->count[lane_id]) % sm.cap;
-    const unsigned below = (1u << lane_id) - 1u;
-#pragma unroll
-    for (int q = 0; q < kWaveQueues; ++q) {
-        const unsigned n0 = (unsigned)__popc(b0[q]), n1 = (unsigned)__popc(b1[q]);
-        if (n0 + n1 == 0u) continue;  // warp-uniform
-        const unsigned t = __shfl_sync(kFullMask, tail, q);
-        uint16_t* ring = sm.queue(q);
-        if (q0 == q) ring[(t + (unsigned)__popc(b0[q] & below)) % sm.cap] = (uint16_t)slot0;
-        if (q1 == q) ring[(t + n0 + (unsigned)__popc(b1[q] & below)) % sm.cap] = (uint16_t)slot1;
-        if (lane_id == 0u) ctl->count[q] += n0 + n1;
-    }
-    if (lane_id == 0u && retired != 0) ctl->live -= retired;
-    wave_unlock(ctl, lane_id);
+    if (valid) *e = kWaveEmpty;
+    return valid && v != kWaveEmpty ? (uint32_t)v : 0u;
 }
 
-// Second half of a SWEEP job, out of line (see wave_get_job): exact re-tests of the flagged spheres of the lane's two rays
-// (their origin and direction are read back from the records), nearest hits into the records, every path filed under what
-// it does next.  slot < 0: the lane has no path in that row.
+// Second half of the SWEEP, out of line (see wave_exchange): exact re-tests of the flagged spheres of the lane's two rays
+// (origin and direction are read back from the records), nearest hits into the records; returns what the two paths do next
+// (category of row 0 in the low byte, of row 1 in the next; 0xff = no path).  slot < 0: the lane has no path in that row.
 template <bool MOTION>
-__device__ __noinline__ void wave_sweep_finish(const KernelArgs& a, const WaveSmem& sm, volatile WaveCtl* ctl, unsigned lane_id, int slot0, int slot1, int cnt0,
-                                               int cnt1, int overflow0, int overflow1) {
-    int cat[2] = {-1, -1};
+__device__ __noinline__ unsigned wave_sweep_finish(const KernelArgs& a, const WaveSmem& sm, int slot0, int slot1, int cnt0, int cnt1, int overflow0, int overflow1) {
+    unsigned cats = 0xffffu;
 #pragma unroll 1
     for (int r = 0; r < 2; ++r) {
         const int slot = r ? slot1 : slot0;
@@ -230,42 +257,43 @@ __device__ __noinline__ void wave_sweep_finish(const KernelArgs& a, const WaveSm
         if (first < a.n_blocks) sweep_overflow<MOTION>(a.blocks, mc, first, a.n_blocks, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
         w[11] = __float_as_uint(hit_t);
         w[15] = (uint32_t)hit_index;
-        const int c = wave_category(a, hit_index, w[26]);
-        if (r) cat[1] = c; else cat[0] = c;
+        const unsigned c = (unsigned)wave_category(a, hit_index, w[26]);
+        cats = r ? ((cats & 0x00ffu) | (c << 8)) : ((cats & 0xff00u) | c);
     }
-    __syncwarp();
-    wave_push2(ctl, sm, lane_id, cat[0], (uint32_t)max(slot0, 0), cat[1], (uint32_t)max(slot1, 0), 0);
+    return cats;
 }
 
-// SHADE job: up to 32 paths of ONE category (queue `kind`), convergent.  Returns the number of rays traced (0 or 1 per lane).
-// Out of line: the job loop stays small enough for ptxas to keep the sweep in uniform registers (see wave_get_job).
+// SHADE: up to 32 paths of ONE category (ring entries [head, head + n) of queue `cat`), convergent.  Returns the slot the
+// lane now holds a ray for (next hand) or -1, plus 0x10000 if the lane traced a ray and 0x20000 if its path retired.
+// Out of line: the warp's loop stays small enough for ptxas to keep the sweep in uniform registers (see wave_exchange).
 template <bool MOTION>
-__device__ __noinline__ unsigned wave_shade_job(const KernelArgs& a, const WaveSmem& sm, volatile WaveCtl* ctl, unsigned lane_id, int kind, int n, unsigned head) {
+__device__ __noinline__ int wave_shade_batch(const KernelArgs& a, const WaveSmem& sm, volatile WaveCtl* ctl, unsigned lane_id, int cat, int n, unsigned head,
+                                             int& requeue_slot) {
     const bool valid = lane_id < (unsigned)n;
-    const uint32_t slot = valid ? sm.queue(kind)[(head + lane_id) % sm.cap] : 0u;
+    const uint32_t slot = wave_take_entry(ctl, sm.queues, sm.cap, cat, head, valid, lane_id);
     Lane L;
     lane_init(L);
     L.finished = true;  // lanes without a path take part in the collectives of lane_refill and nothing else
     float hit_t = kMaxT;
     int hit_index = -1;
-    unsigned rays = 0u;
+    int result = -1;
+    requeue_slot = -1;
     if (valid) wave_load(sm.rec(slot), L, hit_t, hit_index);
     if (L.active) {
-        rays = 1u;  // scene.rs:57
+        result = 0x10000;  // scene.rs:57: one more ray traced
         const MotionCtx mc{a.motion, nullptr, a.order};
         lane_shade<MOTION>(a, L, a.blocks, *sm.P, mc, hit_t, hit_index);
+    } else {
+        result = 0;
     }
     lane_refill<MOTION>(a, L, lane_id);
-    int q = -1, retired = 0;
     if (valid) {
         wave_store(sm.rec(slot), L);
-        if (L.active) q = WQ_SWEEP;          // a new ray (next bounce, or the next sample's camera ray)
-        else if (!L.finished) q = WQ_END;    // holds a ticket whose predecessor chunk is not published yet: ask again
-        else retired = 1;                    // no tickets left
+        if (L.active) result = (result & 0x10000) | (int)slot | 0x40000;  // a new ray (next bounce, or the next sample's camera ray)
+        else if (!L.finished) requeue_slot = (int)slot;                   // holds a ticket whose predecessor chunk is not published yet: ask again
+        else result |= 0x20000;                                           // no tickets left: the path retires
     }
-    const int n_retired = __popc(__ballot_sync(kFullMask, retired != 0));
-    wave_push2(ctl, sm, lane_id, q, slot, -1, 0u, n_retired);
-    return rays;
+    return result;
 }
 
 template <bool MOTION>
@@ -278,11 +306,17 @@ __global__ void __launch_bounds__(kWaveThreads, 1) pt_megakernel_wave(const __gr
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         fence_mbar_init();
-        ctl.lock = 0u;
-        for (int q = 0; q < kWaveQueues; ++q) ctl.head[q] = ctl.count[q] = 0u;
-        ctl.count[WQ_END] = (unsigned)a.wave_pool;  // every slot starts as a path that needs its first ticket
+        for (int q = 0; q < kWaveQueues; ++q) {
+            ctl.head[q] = ctl.tail[q] = 0u;
+            ctl.avail[q] = 0;
+        }
+        ctl.tail[WQ_END] = (unsigned)a.wave_pool;  // every slot starts as a path that needs its first ticket
+        ctl.avail[WQ_END] = a.wave_pool;
+        ctl.rr = 0u;
         ctl.live = a.wave_pool;
-        ctl.busy = 0;
+        ctl.abort = 0u;
+        ctl.status = a.status;
+        for (int i = 0; i < 32; ++i) ctl.scratch[i] = 0u;
     }
     __syncthreads();
     if (threadIdx.x == 0 && image_bytes != 0u) {
@@ -293,6 +327,8 @@ __global__ void __launch_bounds__(kWaveThreads, 1) pt_megakernel_wave(const __gr
     {
         Lane L;
         lane_init(L);
+        for (uint32_t i = threadIdx.x; i < kWaveQueues * sm.cap; i += kWaveThreads) sm.queues[i] = kWaveEmpty;
+        __syncthreads();
         for (uint32_t slot = threadIdx.x; slot < (uint32_t)a.wave_pool; slot += kWaveThreads) {
             wave_store(sm.rec(slot), L);
             sm.queue(WQ_END)[slot] = (uint16_t)slot;
@@ -304,33 +340,51 @@ __global__ void __launch_bounds__(kWaveThreads, 1) pt_megakernel_wave(const __gr
     const unsigned lane_id = threadIdx.x & 31u;
     unsigned long long rays = 0ULL;
     unsigned sweeps = 0u;
-    int4 job = wave_get_job(&ctl, sm.cap, lane_id, false);
+    // the hand: the path each lane holds in row 0 / row 1 (-1: none) and what it does next (category, < 0: nothing to file)
+    int slot[2] = {-1, -1}, cat[2] = {-1, -1}, retired = 0;
     for (;;) {
-        const int kind = job.x, n = job.y;
-        const unsigned head = (unsigned)job.z;
+        // ---- EXCHANGE ----
+        const int4 ex = wave_exchange(&ctl, sm.queues, sm.cap, lane_id, cat[0], (uint32_t)max(slot[0], 0), cat[1], (uint32_t)max(slot[1], 0), retired);
         // branch on VOTES: ptxas keeps the sweep's sphere operands in uniform registers only inside control flow it can prove
-        // warp-uniform.  The next job is fetched at the BOTTOM of the loop for the same reason (see wave_lock).
-        if (__ballot_sync(kFullMask, kind == WJ_EXIT) != 0u) break;
-        if (__ballot_sync(kFullMask, kind == WQ_SWEEP) != 0u) {
-            // ---- 64 rays: lane l carries entries l and l + 32 ----
-            float ox[2], oy[2], oz[2], dx[2], dy[2], dz[2];
-            uint32_t slot[2];
-            bool valid[2];
-            const uint16_t* ring = sm.queue(WQ_SWEEP);
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-                const unsigned i = lane_id + 32u * (unsigned)r;
-                valid[r] = i < (unsigned)n;
-                slot[r] = valid[r] ? ring[(head + i) % sm.cap] : 0u;
-                ox[r] = 0.0f; oy[r] = 1.0e18f; oz[r] = 0.0f;  // parked ray: never a candidate
-                dx[r] = dy[r] = dz[r] = 0.0f;
-                if (valid[r]) {
-                    const uint4 c = sm.rec(slot[r])[2], d = sm.rec(slot[r])[3];
-                    ox[r] = __uint_as_float(c.x); oy[r] = __uint_as_float(c.y); oz[r] = __uint_as_float(c.z);
-                    dx[r] = __uint_as_float(d.x); dy[r] = __uint_as_float(d.y); dz[r] = __uint_as_float(d.z);
-                }
+        // warp-uniform, and it knows that of a ballot
+        if (__ballot_sync(kFullMask, ex.x == -2) != 0u) break;
+        // ---- SHADE the two batches; the paths that come out with a ray are the next hand ----
+        retired = 0;
+#pragma unroll 1
+        for (int k = 0; k < 2; ++k) {
+            const int bc = k ? ((ex.w & 0xff) == 0xff ? -1 : (ex.w & 0xff)) : ex.x;
+            const int bn = k ? ((ex.w >> 8) & 0xff) : ex.y;
+            const unsigned bh = k ? ((unsigned)ex.w >> 16) : (unsigned)ex.z;
+            int keep = -1, requeue = -1;
+            if (bn > 0) {
+                const int res = wave_shade_batch<MOTION>(a, sm, &ctl, lane_id, bc, bn, bh, requeue);
+                rays += (res & 0x10000) ? 1ULL : 0ULL;
+                if (res & 0x40000) keep = res & 0xffff;
+                retired += __popc(__ballot_sync(kFullMask, (res & 0x20000) != 0)) * (lane_id == 0u ? 1 : 0);
             }
-            sweeps += 1u + (n > 32 ? 1u : 0u);
+            // a path without a ray that is still waiting for its pixel's previous chunk goes back to the END queue
+            const int s_ = keep >= 0 ? keep : requeue;
+            const int c_ = keep >= 0 ? -1 : (requeue >= 0 ? WQ_END : -1);
+            if (k) { slot[1] = s_; cat[1] = c_; } else { slot[0] = s_; cat[0] = c_; }
+        }
+        retired = __shfl_sync(kFullMask, retired, 0);
+        // ---- SWEEP the hand (paths with cat < 0 and slot >= 0 hold a ray) ----
+        float ox[2], oy[2], oz[2], dx[2], dy[2], dz[2];
+        bool valid[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            valid[r] = slot[r] >= 0 && cat[r] < 0;
+            ox[r] = 0.0f; oy[r] = 1.0e18f; oz[r] = 0.0f;  // parked ray: never a candidate
+            dx[r] = dy[r] = dz[r] = 0.0f;
+            if (valid[r]) {
+                const uint4 c = sm.rec((uint32_t)slot[r])[2], d = sm.rec((uint32_t)slot[r])[3];
+                ox[r] = __uint_as_float(c.x); oy[r] = __uint_as_float(c.y); oz[r] = __uint_as_float(c.z);
+                dx[r] = __uint_as_float(d.x); dy[r] = __uint_as_float(d.y); dz[r] = __uint_as_float(d.z);
+            }
+        }
+        const unsigned m0 = __ballot_sync(kFullMask, valid[0]), m1 = __ballot_sync(kFullMask, valid[1]);
+        if ((m0 | m1) != 0u) {
+            sweeps += (m0 != 0u ? 1u : 0u) + (m1 != 0u ? 1u : 0u);
             float o2x[2], o2y[2], o2z[2], nod[2], oo[2];
 #pragma unroll
             for (int r = 0; r < 2; ++r) {
@@ -341,11 +395,10 @@ __global__ void __launch_bounds__(kWaveThreads, 1) pt_megakernel_wave(const __gr
             int cnt0 = 0, cnt1 = 0;
             int overflow[2] = {a.n_blocks, a.n_blocks};
             sweep_two<true, kWaveThreads, kWaveCandCap>(ci, sm.kplane, a.n_blocks, sm.cand, cnt0, cnt1, dx, dy, dz, o2x, o2y, o2z, nod, oo, overflow);
-            wave_sweep_finish<MOTION>(a, sm, &ctl, lane_id, valid[0] ? (int)slot[0] : -1, valid[1] ? (int)slot[1] : -1, cnt0, cnt1, overflow[0], overflow[1]);
-        } else {
-            rays += wave_shade_job<MOTION>(a, sm, &ctl, lane_id, kind, n, head);
+            const unsigned cats = wave_sweep_finish<MOTION>(a, sm, valid[0] ? slot[0] : -1, valid[1] ? slot[1] : -1, cnt0, cnt1, overflow[0], overflow[1]);
+            if (valid[0]) cat[0] = (int)(cats & 0xffu);
+            if (valid[1]) cat[1] = (int)((cats >> 8) & 0xffu);
         }
-        job = wave_get_job(&ctl, sm.cap, lane_id, true);
     }
     flush_ray_count(a, rays, lane_id, sweeps);
 }

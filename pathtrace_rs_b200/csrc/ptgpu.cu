@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "../../include/ptgpu.h"
+#include "pt_regroup.cuh"
 #include "pt_wave.cuh"
 
 namespace {
@@ -83,6 +84,7 @@ struct Replica {
     float4* d_kplane = nullptr;     // its K plane alone (resident kernel with the X,Y,Z planes in the parameter image)
     bool const_image = false;       // resident kernel reads X,Y,Z through the kernel-parameter image
     bool wave = false;              // ... in its wavefront form (pt_wave.cuh): one CTA per SM, wave_pool paths in shared memory
+    bool regroup = false;           // resident scene rendered by the one-path-per-lane kernel with the CTA regroup (pt_regroup.cuh): the default
     int wave_pool = 0;
     const pt::ConstImageT<true>* h_const_image = nullptr;  // owned by the PtScene; passed by value at every launch (24 KB)
     // per-render scratch.  At most one render is in flight per replica: every launch waits for the previous one's
@@ -90,6 +92,7 @@ struct Replica {
     unsigned long long* d_ray_count = nullptr;  // [0] ray count
     unsigned long long* d_sweep_count = nullptr;  // warp-level sweeps of the last launch (lane-efficiency diagnostic)
     unsigned int* d_next_pixel = nullptr;
+    unsigned int* d_status = nullptr;  // wavefront kernel's watchdog word
     uint32_t* d_pixstate = nullptr;  // chunk queue: 12 words per owned pixel (pt_megakernel.cuh, PixState)
     size_t d_pixstate_pixels = 0;
     float* d_rgb = nullptr;  // device image for the host-buffer entry points
@@ -151,21 +154,35 @@ size_t resident_smem(int n_blocks, bool const_image) {
     const size_t image = ((size_t)n_blocks * (const_image ? 16 : 64) + 127) & ~(size_t)127;
     return image + sizeof(pt::PerlinSmem) + kQueueBytes + kPathBytes;
 }
+constexpr size_t kRegroupBytes = (size_t)pt::kRegroupWords * pt::kCtaThreads * sizeof(uint32_t) + 64;  // regroup kernel: path-state exchange + category counters
+size_t regroup_smem(int n_blocks) { return (size_t)n_blocks * 64 + kStreamedFixedBytes + kRegroupBytes; }
 bool fits_resident(int n_blocks, const PtOptions& opt) {
     if (opt.force_stream_tile_blocks > 0 && n_blocks > 0) return false;
-    return resident_smem(n_blocks, n_blocks <= pt::kMaxConstBlocks) <= kMaxDynSmem;
+    if (opt.resident_kernel == 0 || opt.resident_kernel == 4) return regroup_smem(n_blocks) <= kMaxDynSmem;
+    return resident_smem(n_blocks, n_blocks <= pt::kMaxConstBlocks && opt.resident_kernel != 3) <= kMaxDynSmem;
 }
 
 int plan_launch(Replica* s) {
     int forced_tile = s->opt.force_stream_tile_blocks;
     if (fits_resident(s->n_blocks, s->opt)) {
         s->resident = true;
-        s->const_image = s->n_blocks <= pt::kMaxConstBlocks;
+        s->const_image = s->n_blocks <= pt::kMaxConstBlocks && s->opt.resident_kernel != 3;
         s->smem_bytes = resident_smem(s->n_blocks, s->const_image);
         s->tile_blocks = s->n_blocks;
         s->n_tiles = 1;
         int rc;
-        if (s->const_image && s->opt.resident_kernel != 2) {
+        if (s->opt.resident_kernel == 0 || s->opt.resident_kernel == 4) {  // default: one path per lane + CTA regroup, the fastest measured
+            s->regroup = true;
+            s->const_image = false;
+            s->smem_bytes = regroup_smem(s->n_blocks);
+            rc = s->d_motion ? configure_kernel(pt::pt_megakernel_regroup<true>, s->smem_bytes, &s->ctas_per_sm)
+                             : configure_kernel(pt::pt_megakernel_regroup<false>, s->smem_bytes, &s->ctas_per_sm);
+            if (rc == PT_OK)
+                rc = s->d_motion ? configure_kernel(pt::pt_debug_hits_regroup<true>, s->smem_bytes, nullptr)
+                                 : configure_kernel(pt::pt_debug_hits_regroup<false>, s->smem_bytes, nullptr);
+            return rc;
+        }
+        if (s->const_image && s->opt.resident_kernel == 1) {
             // wavefront kernel: everything that is left of the SM's shared memory becomes the path pool
             const size_t fixed = (((size_t)s->n_blocks * 16 + 127) & ~(size_t)127) + sizeof(pt::PerlinSmem) + (size_t)pt::kWaveCandCap * pt::kWaveThreads * sizeof(uint32_t) + 64;
             const size_t per_path = (size_t)pt::kWaveRecWords * 4 + pt::kWaveQueues * sizeof(uint16_t);
@@ -248,7 +265,7 @@ int normalise_options(const PtOptions* in, PtOptions* out) {
     if (in) {
         if (in->struct_size != sizeof(PtOptions)) return fail(PT_ERR_INVALID, "PtOptions.struct_size %u != %zu (ABI mismatch)", in->struct_size, sizeof(PtOptions));
         o = *in;
-        if (o.force_stream_tile_blocks < 0 || o.stream_ctas < 0 || o.stream_ctas > 4 || o.chunk_samples < -1 || o.spatial_order < -1 || o.spatial_order > 2 || o.resident_kernel > 2)
+        if (o.force_stream_tile_blocks < 0 || o.stream_ctas < 0 || o.stream_ctas > 4 || o.chunk_samples < -1 || o.spatial_order < -1 || o.spatial_order > 2 || o.resident_kernel > 4)
             return fail(PT_ERR_INVALID, "PtOptions field out of range");
     }
     if (o.tile_rows == 0) o.tile_rows = 4;
@@ -347,6 +364,7 @@ int launch_update(Replica* s, const PtParams* params, const PtCamera* cam, uint3
     a.ray_count = d_ray_count;
     a.sweep_count = s->d_sweep_count;
     a.next_pixel = s->d_next_pixel;
+    a.status = s->d_status;
 
     int rc = validate_camera_domain(s, cam);
     if (rc != PT_OK) return rc;
@@ -356,6 +374,7 @@ int launch_update(Replica* s, const PtParams* params, const PtCamera* cam, uint3
     rc = serialise_begin(s, stream);
     if (rc != PT_OK) return rc;
     PT_CUDA(cudaMemsetAsync(s->d_next_pixel, 0, sizeof(unsigned int), stream));
+    PT_CUDA(cudaMemsetAsync(s->d_status, 0, 16 * sizeof(unsigned int), stream));
     PT_CUDA(cudaMemsetAsync(d_ray_count, 0, sizeof(unsigned long long), stream));
     PT_CUDA(cudaMemsetAsync(s->d_sweep_count, 0, sizeof(unsigned long long), stream));
     s->stats.kernel_launches = 0;
@@ -366,11 +385,11 @@ int launch_update(Replica* s, const PtParams* params, const PtCamera* cam, uint3
     // an image with fewer pixels than the machine has lanes keeps one path per lane (latency, not throughput, is what
     // counts there) and the second row stays parked.
     const uint32_t max_ctas = (uint32_t)(s->sm_count * s->ctas_per_sm);
-    const uint32_t paths_per_cta = s->wave ? (uint32_t)s->wave_pool : (uint32_t)pt::kCtaThreads * (s->resident ? pt::kPathRows : 1);
+    const uint32_t paths_per_cta = s->wave ? (uint32_t)s->wave_pool : (uint32_t)pt::kCtaThreads * (s->resident && !s->regroup ? pt::kPathRows : 1);
     a.wave_pool = s->wave_pool;
     uint32_t want = (a.n_owned_pixels + paths_per_cta - 1) / paths_per_cta;
     a.single_row = 0;
-    if (s->resident && !s->wave && (uint64_t)a.n_owned_pixels <= (uint64_t)max_ctas * pt::kCtaThreads) {
+    if (s->resident && !s->wave && !s->regroup && (uint64_t)a.n_owned_pixels <= (uint64_t)max_ctas * pt::kCtaThreads) {
         a.single_row = 1;
         want = (a.n_owned_pixels + pt::kCtaThreads - 1) / pt::kCtaThreads;
     }
@@ -420,7 +439,10 @@ int launch_update(Replica* s, const PtParams* params, const PtCamera* cam, uint3
         PT_CUDA(cudaMemsetAsync(s->d_pixstate, 0, (size_t)a.n_owned_pixels * pt::kPixStateWords * sizeof(uint32_t), stream));
         a.pixstate = s->d_pixstate;
     }
-    if (s->wave) {
+    if (s->regroup) {
+        if (s->d_motion) pt::pt_megakernel_regroup<true><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a);
+        else pt::pt_megakernel_regroup<false><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a);
+    } else if (s->wave) {
         if (s->d_motion) pt::pt_megakernel_wave<true><<<grid, pt::kWaveThreads, s->smem_bytes, stream>>>(a, *s->h_const_image);
         else pt::pt_megakernel_wave<false><<<grid, pt::kWaveThreads, s->smem_bytes, stream>>>(a, *s->h_const_image);
     } else if (s->resident) {
@@ -811,6 +833,7 @@ void destroy_replica(Replica* s) {
     cudaFree(s->d_ray_count);
     cudaFree(s->d_sweep_count);
     cudaFree(s->d_next_pixel);
+    cudaFree(s->d_status);
     cudaFree(s->d_pixstate);
     cudaFree(s->d_rgb);
     cudaFree(s->d_rgb8);
@@ -866,6 +889,7 @@ int create_replica(const FlatScene& fs, int device, const PtOptions& opt, Replic
     if (rc == PT_OK) cuda_ok(cudaMalloc(&s->d_ray_count, sizeof(unsigned long long)), "cudaMalloc");
     if (rc == PT_OK) cuda_ok(cudaMalloc(&s->d_sweep_count, sizeof(unsigned long long)), "cudaMalloc");
     if (rc == PT_OK) cuda_ok(cudaMalloc(&s->d_next_pixel, sizeof(unsigned int)), "cudaMalloc");
+    if (rc == PT_OK) cuda_ok(cudaMalloc(&s->d_status, 16 * sizeof(unsigned int)), "cudaMalloc");
     if (rc == PT_OK) cuda_ok(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking), "cudaStreamCreate");
     for (auto& e : s->ev)
         if (rc == PT_OK) cuda_ok(cudaEventCreate(&e), "cudaEventCreate");
@@ -903,10 +927,18 @@ int render_part_host(Replica* s, const PtParams* params, const PtCamera* camera,
     PT_CUDA(cudaEventRecord(s->ev[2], s->stream));
     rc = copy_owned_rows(s, params, part, rgb_inout, false, &d2h);
     if (rc != PT_OK) return rc;
-    unsigned long long rays = 0;
+    unsigned long long rays = 0, sweeps = 0;
     PT_CUDA(cudaMemcpyAsync(&rays, s->d_ray_count, sizeof(rays), cudaMemcpyDeviceToHost, s->stream));
+    PT_CUDA(cudaMemcpyAsync(&sweeps, s->d_sweep_count, sizeof(sweeps), cudaMemcpyDeviceToHost, s->stream));
+    unsigned int status_words[16] = {0};
+    PT_CUDA(cudaMemcpyAsync(status_words, s->d_status, sizeof(status_words), cudaMemcpyDeviceToHost, s->stream));
     PT_CUDA(cudaEventRecord(s->ev[3], s->stream));
     PT_CUDA(cudaStreamSynchronize(s->stream));
+    if (status_words[0] != 0)
+        return fail(PT_ERR_CUDA, "render kernel watchdog fired (code %u: %s; live %d, lock %u, queues %u %u %u %u %u, CTA %u thread %u): the image is incomplete",
+                    status_words[0], status_words[0] & 1u ? "lost queue lock" : "warp starved with paths outstanding", (int)status_words[1], status_words[2],
+                    status_words[3], status_words[4], status_words[5], status_words[6], status_words[7], status_words[8], status_words[9]);
+    s->stats.warp_sweeps = sweeps;
     float ms = 0;
     PT_CUDA(cudaEventElapsedTime(&ms, s->ev[0], s->ev[1]));
     s->stats.h2d_ms = ms;
@@ -960,10 +992,18 @@ int render_part_progressive(Replica* s, const PtParams* params, const PtCamera* 
             }
         }
     }
-    unsigned long long rays = 0;
+    unsigned long long rays = 0, sweeps = 0;
     PT_CUDA(cudaMemcpyAsync(&rays, s->d_ray_count, sizeof(rays), cudaMemcpyDeviceToHost, s->stream));
+    PT_CUDA(cudaMemcpyAsync(&sweeps, s->d_sweep_count, sizeof(sweeps), cudaMemcpyDeviceToHost, s->stream));
+    unsigned int status_words[16] = {0};
+    PT_CUDA(cudaMemcpyAsync(status_words, s->d_status, sizeof(status_words), cudaMemcpyDeviceToHost, s->stream));
     PT_CUDA(cudaEventRecord(s->ev[3], s->stream));
     PT_CUDA(cudaStreamSynchronize(s->stream));
+    if (status_words[0] != 0)
+        return fail(PT_ERR_CUDA, "render kernel watchdog fired (code %u: %s; live %d, lock %u, queues %u %u %u %u %u, CTA %u thread %u): the image is incomplete",
+                    status_words[0], status_words[0] & 1u ? "lost queue lock" : "warp starved with paths outstanding", (int)status_words[1], status_words[2],
+                    status_words[3], status_words[4], status_words[5], status_words[6], status_words[7], status_words[8], status_words[9]);
+    s->stats.warp_sweeps = sweeps;
     float ms = 0;
     PT_CUDA(cudaEventElapsedTime(&ms, s->ev[1], s->ev[2]));
     s->stats.kernel_ms = ms;
@@ -1013,6 +1053,7 @@ int for_each_replica(PtScene* sc, F fn, uint64_t* ray_count_out) {
         sc->stats.smem_bytes = st.smem_bytes;
         sc->stats.resident = st.resident;
         sc->stats.n_spheres = st.n_spheres;
+        sc->stats.warp_sweeps += st.warp_sweeps;
         total += rays[i];
     }
     sc->stats.ray_count = total;
@@ -1305,6 +1346,10 @@ int pt_debug_hits(PtScene* sc, const float* rays6, const float* times, uint32_t 
             const uint32_t grid = std::min<uint32_t>((n + 255u) / 256u, (uint32_t)s->sm_count * 8u);
             if (s->d_motion) pt::pt_debug_hits_exact_all<true><<<grid, 256, 0, s->stream>>>(a);
             else pt::pt_debug_hits_exact_all<false><<<grid, 256, 0, s->stream>>>(a);
+        } else if (rc == PT_OK && s->regroup) {
+            const uint32_t grid = std::min<uint32_t>((n + pt::kCtaThreads - 1) / pt::kCtaThreads, max_ctas);
+            if (s->d_motion) pt::pt_debug_hits_regroup<true><<<grid, pt::kCtaThreads, s->smem_bytes, s->stream>>>(a);
+            else pt::pt_debug_hits_regroup<false><<<grid, pt::kCtaThreads, s->smem_bytes, s->stream>>>(a);
         } else if (rc == PT_OK && s->resident) {
             const uint32_t batch = (uint32_t)pt::kCtaThreads * pt::kPathRows;
             const uint32_t grid = std::min<uint32_t>((n + batch - 1) / batch, (uint32_t)s->sm_count * 2u);

@@ -88,7 +88,7 @@ class PtRenderStats(C.Structure):
     _fields_ = [("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("ray_count", C.c_uint64),
                 ("n_spheres", C.c_uint32), ("kernel_launches", C.c_uint32), ("grid_ctas", C.c_uint32),
-                ("cta_threads", C.c_uint32), ("smem_bytes", C.c_uint32), ("resident", C.c_uint32)]
+                ("cta_threads", C.c_uint32), ("smem_bytes", C.c_uint32), ("resident", C.c_uint32), ("warp_sweeps", C.c_uint64)]
 
 
 class PthParams(C.Structure):

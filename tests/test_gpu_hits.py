@@ -71,13 +71,15 @@ def test_ten_million_recorded_rays_of_cfg1():
 
 
 def test_recorded_rays_through_every_kernel_flavour():
-    """The same rays through the LDS-operand resident kernel is covered by larger scenes below; here: the L2-streamed
-    kernel forced onto the 488-sphere scene (8 tiles, the last one ragged) and every storage order."""
+    """The same rays through every sweep the library has: the default resident kernel, the L2-streamed kernel forced onto
+    the 488-sphere scene (8 tiles, the last one ragged), every storage order, and the two-rays-per-lane sweeps with the
+    sphere pairs as uniform operands (kernel-parameter image) and as LDS.128 operands."""
     w, h = 96, 48
     sc = orc.Scene("random_spheres", w, h)
     rays, _ = sc.record_rays(16, 50, 400_000)
     base = None
-    for opt in (None, pt.PtOptions(force_stream_tile_blocks=16), pt.PtOptions(spatial_order=0), pt.PtOptions(spatial_order=1)):
+    for opt in (None, pt.PtOptions(force_stream_tile_blocks=16), pt.PtOptions(spatial_order=0), pt.PtOptions(spatial_order=1),
+                pt.PtOptions(resident_kernel=2), pt.PtOptions(resident_kernel=3), pt.PtOptions(resident_kernel=1)):
         pr = pt.Preset("random_spheres", pt.Params(w, h, 1, 50)).create_scene(0, opt)
         idx, t, _ = _check(pr, sc, rays)
         if base is not None:

@@ -309,6 +309,42 @@ def test_chunk_queue_with_partition_and_streamed_kernel():
     assert pr2.stats().resident == 0 and rays_st == rays_whole and np.array_equal(st, whole)
 
 
+# ---- the resident kernel flavours (PtOptions.resident_kernel) ---------------------------------------------------------
+@pytest.mark.parametrize("preset,w,h,spp", [("random_spheres", 160, 90, 12), ("random", 128, 64, 8), ("two_perlin_spheres", 96, 54, 8),
+                                             ("small", 64, 32, 16), ("smallpt", 48, 48, 8)])
+def test_resident_kernel_flavours_render_the_same_image(preset, w, h, spp):
+    """One path per lane + CTA regroup (the default), two paths per lane with uniform / shared-memory sphere operands, and
+    the wavefront form with its path pool and per-material queues: a path's RNG stream and arithmetic do not depend on which
+    lane, warp or kernel runs it, so all four must produce the same bits and the same ray count — also for a second,
+    blended frame and through a row partition."""
+    base, rays0, pr0 = gpu_render(preset, w, h, spp, 50)
+    assert pr0.stats().resident == 1
+    for flavour in (4, 3, 2, 1):
+        opt = pt.PtOptions(resident_kernel=flavour)
+        img, rays, pr = gpu_render(preset, w, h, spp, 50, options=opt)
+        assert rays == rays0 and np.array_equal(img, base), flavour
+        a, b = base.copy(), img.copy()
+        pr0.update(pt.Params(w, h, spp, 50), frame_num=3, buffer=a)
+        pr.update(pt.Params(w, h, spp, 50), frame_num=3, buffer=b)
+        assert np.array_equal(a, b), flavour
+        parts = np.full((h, w, 3), -1.0, np.float32)
+        total = 0
+        for idx in range(2):
+            _, r = pr.update(pt.Params(w, h, spp, 50), buffer=parts, part=ffi.PtPartition(3, idx, 2, 0))
+            total += r
+        assert total == rays0 and np.array_equal(parts, base), flavour
+
+
+def test_wavefront_kernel_on_a_large_image_with_the_chunk_queue():
+    """640x400 = 256 000 pixels on 148 x 1 600 pooled paths: the chunk queue engages (pixel state travels through global
+    memory between chunks, tickets of later chunks wait for their predecessors) inside the asynchronous wavefront kernel."""
+    w, h, spp, depth = 640, 400, 24, 50
+    whole, rays_whole, _ = gpu_render("random_spheres", w, h, spp, depth, options=pt.PtOptions(**WHOLE_PIXELS))
+    for flavour in (1, 2):
+        img, rays, _ = gpu_render("random_spheres", w, h, spp, depth, options=pt.PtOptions(resident_kernel=flavour))
+        assert rays == rays_whole and np.array_equal(img, whole), flavour
+
+
 # ---- scenes larger than shared memory: streamed kernel -------------------------------------------------------------
 def test_streamed_kernel_equals_resident_kernel():
     w, h, spp, depth = 64, 36, 4, 10

@@ -68,7 +68,7 @@ def test_library_is_sm100a_cuda_with_packed_fp32_and_tma():
         assert len(re.findall(r"FFMA2 R\d+, R\d+(?:\.reuse)?\.F32, UR\d+\.F32x2\.HI_LO, ", body[0])) >= 96, "FFMA2 with uniform sphere pairs lost"
     # LDS flavours (larger resident scenes, streamed scenes): broadcast LDS.128 of the pre-filter image (not generic loads,
     # not local memory) feeding FFMA2 Rpair(spheres) * Rscalar(ray) + Rpair.
-    for name in ("_ZN2pt22pt_megakernel_residentILb0E", "_ZN2pt22pt_megakernel_streamed"):  # mangled prefixes
+    for name in ("_ZN2pt21pt_megakernel_regroup", "_ZN2pt22pt_megakernel_residentILb0E", "_ZN2pt22pt_megakernel_streamed"):  # mangled prefixes
         body = pick(name)
         assert body, name
         assert len(re.findall(r"LDS\.128", body[0])) >= 8, name + ": sweep loads are not LDS.128"
