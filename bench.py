@@ -1,21 +1,24 @@
 #!/usr/bin/env python
 """bench.py — throughput of the path-tracing hot path (Scene::update) on B200, BASELINE.json's metric.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg2] [--partition samples|rows]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg4] [--partition rows|samples|samples-strong]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
+Default workload: BASELINE config 4, the north-star target (random_spheres 3840x2160, 4096 spp, depth 50), at every N.
 One "step" = one `Scene::update` of the workload (one frame of `samples` spp over the whole image).
   value   : Mrays/s, whole job, image resident in HBM (pt_render_device on torch's current stream, CUDA events).
-  e2e     : same metric through the reference-facing call with HOST buffers (N=1: the C++ Scene::update mirror ->
-            pt_render, pinned host accumulation buffer uploaded and downloaded every step, frame_num >= 1).
+  e2e     : same metric through the reference-facing call with a HOST buffer — ONE `Scene::update` mirror -> pt_render
+            call per step whatever N is (N > 1: a multi-device scene, the library fans out one host thread per GPU),
+            previous frame uploaded and result downloaded every step (frame_num >= 1).  Steps longer than 2 s: one e2e step.
   roofline: the megakernel against the FP32 FMA peak (this path is FP32-FMA bound, not HBM or tensor bound:
             16 flop per (ray, sphere) test x rays x spheres — SURVEY §8d / DESIGN.md).
   cpu_baseline: the CPU oracle (restated reference, list mode = the reference's live path) on the host cores,
             bounded sample, rank 0 at N=1 only.
-N > 1 (one process per GPU): default `--partition samples` is weak scaling — every rank renders the same image with
-its own frame seed (the reference's progressive-frame semantics, scene.rs:86-87,99-101) and one NCCL reduce
-forms the equal-weight mean; `--partition rows` is strong scaling of one frame by interleaved row tiles with no
-collective in the data path.
+N > 1 (one process per GPU): default `--partition rows` is STRONG scaling of one frame by interleaved row tiles with no
+collective in the data path (the image partitions by rows, north_star); `--partition samples` is weak scaling — every
+rank renders the same image with its own frame seed (the reference's progressive-frame semantics, scene.rs:86-87,99-101)
+and one NCCL reduce forms the equal-weight mean.
+  extras  : (N=1) one short run each of the other BASELINE configs so that every config has a driver-visible figure.
 """
 import argparse
 import json
@@ -116,7 +119,8 @@ def run_reference(args):
     sample = "%s at %d spp of %d (full resolution, list mode = live reference path, %d threads)" % (workload_name(args.workload, spp_full), spp, spp_full, cores)
     line = {
         "impl": "reference", "metric": "Mrays/s", "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True,
+        "scaling": "strong" if (args.gpus > 1 and args.partition != "samples") else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.workload, spp_full), "sample": sample},
         "samples_per_s": w * h * spp * args.steps / total,
@@ -158,17 +162,19 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--partition", default="samples", choices=["samples", "rows", "samples-strong"],
-                    help="N>1: samples = every rank renders the workload's full spp with its own frame seed (weak scaling); rows = one frame "
-                         "split by interleaved row tiles (strong); samples-strong = the workload's spp split into N frame seeds of spp/N (strong)")
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS),
+                    help="default cfg4 = the north-star target (random_spheres 3840x2160, 4096 spp, depth 50) at every N")
+    ap.add_argument("--partition", default="rows", choices=["rows", "samples", "samples-strong"],
+                    help="N>1: rows = ONE frame split by interleaved row tiles, no collective (strong scaling, the default); samples = every "
+                         "rank renders the workload's full spp with its own frame seed + one NCCL reduce (weak); samples-strong = the "
+                         "workload's spp split into N frame seeds of spp/N + one reduce (strong)")
     ap.add_argument("--spp", type=int, default=0, help="override samples per pixel (a reduced run is labelled as such)")
-    ap.add_argument("--ref-spp", type=int, default=2, help="--impl reference: spp of the bounded CPU sample per step")
+    ap.add_argument("--ref-spp", type=int, default=1, help="--impl reference: spp of the bounded CPU sample per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--fast", action="store_true", help="long workloads: the kernel-only and e2e legs run one step each without their own warm-up")
+    ap.add_argument("--no-extras", action="store_true", help="skip the short runs of the other BASELINE configs (N=1 only)")
+    ap.add_argument("--fast", action="store_true", help="the e2e leg runs one step without its own warm-up (automatic when a step exceeds 2 s)")
+    ap.add_argument("--resident-kernel", type=int, default=0, help="PtOptions.resident_kernel (0 = the library's default)")
     args = ap.parse_args()
-    if args.warmup < 3 and args.impl == "b200":
-        args.warmup = max(args.warmup, 0)  # the driver passes W; the contract asks for >= 3 and the default is 3
     if args.impl == "reference":
         return run_reference(args)
 
@@ -189,8 +195,6 @@ def main():
     dist = None
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     preset_name, w, h, spp, depth = WORKLOADS[args.workload]
@@ -204,7 +208,8 @@ def main():
             raise SystemExit("--partition samples-strong needs spp divisible by the number of GPUs")
         spp //= world  # each rank renders spp/N samples of every pixel with its own frame seed; one reduce forms the mean
     params = pt.Params(w, h, spp, depth)
-    preset = pt.Preset(preset_name, params).create_scene(local_rank)
+    options = pt.PtOptions(resident_kernel=args.resident_kernel) if args.resident_kernel else None
+    preset = pt.Preset(preset_name, params).create_scene(local_rank, options)
     n_spheres = len(preset)
     info = pt.device_info(local_rank)
 
@@ -257,45 +262,51 @@ def main():
         sampler.start()
     ms, rays, wall = timed_run(lambda i: step_device(frame_of(i)), args.warmup, args.steps)
     clocks = sampler.stop() if rank == 0 else None
+    step_ms = ms / max(1, args.steps)
+    long_steps = step_ms > 2000.0 or args.fast
 
-    # kernel-only time for the roofline: the same launch without the collective, CUDA events on the launching stream
-    k_ms, k_rays, _ = timed_run(lambda i: preset.update_device(params, frame_of(i), d_rgb.data_ptr(), d_rays.data_ptr(), stream.cuda_stream, part),
-                                0 if args.fast else 1, 1 if args.fast else max(1, min(args.steps, 3)))
-    k_steps = 1 if args.fast else max(1, min(args.steps, 3))
+    # kernel time for the roofline.  With row tiles (or one GPU) a step IS one megakernel launch between the two events, so
+    # the value leg's own events are the measurement; only the sample-slice modes (zero fill + NCCL reduce inside the step)
+    # time the bare launch separately.
+    if world > 1 and not rows_mode:
+        k_steps = 1 if long_steps else max(1, min(args.steps, 3))
+        k_ms, k_rays, _ = timed_run(lambda i: preset.update_device(params, frame_of(i), d_rgb.data_ptr(), d_rays.data_ptr(), stream.cuda_stream, part),
+                                    0 if long_steps else 1, k_steps)
+    else:
+        k_steps, k_ms, k_rays = args.steps, ms, rays
 
     # ---- end to end through the reference-facing call, host buffers ----------------------------------------------
-    pinned = torch.zeros((h, w, 3), dtype=torch.float32).pin_memory()
-    host_buf = pinned.numpy()
-    if world == 1:
-        def step_e2e(i):
-            _, r = preset.update(params, frame_num=1 + i, buffer=host_buf)  # Scene::update mirror -> pt_render: H2D + kernel + D2H
-            return r
-        h2d_b = d2h_b = w * h * 12
-        d2h_b += 8
-    else:
-        d_prev = torch.zeros_like(d_rgb) if (rank == 0 and not rows_mode) else None
-
-        def step_e2e(i):
-            if rows_mode:
-                # strong scaling of one progressive frame: every rank uploads the previous accumulation (its rows are the ones
-                # read), blends frame 1 + i into it and downloads
-                d_rgb.copy_(pinned, non_blocking=True)
-                preset.update_device(params, 1 + i, d_rgb.data_ptr(), d_rays.data_ptr(), stream.cuda_stream, part)
-                pinned.copy_(d_rgb, non_blocking=True)
-            else:
-                # sample slices: G new frames per step.  Rank 0 uploads the accumulation so far, all ranks render their
-                # frame seed, one reduce forms the mean of the G frames, rank 0 blends it in (running mean) and downloads.
-                if rank == 0:
-                    d_prev.copy_(pinned, non_blocking=True)
-                step_device(frame_of(i))
-                if rank == 0:
-                    torch.lerp(d_rgb, d_prev, float(i + 1) / float(i + 2), out=d_rgb)
-                    pinned.copy_(d_rgb, non_blocking=True)
-            return int(d_rays.item())
-        h2d_b = w * h * 12
-        d2h_b = w * h * 12 + 8
-    e_steps = 1 if args.fast else args.steps
-    e_ms, e_rays, e_wall = timed_run(step_e2e, 0 if args.fast else 1, e_steps)
+    # ONE call per step — `scene.update(&params, &camera, frame_num, &mut buffer)` (src/offline.rs:29) -> pt_render — whatever
+    # the number of GPUs: at N > 1 rank 0 owns a multi-device scene (pt_scene_create_multi over all N devices) and the library
+    # fans the call out to one host thread per GPU, each copying its rows from / into the caller's buffer; the other ranks
+    # wait at the barrier.  frame_num >= 1, so the previous accumulation is uploaded and the result downloaded every step.
+    # The buffer is registered with pt_host_register (the contract asks for pinned memory; a Rust caller's pageable Vec is
+    # measured beside it in `extras` at cfg2's size).
+    e_steps = 1 if long_steps else args.steps
+    host_img = np.zeros((h, w, 3), np.float32)
+    e_ms = e_rays = e_wall = 0.0
+    multi = None
+    if rank == 0:
+        L = pt.libptgpu()
+        import ctypes as C
+        pt.ffi.check(L.pt_host_register(host_img.ctypes.data_as(C.c_void_p), host_img.nbytes))
+        if world > 1:
+            multi = pt.Preset(preset_name, pt.Params(w, h, full_spp, depth)).create_scene(list(range(world)), options)
+        e2e_scene, e2e_params = (multi, pt.Params(w, h, full_spp, depth)) if world > 1 else (preset, params)
+    barrier()
+    if rank == 0:
+        if not long_steps:
+            e2e_scene.update(e2e_params, frame_num=1, buffer=host_img)
+        t0 = time.perf_counter()
+        for i in range(e_steps):
+            _, r = e2e_scene.update(e2e_params, frame_num=1 + i, buffer=host_img)
+            e_rays += r
+        e_wall = time.perf_counter() - t0
+        per_gpu_kernel_ms = [st.kernel_ms for st in e2e_scene.device_stats()]
+        pt.ffi.check(L.pt_host_unregister(host_img.ctypes.data_as(C.c_void_p)))
+    barrier()
+    h2d_b = w * h * 12
+    d2h_b = w * h * 12 + 8 * world
 
     # ---- reduce over ranks: time = max, work = sum ------------------------------------------------------------------
     def allmax(x):
@@ -311,8 +322,8 @@ def main():
         return float(t.item())
 
     ms_max, rays_sum = allmax(ms), allsum(rays)
-    e_wall_max, e_rays_sum = allmax(e_wall), allsum(e_rays)
     k_ms_max, k_rays_sum = allmax(k_ms), allsum(k_rays)
+    ms_min = -allmax(-ms)
     samples_per_step = w * h * spp * (world if (world > 1 and not rows_mode) else 1)
 
     if rank == 0:
@@ -331,6 +342,7 @@ def main():
                 traffic_note = "dram bytes read+written per launch, ncu --set full: %s; %s" % (t["source"], t["note"])
         except (OSError, ValueError, KeyError):
             pass
+        st = preset.stats()
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -339,25 +351,34 @@ def main():
                        "n_spheres": n_spheres, "partition": ("rows: interleaved 4-row tiles, no collective" if rows_mode else
                                                              (("samples-strong: %d spp per GPU x %d frame seeds + one NCCL reduce" % (spp, world)) if samples_strong else
                                                               ("samples: one frame seed per GPU + one NCCL reduce" if world > 1 else "single GPU"))),
-                       "l2": "flushed between timed iterations (256 MB fill); the scene is a %d KB pre-filter image %s" % (max(1, n_spheres * 16 // 1024), "resident in shared memory" if n_spheres * 16 < 200 * 1024 else "streamed from L2 in TMA tiles"),
-                       "timing": "CUDA events per step on the launching stream, max over ranks"},
+                       "l2": "flushed between timed iterations (256 MB fill); the scene is a %d KB pre-filter image %s" % (max(1, n_spheres * 16 // 1024), "resident in shared memory" if st.resident else "streamed from L2 in TMA tiles"),
+                       "kernel": "%d CTAs x %d threads, %d B shared memory per CTA" % (st.grid_ctas, st.cta_threads, st.smem_bytes),
+                       "timing": "CUDA events per step on the launching stream, max over ranks (slowest rank %.1f ms, fastest %.1f ms per step)" % (ms_max / args.steps, ms_min / args.steps)},
             "samples_per_s": samples_per_step * args.steps / (ms_max * 1e-3),
             "rays_per_sample": rays_sum / (samples_per_step * args.steps),
-            "e2e": {"value": e_rays_sum / 1e6 / e_wall_max, "unit": "Mrays/s", "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
-                    "ms_per_step": 1e3 * e_wall_max / e_steps,
-                    "path": "Scene::update mirror -> pt_render (pinned host buffer, frame_num>=1)" if world == 1 else
-                            "pinned H2D -> pt_render_device -> NCCL reduce -> D2H on rank 0"},
+            "e2e": {"value": e_rays / 1e6 / e_wall, "unit": "Mrays/s", "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
+                    "ms_per_step": 1e3 * e_wall / e_steps, "steps": e_steps,
+                    "path": ("Scene::update mirror -> ONE pt_render call on a %d-device scene (pt_scene_create_multi: host thread per GPU, interleaved row tiles, "
+                             "each GPU copies its rows from/into the caller's buffer)" % world) if world > 1 else
+                            "Scene::update mirror -> pt_render (host buffer up and down every step, frame_num >= 1)",
+                    "host_buffer": "numpy array registered with pt_host_register (pinned)",
+                    "per_gpu_kernel_ms": per_gpu_kernel_ms},
             "gpu_launches": args.steps * world,
             "roofline": {"bound": "fp32_fma", "achieved": achieved / 1e12, "peak": peak_nominal / 1e12, "unit": "TFLOP/s",
                          "frac": achieved / peak_nominal, "traffic": traffic, "traffic_unit": "bytes", "traffic_note": traffic_note,
                          "peak_source": "sm_count*128*2*max SM clock (%d SMs, %d MHz); MEASURED_PEAKS.json has no FP32 figure — "
                                         "a pure-FFMA probe kernel measured %s TFLOP/s on this GPU in this run"
                                         % (info.sm_count, info.sm_clock_khz // 1000, ("%.1f" % (peak_probe / 1e12)) if peak_probe else "n/a"),
-                         "algorithmic": "16 flop x %d spheres x %d rays per launch (brute force, every ray tests every sphere)" % (n_spheres, int(k_rays_sum / k_steps)),
+                         "algorithmic": "16 flop x %d spheres x %d rays per launch (brute force, every ray tests every sphere)" % (n_spheres, int(k_rays_sum / k_steps / world)),
                          "kernel_ms": k_ms_max / k_steps,
                          "note": "bound by the FP32 FMA pipe, not by HBM: algorithmic HBM bytes are 12-24 B/pixel/launch (accumulation buffer)"},
             "clocks": clocks,
         }
+        if world == 1 and not args.no_extras:
+            try:
+                line["extras"] = extras(pt, np, torch, local_rank, options)
+            except Exception as e:
+                line["extras"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_baseline(args.workload)
@@ -368,6 +389,43 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def extras(pt, np, torch, device, options):
+    """Short driver-visible figures for the other BASELINE configs (one warm-up + one timed `pt_render` each, kernel time from
+    the library's own CUDA events): cfg1 and cfg2 and cfg3 at FULL size, cfg5 at full resolution but 8 spp (labelled)."""
+    out = {}
+    info = pt.device_info(device)
+    for key, spp_override in (("cfg1", 0), ("cfg2", 0), ("cfg3", 0), ("cfg5", 8)):
+        preset_name, w, h, spp, depth = WORKLOADS[key]
+        full = spp
+        if spp_override:
+            spp = spp_override
+        params = pt.Params(w, h, spp, depth)
+        pr = pt.Preset(preset_name, params).create_scene(device, options)
+        buf = np.zeros((h, w, 3), np.float32)
+        pr.update(params, frame_num=0, buffer=buf)
+        t0 = time.perf_counter()
+        _, rays = pr.update(params, frame_num=1, buffer=buf)
+        wall = time.perf_counter() - t0
+        st = pr.stats()
+        n = len(pr)
+        rec = {"workload": workload_name(key, full) + ("" if spp == full else " [REDUCED to %d spp]" % spp), "kernel_ms": st.kernel_ms,
+               "mrays_s": rays / 1e3 / st.kernel_ms, "samples_per_s": w * h * spp / (st.kernel_ms * 1e-3),
+               "e2e_mrays_s_pageable_host_buffer": rays / 1e6 / wall, "rays_per_sample": rays / (w * h * spp),
+               "fp32_frac": rays * FLOP_PER_TEST * n / (st.kernel_ms * 1e-3) / info.fp32_fma_peak_flops, "n_spheres": n,
+               "lane_efficiency_of_the_sweep": rays / 32.0 / max(1, st.warp_sweeps)}
+        if key == "cfg3":
+            # every scatter evaluates the Noise texture once (both spheres are noise-textured Lambertians, presets.rs:271-315) and a
+            # sample ends by exactly one miss or one depth-limit hit, so texture lookups = rays - samples; turb = 7 octaves of noise
+            turb = rays - w * h * spp
+            rec["noise_evals_per_s"] = 7.0 * turb / (st.kernel_ms * 1e-3)
+            rec["turb_evals_per_s"] = turb / (st.kernel_ms * 1e-3)
+            rec["note"] = ("N = 2 spheres: the FP32-FMA roofline of the sweep does not bound this config (SURVEY §8d); it is bound by instruction issue in "
+                           "Perlin turb (7 octaves x 8 lattice corners of gathers + Hermite/trilinear arithmetic, perlin.rs:54-111)")
+        out[key] = rec
+        del pr
+    return out
 
 
 if __name__ == "__main__":

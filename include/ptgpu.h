@@ -212,7 +212,9 @@ void pt_scene_destroy(PtScene* scene);
  * rows straight from / into the caller's buffer: the caller still makes ONE call (src/offline.rs:29,
  * src/glium_window.rs:102) and there is no collective in the data path.  Pixel seeds depend only on (x, y, frame)
  * (src/scene.rs:99-101), so the image and the ray count are identical for any device list.
- * `options` may be NULL.  pt_render_device / pt_srgb8_device take device pointers and therefore need a one-device scene. */
+ * `options` may be NULL.  pt_render_device / pt_srgb8_device take device pointers and therefore need a one-device scene.
+ * A device may be listed more than once: every entry is an independent replica with its own stream and buffers (no use in
+ * production, but it lets a one-GPU machine exercise the whole fan-out). */
 int pt_scene_create_multi(const PtSceneDesc* desc, const int* devices, uint32_t n_devices, const PtOptions* options,
                           PtScene** out);
 uint32_t pt_scene_device_count(const PtScene* scene);

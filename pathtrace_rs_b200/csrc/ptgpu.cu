@@ -1156,9 +1156,6 @@ int pt_scene_create_multi(const PtSceneDesc* desc, const int* devices, uint32_t 
     *out = nullptr;
     if (!devices || n_devices == 0) return fail(PT_ERR_INVALID, "empty device list");
     if (n_devices > 64) return fail(PT_ERR_INVALID, "too many devices: %u", n_devices);
-    for (uint32_t i = 0; i < n_devices; ++i)
-        for (uint32_t j = 0; j < i; ++j)
-            if (devices[i] == devices[j]) return fail(PT_ERR_INVALID, "device %d is listed twice", devices[i]);
     PtOptions opt;
     int rc = normalise_options(options, &opt);
     if (rc != PT_OK) return rc;

@@ -309,6 +309,94 @@ def test_chunk_queue_with_partition_and_streamed_kernel():
     assert pr2.stats().resident == 0 and rays_st == rays_whole and np.array_equal(st, whole)
 
 
+# ---- multi-device scenes: ONE Scene::update call, fanned out inside the library ----------------------------
+def _device_lists():
+    n = pt.libptgpu().pt_device_count()
+    lists = [[0, 0], [0, 0, 0]]  # replicas on one GPU: the whole fan-out (threads, row tiles, strided copies) on any box
+    if n >= 2:
+        lists.append(list(range(n)))
+    return lists
+
+
+@pytest.mark.parametrize("preset,w,h,spp", [("random_spheres", 150, 93, 8), ("random", 96, 50, 8), ("two_perlin_spheres", 64, 37, 4)])
+def test_multi_device_scene_renders_the_single_device_image_in_one_call(preset, w, h, spp):
+    """pt_scene_create_multi + the ordinary pt_render: interleaved row tiles over the devices, one host thread per GPU, every
+    GPU copying its own rows from / into the caller's buffer.  Pixel seeds depend only on (x, y, frame) (scene.rs:99-101), so
+    image and ray count are identical to the one-device call — for frame 0, for a blended frame, for ragged last tiles
+    (h is not a multiple of the tile height) and for other tile heights."""
+    params = pt.Params(w, h, spp, 50)
+    single = pt.Preset(preset, params).create_scene(0)
+    img0, rays0 = single.update(params)
+    img1 = img0.copy()
+    _, rays1 = single.update(params, frame_num=5, buffer=img1)
+    for devices in _device_lists():
+        for opt in (None, pt.PtOptions(tile_rows=7), pt.PtOptions(tile_rows=1)):
+            multi = pt.Preset(preset, params).create_scene(devices, opt)
+            assert pt.libptgpu().pt_scene_device_count(multi.scene_handle) == len(devices)
+            a = np.full((h, w, 3), -7.0, np.float32)
+            _, r = multi.update(params, buffer=a)
+            assert r == rays0 and np.array_equal(a, img0), (devices, opt)
+            b = img0.copy()
+            _, r = multi.update(params, frame_num=5, buffer=b)
+            assert r == rays1 and np.array_equal(b, img1), (devices, opt)
+            per = multi.device_stats()
+            assert len(per) == len(devices) and sum(st.ray_count for st in per) == rays1
+            assert all(st.kernel_launches == 1 for st in per) and multi.stats().kernel_launches == len(devices)
+            assert multi.stats().h2d_bytes == w * h * 12 and multi.stats().d2h_bytes == w * h * 12 + 8 * len(devices)
+
+
+def test_multi_device_progressive_accumulation_and_srgb8():
+    """pt_render_progressive on a multi-device scene: every GPU keeps its rows resident across frames; f32 and sRGB8
+    downloads are assembled from the devices' rows."""
+    w, h, spp = 90, 61, 4
+    params = pt.Params(w, h, spp, 20)
+    single = pt.Preset("random_spheres", params).create_scene(0)
+    multi = pt.Preset("random_spheres", params).create_scene([0, 0, 0], pt.PtOptions(tile_rows=5))
+    for frame in range(3):
+        a, a8, ra = single.update_progressive(params, frame, want_rgb=True, want_rgb8=True)
+        b, b8, rb = multi.update_progressive(params, frame, want_rgb=True, want_rgb8=True)
+        assert ra == rb and np.array_equal(a, b) and np.array_equal(a8, b8), frame
+
+
+def test_multi_device_scene_rejects_device_pointer_entry_points():
+    params = pt.Params(32, 16, 1, 5)
+    multi = pt.Preset("small", params).create_scene([0, 0])
+    L = ffi.libptgpu()
+    p, cam = params.to_ffi(), multi.camera
+    rays = C.c_uint64(0)
+    buf = np.zeros((16, 32, 3), np.float32)
+    rc = L.pt_render_device(multi.scene_handle, C.byref(p), C.byref(cam), 0, None, buf.ctypes.data_as(C.c_void_p), C.byref(rays), None)
+    assert rc == ffi.PT_ERR_UNSUPPORTED and b"one-device" in L.pt_last_error()
+    part = ffi.PtPartition(4, 0, 2, 0)
+    rc = L.pt_render_part(multi.scene_handle, C.byref(p), C.byref(cam), 0, C.byref(part), buf.ctypes.data_as(C.c_void_p), C.byref(rays))
+    assert rc == ffi.PT_ERR_UNSUPPORTED and b"partitions the image itself" in L.pt_last_error()
+    assert L.pt_scene_create_multi(None, None, 0, None, None) == ffi.PT_ERR_INVALID
+
+
+def test_zero_samples_is_rejected():
+    """Scene::update divides by `samples` (scene.rs:85): 0 would blend NaN into every pixel; the library refuses."""
+    params = pt.Params(16, 8, 0, 5)
+    pr = pt.Preset("small", pt.Params(16, 8, 1, 5)).create_scene(0)
+    with pytest.raises(RuntimeError, match="samples must be at least 1"):
+        pr.update(params)
+
+
+def test_host_register_round_trip():
+    """pt_host_register / pt_host_unregister: a pinned caller buffer renders the same image as a pageable one."""
+    params = pt.Params(120, 67, 4, 20)
+    pr = pt.Preset("random_spheres", params).create_scene(0)
+    a, ra = pr.update(params)
+    b = np.zeros_like(a)
+    L = ffi.libptgpu()
+    ffi.check(L.pt_host_register(b.ctypes.data_as(C.c_void_p), b.nbytes))
+    try:
+        _, rb = pr.update(params, buffer=b)
+    finally:
+        ffi.check(L.pt_host_unregister(b.ctypes.data_as(C.c_void_p)))
+    assert ra == rb and np.array_equal(a, b)
+    assert L.pt_host_register(None, 16) == ffi.PT_ERR_INVALID
+
+
 # ---- the resident kernel flavours (PtOptions.resident_kernel) ---------------------------------------------------------
 @pytest.mark.parametrize("preset,w,h,spp", [("random_spheres", 160, 90, 12), ("random", 128, 64, 8), ("two_perlin_spheres", 96, 54, 8),
                                              ("small", 64, 32, 16), ("smallpt", 48, 48, 8)])
