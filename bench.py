@@ -196,6 +196,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
+        # host-side rendezvous for the e2e leg: an NCCL barrier parks a spinning kernel on every waiting rank's GPU, and rank 0
+        # drives ALL GPUs through one library call there — the waiting ranks must leave their GPUs idle
+        cpu_group = dist.new_group(backend="gloo")
 
     preset_name, w, h, spp, depth = WORKLOADS[args.workload]
     reduced = args.spp > 0 and args.spp != spp
@@ -293,7 +296,13 @@ def main():
         if world > 1:
             multi = pt.Preset(preset_name, pt.Params(w, h, full_spp, depth)).create_scene(list(range(world)), options)
         e2e_scene, e2e_params = (multi, pt.Params(w, h, full_spp, depth)) if world > 1 else (preset, params)
+    def cpu_barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=cpu_group)
+
     barrier()
+    cpu_barrier()
     if rank == 0:
         if not long_steps:
             e2e_scene.update(e2e_params, frame_num=1, buffer=host_img)
@@ -304,7 +313,7 @@ def main():
         e_wall = time.perf_counter() - t0
         per_gpu_kernel_ms = [st.kernel_ms for st in e2e_scene.device_stats()]
         pt.ffi.check(L.pt_host_unregister(host_img.ctypes.data_as(C.c_void_p)))
-    barrier()
+    cpu_barrier()
     h2d_b = w * h * 12
     d2h_b = w * h * 12 + 8 * world
 
