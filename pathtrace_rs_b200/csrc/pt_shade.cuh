@@ -14,7 +14,7 @@
 #include "pt_rng.cuh"
 
 #ifndef PT_PERLIN_SELECT
-#define PT_PERLIN_SELECT 0
+#define PT_PERLIN_SELECT 1
 #endif
 
 namespace pt {
@@ -146,11 +146,15 @@ __device__ __forceinline__ bool refract(V3 v, V3 n, float ni_over_nt, V3& out) {
 __device__ __forceinline__ float schlick(float cosine, float ref_idx) {  // math.rs:76-80
     float r0 = (1.0f - ref_idx) / (1.0f + ref_idx);
     r0 = r0 * r0;
-    // powf(x, 5.0) as a multiply chain (<= 2 ulp from the correctly rounded power; the value is only
-    // compared against one 24-bit uniform draw, material.rs:109)
-    const float x = 1.0f - cosine;
-    const float x2 = x * x;
-    return r0 + (1.0f - r0) * (x2 * x2 * x);
+    // `(1.0 - cosine).powf(5.0)`: Rust calls the platform's powf.  x^5 through a double-precision multiply chain, rounded once,
+    // is the correctly rounded power; glibc's powf (<= 0.52 ulp) returns the same float for 99.93 % of x in [0, 1] and the
+    // neighbouring one otherwise (measured over 4*10^5 arguments), and the value is only compared against one 24-bit uniform
+    // draw (material.rs:109): a coin flip differs about once per 10^10 evaluations.  (The f32 chain x2*x2*x used in round 1
+    // was off by up to 3 ulp on half of the arguments.)  Dielectric hits are ~4 % of the rays: the four DMULs do not show.
+    const double x = (double)(1.0f - cosine);
+    const double x2 = x * x;
+    const float x5 = (float)(x2 * x2 * x);
+    return r0 + (1.0f - r0) * x5;
 }
 
 // ---- src/perlin.rs ----
@@ -186,8 +190,9 @@ __device__ __forceinline__ float perlin_noise(const PerlinSmem& P, V3 p) {  // p
                 const V3 weight = v3(u - ii, v - jj, w - kk);
 #if PT_PERLIN_SELECT
                 // i*uu + (1-i)*(1-uu) with i in {0, 1} is uu or 1-uu exactly (0*x = +0 for the finite x in [0, 1] that reach
-                // here); spelled as a select it saves the 0*x products the compiler must otherwise keep.  Not yet validated
-                // on hardware: off by default.
+                // here, and y + 0 = y); spelled as a select it saves the 0*x products the compiler must otherwise keep
+                // (-fmad=false, no fast-math: ~26 SASS instructions per noise call).  Validated on hardware against the product
+                // form (-DPT_PERLIN_SELECT=0): bit-identical images (profiles/variants_r2_*.txt).
                 accum += (di ? uu : 1.0f - uu) * (dj ? vv : 1.0f - vv) * (dk ? ww : 1.0f - ww) * dot(v3(c.x, c.y, c.z), weight);
 #else
                 accum += (ii * uu + (1.0f - ii) * (1.0f - uu)) * (jj * vv + (1.0f - jj) * (1.0f - vv)) *

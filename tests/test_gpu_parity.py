@@ -42,8 +42,7 @@ def test_bit_exact_presets(preset, w, h, spp, depth):
     img, rays, _ = gpu_render(preset, w, h, spp, depth)
     ref, ref_rays = orc.Scene(preset, w, h).update(spp, depth, mode=SOA_ITER)
     assert rays == ref_rays
-    assert np.mean(np.all(img == ref, axis=2)) >= 0.999
-    np.testing.assert_allclose(img, ref, rtol=0, atol=2e-2)
+    assert np.array_equal(img, ref)  # measured on B200 (tools/parity_report.py): 0 pixels differ
 
 
 def test_cfg1_random_spheres_vs_oracle():
@@ -53,9 +52,8 @@ def test_cfg1_random_spheres_vs_oracle():
     sc = orc.Scene("random_spheres", w, h)
     soa, soa_rays = sc.update(spp, depth, mode=SOA_ITER)
     lst, lst_rays = sc.update(spp, depth, mode=orc.HIT_LIST)
-    # (a) same arithmetic: almost every pixel identical to 1e-5
-    assert np.mean(np.all(np.abs(img - soa) < 1e-5, axis=2)) > 0.99
-    assert abs(rays - soa_rays) <= 1e-3 * soa_rays
+    # (a) same arithmetic as the oracle's SoA mode: the image and the ray count are bit-identical (5 212 563 rays)
+    assert rays == soa_rays and np.array_equal(img, soa)
     # (b) north-star tolerance against the reference's live (list) path
     assert rel_mean_diff(img, lst).max() < 5e-3
     assert abs(rays / (w * h * spp) - lst_rays / (w * h * spp)) < 0.01 * lst_rays / (w * h * spp)
@@ -75,8 +73,7 @@ def test_random_preset_moving_spheres_vs_oracle():
     assert int(sc.flat()["motion"][:, 5].sum()) == 393
     hyb, hyb_rays = sc.update(spp, depth, mode=SOA_ITER)
     lst, lst_rays = sc.update(spp, depth, mode=orc.HIT_LIST)
-    assert np.mean(np.all(np.abs(img - hyb) < 1e-5, axis=2)) > 0.99
-    assert abs(rays - hyb_rays) <= 1e-3 * hyb_rays
+    assert rays == hyb_rays and np.array_equal(img, hyb)  # bit-identical, 393 moving spheres included
     assert rel_mean_diff(img, lst).max() < 5e-3
     assert abs(rays - lst_rays) < 0.01 * lst_rays
     # motion blur is really there: the same pixels of the static preset differ
@@ -102,9 +99,10 @@ def test_moving_sphere_shutter_must_lie_inside_the_motion_interval():
 
 
 def test_rmse_against_converged_reference():
-    """RMSE(GPU, converged) <= 1.05 x RMSE(oracle at equal spp, converged).  The converged image is the oracle's
-    equal-weight mean of 64 further frames x 256 spp (frame seeds differ: scene.rs:100), 16 384 spp in total."""
-    w, h, spp, depth = 100, 50, 64, 50
+    """north_star's acceptance test at BASELINE config 1's own size (200x100, 100 spp, depth 50):
+    RMSE(GPU, converged) <= 1.05 x RMSE(oracle at equal spp, converged).  The converged image is the oracle's equal-weight
+    mean of 64 further frames x 256 spp (frame seeds differ: scene.rs:100), 16 384 spp in total."""
+    w, h, spp, depth = 200, 100, 100, 50
     sc = orc.Scene("random_spheres", w, h)
     conv = np.zeros((h, w, 3), np.float32)
     for k in range(64):
@@ -134,8 +132,9 @@ def test_cfg3_two_perlin_spheres_vs_oracle():
     sc = orc.Scene("two_perlin_spheres", w, h)
     soa, soa_rays = sc.update(spp, depth, mode=SOA_ITER)
     lst, _ = sc.update(spp, depth, mode=orc.HIT_LIST)
-    assert abs(rays - soa_rays) <= 1e-3 * soa_rays
-    assert np.mean(np.all(np.abs(img - soa) < 1e-4, axis=2)) > 0.99  # device sinf vs libm sinf in the noise texture
+    # same hits, same draws; the colours differ by the last ulp of sinf in the Noise texture (device sinf vs libm): measured
+    # max |diff| 8.9e-8 on 28 % of the pixels, nothing beyond
+    assert rays == soa_rays and np.abs(img - soa).max() <= 2.5e-7
     assert rel_mean_diff(img, lst).max() < 5e-3
 
 
@@ -206,7 +205,7 @@ def test_frame_blending_matches_reference_formula():
         pr.update(params, frame_num=f, buffer=buf)  # frame > 0 uploads the host buffer, blends, downloads
         sc.update(spp, depth, frame_num=f, buffer=ref, mode=SOA_ITER)
         assert pr.stats().h2d_bytes == (0 if f == 0 else w * h * 12)
-    assert np.mean(np.all(buf == ref, axis=2)) >= 0.999
+    assert np.array_equal(buf, ref)
     # frame 0 ignores whatever is in the buffer (mix_prev = 0)
     junk = np.full((h, w, 3), 7.0, np.float32)
     pr.update(params, frame_num=0, buffer=junk)
@@ -277,7 +276,7 @@ def test_chunk_queue_is_bit_exact_for_any_chunk_size(chunk):
     img, rays, _ = gpu_render("random_spheres", w, h, spp, depth, options=pt.PtOptions(chunk_samples=chunk))
     assert rays == rays_whole and np.array_equal(img, whole)
     ref, ref_rays = orc.Scene("random_spheres", w, h).update(spp, depth, mode=SOA_ITER)
-    assert rays == ref_rays and np.mean(np.all(img == ref, axis=2)) >= 0.999
+    assert rays == ref_rays and np.array_equal(img, ref)
 
 
 def test_chunk_queue_default_engages_on_large_images_and_blends_frames():
@@ -449,8 +448,7 @@ def test_cfg5_stress100k_small_vs_oracle():
     img, rays, pr = gpu_render("stress100k", w, h, spp, depth)
     assert pr.stats().resident == 0 and pr.stats().n_spheres == 99860
     ref, ref_rays = orc.Scene("stress100k", w, h).update(spp, depth, mode=SOA_ITER)
-    assert abs(rays - ref_rays) <= 0.01 * ref_rays
-    assert np.mean(np.all(np.abs(img - ref) < 1e-5, axis=2)) > 0.99
+    assert rays == ref_rays and np.array_equal(img, ref)  # 99 860 spheres through the streamed kernel: bit-identical
 
 
 # ---- output stage ----------------------------------------------------------------------------------------------------
