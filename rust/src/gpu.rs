@@ -1,13 +1,15 @@
-//! gpu.rs — `mod gpu;` in src/main.rs (feature "gpu").  Thin FFI over include/ptgpu.h: flattens a `Scene` whose world is
-//! a `Hitable::List` of spheres / moving spheres and forwards `Scene::update` to the CUDA library.  NOT compiled in this repository's CI
-//! (no Rust toolchain in the build image); the identical C ABI is exercised by the C++ mirror and the ctypes tests.
+//! gpu.rs — copy to src/gpu.rs of pathtrace-rs (`mod gpu;` behind feature "gpu", rust/patches/06-src-main_rs.diff).  Thin FFI over
+//! include/ptgpu.h (ABI v4): flattens a `Scene` whose world is a `Hitable::List` of spheres / moving spheres, uploads it to
+//! one or several GPUs and serves `Scene::update` from the CUDA library.  NOT compiled in this repository's CI (no Rust
+//! toolchain in the build image); the identical C ABI is exercised by the C++ mirror and the ctypes tests.
 //!
-//! Needs five small `pub(crate)` accessors in the reference:
-//!   Camera::to_ffi(&self) -> PtCamera                      (src/camera.rs, fields are private)
-//!   Scene::world(&self) -> &Hitable, Scene::sky(&self) -> Option<Vec3>      (src/scene.rs:18-22)
-//!   HitableList::hitables(&self) -> &[Hitable]             (src/collision/hitable_list.rs:9-11)
-//!   Perlin::tables(&self) -> (&[Vec3], &[u32], &[u32], &[u32])               (src/perlin.rs:7-12)
-//!   RgbImage::raw(&self) -> (u32, u32, &[u8])              (src/texture.rs:6-10, fields are private)
+//! The accessors it needs are added by rust/patches/*.diff (all `pub(crate)`, the fields are private):
+//!   Camera::to_ffi(&self) -> PtCamera                                   03-src-camera_rs.diff        (src/camera.rs:8-19)
+//!   Scene::world(&self) -> &Hitable, Scene::sky_colour(&self) -> Option<Vec3>, Scene::attach_gpu     09-src-scene_rs.diff
+//!   HitableList::hitables(&self) -> &[Hitable]                          04-...hitable_list_rs.diff   (hitable_list.rs:9-11)
+//!   MovingSphere::endpoints(&self) -> (centre0, centre1, time0, time1)  05-...moving_sphere_rs.diff  (moving_sphere.rs:7-26)
+//!   Perlin::tables(&self) -> (&[Vec3], &[u32], &[u32], &[u32])          08-src-perlin_rs.diff        (src/perlin.rs:7-12)
+//!   RgbImage::raw(&self) -> (u32, u32, &[u8])                           10-src-texture_rs.diff       (src/texture.rs:6-10)
 #![cfg(feature = "gpu")]
 use crate::{camera::Camera, collision::Hitable, material::Material, params::Params, perlin::Perlin, scene::Scene, texture::{RgbImage, Texture}};
 use std::{collections::HashMap, ffi::CStr, os::raw::{c_char, c_int, c_void}, ptr};
@@ -37,13 +39,16 @@ pub struct PtSceneDesc {
 /// src/collision/moving_sphere.rs:16-26 inverted to its constructor arguments (centre0/radius travel in the sphere arrays)
 #[repr(C)] #[derive(Copy, Clone, Default)]
 pub struct PtMotion { pub centre1: [f32; 3], pub time0: f32, pub time1: f32, pub moving: u32 }
+/// explicit launch options; the shim passes NULL (every field "library decides") except `tile_rows`
+#[repr(C)] #[derive(Copy, Clone, Default)]
+pub struct PtOptions { pub struct_size: u32, pub force_stream_tile_blocks: i32, pub stream_ctas: i32, pub chunk_samples: i32, pub spatial_order: i32, pub tile_rows: u32, pub resident_kernel: u32 }
 #[repr(C)] pub struct PtScene { _private: [u8; 0] }
 
 extern "C" {
     fn pt_abi_version() -> c_int;
     fn pt_abi_struct_size(which: c_int) -> u32;
     fn pt_last_error() -> *const c_char;
-    fn pt_scene_create(desc: *const PtSceneDesc, device: c_int, out: *mut *mut PtScene) -> c_int;
+    fn pt_scene_create_multi(desc: *const PtSceneDesc, devices: *const c_int, n_devices: u32, options: *const PtOptions, out: *mut *mut PtScene) -> c_int;
     fn pt_scene_destroy(scene: *mut PtScene);
     fn pt_render(scene: *mut PtScene, params: *const PtParams, camera: *const PtCamera, frame_num: u32, rgb_inout: *mut f32, ray_count_out: *mut u64) -> c_int;
     fn pt_render_progressive(scene: *mut PtScene, params: *const PtParams, camera: *const PtCamera, frame_num: u32, rgb_out: *mut f32, rgb8_out: *mut u8, ray_count_out: *mut u64) -> c_int;
@@ -53,13 +58,20 @@ fn last_error() -> String { unsafe { CStr::from_ptr(pt_last_error()).to_string_l
 
 /// Device copy of a flattened `Scene`.  Dropping it frees the device memory (ties `pt_scene_destroy` to a Rust `Drop`).
 pub struct GpuScene { handle: *mut PtScene }
-unsafe impl Send for GpuScene {} // `update` is called from one thread at a time (main thread offline, worker thread windowed)
+// `Scene` must stay `Sync` (its CPU `update` hands `&self` to rayon); the handle is only ever used by `update`, which the
+// reference calls from one thread at a time (main thread offline, one worker thread in the windowed mode)
+unsafe impl Send for GpuScene {}
+unsafe impl Sync for GpuScene {}
 
 impl GpuScene {
     /// The GPU arm of `Params::new_scene` (src/params.rs:29-46): walk `Hitable::List`, reject anything that is not a sphere
     /// (same message as the panic in src/collision/spheres_soa.rs:49-51), dedupe arena pointers into indices, upload.
-    pub fn new(scene: &Scene, perlin: &Perlin, device: i32) -> GpuScene {
-        assert_eq!(unsafe { pt_abi_version() }, 3);
+    /// `devices`: CUDA device ordinals.  With more than one, every `update` is split over them by interleaved row tiles inside
+    /// the library (one host thread per GPU, each copying its rows from / into `buffer`); the image does not depend on the list.
+    pub fn new(scene: &Scene, perlin: &Perlin, devices: &[i32]) -> GpuScene {
+        assert_eq!(unsafe { pt_abi_version() }, 4);
+        assert_eq!(unsafe { pt_abi_struct_size(11) } as usize, std::mem::size_of::<PtOptions>());
+        assert!(!devices.is_empty(), "empty GPU device list");
         assert_eq!(unsafe { pt_abi_struct_size(5) } as usize, std::mem::size_of::<PtSceneDesc>());
         let hitables = match scene.world() { Hitable::List(list) => list.hitables(), other => panic!("Expected Hitable::List, got {:?}", other) };
         let (mut cx, mut cy, mut cz, mut radius, mut mat_index) = (vec![], vec![], vec![], vec![], vec![]);
@@ -98,7 +110,6 @@ impl GpuScene {
         }
         for hitable in hitables {
             // Hitable::Sphere and Hitable::MovingSphere (src/collision/hitable.rs:16-17) are the two arms the GPU path takes.
-            // MovingSphere needs `pub(crate)` accessors centre0()/centre1()/time0()/time1() next to radius() (moving_sphere.rs:33-36).
             let material = match hitable {
                 Hitable::Sphere(sphere, material) => {
                     cx.push(sphere.centre().x); cy.push(sphere.centre().y); cz.push(sphere.centre().z); radius.push(sphere.radius());
@@ -106,9 +117,9 @@ impl GpuScene {
                     Some(material)
                 }
                 Hitable::MovingSphere(ms, material) => {
-                    let (c0, c1) = (ms.centre0(), ms.centre1());
+                    let (c0, c1, time0, time1) = ms.endpoints();
                     cx.push(c0.x); cy.push(c0.y); cz.push(c0.z); radius.push(ms.radius());
-                    motion.push(PtMotion { centre1: [c1.x, c1.y, c1.z], time0: ms.time0(), time1: ms.time1(), moving: 1 });
+                    motion.push(PtMotion { centre1: [c1.x, c1.y, c1.z], time0, time1, moving: 1 });
                     any_moving = true;
                     Some(material)
                 }
@@ -139,7 +150,7 @@ impl GpuScene {
             for i in 0..256 { t.randvec[i] = [rv[i].x, rv[i].y, rv[i].z]; t.perm_x[i] = px[i]; t.perm_y[i] = py[i]; t.perm_z[i] = pz[i]; }
             Some(t)
         } else { None };
-        let sky = scene.sky();
+        let sky = scene.sky_colour();
         let desc = PtSceneDesc {
             struct_size: std::mem::size_of::<PtSceneDesc>() as u32, n_spheres: cx.len() as u32,
             centre_x: cx.as_ptr(), centre_y: cy.as_ptr(), centre_z: cz.as_ptr(), radius: radius.as_ptr(), material_index: mat_index.as_ptr(),
@@ -150,8 +161,8 @@ impl GpuScene {
             n_images: images.len() as u32, _pad: 0, images: if images.is_empty() { ptr::null() } else { images.as_ptr() },
         };
         let mut handle: *mut PtScene = ptr::null_mut();
-        let rc = unsafe { pt_scene_create(&desc, device, &mut handle) };
-        if rc != 0 { panic!("pt_scene_create failed: {}", last_error()); }
+        let rc = unsafe { pt_scene_create_multi(&desc, devices.as_ptr(), devices.len() as u32, ptr::null(), &mut handle) };
+        if rc != 0 { panic!("pt_scene_create_multi failed: {}", last_error()); }
         GpuScene { handle }
     }
 
