@@ -345,8 +345,13 @@ def main():
             peak_probe = None
         traffic, traffic_note = None, "no ncu capture of this workload at this size is committed (profiles/ncu_traffic.json)"
         try:
-            t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload)
-            if t and not reduced:
+            table = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            t = table.get(args.workload) if not reduced else table.get("%s@%d" % (args.workload, full_spp))
+            if t is None and not reduced:
+                near = sorted(k for k in table if k.startswith(args.workload + "@"))
+                if near:
+                    traffic_note = "no capture of the full-size launch; at reduced spp (%s): %s" % (near[0], table[near[0]]["note"])
+            if t:
                 traffic = (t["dram_read_bytes"] + t["dram_write_bytes"]) * (1 if rows_mode or world == 1 else world)
                 traffic_note = "dram bytes read+written per launch, ncu --set full: %s; %s" % (t["source"], t["note"])
         except (OSError, ValueError, KeyError):

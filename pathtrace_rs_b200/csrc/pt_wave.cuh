@@ -26,6 +26,12 @@ namespace pt {
 #ifndef PT_WAVE_THREADS
 #define PT_WAVE_THREADS 640
 #endif
+// PT_WAVE_LDS=1: the sweep reads its sphere pairs from a staged image in shared memory (LDS.128) instead of the
+// kernel-parameter image through the uniform datapath
+#ifndef PT_WAVE_LDS
+#define PT_WAVE_LDS 0
+#endif
+constexpr bool kWaveConstImg = PT_WAVE_LDS == 0;
 constexpr int kWaveThreads = PT_WAVE_THREADS;
 constexpr int kWaveWarps = kWaveThreads / 32;
 constexpr int kWaveRecWords = 28;  // 7 x 16 bytes: the 112-byte stride spreads LDS.128 of random slots over all banks
@@ -69,7 +75,7 @@ struct WaveSmem {
     uint4* pool;       // [pool_paths][7]
     uint32_t cap;      // ring capacity of every queue (>= pool_paths + 64)
     __device__ __forceinline__ WaveSmem(unsigned char* raw, const KernelArgs& a) {
-        const uint32_t image_bytes = ((uint32_t)a.n_blocks * 16u + 127u) & ~127u;
+        const uint32_t image_bytes = ((uint32_t)a.n_blocks * (kWaveConstImg ? 16u : 64u) + 127u) & ~127u;
         kplane = reinterpret_cast<float4*>(raw);
         P = reinterpret_cast<PerlinSmem*>(raw + image_bytes);
         cand = reinterpret_cast<uint32_t*>(P + 1) + threadIdx.x;
@@ -302,7 +308,7 @@ __global__ void __launch_bounds__(kWaveThreads, 1) pt_megakernel_wave(const __gr
     __shared__ __align__(8) uint64_t bar;
     __shared__ WaveCtl ctl;
     const WaveSmem sm(smem_raw, a);
-    const uint32_t image_bytes = (uint32_t)a.n_blocks * 16u;
+    const uint32_t image_bytes = (uint32_t)a.n_blocks * (kWaveConstImg ? 16u : 64u);
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         fence_mbar_init();
@@ -321,7 +327,7 @@ __global__ void __launch_bounds__(kWaveThreads, 1) pt_megakernel_wave(const __gr
     __syncthreads();
     if (threadIdx.x == 0 && image_bytes != 0u) {
         mbar_arrive_expect_tx(&bar, image_bytes);
-        tma_bulk_g2s_chunked(sm.kplane, a.kplane, image_bytes, &bar);
+        tma_bulk_g2s_chunked(sm.kplane, kWaveConstImg ? a.kplane : a.prefilter, image_bytes, &bar);
     }
     stage_perlin(a, sm.P);
     {
@@ -394,7 +400,12 @@ __global__ void __launch_bounds__(kWaveThreads, 1) pt_megakernel_wave(const __gr
             }
             int cnt0 = 0, cnt1 = 0;
             int overflow[2] = {a.n_blocks, a.n_blocks};
+#if PT_WAVE_LDS
+            const ConstImageT<false> none{};
+            sweep_two<false, kWaveThreads, kWaveCandCap>(none, sm.kplane, a.n_blocks, sm.cand, cnt0, cnt1, dx, dy, dz, o2x, o2y, o2z, nod, oo, overflow);
+#else
             sweep_two<true, kWaveThreads, kWaveCandCap>(ci, sm.kplane, a.n_blocks, sm.cand, cnt0, cnt1, dx, dy, dz, o2x, o2y, o2z, nod, oo, overflow);
+#endif
             const unsigned cats = wave_sweep_finish<MOTION>(a, sm, valid[0] ? slot[0] : -1, valid[1] ? slot[1] : -1, cnt0, cnt1, overflow[0], overflow[1]);
             if (valid[0]) cat[0] = (int)(cats & 0xffu);
             if (valid[1]) cat[1] = (int)((cats >> 8) & 0xffu);

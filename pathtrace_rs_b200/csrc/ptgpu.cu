@@ -184,7 +184,7 @@ int plan_launch(Replica* s) {
         }
         if (s->const_image && s->opt.resident_kernel == 1) {
             // wavefront kernel: everything that is left of the SM's shared memory becomes the path pool
-            const size_t fixed = (((size_t)s->n_blocks * 16 + 127) & ~(size_t)127) + sizeof(pt::PerlinSmem) + (size_t)pt::kWaveCandCap * pt::kWaveThreads * sizeof(uint32_t) + 64;
+            const size_t fixed = (((size_t)s->n_blocks * (pt::kWaveConstImg ? 16 : 64) + 127) & ~(size_t)127) + sizeof(pt::PerlinSmem) + (size_t)pt::kWaveCandCap * pt::kWaveThreads * sizeof(uint32_t) + 64;
             const size_t per_path = (size_t)pt::kWaveRecWords * 4 + pt::kWaveQueues * sizeof(uint16_t);
             long pool = ((long)kMaxDynSmem - (long)fixed - (long)(pt::kWaveQueues * 64 * sizeof(uint16_t))) / (long)per_path;
             pool = std::min<long>(pool / 64 * 64, pt::kWaveMaxPool / 64 * 64);
