@@ -120,7 +120,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "Mrays/s", "value": mrays, "unit": "Mrays/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True,
-        "scaling": "strong" if (args.gpus > 1 and args.partition != "samples") else "weak",
+        "scaling": "strong" if args.partition != "samples" else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.workload, spp_full), "sample": sample},
         "samples_per_s": w * h * spp * args.steps / total,
@@ -360,7 +360,7 @@ def main():
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True,
-            "scaling": "strong" if (rows_mode or samples_strong) else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "strong" if args.partition in ("rows", "samples-strong") else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args.workload, full_spp) + (" [REDUCED spp]" if reduced else ""),
                        "n_spheres": n_spheres, "partition": ("rows: interleaved 4-row tiles, no collective" if rows_mode else
                                                              (("samples-strong: %d spp per GPU x %d frame seeds + one NCCL reduce" % (spp, world)) if samples_strong else
