@@ -340,7 +340,11 @@ def test_multi_device_scene_renders_the_single_device_image_in_one_call(preset, 
             assert r == rays1 and np.array_equal(b, img1), (devices, opt)
             per = multi.device_stats()
             assert len(per) == len(devices) and sum(st.ray_count for st in per) == rays1
-            assert all(st.kernel_launches == 1 for st in per) and multi.stats().kernel_launches == len(devices)
+            # a device without a row tile (more devices than tiles: 8 GPUs, 37 rows in tiles of 7) launches nothing
+            tile_rows = opt.tile_rows if opt is not None and opt.tile_rows else 4
+            busy = min(len(devices), -(-h // tile_rows))
+            assert sorted(st.kernel_launches for st in per) == [0] * (len(devices) - busy) + [1] * busy
+            assert multi.stats().kernel_launches == busy
             assert multi.stats().h2d_bytes == w * h * 12 and multi.stats().d2h_bytes == w * h * 12 + 8 * len(devices)
 
 
