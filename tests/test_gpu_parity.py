@@ -311,7 +311,7 @@ def test_chunk_queue_with_partition_and_streamed_kernel():
 # ---- multi-device scenes: ONE Scene::update call, fanned out inside the library ----------------------------
 def _device_lists():
     n = pt.libptgpu().pt_device_count()
-    lists = [[0, 0], [0, 0, 0]]  # replicas on one GPU: the whole fan-out (threads, row tiles, strided copies) on any box
+    lists = [[0, 0], [0, 0, 0], [0] * 8]  # replicas on one GPU: the whole fan-out (threads, row tiles, strided copies) on any box
     if n >= 2:
         lists.append(list(range(n)))
     return lists
