@@ -365,7 +365,10 @@ def main():
                        "n_spheres": n_spheres, "partition": ("rows: interleaved 4-row tiles, no collective" if rows_mode else
                                                              (("samples-strong: %d spp per GPU x %d frame seeds + one NCCL reduce" % (spp, world)) if samples_strong else
                                                               ("samples: one frame seed per GPU + one NCCL reduce" if world > 1 else "single GPU"))),
-                       "l2": "flushed between timed iterations (256 MB fill); the scene is a %d KB pre-filter image %s" % (max(1, n_spheres * 16 // 1024), "resident in shared memory" if st.resident else "streamed from L2 in TMA tiles"),
+                       "l2": "flushed between timed iterations (256 MB fill); the scene is a %d KB pre-filter image %s" % (max(1, n_spheres * (32 if st.resident == 2 else 16) // 1024), "resident in shared memory" if st.resident else "streamed from L2 in TMA tiles"),
+                       "prefilter": ("tensor path: the two dot products of every (ray, sphere) test as mma.sync.m16n8k16 f16 split-operand MMAs (HMMA.16816.F32), "
+                                     "A'^2 + B' and the sign test in packed FP32; the exact f32 test of the flagged spheres decides every hit" if st.resident == 2 else
+                                     "packed FP32 (FFMA2), 7 instructions per 2 tests; the exact f32 test of the flagged spheres decides every hit"),
                        "kernel": "%d CTAs x %d threads, %d B shared memory per CTA" % (st.grid_ctas, st.cta_threads, st.smem_bytes),
                        "timing": "CUDA events per step on the launching stream, max over ranks (slowest rank %.1f ms, fastest %.1f ms per step)" % (ms_max / args.steps, ms_min / args.steps)},
             "samples_per_s": samples_per_step * args.steps / (ms_max * 1e-3),
@@ -385,7 +388,11 @@ def main():
                                         % (info.sm_count, info.sm_clock_khz // 1000, ("%.1f" % (peak_probe / 1e12)) if peak_probe else "n/a"),
                          "algorithmic": "16 flop x %d spheres x %d rays per launch (brute force, every ray tests every sphere)" % (n_spheres, int(k_rays_sum / k_steps / world)),
                          "kernel_ms": k_ms_max / k_steps,
-                         "note": "bound by the FP32 FMA pipe, not by HBM: algorithmic HBM bytes are 12-24 B/pixel/launch (accumulation buffer)"},
+                         "note": ("algorithmic flop (the FP32 formulation's 16 per test) against the FP32 FMA peak, as in round 1, so the two builds compare; "
+                                  "in this build 12 of the 16 (the two 3-term dot products) execute on the tensor pipe as 2 x 16-deep f16 products = 64 flop per test: %.0f TFLOP/s of HMMA work "
+                                  "(mma.sync ceiling measured on B200: 550 TFLOP/s with a register accumulator, tools/probe_mma.cu); the kernel is bound by instruction issue around the MMAs, "
+                                  "not by HBM: algorithmic HBM bytes are 12-24 B/pixel/launch (accumulation buffer)" % (achieved / FLOP_PER_TEST * 64.0 / 1e12)) if st.resident == 2 else
+                                 "bound by the FP32 FMA pipe, not by HBM: algorithmic HBM bytes are 12-24 B/pixel/launch (accumulation buffer)"},
             "clocks": clocks,
         }
         if world == 1 and not args.no_extras:

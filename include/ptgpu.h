@@ -166,7 +166,8 @@ typedef struct PtRenderStats {
     uint32_t grid_ctas;
     uint32_t cta_threads;
     uint32_t smem_bytes;
-    uint32_t resident; /* 1: sphere SoA resident in shared memory; 0: streamed through L2 in tiles */
+    uint32_t resident; /* 0: sphere image streamed through L2 in tiles; 1: resident in shared memory, pre-filter in packed FP32;
+                          2: resident, pre-filter's dot products on the tensor path (PtOptions.resident_kernel 5) */
     uint64_t warp_sweeps; /* warp-level sweeps of 32 ray slots performed: ray_count / (32 * warp_sweeps) = lane efficiency of the sweep */
 } PtRenderStats;
 
@@ -183,11 +184,15 @@ typedef struct PtOptions {
     int32_t spatial_order;            /* -1: automatic; 0: store spheres in the caller's order; 1: Morton order;
                                          2: large spheres first, then Morton order */
     uint32_t tile_rows;               /* multi-device scenes: rows per interleaved row tile (0 -> 4) */
-    uint32_t resident_kernel;         /* which kernel renders a scene that fits in shared memory.  0 automatic (= 4, the fastest
-                                         measured); 4 one path per lane + CTA regroup; 2 / 3 two paths per lane with the
-                                         sphere pairs as uniform operands from a kernel-parameter image / from shared
-                                         memory; 1 wavefront form (path pool + per-material queues).  1 and 2 need a scene
-                                         of at most 2048 spheres and fall back to 3 beyond.  All produce the same image. */
+    uint32_t resident_kernel;         /* which kernel renders a scene that fits in shared memory.  0 automatic: 5 where the
+                                         scene suits it (>= 128 spheres of a size comparable to the scene's extent), else 4.
+                                         4 one path per lane + CTA regroup, pre-filter in packed FP32; 5 the same kernel with
+                                         the pre-filter's dot products on the tensor path (mma.sync f16 split operands,
+                                         pt_sweep_mma.cuh; a render whose camera lies outside the scene's extent falls back
+                                         to 4); 2 / 3 two paths per lane with the sphere pairs as uniform operands from a
+                                         kernel-parameter image / from shared memory; 1 wavefront form (path pool +
+                                         per-material queues).  1 and 2 need a scene of at most 2048 spheres and fall back
+                                         to 3 beyond.  All produce the same image. */
 } PtOptions;
 
 typedef struct PtScene PtScene; /* opaque: device copies of one scene on one or several GPUs */

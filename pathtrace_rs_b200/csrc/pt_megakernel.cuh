@@ -16,6 +16,7 @@
 #pragma once
 #include "pt_shade.cuh"
 #include "pt_sweep.cuh"
+#include "pt_sweep_mma.cuh"
 
 namespace pt {
 
@@ -31,6 +32,9 @@ struct KernelArgs {
     const DevMotion* motion;   // per-sphere MovingSphere records, nullptr when the scene has none (moving_sphere.rs)
     const float4* prefilter;   // pre-filter image X,Y,Z,K per block (global copy; staged/streamed by the LDS kernels)
     const float4* kplane;      // K plane alone, one float4 per block (resident kernel with the X,Y,Z planes in its parameter image)
+    const uint4* mma_image;    // tensor-path pre-filter: fragment-ordered sphere operand, (n_steps + 1) x 32 uint4 (pt_sweep_mma.cuh)
+    int n_steps;               // ... steps of 16 spheres (= n_blocks / 4)
+    MmaScale mma;              // ... its scene scale
     int single_row;            // resident kernel: fewer pixels than lanes, only path row 0 takes work
     int wave_pool;             // wavefront kernel: paths in the CTA's shared-memory pool
     unsigned int* status;      // wavefront kernel: watchdog report (0 = clean), see pt_wave.cuh

@@ -25,6 +25,9 @@ namespace pt {
 // consumes exactly its own RNG stream and performs exactly the same arithmetic, so images stay bit-identical; only the
 // assignment of paths to lanes changes.  Finished lanes collect in whole warps, which then skip the sweep.
 // =====================================================================================================
+#ifndef PT_REGROUP_PERIOD
+#define PT_REGROUP_PERIOD 1
+#endif
 constexpr int kRegroupCats = 6;
 constexpr int kRegroupWords = 28;  // 8 rng + 6 ray + 3 thr + 3 col + px, py, sample, depth, flags, hit_t, hit_index, time
 enum { CAT_LAMBERT_CONST = 0, CAT_LAMBERT_TEX = 1, CAT_METAL = 2, CAT_DIELECTRIC = 3, CAT_ENDING = 4, CAT_IDLE = 5 };
@@ -110,25 +113,33 @@ struct RegroupSmem {
     float4* pf;
     PerlinSmem* P;
     uint32_t* queue;           // this lane's candidate queue: [kQueueCap][kCtaThreads]
+    uint32_t* queue_base;      // the queue array without the lane offset (the tensor-path drain reads the quad's queues)
     volatile uint32_t* pend;   // this lane's slot
     volatile float* tslot;     // this lane's slot
     uint32_t* xchg;            // [kRegroupWords][kCtaThreads]
     uint32_t* cat_count;       // two sets of kRegroupCats counters, 8 words apart
-    __device__ __forceinline__ RegroupSmem(unsigned char* raw, int n_blocks) {
+    // image_bytes: n_blocks * 64 (FP32 pre-filter image) or (n_steps + 1) * 512 (tensor-path fragment image)
+    __device__ __forceinline__ RegroupSmem(unsigned char* raw, size_t image_bytes) {
         pf = reinterpret_cast<float4*>(raw);
-        P = reinterpret_cast<PerlinSmem*>(raw + (size_t)n_blocks * 64);
-        queue = reinterpret_cast<uint32_t*>(P + 1) + threadIdx.x;
+        P = reinterpret_cast<PerlinSmem*>(raw + image_bytes);
+        queue_base = reinterpret_cast<uint32_t*>(P + 1);
+        queue = queue_base + threadIdx.x;
         pend = queue + kQueueCap * kCtaThreads;
         tslot = reinterpret_cast<volatile float*>(pend + kCtaThreads);
         xchg = reinterpret_cast<uint32_t*>(P + 1) + (kQueueCap + 2) * kCtaThreads;
         cat_count = xchg + kRegroupWords * kCtaThreads;
     }
 };
+template <bool MMA>
+__device__ __forceinline__ size_t regroup_image_bytes(const KernelArgs& a) {
+    return MMA ? (size_t)(a.n_steps + 1) * 512 : (size_t)a.n_blocks * 64;
+}
+template <bool MMA>
 __device__ __forceinline__ void regroup_stage(const KernelArgs& a, const RegroupSmem& sm, uint64_t* bar) {
     *sm.pend = 0u;
     *sm.tslot = 0.0f;
     if (threadIdx.x < 16) sm.cat_count[threadIdx.x] = 0u;
-    const uint32_t bytes = (uint32_t)a.n_blocks * 64u;
+    const uint32_t bytes = (uint32_t)regroup_image_bytes<MMA>(a);
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
@@ -136,18 +147,27 @@ __device__ __forceinline__ void regroup_stage(const KernelArgs& a, const Regroup
     __syncthreads();
     if (threadIdx.x == 0 && bytes != 0u) {
         mbar_arrive_expect_tx(bar, bytes);
-        tma_bulk_g2s_chunked(sm.pf, a.prefilter, bytes, bar);
+        tma_bulk_g2s_chunked(sm.pf, MMA ? reinterpret_cast<const void*>(a.mma_image) : reinterpret_cast<const void*>(a.prefilter), bytes, bar);
     }
     stage_perlin(a, sm.P);
     __syncthreads();
     if (bytes != 0u) mbar_wait(bar, 0);
 }
 // the sweep phase of one trip for the lane's ray (already replaced by the parked ray for lanes without a path in flight)
-template <bool MOTION>
-__device__ __forceinline__ void regroup_sweep(const KernelArgs& a, const RegroupSmem& sm, const MotionCtx& mc, float ox, float oy, float oz, float dx, float dy,
-                                              float dz, float& hit_t, int& hit_index, unsigned& flagged) {
+// MMA: stage 1 on the tensor path (pt_sweep_mma.cuh); the ray fragments pass through the warp's own 32 columns of the
+// exchange buffer, which nobody else touches between this warp's read-back in cta_regroup and the next trip's first barrier.
+// `active`: the lane has a path in flight (its ray is the parked ray otherwise).
+template <bool MOTION, bool MMA>
+__device__ __forceinline__ void regroup_sweep(const KernelArgs& a, const RegroupSmem& sm, const MotionCtx& mc, bool active, float ox, float oy, float oz, float dx,
+                                              float dy, float dz, float& hit_t, int& hit_index, unsigned& flagged) {
     hit_t = kMaxT;
     hit_index = -1;
+    if (MMA) {
+        int ovf_step;
+        const int n = sweep_mma(reinterpret_cast<const uint4*>(sm.pf), a.n_steps, sm.xchg, sm.queue, a.mma, active, ox, oy, oz, dx, dy, dz, ovf_step);
+        sweep_mma_drain<MOTION>(a.blocks, mc, sm.queue_base, n, ovf_step, a.n_steps, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
+        return;
+    }
     const float nod = -((ox * dx + oy * dy) + oz * dz);
     const float oo = ((ox * ox + oy * oy) + oz * oz) * (1.0f - kSlack);
     int cnt = 0;
@@ -155,12 +175,12 @@ __device__ __forceinline__ void regroup_sweep(const KernelArgs& a, const Regroup
     sweep_drain<MOTION, true>(a.blocks, mc, sm.queue, cnt, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
 }
 
-template <bool MOTION>
+template <bool MOTION, bool MMA>
 __global__ void __launch_bounds__(kCtaThreads) pt_megakernel_regroup(const __grid_constant__ KernelArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
-    const RegroupSmem sm(smem_raw, a.n_blocks);
-    regroup_stage(a, sm, &bar);
+    const RegroupSmem sm(smem_raw, regroup_image_bytes<MMA>(a));
+    regroup_stage<MMA>(a, sm, &bar);
     const MotionCtx mc{a.motion, const_cast<const float*>(sm.tslot), a.order};
 
     const unsigned lane_id = threadIdx.x & 31u;
@@ -183,12 +203,14 @@ __global__ void __launch_bounds__(kCtaThreads) pt_megakernel_regroup(const __gri
         if (__any_sync(kFullMask, L.active)) {  // regrouping collects idle lanes in whole warps: they skip the sweep
             sweeps += 1u;
             unsigned flagged = 0u;
-            regroup_sweep<MOTION>(a, sm, mc, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
+            regroup_sweep<MOTION, MMA>(a, sm, mc, L.active, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
         }
         __syncwarp();
         L.pend = *sm.pend != 0u;  // (parked in shared memory across the sweep)
         L.time = *sm.tslot;
-        if (!cta_regroup(a, L, hit_t, hit_index, sm.xchg, sm.cat_count + (trip & 1u) * 8u, lane_id)) break;
+        // (PT_REGROUP_PERIOD > 1, an experiment knob: regroup only every n-th trip; between two regroups a path is shaded by the lane that swept it)
+        if (PT_REGROUP_PERIOD == 1 || trip % PT_REGROUP_PERIOD == 0u)
+            if (!cta_regroup(a, L, hit_t, hit_index, sm.xchg, sm.cat_count + ((trip / PT_REGROUP_PERIOD) & 1u) * 8u, lane_id)) break;
         if (L.active) {
             rays += 1ULL;  // scene.rs:57
             lane_shade<MOTION>(a, L, a.blocks, *sm.P, mc, hit_t, hit_index);
@@ -203,12 +225,12 @@ __global__ void __launch_bounds__(kCtaThreads) pt_megakernel_regroup(const __gri
 
 // pt_debug_hits for scenes this kernel renders: caller-supplied rays through regroup_sweep (same staging, operands, queue,
 // re-tests)
-template <bool MOTION>
+template <bool MOTION, bool MMA>
 __global__ void __launch_bounds__(kCtaThreads) pt_debug_hits_regroup(const __grid_constant__ KernelArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
-    const RegroupSmem sm(smem_raw, a.n_blocks);
-    regroup_stage(a, sm, &bar);
+    const RegroupSmem sm(smem_raw, regroup_image_bytes<MMA>(a));
+    regroup_stage<MMA>(a, sm, &bar);
     const MotionCtx mc{a.motion, const_cast<const float*>(sm.tslot), a.order};
     for (uint32_t base = blockIdx.x * kCtaThreads; base < a.dbg_n; base += gridDim.x * kCtaThreads) {
         const uint32_t i = base + threadIdx.x;
@@ -223,7 +245,7 @@ __global__ void __launch_bounds__(kCtaThreads) pt_debug_hits_regroup(const __gri
         float hit_t;
         int hit_index;
         unsigned flagged = 0u;
-        regroup_sweep<MOTION>(a, sm, mc, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
+        regroup_sweep<MOTION, MMA>(a, sm, mc, i < a.dbg_n, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
         if (i < a.dbg_n) {
             a.dbg_idx[i] = hit_index < 0 ? -1 : (a.order ? (int32_t)__ldg(a.order + hit_index) : hit_index);
             a.dbg_t[i] = hit_t;

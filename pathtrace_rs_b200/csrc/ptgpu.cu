@@ -60,6 +60,11 @@ struct FlatScene {
     std::vector<pt::DevMotion> motion;
     std::vector<unsigned char> perlin_raw;
     std::unique_ptr<pt::ConstImageT<true>> const_image;  // X,Y,Z planes for the kernel-parameter image (n_blocks <= kMaxConstBlocks)
+    // tensor-path pre-filter (pt_sweep_mma.cuh): fragment-ordered f16 sphere operand + the scene's scales; mma_ok = the
+    // scene is one the tensor path is worth using on (enough spheres, absolute slack small against the spheres' size)
+    std::vector<uint4> mma_image;
+    pt::MmaScale mma{0.f, 0.f, 0.f, 0.f};
+    bool mma_ok = false;
 };
 
 // One device's copy of a scene plus its per-render scratch.
@@ -85,6 +90,12 @@ struct Replica {
     bool const_image = false;       // resident kernel reads X,Y,Z through the kernel-parameter image
     bool wave = false;              // ... in its wavefront form (pt_wave.cuh): one CTA per SM, wave_pool paths in shared memory
     bool regroup = false;           // resident scene rendered by the one-path-per-lane kernel with the CTA regroup (pt_regroup.cuh): the default
+    bool mma = false;               // ... with stage 1 of its sweep on the tensor path (pt_sweep_mma.cuh)
+    bool mma_ok = false;            // the scene has a usable tensor-path image
+    uint4* d_mma_image = nullptr;
+    pt::MmaScale mma_scale{0.f, 0.f, 0.f, 0.f};
+    size_t fp32_smem_bytes = 0;     // the FP32 regroup kernel's launch geometry, kept as the per-render fallback of the tensor path
+    int fp32_ctas_per_sm = 0;       // (camera outside the extent the f16 operands were scaled for)
     int wave_pool = 0;
     const pt::ConstImageT<true>* h_const_image = nullptr;  // owned by the PtScene; passed by value at every launch (24 KB)
     // per-render scratch.  At most one render is in flight per replica: every launch waits for the previous one's
@@ -156,9 +167,17 @@ size_t resident_smem(int n_blocks, bool const_image) {
 }
 constexpr size_t kRegroupBytes = (size_t)pt::kRegroupWords * pt::kCtaThreads * sizeof(uint32_t) + 64;  // regroup kernel: path-state exchange + category counters
 size_t regroup_smem(int n_blocks) { return (size_t)n_blocks * 64 + kStreamedFixedBytes + kRegroupBytes; }
+size_t regroup_mma_smem(int n_blocks) { return (size_t)(n_blocks / pt::kLdsGroupBlocks + 1) * 512 + kStreamedFixedBytes + kRegroupBytes; }  // 32 B per sphere + one step of padding
+// which resident kernel renders the scene: 0 automatic = the tensor-path regroup kernel where the scene suits it (5), else the FP32 one (4)
+uint32_t resident_choice(const PtOptions& opt, bool mma_ok, int n_blocks) {
+    uint32_t k = opt.resident_kernel;
+    if (k == 0) k = 5;
+    if (k == 5 && !(mma_ok && regroup_mma_smem(n_blocks) <= kMaxDynSmem / 2)) k = 4;  // two CTAs per SM at least
+    return k;
+}
 bool fits_resident(int n_blocks, const PtOptions& opt) {
     if (opt.force_stream_tile_blocks > 0 && n_blocks > 0) return false;
-    if (opt.resident_kernel == 0 || opt.resident_kernel == 4) return regroup_smem(n_blocks) <= kMaxDynSmem;
+    if (opt.resident_kernel == 0 || opt.resident_kernel == 4 || opt.resident_kernel == 5) return regroup_smem(n_blocks) <= kMaxDynSmem;
     return resident_smem(n_blocks, n_blocks <= pt::kMaxConstBlocks && opt.resident_kernel != 3) <= kMaxDynSmem;
 }
 
@@ -171,15 +190,27 @@ int plan_launch(Replica* s) {
         s->tile_blocks = s->n_blocks;
         s->n_tiles = 1;
         int rc;
-        if (s->opt.resident_kernel == 0 || s->opt.resident_kernel == 4) {  // default: one path per lane + CTA regroup, the fastest measured
+        const uint32_t choice = resident_choice(s->opt, s->mma_ok, s->n_blocks);
+        if (choice == 4 || choice == 5) {  // one path per lane + CTA regroup (pt_regroup.cuh), the fastest measured
             s->regroup = true;
             s->const_image = false;
             s->smem_bytes = regroup_smem(s->n_blocks);
-            rc = s->d_motion ? configure_kernel(pt::pt_megakernel_regroup<true>, s->smem_bytes, &s->ctas_per_sm)
-                             : configure_kernel(pt::pt_megakernel_regroup<false>, s->smem_bytes, &s->ctas_per_sm);
+            rc = s->d_motion ? configure_kernel(pt::pt_megakernel_regroup<true, false>, s->smem_bytes, &s->ctas_per_sm)
+                             : configure_kernel(pt::pt_megakernel_regroup<false, false>, s->smem_bytes, &s->ctas_per_sm);
             if (rc == PT_OK)
-                rc = s->d_motion ? configure_kernel(pt::pt_debug_hits_regroup<true>, s->smem_bytes, nullptr)
-                                 : configure_kernel(pt::pt_debug_hits_regroup<false>, s->smem_bytes, nullptr);
+                rc = s->d_motion ? configure_kernel(pt::pt_debug_hits_regroup<true, false>, s->smem_bytes, nullptr)
+                                 : configure_kernel(pt::pt_debug_hits_regroup<false, false>, s->smem_bytes, nullptr);
+            s->fp32_smem_bytes = s->smem_bytes;
+            s->fp32_ctas_per_sm = s->ctas_per_sm;
+            if (rc == PT_OK && choice == 5) {  // stage 1 of the sweep on the tensor path; the FP32 kernel above stays configured as its fallback
+                s->mma = true;
+                s->smem_bytes = regroup_mma_smem(s->n_blocks);
+                rc = s->d_motion ? configure_kernel(pt::pt_megakernel_regroup<true, true>, s->smem_bytes, &s->ctas_per_sm)
+                                 : configure_kernel(pt::pt_megakernel_regroup<false, true>, s->smem_bytes, &s->ctas_per_sm);
+                if (rc == PT_OK)
+                    rc = s->d_motion ? configure_kernel(pt::pt_debug_hits_regroup<true, true>, s->smem_bytes, nullptr)
+                                     : configure_kernel(pt::pt_debug_hits_regroup<false, true>, s->smem_bytes, nullptr);
+            }
             return rc;
         }
         if (s->const_image && s->opt.resident_kernel == 1) {
@@ -265,7 +296,7 @@ int normalise_options(const PtOptions* in, PtOptions* out) {
     if (in) {
         if (in->struct_size != sizeof(PtOptions)) return fail(PT_ERR_INVALID, "PtOptions.struct_size %u != %zu (ABI mismatch)", in->struct_size, sizeof(PtOptions));
         o = *in;
-        if (o.force_stream_tile_blocks < 0 || o.stream_ctas < 0 || o.stream_ctas > 4 || o.chunk_samples < -1 || o.spatial_order < -1 || o.spatial_order > 2 || o.resident_kernel > 4)
+        if (o.force_stream_tile_blocks < 0 || o.stream_ctas < 0 || o.stream_ctas > 4 || o.chunk_samples < -1 || o.spatial_order < -1 || o.spatial_order > 2 || o.resident_kernel > 5)
             return fail(PT_ERR_INVALID, "PtOptions field out of range");
     }
     if (o.tile_rows == 0) o.tile_rows = 4;
@@ -309,6 +340,9 @@ void fill_scene_args(const Replica* s, pt::KernelArgs& a) {
     a.perlin = s->d_perlin;
     a.prefilter = s->d_prefilter;
     a.kplane = s->d_kplane;
+    a.mma_image = s->d_mma_image;
+    a.n_steps = s->n_blocks / pt::kLdsGroupBlocks;
+    a.mma = s->mma_scale;
     a.motion = s->d_motion;
     a.has_noise = s->has_noise ? 1 : 0;
     a.tile_blocks = s->tile_blocks;
@@ -381,10 +415,23 @@ int launch_update(Replica* s, const PtParams* params, const PtCamera* cam, uint3
     s->stats.grid_ctas = 0;
     if (a.n_owned_pixels == 0) return serialise_end(s, stream);
 
+    // tensor-path sweep: its f16 operands are scaled for ray origins inside the scene's extent (bounce rays start on sphere
+    // surfaces).  A camera outside it would send every primary ray down the exact-test-on-everything path (correct, slow):
+    // such a render goes to the FP32 kernel instead.
+    bool use_mma = s->mma;
+    if (use_mma) {
+        double reach = 0.0;
+        for (int i = 0; i < 3; ++i) reach += ((double)std::fabs(cam->origin[i]) + (double)std::fabs(cam->lens_radius) * (std::fabs(cam->u[i]) + std::fabs(cam->v[i]))) *
+                                             ((double)std::fabs(cam->origin[i]) + (double)std::fabs(cam->lens_radius) * (std::fabs(cam->u[i]) + std::fabs(cam->v[i])));
+        if (!(reach <= (double)s->mma_scale.max_o2)) use_mma = false;
+    }
+    const int ctas_per_sm = (s->mma && !use_mma) ? s->fp32_ctas_per_sm : s->ctas_per_sm;
+    const size_t smem_bytes = (s->mma && !use_mma) ? s->fp32_smem_bytes : s->smem_bytes;
+
     // persistent grid: one wave of CTAs, never more lanes than pixels.  The resident kernel carries two paths per lane;
     // an image with fewer pixels than the machine has lanes keeps one path per lane (latency, not throughput, is what
     // counts there) and the second row stays parked.
-    const uint32_t max_ctas = (uint32_t)(s->sm_count * s->ctas_per_sm);
+    const uint32_t max_ctas = (uint32_t)(s->sm_count * ctas_per_sm);
     const uint32_t paths_per_cta = s->wave ? (uint32_t)s->wave_pool : (uint32_t)pt::kCtaThreads * (s->resident && !s->regroup ? pt::kPathRows : 1);
     a.wave_pool = s->wave_pool;
     uint32_t want = (a.n_owned_pixels + paths_per_cta - 1) / paths_per_cta;
@@ -439,9 +486,12 @@ int launch_update(Replica* s, const PtParams* params, const PtCamera* cam, uint3
         PT_CUDA(cudaMemsetAsync(s->d_pixstate, 0, (size_t)a.n_owned_pixels * pt::kPixStateWords * sizeof(uint32_t), stream));
         a.pixstate = s->d_pixstate;
     }
-    if (s->regroup) {
-        if (s->d_motion) pt::pt_megakernel_regroup<true><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a);
-        else pt::pt_megakernel_regroup<false><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a);
+    if (s->regroup && use_mma) {
+        if (s->d_motion) pt::pt_megakernel_regroup<true, true><<<grid, pt::kCtaThreads, smem_bytes, stream>>>(a);
+        else pt::pt_megakernel_regroup<false, true><<<grid, pt::kCtaThreads, smem_bytes, stream>>>(a);
+    } else if (s->regroup) {
+        if (s->d_motion) pt::pt_megakernel_regroup<true, false><<<grid, pt::kCtaThreads, smem_bytes, stream>>>(a);
+        else pt::pt_megakernel_regroup<false, false><<<grid, pt::kCtaThreads, smem_bytes, stream>>>(a);
     } else if (s->wave) {
         if (s->d_motion) pt::pt_megakernel_wave<true><<<grid, pt::kWaveThreads, s->smem_bytes, stream>>>(a, *s->h_const_image);
         else pt::pt_megakernel_wave<false><<<grid, pt::kWaveThreads, s->smem_bytes, stream>>>(a, *s->h_const_image);
@@ -464,8 +514,8 @@ int launch_update(Replica* s, const PtParams* params, const PtCamera* cam, uint3
     s->stats.kernel_launches = 1;
     s->stats.grid_ctas = grid;
     s->stats.cta_threads = s->wave ? pt::kWaveThreads : pt::kCtaThreads;
-    s->stats.smem_bytes = (uint32_t)s->smem_bytes;
-    s->stats.resident = s->resident ? 1u : 0u;
+    s->stats.smem_bytes = (uint32_t)smem_bytes;
+    s->stats.resident = s->resident ? ((s->regroup && use_mma) ? 2u : 1u) : 0u;
     s->stats.n_spheres = s->n_spheres;
     return PT_OK;
 }
@@ -522,6 +572,72 @@ int copy_owned_rows(Replica* s, const PtParams* params, const PtPartition& part,
     *bytes_out = bytes;
     return PT_OK;
 }
+
+// Tensor-path pre-filter image (pt_sweep_mma.cuh).  bound: per stored sphere the centre and radius the filter tests.
+// extent = twice the reach of the spheres (so a camera up to one scene-size away still renders on this path); sigma maps it
+// to kMmaExtentTarget, s keeps K' / s and sigma^2 |o|^2 / s inside the f16 range.  Not built (mma_ok = false) for scenes
+// where it cannot pay: fewer than 128 spheres (one or two loop steps: the FP32 loop has less set-up per sweep), or spheres so
+// small against the scene's extent that the absolute slack of the f16 subnormal range would flag them for every nearby ray.
+void build_mma_image(FlatScene& fs, const std::vector<double>& bound) {
+    fs.mma_ok = false;
+    const uint32_t n = fs.n_spheres;
+    if (n < 128) return;
+    double reach = 0.0;
+    std::vector<double> r2s;
+    r2s.reserve(n);
+    for (uint32_t j = 0; j < n; ++j) {
+        const double* b = &bound[(size_t)j * 4];
+        const double d = std::sqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]) + b[3];
+        if (!std::isfinite(d)) return;
+        reach = std::max(reach, d);
+        r2s.push_back(b[3] * b[3]);
+    }
+    const double extent = 2.0 * reach;
+    if (!(extent > 1.0e-12 && extent < 1.0e15)) return;
+    const double sigma = std::exp2(std::floor(std::log2(pt::kMmaExtentTarget / extent)));
+    const double s = std::exp2(std::ceil(std::log2(sigma * sigma * extent * extent / 32768.0)));
+    std::nth_element(r2s.begin(), r2s.begin() + r2s.size() / 2, r2s.end());
+    const double median_r2 = r2s[r2s.size() / 2];
+    if (!(pt::kMmaAbsSlack / (sigma * sigma) <= 0.05 * median_r2)) return;
+    fs.mma.sigma = (float)sigma;
+    fs.mma.s = (float)s;
+    fs.mma.inv_s = (float)(1.0 / s);
+    fs.mma.max_o2 = (float)(extent * extent * (1.0 - 1e-6));
+    const int n_steps = fs.n_blocks / pt::kLdsGroupBlocks;
+    auto h16 = [](float x) { const __half h = __float2half_rn(x); unsigned short u; std::memcpy(&u, &h, 2); return u; };
+    auto h2f = [](unsigned short u) { __half h; std::memcpy(&h, &u, 2); return __half2float(h); };
+    std::vector<unsigned short> row((size_t)n_steps * 16 * 16, 0);  // per stored sphere its 16 K halves
+    for (int j = 0; j < n_steps * 16; ++j) {
+        float S[5] = {0.0f, 0.0f, 0.0f, (float)s, -65504.0f};  // padding: B' <= -65504 s + slack terms < 0 for every ray in range
+        if ((uint32_t)j < n) {
+            const double* b = &bound[(size_t)j * 4];
+            const double c2 = b[0] * b[0] + b[1] * b[1] + b[2] * b[2], r2 = b[3] * b[3];
+            const double Kp = sigma * sigma * (r2 - c2 + pt::kMmaSlackSphere * (c2 + r2)) + pt::kMmaAbsSlack;
+            S[0] = (float)(sigma * b[0]);
+            S[1] = (float)(sigma * b[1]);
+            S[2] = (float)(sigma * b[2]);
+            S[4] = std::nextafter((float)(Kp / s), INFINITY);  // round towards "candidate"
+        }
+        for (int e = 0; e < 5; ++e) {
+            const unsigned short hi = h16(S[e]);
+            const unsigned short lo = h16(S[e] - h2f(hi));
+            row[(size_t)j * 16 + e] = hi;
+            row[(size_t)j * 16 + 5 + e] = hi;
+            row[(size_t)j * 16 + 10 + e] = lo;
+        }
+    }
+    // B-operand fragments: lane (g, t) of step st holds {b0, b1} of sphere group 0 (sphere 16 st + g) and of group 1
+    // (sphere 16 st + 8 + g): K halves (2t, 2t+1) and (2t+8, 2t+9).  One zero step of padding (the loop fetches ahead).
+    fs.mma_image.assign((size_t)(n_steps + 1) * 32, make_uint4(0u, 0u, 0u, 0u));
+    for (int st = 0; st < n_steps; ++st)
+        for (int lane = 0; lane < 32; ++lane) {
+            const int g = lane >> 2, t = lane & 3;
+            auto pk = [&](int r, int k) { return (uint32_t)row[(size_t)(st * 16 + r) * 16 + k] | ((uint32_t)row[(size_t)(st * 16 + r) * 16 + k + 1] << 16); };
+            fs.mma_image[(size_t)st * 32 + lane] = make_uint4(pk(g, 2 * t), pk(g, 2 * t + 8), pk(8 + g, 2 * t), pk(8 + g, 2 * t + 8));
+        }
+    fs.mma_ok = true;
+}
+
 
 // Storage order of a scene's spheres (see pt_scene_create).  Fills order_of[j] = position in the caller's list of the
 // sphere stored at j and returns the mode: 0 the caller's order, 1 Morton, 2 large spheres first, then Morton.
@@ -698,6 +814,7 @@ int flatten_scene(const PtSceneDesc* desc, const PtOptions& opt, FlatScene& fs) 
     // error), so every sphere the exact expression accepts is a candidate.  Proven per ray, not assumed:
     // pt_debug_hits mode 0 against mode 1 in tests/test_gpu_hits.py.
     fs.prefilter.assign((size_t)std::max(fs.n_blocks, 1) * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+    std::vector<double> bound((size_t)n * 4, 0.0);  // per stored sphere: centre and radius of what the filter tests (a MovingSphere's static bound)
     for (int j = 0; j < fs.n_blocks; ++j) {
         float* f = reinterpret_cast<float*>(&fs.prefilter[(size_t)j * 4]);
         for (int e = 0; e < 4; ++e) {
@@ -712,6 +829,8 @@ int flatten_scene(const PtSceneDesc* desc, const PtOptions& opt, FlatScene& fs) 
                 r += 0.5 * std::sqrt(ex * ex + ey * ey + ez * ez) * (1.0 + 1e-5) + 1e-6 * (std::fabs(cx) + std::fabs(cy) + std::fabs(cz) + r);
             }
             const double c2 = cx * cx + cy * cy + cz * cz, r2 = r * r;
+            double* bd = &bound[((size_t)j * 4 + e) * 4];
+            bd[0] = cx; bd[1] = cy; bd[2] = cz; bd[3] = r;
             if (!(c2 + r2 < 1.0e24)) {  // too large (or NaN) for the expanded form: always a candidate, the exact test decides
                 f[12 + e] = INFINITY;
                 continue;
@@ -723,6 +842,7 @@ int flatten_scene(const PtSceneDesc* desc, const PtOptions& opt, FlatScene& fs) 
             f[12 + e] = std::nextafter((float)k, INFINITY);  // round towards "candidate"
         }
     }
+    build_mma_image(fs, bound);
     // K plane alone + the kernel-parameter image of the X, Y, Z planes (resident kernel, small scenes)
     fs.kplane.assign((size_t)std::max(fs.n_blocks, 1), make_float4(0.f, 0.f, 0.f, 0.f));
     for (int j = 0; j < fs.n_blocks; ++j) fs.kplane[j] = fs.prefilter[(size_t)j * 4 + 3];
@@ -829,6 +949,7 @@ void destroy_replica(Replica* s) {
     cudaFree(s->d_perlin);
     cudaFree(s->d_prefilter);
     cudaFree(s->d_kplane);
+    cudaFree(s->d_mma_image);
     cudaFree(s->d_motion);
     cudaFree(s->d_ray_count);
     cudaFree(s->d_sweep_count);
@@ -877,6 +998,9 @@ int create_replica(const FlatScene& fs, int device, const PtOptions& opt, Replic
     if (rc == PT_OK) rc = upload(&s->d_motion, fs.motion);
     if (rc == PT_OK) rc = upload(&s->d_prefilter, fs.prefilter);
     if (rc == PT_OK) rc = upload(&s->d_kplane, fs.kplane);
+    if (rc == PT_OK && fs.mma_ok) rc = upload(&s->d_mma_image, fs.mma_image);
+    s->mma_ok = fs.mma_ok;
+    s->mma_scale = fs.mma;
     if (rc == PT_OK) {
         std::vector<unsigned char> raw = fs.perlin_raw;
         unsigned char* d = nullptr;
@@ -1345,8 +1469,13 @@ int pt_debug_hits(PtScene* sc, const float* rays6, const float* times, uint32_t 
             else pt::pt_debug_hits_exact_all<false><<<grid, 256, 0, s->stream>>>(a);
         } else if (rc == PT_OK && s->regroup) {
             const uint32_t grid = std::min<uint32_t>((n + pt::kCtaThreads - 1) / pt::kCtaThreads, max_ctas);
-            if (s->d_motion) pt::pt_debug_hits_regroup<true><<<grid, pt::kCtaThreads, s->smem_bytes, s->stream>>>(a);
-            else pt::pt_debug_hits_regroup<false><<<grid, pt::kCtaThreads, s->smem_bytes, s->stream>>>(a);
+            if (s->mma) {
+                if (s->d_motion) pt::pt_debug_hits_regroup<true, true><<<grid, pt::kCtaThreads, s->smem_bytes, s->stream>>>(a);
+                else pt::pt_debug_hits_regroup<false, true><<<grid, pt::kCtaThreads, s->smem_bytes, s->stream>>>(a);
+            } else {
+                if (s->d_motion) pt::pt_debug_hits_regroup<true, false><<<grid, pt::kCtaThreads, s->smem_bytes, s->stream>>>(a);
+                else pt::pt_debug_hits_regroup<false, false><<<grid, pt::kCtaThreads, s->smem_bytes, s->stream>>>(a);
+            }
         } else if (rc == PT_OK && s->resident) {
             const uint32_t batch = (uint32_t)pt::kCtaThreads * pt::kPathRows;
             const uint32_t grid = std::min<uint32_t>((n + batch - 1) / batch, (uint32_t)s->sm_count * 2u);

@@ -60,7 +60,7 @@ def test_ten_million_recorded_rays_of_cfg1():
     rays, each through the shipped sweep, the device's exact-on-all test and the oracle."""
     w, h = 200, 100
     pr = pt.Preset("random_spheres", pt.Params(w, h, 1, 50)).create_scene(0)
-    assert pr.stats().resident in (0, 1)
+    assert pr.stats().resident in (0, 1, 2)
     sc = orc.Scene("random_spheres", w, h)
     rays, _ = sc.record_rays(200, 50, 12_000_000)
     assert len(rays) > 10_000_000
@@ -71,14 +71,16 @@ def test_ten_million_recorded_rays_of_cfg1():
 
 
 def test_recorded_rays_through_every_kernel_flavour():
-    """The same rays through every sweep the library has: the default resident kernel, the L2-streamed kernel forced onto
-    the 488-sphere scene (8 tiles, the last one ragged), every storage order, and the two-rays-per-lane sweeps with the
-    sphere pairs as uniform operands (kernel-parameter image) and as LDS.128 operands."""
+    """The same rays through every sweep the library has: the default resident kernel (pre-filter on the tensor path), the
+    same kernel with the packed-FP32 pre-filter, the L2-streamed kernel forced onto the 488-sphere scene (8 tiles, the last
+    one ragged), every storage order, and the two-rays-per-lane sweeps with the sphere pairs as uniform operands
+    (kernel-parameter image) and as LDS.128 operands."""
     w, h = 96, 48
     sc = orc.Scene("random_spheres", w, h)
     rays, _ = sc.record_rays(16, 50, 400_000)
     base = None
-    for opt in (None, pt.PtOptions(force_stream_tile_blocks=16), pt.PtOptions(spatial_order=0), pt.PtOptions(spatial_order=1),
+    for opt in (None, pt.PtOptions(resident_kernel=5), pt.PtOptions(resident_kernel=4), pt.PtOptions(force_stream_tile_blocks=16),
+                pt.PtOptions(spatial_order=0), pt.PtOptions(spatial_order=1), pt.PtOptions(resident_kernel=5, spatial_order=0),
                 pt.PtOptions(resident_kernel=2), pt.PtOptions(resident_kernel=3), pt.PtOptions(resident_kernel=1)):
         pr = pt.Preset("random_spheres", pt.Params(w, h, 1, 50)).create_scene(0, opt)
         idx, t, _ = _check(pr, sc, rays)
@@ -292,6 +294,75 @@ def test_duplicate_and_concentric_spheres_tie_rule():
         assert (idx[idx >= 0] < 120).all()  # always the first copy
     finally:
         h.close()
+
+
+def _renders_on_the_tensor_path(h):
+    """One 8x8 render through the raw ABI, camera at the origin: PtRenderStats.resident == 2 <=> the scene's sweep runs its
+    pre-filter on the tensor path (pt_sweep_mma.cuh)."""
+    L = ffi.libptgpu()
+    p = pt.Params(8, 8, 1, 2).to_ffi()
+    cam = ffi.PtCamera()
+    cam.lower_left_corner[:] = [-1.0, -1.0, -1.0]
+    cam.horizontal[:] = [2.0, 0.0, 0.0]
+    cam.vertical[:] = [0.0, 2.0, 0.0]
+    cam.u[:] = [1.0, 0.0, 0.0]
+    cam.v[:] = [0.0, 1.0, 0.0]
+    cam.time1 = 1.0
+    buf = np.zeros((8, 8, 3), np.float32)
+    rays = C.c_uint64(0)
+    ffi.check(L.pt_render(h.scene_handle, C.byref(p), C.byref(cam), 0, buf.ctypes.data_as(C.c_void_p), C.byref(rays)))
+    st = ffi.PtRenderStats()
+    ffi.check(L.pt_scene_stats(h.scene_handle, C.byref(st)))
+    return st.resident == 2
+
+
+def test_tensor_path_queue_overflow_and_rays_outside_its_domain():
+    """What the tensor-path pre-filter does when it cannot do its job: (1) 400 nested shells around the origin — every ray
+    flags every 16-sphere step, the finder lanes' 12-entry queues fill up and the quad falls back to the exact test on every
+    sphere from the first dropped step on; (2) rays whose origin lies beyond the extent the f16 operands are scaled for
+    (twice the scene's reach), with non-finite-free but non-unit directions among them — they bypass stage 1 altogether.
+    Both must still give the exact sweep's (index, t) bit for bit."""
+    rng = np.random.default_rng(11)
+    cr = np.zeros((400, 4))
+    cr[:, :3] = rng.normal(size=(400, 3)) * 0.05
+    cr[:, 3] = np.linspace(5.0, 45.0, 400)
+    h, sc = _custom_scene(cr.astype(np.float32), pt.PtOptions(resident_kernel=5))
+    try:
+        assert _renders_on_the_tensor_path(h)
+        o = rng.uniform(-1.0, 1.0, (60_000, 3))
+        inside = np.hstack([o, _unit(rng.normal(size=(60_000, 3)))])                       # inside every shell: 400 candidates per ray
+        far_o = _unit(rng.normal(size=(60_000, 3))) * rng.choice([150.0, 1.0e3, 1.0e5], size=(60_000, 1))
+        tgt = rng.uniform(-40.0, 40.0, (60_000, 3))
+        far = np.hstack([far_o, _unit(tgt - far_o)])                                      # beyond the extent (2 x 45 = 90)
+        rays = np.vstack([inside, far]).astype(np.float32)
+        rays[:, 3:] = _unit(rays[:, 3:])
+        idx, _, flagged = _check(h, sc, rays)
+        assert (flagged[:60_000] == 400).all() and (idx[:60_000] >= 0).all()
+        assert (flagged[60_000:] == 400).all()   # out of domain: the exact test on everything
+    finally:
+        h.close()
+
+
+def test_tensor_path_is_chosen_only_where_it_can_pay():
+    """resident_kernel = 5 (or automatic) needs at least 128 spheres and spheres that are not tiny against the scene's extent
+    (the f16 subnormal range costs an absolute slack); otherwise the scene keeps the packed-FP32 pre-filter.  Either way the
+    hits are the exact sweep's."""
+    rng = np.random.default_rng(12)
+    few = np.hstack([rng.uniform(-6, 6, (100, 3)), rng.uniform(0.2, 1.0, (100, 1))])
+    tiny = np.hstack([rng.uniform(-6, 6, (300, 3)), np.full((300, 1), 1.0e-3)])
+    tiny[0] = [0.0, -1.0e5, 0.0, 1.0e5]                                                   # a huge ground sets the extent
+    normal = np.hstack([rng.uniform(-6, 6, (300, 3)), rng.uniform(0.2, 1.0, (300, 1))])
+    for cr, want in ((few, False), (tiny, False), (normal, True)):
+        h, sc = _custom_scene(cr.astype(np.float32), pt.PtOptions(resident_kernel=5))
+        try:
+            assert _renders_on_the_tensor_path(h) == want
+            o = _unit(rng.normal(size=(50_000, 3))) * 20.0
+            tgt = rng.uniform(-6, 6, (50_000, 3))
+            rays = np.hstack([o, _unit(tgt - o)]).astype(np.float32)
+            rays[:, 3:] = _unit(rays[:, 3:])
+            _check(h, sc, rays)
+        finally:
+            h.close()
 
 
 def test_debug_hits_rejects_bad_arguments():

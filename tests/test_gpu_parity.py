@@ -404,13 +404,14 @@ def test_host_register_round_trip():
 @pytest.mark.parametrize("preset,w,h,spp", [("random_spheres", 160, 90, 12), ("random", 128, 64, 8), ("two_perlin_spheres", 96, 54, 8),
                                              ("small", 64, 32, 16), ("smallpt", 48, 48, 8)])
 def test_resident_kernel_flavours_render_the_same_image(preset, w, h, spp):
-    """One path per lane + CTA regroup (the default), two paths per lane with uniform / shared-memory sphere operands, and
-    the wavefront form with its path pool and per-material queues: a path's RNG stream and arithmetic do not depend on which
-    lane, warp or kernel runs it, so all four must produce the same bits and the same ray count — also for a second,
-    blended frame and through a row partition."""
+    """One path per lane + CTA regroup with the pre-filter on the tensor path (the default where the scene suits it) or in
+    packed FP32, two paths per lane with uniform / shared-memory sphere operands, and the wavefront form with its path pool
+    and per-material queues: a path's RNG stream and arithmetic do not depend on which lane, warp or kernel runs it, and the
+    exact test decides every hit whatever pre-filter handed it the candidates, so all must produce the same bits and the same
+    ray count — also for a second, blended frame and through a row partition."""
     base, rays0, pr0 = gpu_render(preset, w, h, spp, 50)
-    assert pr0.stats().resident == 1
-    for flavour in (4, 3, 2, 1):
+    assert pr0.stats().resident == (2 if preset in ("random_spheres", "random") else 1)  # 488 spheres: tensor path; 2-9 spheres: FP32
+    for flavour in (5, 4, 3, 2, 1):
         opt = pt.PtOptions(resident_kernel=flavour)
         img, rays, pr = gpu_render(preset, w, h, spp, 50, options=opt)
         assert rays == rays0 and np.array_equal(img, base), flavour
@@ -424,6 +425,30 @@ def test_resident_kernel_flavours_render_the_same_image(preset, w, h, spp):
             _, r = pr.update(pt.Params(w, h, spp, 50), buffer=parts, part=ffi.PtPartition(3, idx, 2, 0))
             total += r
         assert total == rays0 and np.array_equal(parts, base), flavour
+
+
+def test_tensor_path_render_falls_back_when_the_camera_leaves_the_scene():
+    """The f16 operands of the tensor-path pre-filter are scaled for ray origins within twice the scene's reach (4000 for the
+    RTIOW scenes).  A render from a camera beyond that goes to the packed-FP32 kernel (PtRenderStats.resident 1 instead of 2);
+    the image is what the FP32-only scene renders from the same camera."""
+    w, h, spp = 96, 48, 4
+    p = pt.Params(w, h, spp, 50)
+    auto = pt.Preset("random_spheres", p).create_scene(0)
+    fp32 = pt.Preset("random_spheres", p).create_scene(0, pt.PtOptions(resident_kernel=4))
+    L = ffi.libptgpu()
+    pf = p.to_ffi()
+    for shift, want in ((0.0, 2), (3.0e3, 2), (5.0e3, 1), (1.0e6, 1)):
+        out = []
+        for pr in (auto, fp32):
+            cam = pr.camera
+            cam.origin[1] += shift
+            cam.lower_left_corner[1] += shift
+            buf = np.zeros((h, w, 3), np.float32)
+            rays = C.c_uint64(0)
+            ffi.check(L.pt_render(pr.scene_handle, C.byref(pf), C.byref(cam), 0, buf.ctypes.data_as(C.c_void_p), C.byref(rays)))
+            out.append((buf, rays.value, pr.stats().resident))
+        assert out[0][2] == want and out[1][2] == 1, shift
+        assert out[0][1] == out[1][1] and np.array_equal(out[0][0], out[1][0]), shift
 
 
 def test_wavefront_kernel_on_a_large_image_with_the_chunk_queue():

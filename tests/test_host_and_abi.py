@@ -68,11 +68,21 @@ def test_library_is_sm100a_cuda_with_packed_fp32_and_tma():
         assert len(re.findall(r"FFMA2 R\d+, R\d+(?:\.reuse)?\.F32, UR\d+\.F32x2\.HI_LO, ", body[0])) >= 96, "FFMA2 with uniform sphere pairs lost"
     # LDS flavours (larger resident scenes, streamed scenes): broadcast LDS.128 of the pre-filter image (not generic loads,
     # not local memory) feeding FFMA2 Rpair(spheres) * Rscalar(ray) + Rpair.
-    for name in ("_ZN2pt21pt_megakernel_regroup", "_ZN2pt22pt_megakernel_residentILb0E", "_ZN2pt22pt_megakernel_streamed"):  # mangled prefixes
+    for name in ("_ZN2pt21pt_megakernel_regroupILb0ELb0E", "_ZN2pt21pt_megakernel_regroupILb1ELb0E", "_ZN2pt22pt_megakernel_residentILb0E",
+                 "_ZN2pt22pt_megakernel_streamed"):  # mangled prefixes
         body = pick(name)
         assert body, name
         assert len(re.findall(r"LDS\.128", body[0])) >= 8, name + ": sweep loads are not LDS.128"
         assert len(re.findall(r"FFMA2 R\d+, R\d+(?:\.reuse)?\.F32x2\.HI_LO, R\d+(?:\.reuse)?\.F32, ", body[0])) >= 20, name + ": packed sweep lost"
+    # Tensor-path flavour of the regroup kernel (the default for the RTIOW scenes, pt_sweep_mma.cuh): 8 HMMA.16816.F32 with a zero
+    # accumulator per loop step (the measured issue rate depends on it: tools/probe_mma_mix.cu), fed by LDS.128 fragments, and
+    # the packed -(A*A) - B that turns the two dot products into the sign the candidate test reads.
+    for name in ("_ZN2pt21pt_megakernel_regroupILb0ELb1E", "_ZN2pt21pt_megakernel_regroupILb1ELb1E", "_ZN2pt21pt_debug_hits_regroupILb0ELb1E"):
+        body = pick(name)
+        assert body, name
+        assert len(re.findall(r"HMMA\.16816\.F32 R\d+, R\d+(?:\.reuse)?, R\d+(?:\.reuse)?, RZ", body[0])) == 8, name + ": the 8 MMAs of a loop step"
+        assert len(re.findall(r"FFMA2 R\d+, -R\d+\.F32x2\.HI_LO, R\d+\.F32x2\.HI_LO, -R\d+\.F32x2\.HI_LO", body[0])) >= 8, name + ": packed L' lost"
+        assert "LDS.128" in body[0]
 
 
 @pytest.mark.parametrize("preset", PRESETS)

@@ -6,8 +6,11 @@ import numpy as np
 import pathtrace_rs_b200 as pt
 O = pt.PtOptions
 CASES = {  # name: (preset, w, h, spp, options, devices)
-    "regroup": ("random_spheres", 64, 32, 4, None, 0),
-    "regroup_motion": ("random", 64, 32, 4, None, 0),
+    "regroup": ("random_spheres", 64, 32, 4, O(resident_kernel=4), 0),
+    "regroup_motion": ("random", 64, 32, 4, O(resident_kernel=4), 0),
+    "mma": ("random_spheres", 64, 32, 4, None, 0),  # the default: regroup kernel with the tensor-path pre-filter
+    "mma_motion": ("random", 64, 32, 4, O(resident_kernel=5), 0),
+    "mma_chunked": ("random_spheres", 200, 120, 16, O(resident_kernel=5, chunk_samples=4), 0),
     "noise": ("two_perlin_spheres", 64, 32, 4, None, 0),
     "image": ("earth", 64, 32, 4, None, 0),
     "streamed": ("random_spheres", 64, 32, 2, O(force_stream_tile_blocks=16), 0),
@@ -28,7 +31,7 @@ if name == "debug_hits":
     rng = np.random.default_rng(0)
     d = rng.normal(size=(5000, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
     rays = np.hstack([np.tile([13.0, 2.0, 3.0], (5000, 1)), -np.abs(d)]).astype(np.float32)
-    for opt in (None, O(force_stream_tile_blocks=16), O(resident_kernel=2)):
+    for opt in (None, O(resident_kernel=4), O(force_stream_tile_blocks=16), O(resident_kernel=2)):
         p2 = pt.Preset("random", pt.Params(64, 32, 1, 5)).create_scene(0, opt)
         for mode in (0, 1):
             idx, t = p2.debug_hits(rays, times=rng.random(5000).astype(np.float32), mode=mode)
