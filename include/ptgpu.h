@@ -167,7 +167,7 @@ typedef struct PtRenderStats {
     uint32_t cta_threads;
     uint32_t smem_bytes;
     uint32_t resident; /* 0: sphere image streamed through L2 in tiles; 1: resident in shared memory, pre-filter in packed FP32;
-                          2: resident, pre-filter's dot products on the tensor path (PtOptions.resident_kernel 5) */
+                          2: resident, pre-filter's dot products on the tensor path (PtOptions.resident_kernel 5); 3: streamed, tensor path */
     uint64_t warp_sweeps; /* warp-level sweeps of 32 ray slots performed: ray_count / (32 * warp_sweeps) = lane efficiency of the sweep */
 } PtRenderStats;
 
@@ -192,7 +192,8 @@ typedef struct PtOptions {
                                          to 4); 2 / 3 two paths per lane with the sphere pairs as uniform operands from a
                                          kernel-parameter image / from shared memory; 1 wavefront form (path pool +
                                          per-material queues).  1 and 2 need a scene of at most 2048 spheres and fall back
-                                         to 3 beyond.  All produce the same image. */
+                                         to 3 beyond.  4 / 5 also choose the pre-filter of the L2-streamed kernel (scenes beyond
+                                         shared memory).  All produce the same image. */
 } PtOptions;
 
 typedef struct PtScene PtScene; /* opaque: device copies of one scene on one or several GPUs */

@@ -681,12 +681,15 @@ struct TileStream {
     uint64_t* empty_bar;  // [2]
     unsigned char* buf0;  // tile buffer b lives at buf0 + b * tile_bytes (computed, not looked up: an array of pointers would
     uint32_t tile_bytes;  // be demoted to local memory and the sweep's loads would lose their shared-memory address space)
+    const char* src;      // the image being streamed: the FP32 pre-filter image (64 B per block of 4 spheres) or the
+    uint32_t block_bytes; // tensor-path fragment image (128 B per block)
     uint32_t full_phase[2];   // parity to wait for on full_bar[b]
     uint32_t empty_phase[2];  // producer side: parity to wait for on empty_bar[b]
     uint32_t produced[2];     // producer: how many times buffer b has been filled
     __device__ __forceinline__ float4* tile_buf(int b) const { return reinterpret_cast<float4*>(buf0 + (size_t)b * tile_bytes); }
-    __device__ __forceinline__ void init(uint64_t* full, uint64_t* empty, unsigned char* raw, uint32_t bytes) {
+    __device__ __forceinline__ void init(uint64_t* full, uint64_t* empty, unsigned char* raw, uint32_t bytes, const void* image, uint32_t bytes_per_block) {
         full_bar = full; empty_bar = empty; buf0 = raw; tile_bytes = bytes;
+        src = reinterpret_cast<const char*>(image); block_bytes = bytes_per_block;
         full_phase[0] = full_phase[1] = empty_phase[0] = empty_phase[1] = produced[0] = produced[1] = 0u;
         if (threadIdx.x == 0) {
             mbar_init(&full_bar[0], 1);
@@ -705,9 +708,9 @@ struct TileStream {
         produced[b] += 1u;
         const int first = tile * a.tile_blocks;
         const int nb = min(a.tile_blocks, a.n_blocks - first);
-        const uint32_t bytes = (uint32_t)nb * 64u;
+        const uint32_t bytes = (uint32_t)nb * block_bytes;
         mbar_arrive_expect_tx(&full_bar[b], bytes);
-        tma_bulk_g2s_chunked(tile_buf(b), a.prefilter + (size_t)first * 4, bytes, &full_bar[b]);
+        tma_bulk_g2s_chunked(tile_buf(b), src + (size_t)first * block_bytes, bytes, &full_bar[b]);
     }
 };
 
@@ -741,22 +744,78 @@ __device__ __forceinline__ void streamed_sweep(const KernelArgs& a, TileStream& 
     }
 }
 
+// Same with stage 1 on the tensor path (pt_sweep_mma.cuh): the tiles are steps of the fragment image, the ray's A fragments are
+// built once per trip (stage: the CTA's transpose buffer) and every tile's candidates are resolved by the quad before the next.
+// The loop fetches one step ahead: past a tile's last step it reads the first bytes of whatever follows the buffer in shared
+// memory (the other tile buffer or the Perlin tables) and never uses them.
 template <bool MOTION>
-__global__ void PT_STREAM_LAUNCH_BOUNDS pt_megakernel_streamed(const __grid_constant__ KernelArgs a) {
+__device__ __forceinline__ void streamed_sweep_mma(const KernelArgs& a, TileStream& ts, const MotionCtx& mc, uint32_t* queue, const uint32_t* queue_base,
+                                                   uint32_t* stage, bool active, float ox, float oy, float oz, float dx, float dy, float dz, float& hit_t,
+                                                   int& hit_index, unsigned& flagged) {
+    hit_t = kMaxT;
+    hit_index = -1;
+    if (threadIdx.x == 0) {
+        ts.produce(a, 0);
+        if (a.n_tiles > 1) ts.produce(a, 1);
+    }
+    MmaRayFrags f;
+    mma_ray_fragments(stage, a.mma, active, ox, oy, oz, dx, dy, dz, f);
+    const int tile_steps = a.tile_blocks / kLdsGroupBlocks;
+    for (int tile = 0; tile < a.n_tiles; ++tile) {
+        const int b = tile & 1;
+        mbar_wait(&ts.full_bar[b], ts.full_phase[b]);
+        ts.full_phase[b] ^= 1u;
+        __syncwarp();
+        const int first_step = tile * tile_steps;
+        const int ns = min(tile_steps, a.n_steps - first_step);
+        int cnt = 0;
+        int ovf_step = (active && !f.in_range) ? 0 : first_step + ns;
+        sweep_mma_steps(reinterpret_cast<const uint4*>(ts.tile_buf(b)), first_step, ns, f, queue, cnt, ovf_step);
+        mbar_arrive(&ts.empty_bar[b]);
+        __syncwarp();
+        if (threadIdx.x == 0 && tile + 2 < a.n_tiles) ts.produce(a, tile + 2);
+        sweep_mma_drain<MOTION>(a.blocks, mc, queue_base, cnt, ovf_step, first_step, first_step + ns, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
+    }
+}
+
+// shared-memory layout of the streamed kernels: [tile 0][tile 1][Perlin tables][queues][pend][ray.time][MMA: transpose buffer]
+template <bool MMA>
+struct StreamedSmem {
+    uint32_t tile_bytes;
+    PerlinSmem* P;
+    uint32_t* queue_base;
+    uint32_t* queue;
+    volatile uint32_t* pend;
+    volatile float* tslot;
+    uint32_t* stage;
+    __device__ __forceinline__ StreamedSmem(unsigned char* raw, const KernelArgs& a) {
+        tile_bytes = (uint32_t)a.tile_blocks * (MMA ? 128u : 64u);
+        P = reinterpret_cast<PerlinSmem*>(raw + 2 * (size_t)tile_bytes);
+        queue_base = reinterpret_cast<uint32_t*>(P + 1);
+        queue = queue_base + threadIdx.x;  // [kQueueCap][kCtaThreads] candidate queues
+        pend = queue + kQueueCap * kCtaThreads;
+        tslot = reinterpret_cast<volatile float*>(pend + kCtaThreads);  // [kCtaThreads] ray.time per lane
+        stage = queue_base + (kQueueCap + 2) * kCtaThreads;              // [kMmaStageRows][kCtaThreads], MMA only
+    }
+};
+
+// (the tensor-path flavour states its two CTAs per SM: left alone ptxas squeezes it into 80 registers with 128 bytes of spills)
+template <bool MOTION, bool MMA>
+__global__ void __launch_bounds__(kCtaThreads, MMA ? 2 : 0) pt_megakernel_streamed(const __grid_constant__ KernelArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[2];
     __shared__ __align__(8) uint64_t empty_bar[2];
     __shared__ int cta_live;  // lanes not finished, recomputed every trip
-    const uint32_t tile_bytes = (uint32_t)a.tile_blocks * 64u;
-    PerlinSmem* P = reinterpret_cast<PerlinSmem*>(smem_raw + 2 * (size_t)tile_bytes);
-    uint32_t* queue = reinterpret_cast<uint32_t*>(P + 1) + threadIdx.x;  // [kQueueCap][kCtaThreads] candidate queues
-    volatile uint32_t* pend = queue + kQueueCap * kCtaThreads;
-    volatile float* tslot = reinterpret_cast<volatile float*>(pend + kCtaThreads);  // [kCtaThreads] ray.time per lane
+    const StreamedSmem<MMA> sm(smem_raw, a);
+    PerlinSmem* P = sm.P;
+    uint32_t* queue = sm.queue;
+    volatile uint32_t* pend = sm.pend;
+    volatile float* tslot = sm.tslot;
     *pend = 0u;
     *tslot = 0.0f;
     const MotionCtx mc{a.motion, const_cast<const float*>(tslot), a.order};
     TileStream ts;
-    ts.init(full_bar, empty_bar, smem_raw, tile_bytes);
+    ts.init(full_bar, empty_bar, smem_raw, sm.tile_bytes, MMA ? reinterpret_cast<const void*>(a.mma_image) : reinterpret_cast<const void*>(a.prefilter), MMA ? 128u : 64u);
     if (threadIdx.x == 0) cta_live = 0;
     stage_perlin(a, P);
     __syncthreads();
@@ -790,7 +849,8 @@ __global__ void PT_STREAM_LAUNCH_BOUNDS pt_megakernel_streamed(const __grid_cons
         int hit_index;
         unsigned flagged = 0u;
         sweeps += 1u;  // every warp of the CTA sweeps every tile of every trip
-        streamed_sweep<MOTION>(a, ts, mc, queue, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
+        if (MMA) streamed_sweep_mma<MOTION>(a, ts, mc, queue, sm.queue_base, sm.stage, L.active, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
+        else streamed_sweep<MOTION>(a, ts, mc, queue, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
         if (L.active) {
             rays += 1ULL;
             L.time = *tslot;  // (re-read: nothing of the lane's bookkeeping is carried across the sweep in a register)
@@ -802,18 +862,17 @@ __global__ void PT_STREAM_LAUNCH_BOUNDS pt_megakernel_streamed(const __grid_cons
 }
 
 // pt_debug_hits, streamed scenes: caller-supplied rays through streamed_sweep (same tiles, barriers, operands, re-tests)
-template <bool MOTION>
+template <bool MOTION, bool MMA>
 __global__ void PT_STREAM_LAUNCH_BOUNDS pt_debug_hits_streamed(const __grid_constant__ KernelArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t full_bar[2];
     __shared__ __align__(8) uint64_t empty_bar[2];
-    const uint32_t tile_bytes = (uint32_t)a.tile_blocks * 64u;
-    PerlinSmem* P = reinterpret_cast<PerlinSmem*>(smem_raw + 2 * (size_t)tile_bytes);
-    uint32_t* queue = reinterpret_cast<uint32_t*>(P + 1) + threadIdx.x;
-    volatile float* tslot = reinterpret_cast<volatile float*>(queue + kQueueCap * kCtaThreads + kCtaThreads);
+    const StreamedSmem<MMA> sm(smem_raw, a);
+    uint32_t* queue = sm.queue;
+    volatile float* tslot = sm.tslot;
     const MotionCtx mc{a.motion, const_cast<const float*>(tslot), a.order};
     TileStream ts;
-    ts.init(full_bar, empty_bar, smem_raw, tile_bytes);
+    ts.init(full_bar, empty_bar, smem_raw, sm.tile_bytes, MMA ? reinterpret_cast<const void*>(a.mma_image) : reinterpret_cast<const void*>(a.prefilter), MMA ? 128u : 64u);
     __syncthreads();
     // `base` is uniform within the CTA: all its threads run the same trips (the sweep is CTA-collective)
     for (uint32_t base = blockIdx.x * kCtaThreads; base < a.dbg_n; base += gridDim.x * kCtaThreads) {
@@ -828,7 +887,8 @@ __global__ void PT_STREAM_LAUNCH_BOUNDS pt_debug_hits_streamed(const __grid_cons
         float hit_t;
         int hit_index;
         unsigned flagged = 0u;
-        streamed_sweep<MOTION>(a, ts, mc, queue, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
+        if (MMA) streamed_sweep_mma<MOTION>(a, ts, mc, queue, sm.queue_base, sm.stage, i < a.dbg_n, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
+        else streamed_sweep<MOTION>(a, ts, mc, queue, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
         if (i < a.dbg_n) {
             a.dbg_idx[i] = hit_index < 0 ? -1 : (a.order ? (int32_t)__ldg(a.order + hit_index) : hit_index);
             a.dbg_t[i] = hit_t;

@@ -165,7 +165,7 @@ __device__ __forceinline__ void regroup_sweep(const KernelArgs& a, const Regroup
     if (MMA) {
         int ovf_step;
         const int n = sweep_mma(reinterpret_cast<const uint4*>(sm.pf), a.n_steps, sm.xchg, sm.queue, a.mma, active, ox, oy, oz, dx, dy, dz, ovf_step);
-        sweep_mma_drain<MOTION>(a.blocks, mc, sm.queue_base, n, ovf_step, a.n_steps, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
+        sweep_mma_drain<MOTION>(a.blocks, mc, sm.queue_base, n, ovf_step, 0, a.n_steps, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
         return;
     }
     const float nod = -((ox * dx + oy * dy) + oz * dz);

@@ -106,23 +106,26 @@ __device__ __forceinline__ void sweep_test_index(const float4* __restrict__ blk,
     }
 }
 
-// Stage 1 for the warp's 32 rays.  simg: fragment-ordered sphere image in shared memory, (n_steps + 1) x 32 uint4 (one step
-// of padding: the loop fetches one step ahead).  stage: kMmaStageRows rows of kSweepThreads words, of which this warp uses
-// its own 32 columns.  q: this lane's queue, [kQueueCap][kSweepThreads].  Returns the number of entries pushed;
-// ovf_step comes back as the first step whose entry found the queue full (n_steps: none).
-__device__ __forceinline__ int sweep_mma(const uint4* __restrict__ simg, int n_steps, uint32_t* __restrict__ stage, uint32_t* __restrict__ q, const MmaScale sc,
-                                         bool active, float ox, float oy, float oz, float dx, float dy, float dz, int& ovf_step) {
+// The lane's ray as A-operand fragments of both row blocks (loop-invariant over the sphere loop).
+struct MmaRayFrags {
+    uint4 fa[2], fb[2];
+    bool in_range;  // the ray lies inside the operands' validity domain (otherwise it takes no part in stage 1)
+};
+
+// stage: kMmaStageRows rows of kSweepThreads words, of which this warp uses its own 32 columns (a transpose buffer).
+__device__ __forceinline__ void mma_ray_fragments(uint32_t* __restrict__ stage, const MmaScale sc, bool active, float ox, float oy, float oz, float dx, float dy,
+                                                  float dz, MmaRayFrags& f) {
     const unsigned lane = threadIdx.x & 31u, g = lane >> 2, t = lane & 3u;
     uint32_t* warp_cols = stage + (threadIdx.x & ~31u);
     // validity domain of the f16 operands: origin inside the extent the scales were chosen for, direction of unit size.
     // A ray outside it (or a non-finite one) takes no part in stage 1 and gets the exact test on every sphere instead.
-    const bool in_range = ((ox * ox + oy * oy) + oz * oz) <= sc.max_o2 && ((dx * dx + dy * dy) + dz * dz) <= 4.0f;
+    f.in_range = ((ox * ox + oy * oy) + oz * oz) <= sc.max_o2 && ((dx * dx + dy * dy) + dz * dz) <= 4.0f;
     // ray operands -> A fragments.  Fragment (quad g, row block rb, t, column type c) is four consecutive words
     // {ray0.word[t], ray1.word[t], ray0.word[t+4], ray1.word[t+4]} at row c*8 + rb*4 + t, columns 4g..4g+3 of the warp:
     // the owner of ray (rb = t >> 1, half = t & 1) scatters its 16 words, every lane reads its four fragments with LDS.128.
     {
         uint32_t w[16];
-        mma_ray_operand(sc, active && in_range, ox, oy, oz, dx, dy, dz, w);
+        mma_ray_operand(sc, active && f.in_range, ox, oy, oz, dx, dy, dz, w);
         uint32_t* base = warp_cols + 4u * g + (t & 1u);
 #pragma unroll
         for (int c = 0; c < 2; ++c)
@@ -130,21 +133,27 @@ __device__ __forceinline__ int sweep_mma(const uint4* __restrict__ simg, int n_s
             for (int k = 0; k < 8; ++k) base[(c * 8 + (int)(t >> 1) * 4 + (k & 3)) * kSweepThreads + 2 * (k >> 2)] = w[c * 8 + k];
     }
     __syncwarp();
-    uint4 fa[2], fb[2];
 #pragma unroll
     for (int rb = 0; rb < 2; ++rb) {
-        fa[rb] = *reinterpret_cast<const uint4*>(warp_cols + (rb * 4 + (int)t) * kSweepThreads + 4u * g);
-        fb[rb] = *reinterpret_cast<const uint4*>(warp_cols + (8 + rb * 4 + (int)t) * kSweepThreads + 4u * g);
+        f.fa[rb] = *reinterpret_cast<const uint4*>(warp_cols + (rb * 4 + (int)t) * kSweepThreads + 4u * g);
+        f.fb[rb] = *reinterpret_cast<const uint4*>(warp_cols + (8 + rb * 4 + (int)t) * kSweepThreads + 4u * g);
     }
     __syncwarp();
+}
+
+// Stage 1 over steps [first_step, first_step + n_steps) of the image, whose fragments start at simg (the loop fetches one
+// step ahead: 512 readable bytes must follow the last step).  q: this lane's queue, [kQueueCap][kSweepThreads]; cnt: entries
+// in it; ovf_step: lowered to the first step whose entry found the queue full.
+__device__ __forceinline__ void sweep_mma_steps(const uint4* __restrict__ simg, int first_step, int n_steps, const MmaRayFrags& f, uint32_t* __restrict__ q, int& cnt,
+                                                int& ovf_step) {
+    const unsigned lane = threadIdx.x & 31u;
     uint32_t qaddr = (uint32_t)__cvta_generic_to_shared(q);
     asm volatile("" : "+r"(qaddr));
-    int cnt = 0;
-    ovf_step = (active && !in_range) ? 0 : n_steps;
     const uint4* p = simg + lane;
     uint4 sp = *p;
+    const int end = first_step + n_steps;
 #pragma unroll 1
-    for (int s = 0; s < n_steps; ++s) {
+    for (int s = first_step; s < end; ++s) {
         p += 32;
         const uint4 cur = sp;
         float A[2][2][4], B[2][2][4];
@@ -152,8 +161,8 @@ __device__ __forceinline__ int sweep_mma(const uint4* __restrict__ simg, int n_s
         for (int rb = 0; rb < 2; ++rb)
 #pragma unroll
             for (int sg = 0; sg < 2; ++sg) {
-                hmma16816(A[rb][sg], fa[rb], sg ? cur.z : cur.x, sg ? cur.w : cur.y);
-                hmma16816(B[rb][sg], fb[rb], sg ? cur.z : cur.x, sg ? cur.w : cur.y);
+                hmma16816(A[rb][sg], f.fa[rb], sg ? cur.z : cur.x, sg ? cur.w : cur.y);
+                hmma16816(B[rb][sg], f.fb[rb], sg ? cur.z : cur.x, sg ? cur.w : cur.y);
             }
         sp = *p;  // next step's sphere fragments
         // N = -(A'^2 + B'): candidate <=> N < 0 <=> sign bit (a -0.0 is a harmless false positive)
@@ -189,14 +198,28 @@ __device__ __forceinline__ int sweep_mma(const uint4* __restrict__ simg, int n_s
             }
         }
     }
+}
+
+// Stage 1 for the warp's 32 rays against a resident image of n_steps steps ((n_steps + 1) x 32 uint4: one step of padding).
+// Returns the number of entries pushed; ovf_step comes back as the first step that needs the exact test on everything
+// (n_steps: none; 0: the ray is outside the operands' domain).
+__device__ __forceinline__ int sweep_mma(const uint4* __restrict__ simg, int n_steps, uint32_t* __restrict__ stage, uint32_t* __restrict__ q, const MmaScale sc,
+                                         bool active, float ox, float oy, float oz, float dx, float dy, float dz, int& ovf_step) {
+    MmaRayFrags f;
+    mma_ray_fragments(stage, sc, active, ox, oy, oz, dx, dy, dz, f);
+    int cnt = 0;
+    ovf_step = (active && !f.in_range) ? 0 : n_steps;
+    sweep_mma_steps(simg, 0, n_steps, f, q, cnt, ovf_step);
     return cnt;
 }
 
-// Stage 2 for this lane's ray: the exact test on every sphere one of the quad's lanes flagged for it.  qbase: the queue
-// array WITHOUT the thread offset ([kQueueCap][kSweepThreads]).  n_steps bounds the step field (entries of up to 65535 steps).
+// Stage 2 for this lane's ray over the steps [first_step, end_step) stage 1 has just covered: the exact test on every sphere
+// one of the quad's lanes flagged for it.  qbase: the queue array WITHOUT the thread offset ([kQueueCap][kSweepThreads]).
+// An entry's step field has 16 bits: scenes of up to 65535 steps (1 M spheres).
 template <bool MOTION>
 __device__ __forceinline__ void sweep_mma_drain(const float4* __restrict__ exact, const MotionCtx& mc, const uint32_t* __restrict__ qbase, int cnt, int ovf_step,
-                                                int n_steps, float ox, float oy, float oz, float dx, float dy, float dz, float& hit_t, int& hit_index, unsigned& flagged) {
+                                                int first_step, int end_step, float ox, float oy, float oz, float dx, float dy, float dz, float& hit_t, int& hit_index,
+                                                unsigned& flagged) {
     const unsigned lane = threadIdx.x & 31u, t = lane & 3u;
     const unsigned quad_thread = threadIdx.x & ~3u;
     __syncwarp();  // the quad's pushes are visible
@@ -205,6 +228,7 @@ __device__ __forceinline__ void sweep_mma_drain(const float4* __restrict__ exact
     int ovf = ovf_step;
     ovf = min(ovf, __shfl_xor_sync(0xffffffffu, ovf, 1));
     ovf = min(ovf, __shfl_xor_sync(0xffffffffu, ovf, 2));
+    ovf = max(ovf, first_step);
 #pragma unroll 1
     for (unsigned tf = 0; tf < 4u; ++tf) {
         const int n = __shfl_sync(0xffffffffu, cnt, (int)((lane & ~3u) + tf));
@@ -224,7 +248,7 @@ __device__ __forceinline__ void sweep_mma_drain(const float4* __restrict__ exact
             }
         }
     }
-    if (ovf < n_steps) sweep_overflow<MOTION>(exact, mc, ovf * kLdsGroupBlocks, n_steps * kLdsGroupBlocks, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
+    if (ovf < end_step) sweep_overflow<MOTION>(exact, mc, ovf * kLdsGroupBlocks, end_step * kLdsGroupBlocks, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
     __syncwarp();  // nobody overwrites a queue its quad is still reading
 }
 

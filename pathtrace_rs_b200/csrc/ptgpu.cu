@@ -96,6 +96,7 @@ struct Replica {
     pt::MmaScale mma_scale{0.f, 0.f, 0.f, 0.f};
     size_t fp32_smem_bytes = 0;     // the FP32 regroup kernel's launch geometry, kept as the per-render fallback of the tensor path
     int fp32_ctas_per_sm = 0;       // (camera outside the extent the f16 operands were scaled for)
+    int fp32_tile_blocks = 0, fp32_n_tiles = 0;
     int wave_pool = 0;
     const pt::ConstImageT<true>* h_const_image = nullptr;  // owned by the PtScene; passed by value at every launch (24 KB)
     // per-render scratch.  At most one render is in flight per replica: every launch waits for the previous one's
@@ -249,23 +250,44 @@ int plan_launch(Replica* s) {
     }
     s->resident = false;
     s->const_image = false;
-    if (forced_tile > 0 && s->n_blocks > 0) {  // PtOptions: any scene through the streamed kernel with n-block tiles
-        forced_tile = (forced_tile + pt::kLdsGroupBlocks - 1) / pt::kLdsGroupBlocks * pt::kLdsGroupBlocks;  // whole groups
-        s->tile_blocks = std::min(forced_tile, s->n_blocks);
-    } else {
-        // two tile buffers; 2 CTAs per SM keeps the FP32 pipe fed while one CTA waits on a barrier
-        const int stream_ctas = s->opt.stream_ctas > 0 ? std::min(4, s->opt.stream_ctas) : 2;
-        const size_t per_cta = (kMaxDynSmem + 1024) / stream_ctas - 2048;
-        const size_t tile_bytes = ((per_cta - kStreamedFixedBytes) / 2) & ~(size_t)1023;
-        s->tile_blocks = (int)(tile_bytes / 64);
-    }
-    s->n_tiles = (s->n_blocks + s->tile_blocks - 1) / s->tile_blocks;
-    s->smem_bytes = 2 * (size_t)s->tile_blocks * 64 + kStreamedFixedBytes;
-    int rc = s->d_motion ? configure_kernel(pt::pt_megakernel_streamed<true>, s->smem_bytes, &s->ctas_per_sm)
-                         : configure_kernel(pt::pt_megakernel_streamed<false>, s->smem_bytes, &s->ctas_per_sm);
+    // streamed kernel: two tile buffers; 2 CTAs per SM keeps the pipes fed while one CTA waits on a barrier.  The FP32 flavour
+    // is always configured (it is the per-render fallback of the tensor path); the tensor-path flavour streams the fragment
+    // image (128 B per block of 4 spheres instead of 64) and carries the CTA's transpose buffer.
+    if (forced_tile > 0) forced_tile = (forced_tile + pt::kLdsGroupBlocks - 1) / pt::kLdsGroupBlocks * pt::kLdsGroupBlocks;  // whole groups
+    auto geometry = [&](bool mma, int* tile_blocks, int* n_tiles, size_t* smem) {
+        const size_t fixed = kStreamedFixedBytes + (mma ? (size_t)pt::kMmaStageRows * pt::kCtaThreads * sizeof(uint32_t) : 0);
+        const size_t block_bytes = mma ? 128 : 64;
+        if (forced_tile > 0 && s->n_blocks > 0) {  // PtOptions: any scene through the streamed kernel with n-block tiles
+            *tile_blocks = std::min(forced_tile, s->n_blocks);
+        } else {
+            const int stream_ctas = s->opt.stream_ctas > 0 ? std::min(4, s->opt.stream_ctas) : 2;
+            const size_t per_cta = (kMaxDynSmem + 1024) / stream_ctas - 2048;
+            const size_t tile_bytes = ((per_cta - fixed) / 2) & ~(size_t)1023;
+            *tile_blocks = (int)(tile_bytes / block_bytes) / pt::kLdsGroupBlocks * pt::kLdsGroupBlocks;
+        }
+        *n_tiles = (s->n_blocks + *tile_blocks - 1) / *tile_blocks;
+        *smem = 2 * (size_t)*tile_blocks * block_bytes + fixed;
+    };
+    geometry(false, &s->tile_blocks, &s->n_tiles, &s->smem_bytes);
+    int rc = s->d_motion ? configure_kernel(pt::pt_megakernel_streamed<true, false>, s->smem_bytes, &s->ctas_per_sm)
+                         : configure_kernel(pt::pt_megakernel_streamed<false, false>, s->smem_bytes, &s->ctas_per_sm);
     if (rc == PT_OK)
-        rc = s->d_motion ? configure_kernel(pt::pt_debug_hits_streamed<true>, s->smem_bytes, nullptr)
-                         : configure_kernel(pt::pt_debug_hits_streamed<false>, s->smem_bytes, nullptr);
+        rc = s->d_motion ? configure_kernel(pt::pt_debug_hits_streamed<true, false>, s->smem_bytes, nullptr)
+                         : configure_kernel(pt::pt_debug_hits_streamed<false, false>, s->smem_bytes, nullptr);
+    s->fp32_smem_bytes = s->smem_bytes;
+    s->fp32_ctas_per_sm = s->ctas_per_sm;
+    s->fp32_tile_blocks = s->tile_blocks;
+    s->fp32_n_tiles = s->n_tiles;
+    const bool want_mma = s->mma_ok && (s->opt.resident_kernel == 0 || s->opt.resident_kernel == 5) && s->n_blocks / pt::kLdsGroupBlocks < 65536;
+    if (rc == PT_OK && want_mma) {
+        s->mma = true;
+        geometry(true, &s->tile_blocks, &s->n_tiles, &s->smem_bytes);
+        rc = s->d_motion ? configure_kernel(pt::pt_megakernel_streamed<true, true>, s->smem_bytes, &s->ctas_per_sm)
+                         : configure_kernel(pt::pt_megakernel_streamed<false, true>, s->smem_bytes, &s->ctas_per_sm);
+        if (rc == PT_OK)
+            rc = s->d_motion ? configure_kernel(pt::pt_debug_hits_streamed<true, true>, s->smem_bytes, nullptr)
+                             : configure_kernel(pt::pt_debug_hits_streamed<false, true>, s->smem_bytes, nullptr);
+    }
     return rc;
 }
 
@@ -427,6 +449,10 @@ int launch_update(Replica* s, const PtParams* params, const PtCamera* cam, uint3
     }
     const int ctas_per_sm = (s->mma && !use_mma) ? s->fp32_ctas_per_sm : s->ctas_per_sm;
     const size_t smem_bytes = (s->mma && !use_mma) ? s->fp32_smem_bytes : s->smem_bytes;
+    if (s->mma && !use_mma && !s->resident) {
+        a.tile_blocks = s->fp32_tile_blocks;
+        a.n_tiles = s->fp32_n_tiles;
+    }
 
     // persistent grid: one wave of CTAs, never more lanes than pixels.  The resident kernel carries two paths per lane;
     // an image with fewer pixels than the machine has lanes keeps one path per lane (latency, not throughput, is what
@@ -504,9 +530,12 @@ int launch_update(Replica* s, const PtParams* params, const PtCamera* cam, uint3
             if (s->d_motion) pt::pt_megakernel_resident<false, true><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a, none);
             else pt::pt_megakernel_resident<false, false><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a, none);
         }
+    } else if (use_mma) {
+        if (s->d_motion) pt::pt_megakernel_streamed<true, true><<<grid, pt::kCtaThreads, smem_bytes, stream>>>(a);
+        else pt::pt_megakernel_streamed<false, true><<<grid, pt::kCtaThreads, smem_bytes, stream>>>(a);
     } else {
-        if (s->d_motion) pt::pt_megakernel_streamed<true><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a);
-        else pt::pt_megakernel_streamed<false><<<grid, pt::kCtaThreads, s->smem_bytes, stream>>>(a);
+        if (s->d_motion) pt::pt_megakernel_streamed<true, false><<<grid, pt::kCtaThreads, smem_bytes, stream>>>(a);
+        else pt::pt_megakernel_streamed<false, false><<<grid, pt::kCtaThreads, smem_bytes, stream>>>(a);
     }
     PT_CUDA(cudaGetLastError());
     rc = serialise_end(s, stream);
@@ -515,7 +544,7 @@ int launch_update(Replica* s, const PtParams* params, const PtCamera* cam, uint3
     s->stats.grid_ctas = grid;
     s->stats.cta_threads = s->wave ? pt::kWaveThreads : pt::kCtaThreads;
     s->stats.smem_bytes = (uint32_t)smem_bytes;
-    s->stats.resident = s->resident ? ((s->regroup && use_mma) ? 2u : 1u) : 0u;
+    s->stats.resident = s->resident ? ((s->regroup && use_mma) ? 2u : 1u) : (use_mma ? 3u : 0u);
     s->stats.n_spheres = s->n_spheres;
     return PT_OK;
 }
@@ -1490,8 +1519,13 @@ int pt_debug_hits(PtScene* sc, const float* rays6, const float* times, uint32_t 
             }
         } else if (rc == PT_OK) {
             const uint32_t grid = std::min<uint32_t>((n + pt::kCtaThreads - 1) / pt::kCtaThreads, max_ctas);
-            if (s->d_motion) pt::pt_debug_hits_streamed<true><<<grid, pt::kCtaThreads, s->smem_bytes, s->stream>>>(a);
-            else pt::pt_debug_hits_streamed<false><<<grid, pt::kCtaThreads, s->smem_bytes, s->stream>>>(a);
+            if (s->mma) {
+                if (s->d_motion) pt::pt_debug_hits_streamed<true, true><<<grid, pt::kCtaThreads, s->smem_bytes, s->stream>>>(a);
+                else pt::pt_debug_hits_streamed<false, true><<<grid, pt::kCtaThreads, s->smem_bytes, s->stream>>>(a);
+            } else {
+                if (s->d_motion) pt::pt_debug_hits_streamed<true, false><<<grid, pt::kCtaThreads, s->smem_bytes, s->stream>>>(a);
+                else pt::pt_debug_hits_streamed<false, false><<<grid, pt::kCtaThreads, s->smem_bytes, s->stream>>>(a);
+            }
         }
         if (rc == PT_OK) step(cudaGetLastError(), "kernel launch");
         if (rc == PT_OK) rc = serialise_end(s, s->stream);

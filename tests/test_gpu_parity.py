@@ -60,7 +60,7 @@ def test_cfg1_random_spheres_vs_oracle():
     assert w * h * spp <= rays <= w * h * spp * (depth + 1)
     assert np.isfinite(img).all() and img.min() >= 0.0 and img.max() <= 1.0 + 1e-5
     st = pr.stats()
-    assert st.kernel_launches == 1 and st.resident == 1 and st.n_spheres == 488 and st.ray_count == rays
+    assert st.kernel_launches == 1 and st.resident == 2 and st.n_spheres == 488 and st.ray_count == rays  # resident, tensor-path pre-filter
 
 
 def test_random_preset_moving_spheres_vs_oracle():
@@ -305,7 +305,9 @@ def test_chunk_queue_with_partition_and_streamed_kernel():
         rays += r
     assert rays == rays_whole and np.array_equal(img, whole)
     st, rays_st, pr2 = gpu_render("random_spheres", w, h, spp, depth, options=pt.PtOptions(chunk_samples=4, force_stream_tile_blocks=16))
-    assert pr2.stats().resident == 0 and rays_st == rays_whole and np.array_equal(st, whole)
+    assert pr2.stats().resident == 3 and rays_st == rays_whole and np.array_equal(st, whole)   # streamed, tensor-path pre-filter
+    st, rays_st, pr2 = gpu_render("random_spheres", w, h, spp, depth, options=pt.PtOptions(chunk_samples=4, force_stream_tile_blocks=16, resident_kernel=4))
+    assert pr2.stats().resident == 0 and rays_st == rays_whole and np.array_equal(st, whole)   # streamed, packed-FP32 pre-filter
 
 
 # ---- multi-device scenes: ONE Scene::update call, fanned out inside the library ----------------------------
@@ -465,19 +467,28 @@ def test_wavefront_kernel_on_a_large_image_with_the_chunk_queue():
 def test_streamed_kernel_equals_resident_kernel():
     w, h, spp, depth = 64, 36, 4, 10
     res, rays_res, pr = gpu_render("random_spheres", w, h, spp, depth)
-    assert pr.stats().resident == 1
-    # 488 spheres = 122 blocks -> 8 tiles, last one ragged
-    st, rays_st, pr2 = gpu_render("random_spheres", w, h, spp, depth, options=pt.PtOptions(force_stream_tile_blocks=16))
-    assert pr2.stats().resident == 0
-    assert rays_st == rays_res and np.array_equal(st, res)
+    assert pr.stats().resident == 2
+    # 488 spheres = 122 blocks (124 with the group padding) -> 8 tiles, last one ragged; both pre-filter flavours, and a tile
+    # size that leaves a single-step last tile
+    for opt, want in ((pt.PtOptions(force_stream_tile_blocks=16), 3), (pt.PtOptions(force_stream_tile_blocks=16, resident_kernel=4), 0),
+                      (pt.PtOptions(force_stream_tile_blocks=20), 3), (pt.PtOptions(force_stream_tile_blocks=4), 3)):
+        st, rays_st, pr2 = gpu_render("random_spheres", w, h, spp, depth, options=opt)
+        assert pr2.stats().resident == want
+        assert rays_st == rays_res and np.array_equal(st, res)
+    # moving spheres through the streamed tensor-path kernel
+    res, rays_res, _ = gpu_render("random", w, h, spp, depth, options=pt.PtOptions(resident_kernel=4))
+    st, rays_st, pr2 = gpu_render("random", w, h, spp, depth, options=pt.PtOptions(force_stream_tile_blocks=12))
+    assert pr2.stats().resident == 3 and rays_st == rays_res and np.array_equal(st, res)
 
 
 def test_cfg5_stress100k_small_vs_oracle():
     w, h, spp, depth = 64, 36, 2, 50
     img, rays, pr = gpu_render("stress100k", w, h, spp, depth)
-    assert pr.stats().resident == 0 and pr.stats().n_spheres == 99860
+    assert pr.stats().resident == 3 and pr.stats().n_spheres == 99860  # streamed, pre-filter on the tensor path
     ref, ref_rays = orc.Scene("stress100k", w, h).update(spp, depth, mode=SOA_ITER)
     assert rays == ref_rays and np.array_equal(img, ref)  # 99 860 spheres through the streamed kernel: bit-identical
+    img4, rays4, pr4 = gpu_render("stress100k", w, h, spp, depth, options=pt.PtOptions(resident_kernel=4))
+    assert pr4.stats().resident == 0 and rays4 == rays and np.array_equal(img4, img)  # ... and with the packed-FP32 pre-filter
 
 
 # ---- output stage ----------------------------------------------------------------------------------------------------

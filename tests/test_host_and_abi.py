@@ -69,7 +69,7 @@ def test_library_is_sm100a_cuda_with_packed_fp32_and_tma():
     # LDS flavours (larger resident scenes, streamed scenes): broadcast LDS.128 of the pre-filter image (not generic loads,
     # not local memory) feeding FFMA2 Rpair(spheres) * Rscalar(ray) + Rpair.
     for name in ("_ZN2pt21pt_megakernel_regroupILb0ELb0E", "_ZN2pt21pt_megakernel_regroupILb1ELb0E", "_ZN2pt22pt_megakernel_residentILb0E",
-                 "_ZN2pt22pt_megakernel_streamed"):  # mangled prefixes
+                 "_ZN2pt22pt_megakernel_streamedILb0ELb0E", "_ZN2pt22pt_megakernel_streamedILb1ELb0E"):  # mangled prefixes
         body = pick(name)
         assert body, name
         assert len(re.findall(r"LDS\.128", body[0])) >= 8, name + ": sweep loads are not LDS.128"
@@ -77,7 +77,8 @@ def test_library_is_sm100a_cuda_with_packed_fp32_and_tma():
     # Tensor-path flavour of the regroup kernel (the default for the RTIOW scenes, pt_sweep_mma.cuh): 8 HMMA.16816.F32 with a zero
     # accumulator per loop step (the measured issue rate depends on it: tools/probe_mma_mix.cu), fed by LDS.128 fragments, and
     # the packed -(A*A) - B that turns the two dot products into the sign the candidate test reads.
-    for name in ("_ZN2pt21pt_megakernel_regroupILb0ELb1E", "_ZN2pt21pt_megakernel_regroupILb1ELb1E", "_ZN2pt21pt_debug_hits_regroupILb0ELb1E"):
+    for name in ("_ZN2pt21pt_megakernel_regroupILb0ELb1E", "_ZN2pt21pt_megakernel_regroupILb1ELb1E", "_ZN2pt21pt_debug_hits_regroupILb0ELb1E",
+                 "_ZN2pt22pt_megakernel_streamedILb0ELb1E", "_ZN2pt22pt_megakernel_streamedILb1ELb1E"):
         body = pick(name)
         assert body, name
         assert len(re.findall(r"HMMA\.16816\.F32 R\d+, R\d+(?:\.reuse)?, R\d+(?:\.reuse)?, RZ", body[0])) == 8, name + ": the 8 MMAs of a loop step"
