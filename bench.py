@@ -10,8 +10,10 @@ One "step" = one `Scene::update` of the workload (one frame of `samples` spp ove
   e2e     : same metric through the reference-facing call with a HOST buffer — ONE `Scene::update` mirror -> pt_render
             call per step whatever N is (N > 1: a multi-device scene, the library fans out one host thread per GPU),
             previous frame uploaded and result downloaded every step (frame_num >= 1).  Steps longer than 2 s: one e2e step.
-  roofline: the megakernel against the FP32 FMA peak (this path is FP32-FMA bound, not HBM or tensor bound:
-            16 flop per (ray, sphere) test x rays x spheres — SURVEY §8d / DESIGN.md).
+  roofline: the megakernel's ALGORITHMIC flop — 16 per (ray, sphere) test x rays x spheres, the FP32 formulation of SURVEY §8d —
+            against the FP32 FMA peak, as in round 1.  Since round 2 the two dot products of every test run on the tensor
+            path (mma.sync f16 split operands, pt_sweep_mma.cuh), so the fraction is a comparison of builds, not a pipe
+            utilisation: the note says how much HMMA work that is; HBM stays idle.
   cpu_baseline: the CPU oracle (restated reference, list mode = the reference's live path) on the host cores,
             bounded sample, rank 0 at N=1 only.
 N > 1 (one process per GPU): default `--partition rows` is STRONG scaling of one frame by interleaved row tiles with no
@@ -365,9 +367,9 @@ def main():
                        "n_spheres": n_spheres, "partition": ("rows: interleaved 4-row tiles, no collective" if rows_mode else
                                                              (("samples-strong: %d spp per GPU x %d frame seeds + one NCCL reduce" % (spp, world)) if samples_strong else
                                                               ("samples: one frame seed per GPU + one NCCL reduce" if world > 1 else "single GPU"))),
-                       "l2": "flushed between timed iterations (256 MB fill); the scene is a %d KB pre-filter image %s" % (max(1, n_spheres * (32 if st.resident == 2 else 16) // 1024), "resident in shared memory" if st.resident else "streamed from L2 in TMA tiles"),
+                       "l2": "flushed between timed iterations (256 MB fill); the scene is a %d KB pre-filter image %s" % (max(1, n_spheres * (32 if st.resident in (2, 3) else 16) // 1024), "resident in shared memory" if st.resident else "streamed from L2 in TMA tiles"),
                        "prefilter": ("tensor path: the two dot products of every (ray, sphere) test as mma.sync.m16n8k16 f16 split-operand MMAs (HMMA.16816.F32), "
-                                     "A'^2 + B' and the sign test in packed FP32; the exact f32 test of the flagged spheres decides every hit" if st.resident == 2 else
+                                     "A'^2 + B' and the sign test in packed FP32; the exact f32 test of the flagged spheres decides every hit" if st.resident in (2, 3) else
                                      "packed FP32 (FFMA2), 7 instructions per 2 tests; the exact f32 test of the flagged spheres decides every hit"),
                        "kernel": "%d CTAs x %d threads, %d B shared memory per CTA" % (st.grid_ctas, st.cta_threads, st.smem_bytes),
                        "timing": "CUDA events per step on the launching stream, max over ranks (slowest rank %.1f ms, fastest %.1f ms per step)" % (ms_max / args.steps, ms_min / args.steps)},
@@ -391,7 +393,7 @@ def main():
                          "note": ("algorithmic flop (the FP32 formulation's 16 per test) against the FP32 FMA peak, as in round 1, so the two builds compare; "
                                   "in this build 12 of the 16 (the two 3-term dot products) execute on the tensor pipe as 2 x 16-deep f16 products = 64 flop per test: %.0f TFLOP/s of HMMA work "
                                   "(mma.sync ceiling measured on B200: 550 TFLOP/s with a register accumulator, tools/probe_mma.cu); the kernel is bound by instruction issue around the MMAs, "
-                                  "not by HBM: algorithmic HBM bytes are 12-24 B/pixel/launch (accumulation buffer)" % (achieved / FLOP_PER_TEST * 64.0 / 1e12)) if st.resident == 2 else
+                                  "not by HBM: algorithmic HBM bytes are 12-24 B/pixel/launch (accumulation buffer)" % (achieved / FLOP_PER_TEST * 64.0 / 1e12)) if st.resident in (2, 3) else
                                  "bound by the FP32 FMA pipe, not by HBM: algorithmic HBM bytes are 12-24 B/pixel/launch (accumulation buffer)"},
             "clocks": clocks,
         }
@@ -435,7 +437,9 @@ def extras(pt, np, torch, device, options):
                "mrays_s": rays / 1e3 / st.kernel_ms, "samples_per_s": w * h * spp / (st.kernel_ms * 1e-3),
                "e2e_mrays_s_pageable_host_buffer": rays / 1e6 / wall, "rays_per_sample": rays / (w * h * spp),
                "fp32_frac": rays * FLOP_PER_TEST * n / (st.kernel_ms * 1e-3) / info.fp32_fma_peak_flops, "n_spheres": n,
-               "lane_efficiency_of_the_sweep": rays / 32.0 / max(1, st.warp_sweeps)}
+               "lane_efficiency_of_the_sweep": rays / 32.0 / max(1, st.warp_sweeps),
+               "kernel": {0: "streamed, packed-FP32 pre-filter", 1: "resident, packed-FP32 pre-filter", 2: "resident, tensor-path pre-filter",
+                          3: "streamed, tensor-path pre-filter"}.get(int(st.resident), "?")}
         if key == "cfg3":
             # every scatter evaluates the Noise texture once (both spheres are noise-textured Lambertians, presets.rs:271-315) and a
             # sample ends by exactly one miss or one depth-limit hit, so texture lookups = rays - samples; turb = 7 octaves of noise
