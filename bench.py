@@ -97,6 +97,25 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner under the driver's
+    NCCL_DEBUG setting, which this script leaves alone): from here on file descriptor 1 points at stderr, and only emit()
+    writes to the real stdout."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path (restated: oracle, list mode) on the host cores, bounded sample."""
     rank = int(os.environ.get("RANK", "0"))
@@ -130,7 +149,7 @@ def run_reference(args):
         "e2e": {"value": mrays, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference is Rust and cannot be built in this image (no rustc/cargo): this is the C++ restatement in oracle/",
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -177,6 +196,7 @@ def main():
     ap.add_argument("--fast", action="store_true", help="the e2e leg runs one step without its own warm-up (automatic when a step exceeds 2 s)")
     ap.add_argument("--resident-kernel", type=int, default=0, help="PtOptions.resident_kernel (0 = the library's default)")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -407,7 +427,7 @@ def main():
                 line["cpu_baseline"] = cpu_baseline(args.workload)
             except Exception as e:  # the baseline is a reported extra; never lose the GPU line over it
                 line["cpu_baseline"] = {"error": repr(e)}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
