@@ -38,6 +38,11 @@
 
 namespace pt {
 
+// steps per trip of the loop (an experiment knob: 2 measured no faster on cfg2/cfg4/cfg5, profiles/variants_r2_mma.txt)
+#ifndef PT_MMA_UNROLL
+#define PT_MMA_UNROLL 1
+#endif
+constexpr int kMmaUnroll = PT_MMA_UNROLL;
 constexpr float kMmaSlack = 3.0517578125e-05f;    // 2^-15
 constexpr double kMmaSlackSphere = 3.0517578125e-05;
 constexpr double kMmaAbsSlack = 1.0 / 128.0;       // scaled units
@@ -152,7 +157,7 @@ __device__ __forceinline__ void sweep_mma_steps(const uint4* __restrict__ simg, 
     const uint4* p = simg + lane;
     uint4 sp = *p;
     const int end = first_step + n_steps;
-#pragma unroll 1
+#pragma unroll kMmaUnroll
     for (int s = first_step; s < end; ++s) {
         p += 32;
         const uint4 cur = sp;
