@@ -5,14 +5,16 @@
 //   * one path = one pixel's current sample.  A path owns a pixel for a whole chunk of its samples (so the pixel's
 //     xoshiro256+ stream is consumed in exactly the reference's order), then pulls the next ticket from a global atomic
 //     queue (warp-aggregated) — the rayon `par_iter_mut` of scene.rs:90-93.
-//   * every trip of the main loop is ONE full sphere sweep for all live paths of the warp (convergent, FP32-bound),
-//     followed by a short divergent shading step.  A path that ended starts its next sample (or next ticket) in the same
-//     trip, so the sweep always runs with all live paths.  The resident kernel carries two paths per lane (sweep_two).
+//   * every trip of the main loop is ONE full sphere sweep for all live paths of the warp (convergent), followed by a
+//     short divergent shading step.  A path that ended starts its next sample (or next ticket) in the same trip, so the
+//     sweep always runs with all live paths.  The default resident kernel (pt_regroup.cuh) keeps one path per lane and
+//     regroups the CTA's paths by material between sweep and shading; pt_megakernel_resident carries two paths per lane.
 //   * the recursion `emitted + attenuation * ray_trace(..)` becomes `colour += throughput * emitted;
 //     throughput *= attenuation`.
-//   * the pre-filter image reaches the FMA pipe through the uniform datapath from a kernel parameter (scenes of up to
-//     2048 spheres), from shared memory staged once per CTA with a TMA bulk copy (cp.async.bulk + mbarrier), or tile by
-//     tile through L2 for scenes that do not fit (pt_megakernel_streamed).
+//   * stage 1 of the sweep (the conservative pre-filter over all spheres) runs on the tensor path (mma.sync f16 split
+//     operands, pt_sweep_mma.cuh) or in packed FP32 (pt_sweep.cuh); its image is staged in shared memory once per CTA with
+//     a TMA bulk copy (cp.async.bulk + mbarrier), streamed tile by tile through L2 for scenes that do not fit
+//     (pt_megakernel_streamed), or — two-paths-per-lane flavour — read through the uniform datapath from a kernel parameter.
 #pragma once
 #include "pt_shade.cuh"
 #include "pt_sweep.cuh"

@@ -1,12 +1,14 @@
-// pt_regroup.cuh — the resident kernel with ONE path per lane and a CTA-level regroup of the paths between sweep and
-// shading (round 1's kernel, still the fastest on every preset: 55.6 % of the FP32 peak on cfg2 in the driver's run).
+// pt_regroup.cuh — the resident kernel: ONE path per lane and a CTA-level regroup of the paths between sweep and shading.
+// The default for every scene that fits in shared memory, in two instantiations of the same kernel: stage 1 of the sweep on
+// the tensor path (MMA = true, pt_sweep_mma.cuh: cfg2 67.9 %, cfg4 70.5 % of the FP32 peak in algorithmic flop) or in packed
+// FP32 (MMA = false, pt_sweep.cuh: 55.2 % / 56.7 %; small scenes, ill-scaled scenes, cameras outside the scene's extent).
 //
-// Round 2 built two alternatives around a cheaper sweep — two paths per lane with the sphere pairs as uniform operands from
-// a kernel-parameter image (pt_megakernel_resident, 44 %) and an asynchronous wavefront form with a path pool and
-// per-material queues in shared memory (pt_wave.cuh, 38 %) — and measured both slower than this kernel on the real
+// Round 2 also built two alternatives around a cheaper FP32 sweep — two paths per lane with the sphere pairs as uniform
+// operands from a kernel-parameter image (pt_megakernel_resident, 44 %) and an asynchronous wavefront form with a path pool
+// and per-material queues in shared memory (pt_wave.cuh, 38 %) — and measured both slower than this kernel on the real
 // workloads although their sweep loops are 10-23 % faster in isolation (tools/probe_sweep2.cu): what they save in the loop
-// they lose around it (DESIGN.md §5.2 has the numbers and the ncu evidence).  They stay selectable through
-// PtOptions.resident_kernel; this kernel is the default.
+// they lose around it (DESIGN.md §4.6 / §5.2 have the numbers and the ncu evidence).  They stay selectable through
+// PtOptions.resident_kernel.
 #pragma once
 #include "pt_megakernel.cuh"
 
