@@ -42,6 +42,9 @@ int fail(int code, const char* fmt, ...) {
     } while (0)
 
 constexpr size_t kMaxDynSmem = 227 * 1024 - 1024;  // leave room for static shared + driver reservation
+#ifndef PT_MMA_RESIDENT_MIN_CTAS
+#define PT_MMA_RESIDENT_MIN_CTAS 2  // the tensor-path regroup kernel is chosen while at least this many CTAs fit on an SM
+#endif
 
 }  // namespace
 
@@ -173,7 +176,7 @@ size_t regroup_mma_smem(int n_blocks) { return (size_t)(n_blocks / pt::kLdsGroup
 uint32_t resident_choice(const PtOptions& opt, bool mma_ok, int n_blocks) {
     uint32_t k = opt.resident_kernel;
     if (k == 0) k = 5;
-    if (k == 5 && !(mma_ok && regroup_mma_smem(n_blocks) <= kMaxDynSmem / 2)) k = 4;  // two CTAs per SM at least
+    if (k == 5 && !(mma_ok && regroup_mma_smem(n_blocks) <= kMaxDynSmem / PT_MMA_RESIDENT_MIN_CTAS)) k = 4;  // two CTAs per SM at least
     return k;
 }
 bool fits_resident(int n_blocks, const PtOptions& opt) {
@@ -184,7 +187,13 @@ bool fits_resident(int n_blocks, const PtOptions& opt) {
 
 int plan_launch(Replica* s) {
     int forced_tile = s->opt.force_stream_tile_blocks;
-    if (fits_resident(s->n_blocks, s->opt)) {
+    // Mid-size scenes (about 2 000 - 13 000 spheres): the FP32 image still fits in shared memory, the tensor-path image no longer
+    // does at two CTAs per SM.  Measured on B200 (tools/midsize_bench.py, profiles/midsize_r2.txt): the L2-streamed kernel with
+    // the tensor-path pre-filter renders them 1.5-1.75x faster than the resident kernel with the FP32 pre-filter (and faster
+    // than the tensor-path resident kernel at one CTA per SM), so the automatic choice streams them.
+    const bool stream_for_mma = s->opt.resident_kernel == 0 && s->mma_ok && s->n_blocks / pt::kLdsGroupBlocks < 65536 &&
+                                regroup_mma_smem(s->n_blocks) > kMaxDynSmem / PT_MMA_RESIDENT_MIN_CTAS;
+    if (fits_resident(s->n_blocks, s->opt) && !stream_for_mma) {
         s->resident = true;
         s->const_image = s->n_blocks <= pt::kMaxConstBlocks && s->opt.resident_kernel != 3;
         s->smem_bytes = resident_smem(s->n_blocks, s->const_image);

@@ -91,8 +91,7 @@ def test_recorded_rays_through_every_kernel_flavour():
 
 
 def test_recorded_rays_of_cfg5_stress100k():
-    """BASELINE config 5 (99 860 spheres, streamed through L2 in TMA tiles): rays of real paths + the mid-size scene that
-    stays resident with LDS operands (more than 2 048 spheres: no parameter image)."""
+    """BASELINE config 5 (99 860 spheres, streamed through L2 in TMA tiles): rays of real paths, both pre-filters."""
     w, h = 48, 27
     sc = orc.Scene("stress100k", w, h)
     rays, _ = sc.record_rays(2, 50, 60_000, nthreads=8)
@@ -298,9 +297,9 @@ def test_duplicate_and_concentric_spheres_tie_rule():
         h.close()
 
 
-def _renders_on_the_tensor_path(h):
-    """One 8x8 render through the raw ABI, camera at the origin: PtRenderStats.resident == 2 <=> the scene's sweep runs its
-    pre-filter on the tensor path (pt_sweep_mma.cuh)."""
+def _kernel_of(h):
+    """One 8x8 render through the raw ABI, camera at the origin -> PtRenderStats.resident: 0 streamed / 1 resident with the
+    packed-FP32 pre-filter, 2 resident / 3 streamed with the pre-filter on the tensor path (pt_sweep_mma.cuh)."""
     L = ffi.libptgpu()
     p = pt.Params(8, 8, 1, 2).to_ffi()
     cam = ffi.PtCamera()
@@ -315,7 +314,36 @@ def _renders_on_the_tensor_path(h):
     ffi.check(L.pt_render(h.scene_handle, C.byref(p), C.byref(cam), 0, buf.ctypes.data_as(C.c_void_p), C.byref(rays)))
     st = ffi.PtRenderStats()
     ffi.check(L.pt_scene_stats(h.scene_handle, C.byref(st)))
-    return st.resident == 2
+    return int(st.resident)
+
+
+def _renders_on_the_tensor_path(h):
+    return _kernel_of(h) == 2
+
+
+def test_mid_size_scene_streams_on_the_tensor_path():
+    """3 000 spheres: the FP32 pre-filter image still fits in shared memory, the tensor-path image no longer does at two CTAs
+    per SM.  The automatic choice streams such a scene through L2 with the tensor-path pre-filter (1.5-1.75x faster than the
+    resident FP32 kernel, tools/midsize_bench.py); resident_kernel = 4 keeps it resident.  Same hits either way — also in the
+    spatial storage order the scene was given as a resident candidate."""
+    rng = np.random.default_rng(21)
+    cr = np.hstack([rng.uniform(-30, 30, (3000, 1)), rng.uniform(0.1, 0.4, (3000, 1)), rng.uniform(-30, 30, (3000, 1)), rng.uniform(0.1, 0.4, (3000, 1))])
+    cr[0] = [0.0, -1000.0, 0.0, 1000.0]
+    o = np.hstack([rng.uniform(-30, 30, (80_000, 1)), rng.uniform(0.5, 6.0, (80_000, 1)), rng.uniform(-30, 30, (80_000, 1))])
+    tgt = np.hstack([rng.uniform(-30, 30, (80_000, 1)), rng.uniform(0.0, 0.4, (80_000, 1)), rng.uniform(-30, 30, (80_000, 1))])
+    rays = np.hstack([o, _unit(tgt - o)]).astype(np.float32)
+    rays[:, 3:] = _unit(rays[:, 3:])
+    base = None
+    for opt, want in ((None, 3), (pt.PtOptions(resident_kernel=4), 1), (pt.PtOptions(spatial_order=0), 3)):
+        h, sc = _custom_scene(cr.astype(np.float32), opt)
+        try:
+            assert _kernel_of(h) == want
+            idx, t, _ = _check(h, sc, rays)
+            if base is not None:
+                assert np.array_equal(idx, base[0]) and np.array_equal(t, base[1])
+            base = (idx, t)
+        finally:
+            h.close()
 
 
 def test_tensor_path_queue_overflow_and_rays_outside_its_domain():
