@@ -185,7 +185,9 @@ typedef struct PtOptions {
                                          2: large spheres first, then Morton order */
     uint32_t tile_rows;               /* multi-device scenes: rows per interleaved row tile (0 -> 4) */
     uint32_t resident_kernel;         /* which kernel renders a scene that fits in shared memory.  0 automatic: 5 where the
-                                         scene suits it (>= 128 spheres of a size comparable to the scene's extent), else 4.
+                                         scene suits it (>= 128 spheres of a size comparable to the scene's extent), else 4;
+                                         a suitable scene whose tensor-path image no longer fits twice per SM (about 2 000
+                                         spheres and up) is streamed through L2 on the tensor path instead (measured faster).
                                          4 one path per lane + CTA regroup, pre-filter in packed FP32; 5 the same kernel with
                                          the pre-filter's dot products on the tensor path (mma.sync f16 split operands,
                                          pt_sweep_mma.cuh; a render whose camera lies outside the scene's extent falls back
