@@ -303,6 +303,17 @@ uint32_t pt_partition_rows(const PtPartition* part, uint32_t height, uint32_t* r
  * depend on it. */
 uint32_t pt_scene_storage_order(const PtSceneDesc* desc, const PtOptions* options, uint32_t* order_out, uint32_t cap);
 
+/* Diagnostic, host only (no GPU needed): the sphere operand of the tensor-path pre-filter (pt_sweep_mma.cuh) as
+ * pt_scene_create* builds it for `desc` under `options`, before the shuffle into MMA fragments.
+ * rows_out: per STORED sphere (padding spheres included, at most `cap` of them) 16 f16 bit patterns = the K halves
+ * [S_hi(5) | S_hi(5) | S_lo(5) | 0] of S = [sigma (c - t), s, K'/s]; scale_out[7] = sigma, s, 1/s, max |o - t|^2, tx, ty, tz;
+ * order_out[j] = position in the caller's list of stored sphere j (n_spheres entries).  Any of the three may be NULL.
+ * Returns the number of stored spheres (a multiple of 16), or 0 when the scene does not take the tensor path (fewer than
+ * 128 spheres, or spheres tiny against the scene's extent).  tests/test_host_and_abi.py evaluates the filter from these
+ * halves in numpy and checks it against the reference's exact expression. */
+uint32_t pt_scene_mma_operand(const PtSceneDesc* desc, const PtOptions* options, uint16_t* rows_out, uint32_t cap, float* scale_out,
+                              uint32_t* order_out);
+
 /* Measurement helper: sustained FP32 FFMA throughput of `device` (flop/s) from a pure-FMA kernel,
  * so bench.py can print the measured ceiling beside the nominal sm_count*128*2*clock figure. */
 int pt_probe_fp32_peak(int device, double* flops_out);

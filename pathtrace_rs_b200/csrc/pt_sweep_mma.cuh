@@ -51,7 +51,10 @@ constexpr int kMmaStageRows = 16;                  // rows of kSweepThreads word
 
 struct MmaScale {
     float sigma, s, inv_s;
-    float max_o2;  // rays with |o|^2 beyond this (the square of the extent the scales were chosen for) bypass stage 1
+    float max_o2;      // rays with |o - t|^2 beyond this (the square of the extent the scales were chosen for) bypass stage 1
+    float tx, ty, tz;  // the scene's offset: the filter works on c - t and o - t (the discriminant does not depend on t).  An axis
+                       // is shifted only when the scene lies at more than four extents from the origin on it, so that o - t is
+                       // exact for every origin inside the extent (Sterbenz) and the ray tested is the ray given, to the bit
 };
 
 __device__ __forceinline__ void hmma16816(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
@@ -62,7 +65,8 @@ __device__ __forceinline__ void hmma16816(float (&d)[4], const uint4& a, uint32_
 __device__ __forceinline__ uint32_t mma_pack(__half a, __half b) { return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16); }
 
 // the 16 words of one ray's operand: words 0..7 the R_A column (K halves 2i, 2i+1 in word i), words 8..15 the R_B column.
-// A lane without a path in flight gets the parked operand: A' = 0, B' = K' - 65504 s < 0 for every sphere.
+// (ox, oy, oz) is the origin relative to the scene's offset.  A lane without a path in flight gets the parked operand:
+// A' = 0, B' = K' - 65504 s < 0 for every sphere.
 __device__ __forceinline__ void mma_ray_operand(const MmaScale sc, bool active, float ox, float oy, float oz, float dx, float dy, float dz, uint32_t (&w)[16]) {
     const float nod = -((ox * dx + oy * dy) + oz * dz);
     const float oo = ((ox * ox + oy * oy) + oz * oz) * (1.0f - kMmaSlack);
@@ -124,13 +128,14 @@ __device__ __forceinline__ void mma_ray_fragments(uint32_t* __restrict__ stage, 
     uint32_t* warp_cols = stage + (threadIdx.x & ~31u);
     // validity domain of the f16 operands: origin inside the extent the scales were chosen for, direction of unit size.
     // A ray outside it (or a non-finite one) takes no part in stage 1 and gets the exact test on every sphere instead.
-    f.in_range = ((ox * ox + oy * oy) + oz * oz) <= sc.max_o2 && ((dx * dx + dy * dy) + dz * dz) <= 4.0f;
+    const float sx = ox - sc.tx, sy = oy - sc.ty, sz = oz - sc.tz;
+    f.in_range = ((sx * sx + sy * sy) + sz * sz) <= sc.max_o2 && ((dx * dx + dy * dy) + dz * dz) <= 4.0f;
     // ray operands -> A fragments.  Fragment (quad g, row block rb, t, column type c) is four consecutive words
     // {ray0.word[t], ray1.word[t], ray0.word[t+4], ray1.word[t+4]} at row c*8 + rb*4 + t, columns 4g..4g+3 of the warp:
     // the owner of ray (rb = t >> 1, half = t & 1) scatters its 16 words, every lane reads its four fragments with LDS.128.
     {
         uint32_t w[16];
-        mma_ray_operand(sc, active && f.in_range, ox, oy, oz, dx, dy, dz, w);
+        mma_ray_operand(sc, active && f.in_range, sx, sy, sz, dx, dy, dz, w);
         uint32_t* base = warp_cols + 4u * g + (t & 1u);
 #pragma unroll
         for (int c = 0; c < 2; ++c)

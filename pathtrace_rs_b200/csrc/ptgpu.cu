@@ -66,7 +66,8 @@ struct FlatScene {
     // tensor-path pre-filter (pt_sweep_mma.cuh): fragment-ordered f16 sphere operand + the scene's scales; mma_ok = the
     // scene is one the tensor path is worth using on (enough spheres, absolute slack small against the spheres' size)
     std::vector<uint4> mma_image;
-    pt::MmaScale mma{0.f, 0.f, 0.f, 0.f};
+    std::vector<uint16_t> mma_rows;  // per stored sphere (incl. padding) its 16 K halves, before the fragment shuffle (pt_scene_mma_operand)
+    pt::MmaScale mma{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     bool mma_ok = false;
 };
 
@@ -96,7 +97,7 @@ struct Replica {
     bool mma = false;               // ... with stage 1 of its sweep on the tensor path (pt_sweep_mma.cuh)
     bool mma_ok = false;            // the scene has a usable tensor-path image
     uint4* d_mma_image = nullptr;
-    pt::MmaScale mma_scale{0.f, 0.f, 0.f, 0.f};
+    pt::MmaScale mma_scale{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     size_t fp32_smem_bytes = 0;     // the FP32 regroup kernel's launch geometry, kept as the per-render fallback of the tensor path
     int fp32_ctas_per_sm = 0;       // (camera outside the extent the f16 operands were scaled for)
     int fp32_tile_blocks = 0, fp32_n_tiles = 0;
@@ -452,8 +453,11 @@ int launch_update(Replica* s, const PtParams* params, const PtCamera* cam, uint3
     bool use_mma = s->mma;
     if (use_mma) {
         double reach = 0.0;
-        for (int i = 0; i < 3; ++i) reach += ((double)std::fabs(cam->origin[i]) + (double)std::fabs(cam->lens_radius) * (std::fabs(cam->u[i]) + std::fabs(cam->v[i]))) *
-                                             ((double)std::fabs(cam->origin[i]) + (double)std::fabs(cam->lens_radius) * (std::fabs(cam->u[i]) + std::fabs(cam->v[i])));
+        const float off[3] = {s->mma_scale.tx, s->mma_scale.ty, s->mma_scale.tz};
+        for (int i = 0; i < 3; ++i) {
+            const double c = std::fabs((double)cam->origin[i] - (double)off[i]) + (double)std::fabs(cam->lens_radius) * (std::fabs(cam->u[i]) + std::fabs(cam->v[i]));
+            reach += c * c;
+        }
         if (!(reach <= (double)s->mma_scale.max_o2)) use_mma = false;
     }
     const int ctas_per_sm = (s->mma && !use_mma) ? s->fp32_ctas_per_sm : s->ctas_per_sm;
@@ -620,11 +624,34 @@ void build_mma_image(FlatScene& fs, const std::vector<double>& bound) {
     fs.mma_ok = false;
     const uint32_t n = fs.n_spheres;
     if (n < 128) return;
+    // the scene's offset t: per axis the middle of the spheres' bounding box, used only where the scene lies at more than four
+    // times its own reach from the origin on that axis (then o - t is exact in f32 for every origin inside the extent, so the
+    // filter sees exactly the ray the exact test sees); 0 elsewhere — every preset of the reference.
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (uint32_t j = 0; j < n; ++j)
+        for (int a = 0; a < 3; ++a) {
+            const double* b = &bound[(size_t)j * 4];
+            if (!std::isfinite(b[a]) || !std::isfinite(b[3])) return;
+            lo[a] = std::min(lo[a], b[a] - b[3]);
+            hi[a] = std::max(hi[a], b[a] + b[3]);
+        }
+    double t[3] = {0.5 * (lo[0] + hi[0]), 0.5 * (lo[1] + hi[1]), 0.5 * (lo[2] + hi[2])};
+    double centred_reach = 0.0;
+    for (uint32_t j = 0; j < n; ++j) {
+        const double* b = &bound[(size_t)j * 4];
+        centred_reach = std::max(centred_reach, std::sqrt((b[0] - t[0]) * (b[0] - t[0]) + (b[1] - t[1]) * (b[1] - t[1]) + (b[2] - t[2]) * (b[2] - t[2])) + b[3]);
+    }
+    for (int a = 0; a < 3; ++a) {
+        t[a] = (double)(float)t[a];  // the kernel subtracts the f32 value
+        if (!(std::fabs(t[a]) > 4.0 * 2.0 * centred_reach)) t[a] = 0.0;  // (extent = twice the reach)
+    }
     double reach = 0.0;
     std::vector<double> r2s;
     r2s.reserve(n);
+    std::vector<double> shifted(bound);
     for (uint32_t j = 0; j < n; ++j) {
-        const double* b = &bound[(size_t)j * 4];
+        double* b = &shifted[(size_t)j * 4];
+        for (int a = 0; a < 3; ++a) b[a] -= t[a];
         const double d = std::sqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]) + b[3];
         if (!std::isfinite(d)) return;
         reach = std::max(reach, d);
@@ -641,6 +668,9 @@ void build_mma_image(FlatScene& fs, const std::vector<double>& bound) {
     fs.mma.s = (float)s;
     fs.mma.inv_s = (float)(1.0 / s);
     fs.mma.max_o2 = (float)(extent * extent * (1.0 - 1e-6));
+    fs.mma.tx = (float)t[0];
+    fs.mma.ty = (float)t[1];
+    fs.mma.tz = (float)t[2];
     const int n_steps = fs.n_blocks / pt::kLdsGroupBlocks;
     auto h16 = [](float x) { const __half h = __float2half_rn(x); unsigned short u; std::memcpy(&u, &h, 2); return u; };
     auto h2f = [](unsigned short u) { __half h; std::memcpy(&h, &u, 2); return __half2float(h); };
@@ -648,7 +678,7 @@ void build_mma_image(FlatScene& fs, const std::vector<double>& bound) {
     for (int j = 0; j < n_steps * 16; ++j) {
         float S[5] = {0.0f, 0.0f, 0.0f, (float)s, -65504.0f};  // padding: B' <= -65504 s + slack terms < 0 for every ray in range
         if ((uint32_t)j < n) {
-            const double* b = &bound[(size_t)j * 4];
+            const double* b = &shifted[(size_t)j * 4];
             const double c2 = b[0] * b[0] + b[1] * b[1] + b[2] * b[2], r2 = b[3] * b[3];
             const double Kp = sigma * sigma * (r2 - c2 + pt::kMmaSlackSphere * (c2 + r2)) + pt::kMmaAbsSlack;
             S[0] = (float)(sigma * b[0]);
@@ -673,6 +703,7 @@ void build_mma_image(FlatScene& fs, const std::vector<double>& bound) {
             auto pk = [&](int r, int k) { return (uint32_t)row[(size_t)(st * 16 + r) * 16 + k] | ((uint32_t)row[(size_t)(st * 16 + r) * 16 + k + 1] << 16); };
             fs.mma_image[(size_t)st * 32 + lane] = make_uint4(pk(g, 2 * t), pk(g, 2 * t + 8), pk(8 + g, 2 * t), pk(8 + g, 2 * t + 8));
         }
+    fs.mma_rows.assign(row.begin(), row.end());
     fs.mma_ok = true;
 }
 
@@ -1287,6 +1318,27 @@ uint32_t pt_scene_storage_order(const PtSceneDesc* desc, const PtOptions* option
     const int mode = storage_order(desc, any_moving, opt, order_of);
     for (uint32_t j = 0; j < n && j < cap && order_out; ++j) order_out[j] = order_of[j];
     return (uint32_t)mode;
+}
+
+uint32_t pt_scene_mma_operand(const PtSceneDesc* desc, const PtOptions* options, uint16_t* rows_out, uint32_t cap, float* scale_out, uint32_t* order_out) {
+    if (!desc) return 0;
+    PtOptions opt;
+    if (normalise_options(options, &opt) != PT_OK) return 0;
+    FlatScene fs;
+    if (flatten_scene(desc, opt, fs) != PT_OK || !fs.mma_ok) return 0;
+    const uint32_t stored = (uint32_t)(fs.mma_rows.size() / 16);
+    for (uint32_t j = 0; j < stored && j < cap && rows_out; ++j) std::memcpy(rows_out + (size_t)j * 16, &fs.mma_rows[(size_t)j * 16], 16 * sizeof(uint16_t));
+    if (scale_out) {
+        scale_out[0] = fs.mma.sigma;
+        scale_out[1] = fs.mma.s;
+        scale_out[2] = fs.mma.inv_s;
+        scale_out[3] = fs.mma.max_o2;
+        scale_out[4] = fs.mma.tx;
+        scale_out[5] = fs.mma.ty;
+        scale_out[6] = fs.mma.tz;
+    }
+    for (uint32_t j = 0; j < fs.n_spheres && j < cap && order_out; ++j) order_out[j] = fs.order_of[j];
+    return stored;
 }
 
 int pt_device_count(void) {

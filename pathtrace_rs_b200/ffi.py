@@ -149,6 +149,8 @@ def libptgpu():
         L.pt_probe_fp32_peak.argtypes = [C.c_int, C.POINTER(C.c_double)]
         L.pt_scene_storage_order.restype = C.c_uint32
         L.pt_scene_storage_order.argtypes = [C.POINTER(PtSceneDesc), C.POINTER(PtOptions), vp, C.c_uint32]
+        L.pt_scene_mma_operand.restype = C.c_uint32
+        L.pt_scene_mma_operand.argtypes = [C.POINTER(PtSceneDesc), C.POINTER(PtOptions), vp, C.c_uint32, vp, vp]
         _ptgpu = L
     return _ptgpu
 

@@ -297,13 +297,14 @@ def test_duplicate_and_concentric_spheres_tie_rule():
         h.close()
 
 
-def _kernel_of(h):
-    """One 8x8 render through the raw ABI, camera at the origin -> PtRenderStats.resident: 0 streamed / 1 resident with the
+def _kernel_of(h, origin=(0.0, 0.0, 0.0)):
+    """One 8x8 render through the raw ABI, camera at `origin` -> PtRenderStats.resident: 0 streamed / 1 resident with the
     packed-FP32 pre-filter, 2 resident / 3 streamed with the pre-filter on the tensor path (pt_sweep_mma.cuh)."""
     L = ffi.libptgpu()
     p = pt.Params(8, 8, 1, 2).to_ffi()
     cam = ffi.PtCamera()
-    cam.lower_left_corner[:] = [-1.0, -1.0, -1.0]
+    cam.origin[:] = [float(x) for x in origin]
+    cam.lower_left_corner[:] = [float(x) - 1.0 for x in origin]
     cam.horizontal[:] = [2.0, 0.0, 0.0]
     cam.vertical[:] = [0.0, 2.0, 0.0]
     cam.u[:] = [1.0, 0.0, 0.0]
@@ -317,8 +318,8 @@ def _kernel_of(h):
     return int(st.resident)
 
 
-def _renders_on_the_tensor_path(h):
-    return _kernel_of(h) == 2
+def _renders_on_the_tensor_path(h, origin=(0.0, 0.0, 0.0)):
+    return _kernel_of(h, origin) == 2
 
 
 def test_mid_size_scene_streams_on_the_tensor_path():
@@ -382,15 +383,20 @@ def test_tensor_path_is_chosen_only_where_it_can_pay():
     tiny = np.hstack([rng.uniform(-6, 6, (300, 3)), np.full((300, 1), 1.0e-3)])
     tiny[0] = [0.0, -1.0e5, 0.0, 1.0e5]                                                   # a huge ground sets the extent
     normal = np.hstack([rng.uniform(-6, 6, (300, 3)), rng.uniform(0.2, 1.0, (300, 1))])
-    for cr, want in ((few, False), (tiny, False), (normal, True)):
+    # far from the origin the filter works relative to the scene's offset (exact subtraction, MmaScale): still the tensor path
+    away = normal.copy()
+    away[:, 0] += 1.0e5
+    away[:, 2] -= 2.0e5
+    for cr, want, shift in ((few, False, np.zeros(3)), (tiny, False, np.zeros(3)), (normal, True, np.zeros(3)), (away, True, np.array([1.0e5, 0.0, -2.0e5]))):
         h, sc = _custom_scene(cr.astype(np.float32), pt.PtOptions(resident_kernel=5))
         try:
-            assert _renders_on_the_tensor_path(h) == want
-            o = _unit(rng.normal(size=(50_000, 3))) * 20.0
-            tgt = rng.uniform(-6, 6, (50_000, 3))
+            assert _renders_on_the_tensor_path(h, shift if want else (0.0, 0.0, 0.0)) == want
+            o = _unit(rng.normal(size=(50_000, 3))) * 14.0 + shift   # inside the operands' extent (twice the reach of the spheres, ~20)
+            tgt = rng.uniform(-6, 6, (50_000, 3)) + shift
             rays = np.hstack([o, _unit(tgt - o)]).astype(np.float32)
             rays[:, 3:] = _unit(rays[:, 3:])
-            _check(h, sc, rays)
+            idx, _, flagged = _check(h, sc, rays)
+            assert (idx >= 0).mean() > 0.3 and flagged.mean() < 30   # the filter filters (300 spheres)
         finally:
             h.close()
 

@@ -86,6 +86,138 @@ def test_library_is_sm100a_cuda_with_packed_fp32_and_tma():
         assert "LDS.128" in body[0]
 
 
+# ---- the tensor-path pre-filter, evaluated on the CPU from the operand the library builds ---------------------------------
+def _mma_operand(cr, options=None):
+    """pt_scene_mma_operand (host only) for Lambertian spheres `cr` [n, 4]: (rows [stored, 16] as f32, scale[4], order[n])."""
+    n = len(cr)
+    cols = [np.ascontiguousarray(cr[:, i], np.float32) for i in range(4)]
+    mats = (ffi.PtMaterial * n)()
+    texs = (ffi.PtTexture * n)()
+    for i in range(n):
+        mats[i].kind, mats[i].texture = 0, i
+        texs[i].kind, texs[i].odd, texs[i].even = 0, -1, -1
+    midx = np.arange(n, dtype=np.int32)
+    d = ffi.PtSceneDesc()
+    d.struct_size, d.n_spheres = C.sizeof(ffi.PtSceneDesc), n
+    fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+    d.centre_x, d.centre_y, d.centre_z, d.radius = fp(cols[0]), fp(cols[1]), fp(cols[2]), fp(cols[3])
+    d.material_index = midx.ctypes.data_as(C.POINTER(C.c_int32))
+    d.n_materials = d.n_textures = n
+    d.materials, d.textures = mats, texs
+    cap = (n + 15) // 16 * 16
+    rows = np.zeros((cap, 16), np.uint16)
+    scale = np.zeros(7, np.float32)
+    order = np.zeros(n, np.uint32)
+    stored = pt.libptgpu().pt_scene_mma_operand(C.byref(d), C.byref(options) if options is not None else None, rows.ctypes.data_as(C.c_void_p), cap,
+                                                scale.ctypes.data_as(C.c_void_p), order.ctypes.data_as(C.c_void_p))
+    return int(stored), rows.view(np.float16).astype(np.float32), scale, order
+
+
+def _mma_filter_margin(cr, rays, options=None):
+    """The tensor-path pre-filter (pt_sweep_mma.cuh) restated in numpy on the library's own sphere operand: the ray operand in
+    f32 as mma_ray_operand builds it, f16 hi/lo split, exact products, and a PESSIMISTIC accumulation: every dot product is
+    moved against the candidate by 2^-20 of the sum of its |terms| (twice what tools/probe_mma.cu measures for the tensor
+    core's f32 accumulate).  Returns (number of (ray, sphere) pairs the reference's exact f32 expression accepts, the smallest
+    worst-case L' among them divided by sigma^2 (|c|^2 + r^2 + |o|^2), flagged pairs per ray)."""
+    stored, rows, (sigma, s, inv_s, max_o2, tx, ty, tz), order = _mma_operand(cr, options)
+    assert stored >= len(cr) and stored % 16 == 0
+    t = np.array([tx, ty, tz], np.float32)
+    S = rows[: len(cr)].astype(np.float64)                     # stored order
+    c = cr[order].astype(np.float32)
+    f32 = np.float32
+    slack = f32(2.0 ** -15)
+    rays = rays[(((rays[:, :3] - t).astype(np.float64)) ** 2).sum(1) <= max_o2]  # the kernel's own guard: rays beyond the extent bypass stage 1
+    o_abs, d = rays[:, :3].astype(f32), rays[:, 3:].astype(f32)
+    o = o_abs - t                                              # the filter works relative to the scene's offset (exact, see MmaScale)
+    assert np.array_equal(o.astype(np.float64), o_abs.astype(np.float64) - t.astype(np.float64))
+    nod = -((o[:, 0] * d[:, 0] + o[:, 1] * d[:, 1]) + o[:, 2] * d[:, 2])
+    oo = ((o[:, 0] * o[:, 0] + o[:, 1] * o[:, 1]) + o[:, 2] * o[:, 2]) * (f32(1.0) - slack)
+    zero = np.zeros_like(nod)
+    ra = np.stack([d[:, 0], d[:, 1], d[:, 2], f32(sigma) * nod * f32(inv_s), zero], 1)
+    rb = np.stack([f32(2.0) * f32(sigma) * o[:, 0], f32(2.0) * f32(sigma) * o[:, 1], f32(2.0) * f32(sigma) * o[:, 2],
+                   -(f32(sigma) * f32(sigma)) * oo * f32(inv_s), np.full_like(nod, s)], 1).astype(f32)
+
+    def operand(r):  # [R_hi(5) | R_lo(5) | R_hi(5) | 0] as exact f64 values of the f16 pieces
+        hi = r.astype(np.float16)
+        lo = (r - hi.astype(f32)).astype(np.float16)
+        return np.concatenate([hi, lo, hi, np.zeros((len(r), 1), np.float16)], 1).astype(np.float64)
+    RA, RB = operand(ra), operand(rb)
+    A = RA @ S.T                                                # [rays, spheres]: exact sums of exact f16 products
+    B = RB @ S.T
+    eA = 2.0 ** -20 * (np.abs(RA) @ np.abs(S).T)
+    eB = 2.0 ** -20 * (np.abs(RB) @ np.abs(S).T)
+    worst = np.maximum(np.abs(A) - eA, 0.0) ** 2 + (B - eB)
+    worst -= 2.0 ** -23 * np.maximum(A * A, np.abs(B))          # the packed FMA that forms L'
+    # the reference's exact expression, unfused f32 (spheres_soa.rs:116-121)
+    co = c[None, :, :3] - o_abs[:, None, :]
+    nb = (co[..., 0] * d[:, None, 0] + co[..., 1] * d[:, None, 1]) + co[..., 2] * d[:, None, 2]
+    cc = ((co[..., 0] * co[..., 0] + co[..., 1] * co[..., 1]) + co[..., 2] * co[..., 2]) - c[None, :, 3] * c[None, :, 3]
+    hit = (nb * nb - cc) > f32(0.0)
+    c64 = c.astype(np.float64)
+    scale = float(sigma) ** 2 * (((c64[None, :, :3] - t.astype(np.float64)) ** 2).sum(2) + c64[None, :, 3] ** 2 + (o.astype(np.float64) ** 2).sum(1)[:, None])
+    margin = (worst / scale)[hit]
+    return int(hit.sum()), float(margin.min()), float((worst > 0).sum() / len(rays))
+
+
+def _tangent_rays(cr, rng, per_sphere):
+    """Lines that graze every sphere within a few 2^-22 steps of its radius, from near and far, plus rays leaving a surface
+    along its tangent plane (what a conservative filter can get wrong)."""
+    out = []
+    for cx, cy, cz, r in np.asarray(cr, np.float64):
+        r = abs(r)
+        u = rng.normal(size=(per_sphere, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+        v = np.cross(u, rng.normal(size=(per_sphere, 3))); v /= np.linalg.norm(v, axis=1, keepdims=True)
+        eps = rng.integers(-8, 9, size=(per_sphere, 1)) * 2.0 ** -22
+        closest = np.array([cx, cy, cz]) + v * r * (1.0 + eps)
+        dist = rng.choice([0.5, 3.0, 40.0], size=(per_sphere, 1)) * max(r, 1e-3)
+        out.append(np.hstack([closest - u * dist, u]))
+        nrm = rng.normal(size=(per_sphere, 3)); nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+        tang = np.cross(nrm, rng.normal(size=(per_sphere, 3))); tang /= np.linalg.norm(tang, axis=1, keepdims=True)
+        dd = tang + rng.choice([0.0, 1e-7, -1e-7, 1e-3, -1e-3], size=(per_sphere, 1)) * nrm
+        out.append(np.hstack([np.array([cx, cy, cz]) + nrm * r, dd / np.linalg.norm(dd, axis=1, keepdims=True)]))
+    rays = np.vstack(out).astype(np.float32)
+    rays[:, 3:] /= np.linalg.norm(rays[:, 3:].astype(np.float64), axis=1, keepdims=True).astype(np.float32)
+    return rays
+
+
+def test_tensor_path_prefilter_is_conservative_in_a_cpu_restatement():
+    """Stage 1 of the sweep on the tensor path must flag every sphere the reference's exact expression accepts.  The GPU tests
+    check that per ray on hardware (tests/test_gpu_hits.py); this is the same statement without a GPU, from the sphere operand
+    the library builds (pt_scene_mma_operand) and with the tensor core's accumulation replaced by a worst case."""
+    sc = orc.Scene("random_spheres", 96, 48)
+    cr = sc.flat()["centre_radius"]
+    rays, _ = sc.record_rays(2, 50, 6000)                      # rays of real paths: camera rays and bounces off surfaces
+    rng = np.random.default_rng(17)
+    extent2 = _mma_operand(cr)[2][3]
+    assert 1.5e7 < extent2 < 1.7e7                             # twice the scene's reach (2 x 2000), squared
+    for batch in (rays[:4000], _tangent_rays(cr[rng.choice(len(cr), 60, replace=False)], rng, 24), _tangent_rays(cr[:1], rng, 800)):
+        hits, margin, flagged = _mma_filter_margin(cr, batch)
+        assert hits > 0.2 * len(batch)
+        assert margin > 0.0, "an accepted hit is not a candidate under the worst-case accumulation: margin %g" % margin
+        assert flagged < 6.0                                   # and the filter still filters: candidates per ray (488 spheres)
+    # the same scene far from the origin (|c|, |o| ~ 60 000 on two axes against radii of 0.2): the filter works relative to the
+    # scene's offset, which it may only do where the subtraction is exact
+    far = cr.copy()
+    far[:, 0] += np.float32(40000.0)
+    far[:, 2] -= np.float32(50000.0)
+    shifted = rays[:3000].copy()
+    shifted[:, 0] += np.float32(40000.0)
+    shifted[:, 2] -= np.float32(50000.0)
+    scale_far = _mma_operand(far)[2]
+    assert abs(scale_far[4] - 40000.0) < 1200 and scale_far[5] == 0.0 and abs(scale_far[6] + 50000.0) < 1200
+    hits, margin, _ = _mma_filter_margin(far, shifted)
+    assert hits > 1000 and margin > 0.0
+    # ... and a scene only moderately off-centre keeps t = 0 (the subtraction would round) and a larger extent instead
+    near = cr.copy()
+    near[:, 0] += np.float32(3000.0)
+    assert _mma_operand(near)[2][4] == 0.0
+    # scenes the tensor path is not offered to: fewer than 128 spheres; spheres tiny against the scene's extent
+    assert _mma_operand(cr[:100])[0] == 0
+    tiny = cr.copy()
+    tiny[1:, 3] = 1.0e-4
+    assert _mma_operand(tiny)[0] == 0
+
+
 @pytest.mark.parametrize("preset", PRESETS)
 def test_host_mirror_builds_the_oracles_scene(preset):
     w, h = 120, 80
