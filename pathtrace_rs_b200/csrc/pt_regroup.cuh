@@ -120,6 +120,7 @@ struct RegroupSmem {
     volatile float* tslot;     // this lane's slot
     uint32_t* xchg;            // [kRegroupWords][kCtaThreads]
     uint32_t* cat_count;       // two sets of kRegroupCats counters, 8 words apart
+    float4* exact;             // EXACT_SMEM kernels: the exact blocks (stage 2 + shading, 16 B per sphere), behind the counters
     // image_bytes: n_blocks * 64 (FP32 pre-filter image) or (n_steps + 1) * 512 (tensor-path fragment image)
     __device__ __forceinline__ RegroupSmem(unsigned char* raw, size_t image_bytes) {
         pf = reinterpret_cast<float4*>(raw);
@@ -130,13 +131,14 @@ struct RegroupSmem {
         tslot = reinterpret_cast<volatile float*>(pend + kCtaThreads);
         xchg = reinterpret_cast<uint32_t*>(P + 1) + (kQueueCap + 2) * kCtaThreads;
         cat_count = xchg + kRegroupWords * kCtaThreads;
+        exact = reinterpret_cast<float4*>(cat_count + 16);
     }
 };
 template <bool MMA>
 __device__ __forceinline__ size_t regroup_image_bytes(const KernelArgs& a) {
     return MMA ? (size_t)(a.n_steps + 1) * 512 : (size_t)a.n_blocks * 64;
 }
-template <bool MMA>
+template <bool MMA, bool EXACT_SMEM = false>
 __device__ __forceinline__ void regroup_stage(const KernelArgs& a, const RegroupSmem& sm, uint64_t* bar) {
     *sm.pend = 0u;
     *sm.tslot = 0.0f;
@@ -148,8 +150,10 @@ __device__ __forceinline__ void regroup_stage(const KernelArgs& a, const Regroup
     }
     __syncthreads();
     if (threadIdx.x == 0 && bytes != 0u) {
-        mbar_arrive_expect_tx(bar, bytes);
+        const uint32_t exact_bytes = EXACT_SMEM ? (uint32_t)a.n_blocks * 64u : 0u;
+        mbar_arrive_expect_tx(bar, bytes + exact_bytes);
         tma_bulk_g2s_chunked(sm.pf, MMA ? reinterpret_cast<const void*>(a.mma_image) : reinterpret_cast<const void*>(a.prefilter), bytes, bar);
+        if (exact_bytes != 0u) tma_bulk_g2s_chunked(sm.exact, a.blocks, exact_bytes, bar);
     }
     stage_perlin(a, sm.P);
     __syncthreads();
@@ -159,7 +163,9 @@ __device__ __forceinline__ void regroup_stage(const KernelArgs& a, const Regroup
 // MMA: stage 1 on the tensor path (pt_sweep_mma.cuh); the ray fragments pass through the warp's own 32 columns of the
 // exchange buffer, which nobody else touches between this warp's read-back in cta_regroup and the next trip's first barrier.
 // `active`: the lane has a path in flight (its ray is the parked ray otherwise).
-template <bool MOTION, bool MMA>
+// EXACT_SMEM: stage 2 reads the exact blocks from shared memory (tensor-path kernel, where the loop leaves the LSU nearly idle:
+// cfg2 +1.8 %, cfg4 +1.3 %; chosen by the host when it does not cost a resident CTA).
+template <bool MOTION, bool MMA, bool EXACT_SMEM = false>
 __device__ __forceinline__ void regroup_sweep(const KernelArgs& a, const RegroupSmem& sm, const MotionCtx& mc, bool active, float ox, float oy, float oz, float dx,
                                               float dy, float dz, float& hit_t, int& hit_index, unsigned& flagged) {
     hit_t = kMaxT;
@@ -167,7 +173,7 @@ __device__ __forceinline__ void regroup_sweep(const KernelArgs& a, const Regroup
     if (MMA) {
         int ovf_step;
         const int n = sweep_mma(reinterpret_cast<const uint4*>(sm.pf), a.n_steps, sm.xchg, sm.queue, a.mma, active, ox, oy, oz, dx, dy, dz, ovf_step);
-        sweep_mma_drain<MOTION>(a.blocks, mc, sm.queue_base, n, ovf_step, 0, a.n_steps, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
+        sweep_mma_drain<MOTION>(EXACT_SMEM ? sm.exact : a.blocks, mc, sm.queue_base, n, ovf_step, 0, a.n_steps, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
         return;
     }
     const float nod = -((ox * dx + oy * dy) + oz * dz);
@@ -177,12 +183,13 @@ __device__ __forceinline__ void regroup_sweep(const KernelArgs& a, const Regroup
     sweep_drain<MOTION, true>(a.blocks, mc, sm.queue, cnt, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
 }
 
-template <bool MOTION, bool MMA>
+template <bool MOTION, bool MMA, bool EXACT_SMEM = false>
 __global__ void __launch_bounds__(kCtaThreads) pt_megakernel_regroup(const __grid_constant__ KernelArgs a) {
+    static_assert(MMA || !EXACT_SMEM, "the exact blocks move to shared memory only in the tensor-path kernel");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t bar;
     const RegroupSmem sm(smem_raw, regroup_image_bytes<MMA>(a));
-    regroup_stage<MMA>(a, sm, &bar);
+    regroup_stage<MMA, EXACT_SMEM>(a, sm, &bar);
     const MotionCtx mc{a.motion, const_cast<const float*>(sm.tslot), a.order};
 
     const unsigned lane_id = threadIdx.x & 31u;
@@ -205,7 +212,7 @@ __global__ void __launch_bounds__(kCtaThreads) pt_megakernel_regroup(const __gri
         if (__any_sync(kFullMask, L.active)) {  // regrouping collects idle lanes in whole warps: they skip the sweep
             sweeps += 1u;
             unsigned flagged = 0u;
-            regroup_sweep<MOTION, MMA>(a, sm, mc, L.active, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
+            regroup_sweep<MOTION, MMA, EXACT_SMEM>(a, sm, mc, L.active, ox, oy, oz, dx, dy, dz, hit_t, hit_index, flagged);
         }
         __syncwarp();
         L.pend = *sm.pend != 0u;  // (parked in shared memory across the sweep)
@@ -215,7 +222,7 @@ __global__ void __launch_bounds__(kCtaThreads) pt_megakernel_regroup(const __gri
             if (!cta_regroup(a, L, hit_t, hit_index, sm.xchg, sm.cat_count + ((trip / PT_REGROUP_PERIOD) & 1u) * 8u, lane_id)) break;
         if (L.active) {
             rays += 1ULL;  // scene.rs:57
-            lane_shade<MOTION>(a, L, a.blocks, *sm.P, mc, hit_t, hit_index);
+            lane_shade<MOTION>(a, L, EXACT_SMEM ? sm.exact : a.blocks, *sm.P, mc, hit_t, hit_index);
         }
         lane_refill<MOTION>(a, L, lane_id);  // ended paths sit side by side now: next sample / next ticket together
         *sm.pend = L.pend ? 1u : 0u;
