@@ -27,6 +27,11 @@ namespace pt {
 // consumes exactly its own RNG stream and performs exactly the same arithmetic, so images stay bit-identical; only the
 // assignment of paths to lanes changes.  Finished lanes collect in whole warps, which then skip the sweep.
 // =====================================================================================================
+// PT_REGROUP_DOMAINS: the CTA's paths are regrouped within this many independent groups of warps (named barriers), an
+// experiment knob: 2 halves the number of warps that wait for each other at the price of a coarser sort
+#ifndef PT_REGROUP_DOMAINS
+#define PT_REGROUP_DOMAINS 1
+#endif
 #ifndef PT_REGROUP_PERIOD
 #define PT_REGROUP_PERIOD 1
 #endif
@@ -49,8 +54,23 @@ __device__ __forceinline__ int lane_category(const KernelArgs& a, const Lane& L,
 // used by trip t is cleared after trip t's second barrier and next touched after trip t+1's first barrier).
 // Two CTA barriers per trip; the second also ORs "some lane still has work" over the CTA and returns it.  Trip t+1's
 // first barrier separates trip t's reads of xchg from trip t+1's writes.
+constexpr int kRegroupDomainThreads = kCtaThreads / PT_REGROUP_DOMAINS;
+__device__ __forceinline__ void regroup_barrier(unsigned dom) {
+    if (PT_REGROUP_DOMAINS == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(1u + dom), "r"((unsigned)kRegroupDomainThreads) : "memory");
+}
+__device__ __forceinline__ bool regroup_barrier_or(unsigned dom, bool flag) {
+    if (PT_REGROUP_DOMAINS == 1) return __syncthreads_or(flag ? 1 : 0) != 0;
+    unsigned out;
+    asm volatile("{ .reg .pred p, q; setp.ne.u32 p, %1, 0; bar.red.or.pred q, %2, %3, p; selp.u32 %0, 1, 0, q; }"
+                 : "=r"(out) : "r"(flag ? 1u : 0u), "r"(1u + dom), "r"((unsigned)kRegroupDomainThreads) : "memory");
+    return out != 0u;
+}
 __device__ __forceinline__ bool cta_regroup(const KernelArgs& a, Lane& L, float& hit_t, int& hit_index, uint32_t* __restrict__ xchg,
                                             uint32_t* __restrict__ cat_count, unsigned lane_id) {
+    const unsigned dom = PT_REGROUP_DOMAINS == 1 ? 0u : threadIdx.x / (unsigned)kRegroupDomainThreads;
+    const unsigned dom_base = dom * (unsigned)kRegroupDomainThreads;
+    cat_count += dom * 16u;
     const int cat = lane_category(a, L, hit_index);
     unsigned mine = 0u;     // ballot of this lane's category
     unsigned warp_off = 0u;  // where this warp's lanes of that category start inside the category
@@ -65,8 +85,8 @@ __device__ __forceinline__ bool cta_regroup(const KernelArgs& a, Lane& L, float&
             warp_off = off;
         }
     }
-    __syncthreads();  // all counts are final
-    unsigned base = 0u;
+    regroup_barrier(dom);  // all counts are final
+    unsigned base = dom_base;
 #pragma unroll
     for (int c = 0; c < kRegroupCats - 1; ++c) base += (c < cat) ? cat_count[c] : 0u;
     const unsigned dest = base + warp_off + (unsigned)__popc(mine & ((1u << lane_id) - 1u));
@@ -85,8 +105,8 @@ __device__ __forceinline__ bool cta_regroup(const KernelArgs& a, Lane& L, float&
     w[25 * kCtaThreads] = __float_as_uint(hit_t);
     w[26 * kCtaThreads] = (uint32_t)hit_index;
     w[27 * kCtaThreads] = __float_as_uint(L.time);
-    const bool live = __syncthreads_or(L.finished ? 0 : 1) != 0;  // every path is in its new slot
-    if (threadIdx.x < kRegroupCats) cat_count[threadIdx.x] = 0u;
+    const bool live = regroup_barrier_or(dom, !L.finished);  // every path is in its new slot
+    if (threadIdx.x - dom_base < (unsigned)kRegroupCats) cat_count[threadIdx.x - dom_base] = 0u;
     const uint32_t* r = xchg + threadIdx.x;
     L.rng.s0 = (uint64_t)r[0 * kCtaThreads] | ((uint64_t)r[1 * kCtaThreads] << 32);
     L.rng.s1 = (uint64_t)r[2 * kCtaThreads] | ((uint64_t)r[3 * kCtaThreads] << 32);
@@ -131,7 +151,7 @@ struct RegroupSmem {
         tslot = reinterpret_cast<volatile float*>(pend + kCtaThreads);
         xchg = reinterpret_cast<uint32_t*>(P + 1) + (kQueueCap + 2) * kCtaThreads;
         cat_count = xchg + kRegroupWords * kCtaThreads;
-        exact = reinterpret_cast<float4*>(cat_count + 16);
+        exact = reinterpret_cast<float4*>(cat_count + 16 * PT_REGROUP_DOMAINS);
     }
 };
 template <bool MMA>
@@ -142,7 +162,7 @@ template <bool MMA, bool EXACT_SMEM = false>
 __device__ __forceinline__ void regroup_stage(const KernelArgs& a, const RegroupSmem& sm, uint64_t* bar) {
     *sm.pend = 0u;
     *sm.tslot = 0.0f;
-    if (threadIdx.x < 16) sm.cat_count[threadIdx.x] = 0u;
+    if (threadIdx.x < 16 * PT_REGROUP_DOMAINS) sm.cat_count[threadIdx.x] = 0u;
     const uint32_t bytes = (uint32_t)regroup_image_bytes<MMA>(a);
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);

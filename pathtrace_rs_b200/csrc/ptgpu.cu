@@ -172,7 +172,7 @@ size_t resident_smem(int n_blocks, bool const_image) {
     const size_t image = ((size_t)n_blocks * (const_image ? 16 : 64) + 127) & ~(size_t)127;
     return image + sizeof(pt::PerlinSmem) + kQueueBytes + kPathBytes;
 }
-constexpr size_t kRegroupBytes = (size_t)pt::kRegroupWords * pt::kCtaThreads * sizeof(uint32_t) + 64;  // regroup kernel: path-state exchange + category counters
+constexpr size_t kRegroupBytes = (size_t)pt::kRegroupWords * pt::kCtaThreads * sizeof(uint32_t) + 64 * PT_REGROUP_DOMAINS;  // regroup kernel: path-state exchange + category counters
 size_t regroup_smem(int n_blocks) { return (size_t)n_blocks * 64 + kStreamedFixedBytes + kRegroupBytes; }
 size_t regroup_mma_smem(int n_blocks) { return (size_t)(n_blocks / pt::kLdsGroupBlocks + 1) * 512 + kStreamedFixedBytes + kRegroupBytes; }  // 32 B per sphere + one step of padding
 // which resident kernel renders the scene: 0 automatic = the tensor-path regroup kernel where the scene suits it (5), else the FP32 one (4)
