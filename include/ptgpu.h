@@ -245,7 +245,10 @@ int pt_render_part(PtScene* scene, const PtParams* params, const PtCamera* camer
 /* Device-resident variant (progressive / windowed use, src/glium_window.rs:98-131: the buffer stays
  * on the GPU across frames).  d_rgb_inout: DEVICE buffer width*height*3 f32 on the scene's device;
  * d_ray_count: DEVICE u64, overwritten with this call's ray count.  Asynchronous on `cuda_stream`
- * (a cudaStream_t; NULL = default stream); no host synchronisation is performed. */
+ * (a cudaStream_t; NULL = default stream); no host synchronisation is performed.
+ * At most one render is in flight per PtScene: its ticket counter and pixel-state table are per scene, so every launch —
+ * through this or any other entry point, on whatever stream — first waits (cudaStreamWaitEvent) for the scene's previous
+ * launch.  Calls on one scene must still come from one host thread at a time. */
 int pt_render_device(PtScene* scene, const PtParams* params, const PtCamera* camera, uint32_t frame_num,
                      const PtPartition* part, float* d_rgb_inout, uint64_t* d_ray_count, void* cuda_stream);
 
