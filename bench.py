@@ -379,6 +379,10 @@ def main():
         except (OSError, ValueError, KeyError):
             pass
         st = preset.stats()
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            peaks = {}
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -410,6 +414,11 @@ def main():
                                         % (info.sm_count, info.sm_clock_khz // 1000, ("%.1f" % (peak_probe / 1e12)) if peak_probe else "n/a"),
                          "algorithmic": "16 flop x %d spheres x %d rays per launch (brute force, every ray tests every sphere)" % (n_spheres, int(k_rays_sum / k_steps / world)),
                          "kernel_ms": k_ms_max / k_steps,
+                         "tensor_work": ({"executed": achieved / FLOP_PER_TEST * 64.0 / 1e12 * ((n_spheres + 15) // 16 * 16) / max(1, n_spheres), "unit": "TFLOP/s",
+                                          "what": "HMMA.16816 work of the pre-filter: 2 dot products x 16-deep f16 products x 2 flop per (ray, sphere) test, padded sphere count",
+                                          "mma_sync_ceiling": 554.0 * world, "mma_sync_ceiling_source": "tools/probe_mma.cu on B200: 8.6 clk per m16n8k16 per SM sub-partition (profiles/probe_mma_r2a.txt)",
+                                          "dense_bf16_peak": (peaks.get("bf16_tflops") or 0.0) * world, "dense_bf16_peak_source": "MEASURED_PEAKS.json bf16_tflops (tcgen05 path, cuBLAS)"}
+                                         if st.resident in (2, 3) else None),
                          "note": ("algorithmic flop (the FP32 formulation's 16 per test) against the FP32 FMA peak, as in round 1, so the two builds compare; "
                                   "in this build 12 of the 16 (the two 3-term dot products) execute on the tensor pipe as 2 x 16-deep f16 products = 64 flop per test: %.0f TFLOP/s of HMMA work "
                                   "(mma.sync ceiling measured on B200: 550 TFLOP/s with a register accumulator, tools/probe_mma.cu); the kernel is bound by instruction issue around the MMAs, "
