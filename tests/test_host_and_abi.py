@@ -87,8 +87,9 @@ def test_library_is_sm100a_cuda_with_packed_fp32_and_tma():
 
 
 # ---- the tensor-path pre-filter, evaluated on the CPU from the operand the library builds ---------------------------------
-def _mma_operand(cr, options=None):
-    """pt_scene_mma_operand (host only) for Lambertian spheres `cr` [n, 4]: (rows [stored, 16] as f32, scale[4], order[n])."""
+def _mma_operand(cr, options=None, motion=None):
+    """pt_scene_mma_operand (host only) for Lambertian spheres `cr` [n, 4] (+ optional MovingSphere records [n, 6]):
+    (stored, rows [stored, 16] as f32, scale[7], order[n])."""
     n = len(cr)
     cols = [np.ascontiguousarray(cr[:, i], np.float32) for i in range(4)]
     mats = (ffi.PtMaterial * n)()
@@ -104,6 +105,12 @@ def _mma_operand(cr, options=None):
     d.material_index = midx.ctypes.data_as(C.POINTER(C.c_int32))
     d.n_materials = d.n_textures = n
     d.materials, d.textures = mats, texs
+    if motion is not None:
+        mot = (ffi.PtMotion * n)()
+        for i in range(n):
+            mot[i].centre1[:] = [float(x) for x in motion[i, :3]]
+            mot[i].time0, mot[i].time1, mot[i].moving = float(motion[i, 3]), float(motion[i, 4]), int(motion[i, 5])
+        d.motion = mot
     cap = (n + 15) // 16 * 16
     rows = np.zeros((cap, 16), np.uint16)
     scale = np.zeros(7, np.float32)
@@ -113,20 +120,23 @@ def _mma_operand(cr, options=None):
     return int(stored), rows.view(np.float16).astype(np.float32), scale, order
 
 
-def _mma_filter_margin(cr, rays, options=None):
+def _mma_filter_margin(cr, rays, options=None, motion=None, times=None):
     """The tensor-path pre-filter (pt_sweep_mma.cuh) restated in numpy on the library's own sphere operand: the ray operand in
     f32 as mma_ray_operand builds it, f16 hi/lo split, exact products, and a PESSIMISTIC accumulation: every dot product is
     moved against the candidate by 2^-20 of the sum of its |terms| (twice what tools/probe_mma.cu measures for the tensor
     core's f32 accumulate).  Returns (number of (ray, sphere) pairs the reference's exact f32 expression accepts, the smallest
     worst-case L' among them divided by sigma^2 (|c|^2 + r^2 + |o|^2), flagged pairs per ray)."""
-    stored, rows, (sigma, s, inv_s, max_o2, tx, ty, tz), order = _mma_operand(cr, options)
+    stored, rows, (sigma, s, inv_s, max_o2, tx, ty, tz), order = _mma_operand(cr, options, motion)
     assert stored >= len(cr) and stored % 16 == 0
     t = np.array([tx, ty, tz], np.float32)
     S = rows[: len(cr)].astype(np.float64)                     # stored order
     c = cr[order].astype(np.float32)
     f32 = np.float32
     slack = f32(2.0 ** -15)
-    rays = rays[(((rays[:, :3] - t).astype(np.float64)) ** 2).sum(1) <= max_o2]  # the kernel's own guard: rays beyond the extent bypass stage 1
+    keep = (((rays[:, :3] - t).astype(np.float64)) ** 2).sum(1) <= max_o2  # the kernel's own guard: rays beyond the extent bypass stage 1
+    rays = rays[keep]
+    if times is not None:
+        times = times[keep]
     o_abs, d = rays[:, :3].astype(f32), rays[:, 3:].astype(f32)
     o = o_abs - t                                              # the filter works relative to the scene's offset (exact, see MmaScale)
     assert np.array_equal(o.astype(np.float64), o_abs.astype(np.float64) - t.astype(np.float64))
@@ -153,6 +163,19 @@ def _mma_filter_margin(cr, rays, options=None):
     nb = (co[..., 0] * d[:, None, 0] + co[..., 1] * d[:, None, 1]) + co[..., 2] * d[:, None, 2]
     cc = ((co[..., 0] * co[..., 0] + co[..., 1] * co[..., 1]) + co[..., 2] * co[..., 2]) - c[None, :, 3] * c[None, :, 3]
     hit = (nb * nb - cc) > f32(0.0)
+    if motion is not None:  # MovingSphere::ray_hit at the ray's time (moving_sphere.rs:28-31,38-48), unfused f32, for the spheres that move
+        mo = motion[order].astype(f32)
+        moving = mo[:, 5] != 0
+        with np.errstate(divide="ignore", invalid="ignore"):  # static spheres have no interval: masked below
+            inv_dt = (f32(1.0) / (mo[:, 4] - mo[:, 3])).astype(f32)                                   # moving_sphere.rs:24
+            tt = ((times.astype(f32)[:, None] - mo[None, :, 3]) * inv_dt[None, :]).astype(f32)        # :29
+            ct = (c[None, :, :3] + tt[..., None] * (mo[None, :, :3] - c[None, :, :3])).astype(f32)    # centre_start + s * centre_delta
+            ct = np.where(moving[None, :, None], ct, c[None, :, :3])
+        oc = o_abs[:, None, :] - ct
+        a_ = (d[:, None, 0] * d[:, None, 0] + d[:, None, 1] * d[:, None, 1]) + d[:, None, 2] * d[:, None, 2]
+        b_ = (oc[..., 0] * d[:, None, 0] + oc[..., 1] * d[:, None, 1]) + oc[..., 2] * d[:, None, 2]
+        c_ = ((oc[..., 0] * oc[..., 0] + oc[..., 1] * oc[..., 1]) + oc[..., 2] * oc[..., 2]) - c[None, :, 3] * c[None, :, 3]
+        hit = np.where(moving[None, :], (b_ * b_ - a_ * c_) > f32(0.0), hit)
     c64 = c.astype(np.float64)
     scale = float(sigma) ** 2 * (((c64[None, :, :3] - t.astype(np.float64)) ** 2).sum(2) + c64[None, :, 3] ** 2 + (o.astype(np.float64) ** 2).sum(1)[:, None])
     margin = (worst / scale)[hit]
@@ -211,6 +234,15 @@ def test_tensor_path_prefilter_is_conservative_in_a_cpu_restatement():
     near = cr.copy()
     near[:, 0] += np.float32(3000.0)
     assert _mma_operand(near)[2][4] == 0.0
+    # Hitable::MovingSphere enters the filter as the static sphere that bounds its sweep: every sphere the reference's moving test
+    # accepts at the ray's time must be a candidate (393 moving spheres of the `random` preset, times over the whole shutter)
+    scm = orc.Scene("random", 96, 48)
+    fm = scm.flat()
+    rays_m, times_m = scm.record_rays(2, 50, 5000)
+    assert (fm["motion"][:, 5] != 0).sum() == 393 and times_m.min() >= 0.0 and times_m.max() <= 1.0
+    for tm in (times_m[:3000], np.zeros(3000, np.float32), np.ones(3000, np.float32)):
+        hits, margin, flagged = _mma_filter_margin(fm["centre_radius"], rays_m[:3000], motion=fm["motion"], times=tm)
+        assert hits > 1500 and margin > 0.0 and flagged < 12.0
     # scenes the tensor path is not offered to: fewer than 128 spheres; spheres tiny against the scene's extent
     assert _mma_operand(cr[:100])[0] == 0
     tiny = cr.copy()
