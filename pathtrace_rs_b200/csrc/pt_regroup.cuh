@@ -39,15 +39,20 @@ constexpr int kRegroupCats = 6;
 constexpr int kRegroupWords = 28;  // 8 rng + 6 ray + 3 thr + 3 col + px, py, sample, depth, flags, hit_t, hit_index, time
 enum { CAT_LAMBERT_CONST = 0, CAT_LAMBERT_TEX = 1, CAT_METAL = 2, CAT_DIELECTRIC = 3, CAT_ENDING = 4, CAT_IDLE = 5 };
 
-__device__ __forceinline__ int lane_category(const KernelArgs& a, const Lane& L, int hit_index) {
-    if (!L.active) return CAT_IDLE;
-    if (hit_index < 0 || L.depth >= a.max_depth) return CAT_ENDING;
-    const float4 s1 = __ldg(reinterpret_cast<const float4*>(a.shade + hit_index) + 1);
+// what a hit on stored sphere `index` does next (the scatter code its material runs)
+__device__ __forceinline__ int sphere_category(const KernelArgs& a, int index) {
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(a.shade + index) + 1);
     const int kind = __float_as_int(s1.y);
     if (kind == MAT_LAMBERTIAN) return __float_as_int(s1.z) < 0 ? CAT_LAMBERT_CONST : CAT_LAMBERT_TEX;
     if (kind == MAT_METAL) return CAT_METAL;
     if (kind == MAT_DIELECTRIC) return CAT_DIELECTRIC;
     return CAT_ENDING;  // DiffuseLight
+}
+// cat_table: one byte per stored sphere in shared memory (EXACT_SMEM kernels), or nullptr: read the shading record
+__device__ __forceinline__ int lane_category(const KernelArgs& a, const Lane& L, int hit_index, const uint8_t* __restrict__ cat_table) {
+    if (!L.active) return CAT_IDLE;
+    if (hit_index < 0 || L.depth >= a.max_depth) return CAT_ENDING;
+    return cat_table ? (int)cat_table[hit_index] : sphere_category(a, hit_index);
 }
 
 // xchg: [kRegroupWords][kCtaThreads] words; cat_count: this trip's [kRegroupCats] counters (two sets alternate: the set
@@ -67,11 +72,11 @@ __device__ __forceinline__ bool regroup_barrier_or(unsigned dom, bool flag) {
     return out != 0u;
 }
 __device__ __forceinline__ bool cta_regroup(const KernelArgs& a, Lane& L, float& hit_t, int& hit_index, uint32_t* __restrict__ xchg,
-                                            uint32_t* __restrict__ cat_count, unsigned lane_id) {
+                                            uint32_t* __restrict__ cat_count, unsigned lane_id, const uint8_t* __restrict__ cat_table = nullptr) {
     const unsigned dom = PT_REGROUP_DOMAINS == 1 ? 0u : threadIdx.x / (unsigned)kRegroupDomainThreads;
     const unsigned dom_base = dom * (unsigned)kRegroupDomainThreads;
     cat_count += dom * 16u;
-    const int cat = lane_category(a, L, hit_index);
+    const int cat = lane_category(a, L, hit_index, cat_table);
     unsigned mine = 0u;     // ballot of this lane's category
     unsigned warp_off = 0u;  // where this warp's lanes of that category start inside the category
 #pragma unroll
@@ -140,7 +145,8 @@ struct RegroupSmem {
     volatile float* tslot;     // this lane's slot
     uint32_t* xchg;            // [kRegroupWords][kCtaThreads]
     uint32_t* cat_count;       // two sets of kRegroupCats counters, 8 words apart
-    float4* exact;             // EXACT_SMEM kernels: the exact blocks (stage 2 + shading, 16 B per sphere), behind the counters
+    float4* exact;             // EXACT_SMEM kernels: the exact blocks (stage 2 + shading, 16 B per sphere), behind the counters,
+                               // followed by one category byte per stored sphere (n_blocks * 4 bytes)
     // image_bytes: n_blocks * 64 (FP32 pre-filter image) or (n_steps + 1) * 512 (tensor-path fragment image)
     __device__ __forceinline__ RegroupSmem(unsigned char* raw, size_t image_bytes) {
         pf = reinterpret_cast<float4*>(raw);
@@ -176,6 +182,10 @@ __device__ __forceinline__ void regroup_stage(const KernelArgs& a, const Regroup
         if (exact_bytes != 0u) tma_bulk_g2s_chunked(sm.exact, a.blocks, exact_bytes, bar);
     }
     stage_perlin(a, sm.P);
+    if (EXACT_SMEM) {  // what the regroup sorts by, one byte per stored sphere (padding spheres are never hit)
+        uint8_t* tab = reinterpret_cast<uint8_t*>(sm.exact + (size_t)a.n_blocks * 4);
+        for (int i = (int)threadIdx.x; i < a.n_blocks * 4; i += (int)blockDim.x) tab[i] = i < a.n_spheres ? (uint8_t)sphere_category(a, i) : (uint8_t)CAT_ENDING;
+    }
     __syncthreads();
     if (bytes != 0u) mbar_wait(bar, 0);
 }
@@ -239,7 +249,9 @@ __global__ void __launch_bounds__(kCtaThreads) pt_megakernel_regroup(const __gri
         L.time = *sm.tslot;
         // (PT_REGROUP_PERIOD > 1, an experiment knob: regroup only every n-th trip; between two regroups a path is shaded by the lane that swept it)
         if (PT_REGROUP_PERIOD == 1 || trip % PT_REGROUP_PERIOD == 0u)
-            if (!cta_regroup(a, L, hit_t, hit_index, sm.xchg, sm.cat_count + ((trip / PT_REGROUP_PERIOD) & 1u) * 8u, lane_id)) break;
+            if (!cta_regroup(a, L, hit_t, hit_index, sm.xchg, sm.cat_count + ((trip / PT_REGROUP_PERIOD) & 1u) * 8u, lane_id,
+                             EXACT_SMEM ? reinterpret_cast<const uint8_t*>(sm.exact + (size_t)a.n_blocks * 4) : nullptr))
+                break;
         if (L.active) {
             rays += 1ULL;  // scene.rs:57
             lane_shade<MOTION>(a, L, EXACT_SMEM ? sm.exact : a.blocks, *sm.P, mc, hit_t, hit_index);

@@ -224,7 +224,7 @@ int plan_launch(Replica* s) {
                     rc = s->d_motion ? configure_kernel(pt::pt_debug_hits_regroup<true, true>, s->smem_bytes, nullptr)
                                      : configure_kernel(pt::pt_debug_hits_regroup<false, true>, s->smem_bytes, nullptr);
                 // the exact blocks (16 B per sphere) in shared memory too, when that does not cost a resident CTA (measured: cfg2 +1.8 %)
-                const size_t with_exact = s->smem_bytes + (size_t)s->n_blocks * 64;
+                const size_t with_exact = s->smem_bytes + (size_t)s->n_blocks * 64 + (((size_t)s->n_blocks * 4 + 15) & ~(size_t)15);  // + one category byte per sphere
                 if (rc == PT_OK && with_exact <= kMaxDynSmem) {
                     int ctas = 0;
                     rc = s->d_motion ? configure_kernel(pt::pt_megakernel_regroup<true, true, true>, with_exact, &ctas)
