@@ -1,6 +1,6 @@
 // pt_regroup.cuh — the resident kernel: ONE path per lane and a CTA-level regroup of the paths between sweep and shading.
 // The default for every scene that fits in shared memory, in two instantiations of the same kernel: stage 1 of the sweep on
-// the tensor path (MMA = true, pt_sweep_mma.cuh: cfg2 69.8 %, cfg4 72.2 % of the FP32 peak in algorithmic flop) or in packed
+// the tensor path (MMA = true, pt_sweep_mma.cuh: cfg2 70.6 %, cfg4 72.9 % of the FP32 peak in algorithmic flop) or in packed
 // FP32 (MMA = false, pt_sweep.cuh: 55.2 % / 56.7 %; small scenes, ill-scaled scenes, cameras outside the scene's extent).
 //
 // Round 2 also built two alternatives around a cheaper FP32 sweep — two paths per lane with the sphere pairs as uniform
