@@ -444,3 +444,21 @@ def test_png_writer_roundtrip(tmp_path):
     assert int.from_bytes(ihdr[:4], "big") == 7 and int.from_bytes(ihdr[4:8], "big") == 5 and ihdr[8:10] == b"\x08\x02"
     raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(5, 1 + 7 * 3)
     assert np.all(raw[:, 0] == 0) and np.array_equal(raw[:, 1:].reshape(5, 7, 3), rgb)
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py's contract: ONE JSON line on stdout.  The reference arm runs without a GPU (the CPU restatement on the host
+    cores); whatever a library prints goes to stderr (bench.claim_stdout), the line carries the keys the driver reads."""
+    import json
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    code = ("import os, sys; sys.argv = ['bench.py', '--impl', 'reference', '--workload', 'cfg1', '--steps', '1', '--warmup', '0'];"
+            "sys.path.insert(0, %r); import bench; bench.claim_stdout(); os.write(1, b'a library banner\\n'); sys.exit(bench.main())" % root)
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=root)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = p.stdout.splitlines()
+    assert len(lines) == 1 and "a library banner" in p.stderr
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "Mrays/s" and line["unit"] == "Mrays/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "cfg1" in line["config"]["workload"]
